@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native BlueSky-Gym step path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload at every N (weak scaling): BASELINE.json configs[1] per GPU -- HorizontalCREnv-v0, 4096 env
+instances, 20 intruders each (21 aircraft), StateBased conflict detection in every simulator substep,
+10 substeps of DT 5 s per env step, autoreset, random actions resident in HBM.  One "step" = one
+batched env step = one launch of the env-step megakernel over all envs of the rank.
+Metric: env-steps/s, whole job.  Extra: CD aircraft-pairs/s at N = 100k (BASELINE configs[4]).
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference's step
+loop (oracle/, "port": the reference's own BlueSky dependency is not installable here) on the host cores.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 4096
+N_INTRUDERS = 20
+N_SUB = 10
+CD_N = 100_000
+# algorithmic work (restated in DESIGN.md)
+F_PAIR = 67.0            # FP32 flop per ordered aircraft pair of state-based CD
+F_KIN = 250.0            # FP32 flop per aircraft-substep of Traffic.update
+F_OBS = 3000.0           # per env step
+A = N_INTRUDERS + 1
+FLOP_PER_ENV_STEP = N_SUB * (A * F_KIN + A * (A - 1) * F_PAIR) + F_OBS
+BYTES_PER_ENV_STEP = 2 * A * 68 + (5 * N_INTRUDERS + 3) * 4 + 2 * (4 * 8 + 4 * 4 + 16 * 4) + 6 * 4 + 10
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    """One host core stepping oracle envs (the restated reference step loop) for `budget` seconds."""
+    seed, budget = args
+    sys.path.insert(0, ROOT)
+    from oracle import envs as oenvs
+    np.random.seed(seed)
+    env = oenvs.HorizontalCREnv(n_intruders=N_INTRUDERS, cd_enabled=True)
+    env.reset()
+    rng = np.random.default_rng(seed)
+    for _ in range(3):
+        env.step(rng.uniform(-1, 1, 1))
+    n, t0, ep = 0, time.perf_counter(), 0
+    while time.perf_counter() - t0 < budget:
+        _, _, term, _, _ = env.step(rng.uniform(-1, 1, 1))
+        n += 1
+        ep += 1
+        if term or ep >= 300:
+            env.reset()
+            ep = 0
+    return n, time.perf_counter() - t0
+
+
+def cpu_baseline(budget_s=12.0, cores=None):
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(1000 + i, budget_s) for i in range(cores)])
+    steps = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return dict(value=steps / wall, unit="env-steps/s", cores=cores, kind="port",
+                sample=f"{steps} env steps of HorizontalCREnv-v0 (20 intruders, CD on) in {wall:.1f} s, "
+                       f"one oracle env per process, {cores} processes")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = max(2.0, min(20.0, 2.0 * args.steps))
+    cb = cpu_baseline(budget_s=budget)
+    line = {"impl": "reference", "metric": "env_steps_per_sec", "value": cb["value"], "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * ENVS_PER_GPU * args.gpus / cb["value"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus), "cpu_baseline": cb, "gpu_launches": 0,
+            "e2e": {"value": cb["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "HorizontalCREnv-v0 batched (BASELINE configs[1])", "envs_per_gpu": ENVS_PER_GPU,
+            "envs_total": ENVS_PER_GPU * n_gpus, "n_intruders": N_INTRUDERS, "aircraft_per_env": A,
+            "substeps_per_step": N_SUB, "simdt_s": 5.0, "cd": "StateBased every substep", "autoreset": "same_step",
+            "max_episode_steps": 300, "actions": "U(-1,1) float32, resident in HBM", "l2": "flushed between timed steps",
+            "parallelism": f"env-sharded x{n_gpus}, no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.stop, self.index = [], False, index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from bluesky_gym_sasha_b200 import _lib, build
+    from bluesky_gym_sasha_b200.cd import StateBasedCD
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    E, K, W = ENVS_PER_GPU, args.steps, max(3, args.warmup)
+    venv = BlueSkyVectorEnv("HorizontalCREnv-v0", E, device=local, seed=0, cd_enabled=True, n_intruders=N_INTRUDERS,
+                            autoreset_mode="same_step", env_id_offset=rank * E)
+    venv.reset_torch()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    bank = torch.rand((K + W, E, 1), generator=g, device=dev) * 2.0 - 1.0      # actions resident in HBM
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+    for i in range(W):
+        venv.step_torch(bank[i])
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = venv.gpu_launches
+    with ClockSampler(local) as clk:
+        for i in range(K):
+            flush.fill_(float(i))                           # evict the sim state from L2 (not timed)
+            ev[i][0].record()
+            venv.step_torch(bank[W + i])
+            ev[i][1].record()
+        barrier()
+    launches = venv.gpu_launches - launches0
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    t_dev = max_over_ranks(t_dev)
+    value = E * world * K / t_dev
+    kernel_ms = 1e3 * t_dev / K
+
+    # back-to-back (L2-warm) figure, for context
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        venv.step_torch(bank[W + i])
+    e1.record()
+    barrier()
+    warm_value = E * world * K / max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+    # end to end through the public numpy API: pinned host actions in, obs/reward/flags/info out, every step
+    host_actions = bank[W:].cpu().numpy()
+    for i in range(3):
+        venv.step(host_actions[i % K])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        obs, rew, term, trunc, info = venv.step(host_actions[i])
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    L = venv.layout
+    h2d = E * L.act_dim * 4
+    d2h = E * (L.obs_dim * 4 + 4 + 1 + 1 + L.info_dim * 4)
+    e2e = {"value": E * world * K / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "api": "BlueSkyVectorEnv.step (numpy in / numpy out, bsg_step_host)"}
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    line = None
+    if rank == 0:
+        fp32 = C_double_probe(lib, local)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        achieved_tf = FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12
+        roof = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32 / 1e12, "unit": "TFLOP/s",
+                "frac": achieved_tf / (fp32 / 1e12), "traffic": None, "kernel": "env_kernel<HorizontalCR,32>",
+                "peak_source": "bsg_probe_fp32 (dense FFMA, measured in this run)",
+                "flop_per_env_step": FLOP_PER_ENV_STEP,
+                "hbm": {"achieved": BYTES_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
+                        "bytes_per_env_step": BYTES_PER_ENV_STEP}}
+        # CD at N = 100k on this GPU (BASELINE configs[4], single-GPU share)
+        cd = bench_cd(torch, dev, StateBasedCD, fp32)
+        cb = cpu_baseline(budget_s=10.0)
+        line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (lat/lon f64)", "data": "synthetic", "config": workload_config(world),
+                "value_l2_warm": warm_value, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+                "cpu_baseline": cb, "clocks": clk.summary(), "cd_pairs": cd}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def C_double_probe(lib, device):
+    import ctypes as C
+    from bluesky_gym_sasha_b200 import _lib
+    out = C.c_double(0.0)
+    _lib.check(lib.bsg_probe_fp32(device, C.byref(out)))
+    return out.value
+
+
+def bench_cd(torch, dev, StateBasedCD, fp32_peak, n=CD_N, reps=5):
+    """All-pairs CD at N = 100k on one GPU: ordered pairs/s and fraction of the measured FP32 peak."""
+    rng = np.random.default_rng(1)
+    lat = 52 + 40 * (rng.random(n) - 0.5)
+    lon = 4 + 40 * (rng.random(n) - 0.5)
+    alt = np.round(rng.uniform(3000, 12000, n) / 304.8) * 304.8
+    gs = rng.uniform(150, 250, n)
+    trk = rng.uniform(0, 360, n)
+    vs = np.where(rng.random(n) < 0.8, 0.0, rng.choice([-1.0, 1.0], n) * rng.uniform(5, 15, n))
+    cd = StateBasedCD(device=dev.index)
+    rec, _ = cd.pack(lat, lon, trk, gs, alt, vs, 52.0, 4.0)
+    for _ in range(2):
+        out = cd.detect_packed(rec, n)
+    torch.cuda.synchronize(dev)
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = cd.detect_packed(rec, n)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    pairs = n * (n - 1)
+    tf = pairs * F_PAIR / best / 1e12
+    return {"n_aircraft": n, "ordered_pairs_per_s": pairs / best, "ms": best * 1e3, "n_conf": int(out["npairs"][0]),
+            "n_los": int(out["npairs"][1]),
+            "roofline": {"bound": "fp32", "achieved": tf, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
+                         "frac": tf / (fp32_peak / 1e12), "flop_per_pair": F_PAIR, "executed_fraction": 1.0,
+                         "kernel": "cd_tiled_kernel"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,107 @@
+"""ctypes binding of libbsg_b200.so (include/bsg.h).  Loading fails loudly: there is no CPU fallback.
+
+The structures mirror include/bsg.h field by field; tests/test_abi.py checks that every symbol the
+header declares is exported and that the struct sizes agree with what the library reports.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbsg_b200.so")
+
+BSG_OK, BSG_EINVAL, BSG_ECUDA, BSG_ESTATE, BSG_ENOMEM = 0, -1, -2, -3, -4
+ENV_DESCENT, ENV_HORIZONTAL_CR, ENV_SECTOR_CR, ENV_MERGE = 0, 1, 2, 3
+AUTORESET_DISABLED, AUTORESET_NEXT_STEP, AUTORESET_SAME_STEP = 0, 1, 2
+CD_LON_WRAP, CD_SYMMETRIC = 1, 2
+
+# indices into the per-env records (include/bsg.h)
+F64_WPT_LAT, F64_WPT_LON, F64_TARGET_ALT, F64_POLY_AREA, F64_COUNT = 0, 1, 2, 3, 4
+F32_TOTAL_REWARD, F32_DRIFT_SUM, F32_FINAL_ALT, F32_LAST_HDG, F32_COUNT = 0, 1, 2, 3, 4
+(I32_STEP, I32_EPISODE, I32_SIMK, I32_WPT_REACH, I32_DRIFT_N, I32_INTRUSIONS, I32_NUM_AC, I32_NVERT,
+ I32_NEEDS_RESET, I32_FAF, I32_NCONF, I32_NLOS, I32_RESET_FLAGS) = range(13)
+I32_COUNT = 16
+FL_ALIVE, FL_LNAV, FL_LASTWP, FL_WPSHIFT = 1, 2, 4, 8
+
+
+class Perf(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("vminto", "vmaxic", "vminer", "vmaxer", "vminap", "vmaxap",
+                                         "vsmin", "vsmax", "hmax", "mmo", "axmax_gd", "axmax_air")]
+
+
+class Config(C.Structure):
+    _fields_ = [("env_type", C.c_int32), ("num_envs", C.c_int32), ("n_intruders", C.c_int32),
+                ("cd_enabled", C.c_int32), ("autoreset_mode", C.c_int32), ("max_episode_steps", C.c_int32),
+                ("default_hdg_random", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64),
+                ("env_id_offset", C.c_int64), ("rpz", C.c_float), ("hpz", C.c_float),
+                ("dtlookahead", C.c_float), ("perf", Perf)]
+
+
+class Layout(C.Structure):
+    _fields_ = [("slots", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("info_dim", C.c_int32),
+                ("n_sub", C.c_int32), ("env_f64", C.c_int32), ("env_f32", C.c_int32), ("env_i32", C.c_int32),
+                ("poly_f64", C.c_int32), ("simdt", C.c_float)]
+
+
+TENSOR_FIELDS = ("pos", "kin", "cmd", "aux", "flags", "tcpamax", "inconf", "env_f64", "env_f32", "env_i32",
+                 "poly", "obs", "final_obs", "reward", "terminated", "truncated", "info", "actions_staging")
+
+
+class TensorTable(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in TENSOR_FIELDS]
+
+
+SYMBOLS = ("bsg_abi_version", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
+           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_traf_update",
+           "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_probe_fp32")
+
+_lib = None
+
+
+class BsgError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the CUDA extension; raises if it has not been built (python -m bluesky_gym_sasha_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BsgError(f"{LIB_PATH} is missing: build it with `python -m bluesky_gym_sasha_b200.build` "
+                       "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float, C.c_double
+    lib.bsg_abi_version.restype = C.c_int
+    lib.bsg_last_error.restype = C.c_char_p
+    lib.bsg_device_count.restype = C.c_int
+    lib.bsg_query_layout.argtypes = [C.POINTER(Config), C.POINTER(Layout)]
+    lib.bsg_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.bsg_destroy.argtypes = [vp]
+    lib.bsg_destroy.restype = None
+    lib.bsg_bind_state.argtypes = [vp, C.POINTER(TensorTable)]
+    lib.bsg_reset.argtypes = [vp, vp, vp]
+    lib.bsg_step.argtypes = [vp, vp, vp]
+    lib.bsg_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.bsg_traf_update.argtypes = [vp, i32, vp]
+    lib.bsg_cd_padded.argtypes = [i64]
+    lib.bsg_cd_padded.restype = i64
+    lib.bsg_cd_pack.argtypes = [vp, vp, vp, vp, vp, vp, i64, f64, f64, vp, vp]
+    lib.bsg_cd_detect.argtypes = [vp, i64, i64, i64, f32, f32, f32, u32, vp, vp, vp, vp, vp, i64, vp, vp]
+    lib.bsg_probe_fp32.argtypes = [i32, C.POINTER(f64)]
+    for name in ("bsg_query_layout", "bsg_create", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host",
+                 "bsg_traf_update", "bsg_cd_pack", "bsg_cd_detect", "bsg_probe_fp32"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != BSG_OK:
+        msg = load().bsg_last_error().decode("utf-8", "replace")
+        raise BsgError(f"libbsg_b200 error {rc}: {msg}")
+
+
+def query_layout(cfg: Config) -> Layout:
+    lay = Layout()
+    check(load().bsg_query_layout(C.byref(cfg), C.byref(lay)))
+    return lay

@@ -1,0 +1,127 @@
+"""StateBasedCD -- single-airspace state-based conflict detection on the GPU (kernel K2).
+
+Interface mirrored: ``StateBased.detect(ownship, intruder, rpz, hpz, dtlookahead)`` of upstream BlueSky
+(restated in oracle/statebased.py) -> ``confpairs, lospairs, inconf, tcpamax, ...``.  The reference
+never switches ASAS on (merge_env.py:157 issues only ``reso off``); BASELINE.json's north_star adds it.
+Inputs are float64 aircraft state (degrees, m/s, m) as numpy arrays or CUDA tensors; the work is done by
+``bsg_cd_pack`` + ``bsg_cd_detect`` (include/bsg.h).  Multi-GPU: rows are block-sharded over ranks after
+an NCCL all-gather of the 32-byte CD records (``detect_sharded``).  No CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+NM, FT = 1852.0, 0.3048
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class StateBasedCD:
+    def __init__(self, device=0, rpz=5.0 * NM, hpz=1000.0 * FT, dtlookahead=300.0, pair_capacity=1 << 22):
+        if not torch.cuda.is_available():
+            raise _lib.BsgError("StateBasedCD needs a CUDA device: there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        self.rpz, self.hpz, self.dtlookahead = float(rpz), float(hpz), float(dtlookahead)
+        self.pair_capacity = int(pair_capacity)
+        self.gpu_launches = 0
+        self._buf = {}
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _as_dev(self, x):
+        if isinstance(x, torch.Tensor):
+            return x.to(device=self.device, dtype=torch.float64).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=self.device)
+
+    def _get(self, name, shape, dtype):
+        t = self._buf.get(name)
+        if t is None or t.shape != tuple(shape) or t.dtype != dtype:
+            t = torch.zeros(shape, dtype=dtype, device=self.device)
+            self._buf[name] = t
+        return t
+
+    # ---------------------------------------------------------------- packing
+    def pack(self, lat, lon, trk, gs, alt, vs, lat0, lon0, out=None):
+        """float64 SoA -> [n_pad, 8] float32 CD records (padding rows are inert aircraft)."""
+        arrs = [self._as_dev(a) for a in (lat, lon, trk, gs, alt, vs)]
+        n = arrs[0].numel()
+        n_pad = int(self.lib.bsg_cd_padded(n))
+        rec = out if out is not None else torch.empty((max(n_pad, 1), 8), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bsg_cd_pack(*[_ptr(a) for a in arrs], n, float(lat0), float(lon0), _ptr(rec),
+                                            self._stream()))
+        self.gpu_launches += 1
+        return rec, n
+
+    # ---------------------------------------------------------------- detection on packed records
+    def detect_packed(self, rec, n_all, row0=0, n_rows=None, lon_wrap=False, want_pairs=True):
+        """Rows [row0, row0+n_rows) x all n_all columns.  Asynchronous; returns device tensors."""
+        n_rows = n_all - row0 if n_rows is None else n_rows
+        m = max(n_rows, 1)
+        nconf = self._get("nconf", (m,), torch.int32)
+        nlos = self._get("nlos", (m,), torch.int32)
+        tcpamax = self._get("tcpamax", (m,), torch.float32)
+        inconf = self._get("inconf", (m,), torch.uint8)
+        npairs = self._get("npairs", (2,), torch.int64)
+        pairs = self._get("pairs", (max(self.pair_capacity, 1), 2), torch.int32) if want_pairs else None
+        flags = _lib.CD_LON_WRAP if lon_wrap else 0
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bsg_cd_detect(_ptr(rec), n_all, row0, n_rows, self.rpz, self.hpz, self.dtlookahead,
+                                              flags, _ptr(nconf), _ptr(nlos), _ptr(tcpamax), _ptr(inconf),
+                                              _ptr(pairs), self.pair_capacity if want_pairs else 0, _ptr(npairs),
+                                              self._stream()))
+        self.gpu_launches += 2 if n_rows else 0
+        return dict(nconf_row=nconf[:n_rows], nlos_row=nlos[:n_rows], tcpamax=tcpamax[:n_rows],
+                    inconf=inconf[:n_rows], pairs=pairs, npairs=npairs)
+
+    # ---------------------------------------------------------------- convenience: StateBased.detect
+    def detect(self, lat, lon, trk, gs, alt, vs, lat0=None, lon0=None):
+        """Full N x N detection.  Returns host results shaped like upstream's ``detect`` outputs."""
+        lat_d, lon_d = self._as_dev(lat), self._as_dev(lon)
+        n = lat_d.numel()
+        if n == 0:
+            z = np.zeros(0)
+            return dict(confpairs=np.zeros((0, 2), np.int32), inconf=z.astype(bool), tcpamax=z,
+                        nconf_row=z.astype(np.int64), nlos_row=z.astype(np.int64), n_conf=0, n_los=0, truncated=False)
+        if lat0 is None:
+            lat0 = float(lat_d.mean())
+        if lon0 is None:
+            lon0 = float(lon_d[0])
+        span = float((((lon_d - lon0) + 180.0) % 360.0 - 180.0).abs().max())
+        rec, n = self.pack(lat_d, lon_d, trk, gs, alt, vs, lat0, lon0)
+        out = self.detect_packed(rec, n, lon_wrap=span >= 90.0)
+        torch.cuda.synchronize(self.device)
+        n_conf, n_los = (int(v) for v in out["npairs"].cpu())
+        k = min(n_conf, self.pair_capacity)
+        return dict(confpairs=out["pairs"][:k].cpu().numpy(), inconf=out["inconf"].cpu().numpy().astype(bool),
+                    tcpamax=out["tcpamax"].cpu().numpy().astype(np.float64),
+                    nconf_row=out["nconf_row"].cpu().numpy().astype(np.int64),
+                    nlos_row=out["nlos_row"].cpu().numpy().astype(np.int64),
+                    n_conf=n_conf, n_los=n_los, truncated=n_conf > self.pair_capacity)
+
+    # ---------------------------------------------------------------- multi-GPU: rows sharded over ranks
+    def detect_sharded(self, rec_local, n_local, group=None, lon_wrap=False, want_pairs=False):
+        """Each rank owns ``n_local`` aircraft (the same count on every rank, a multiple of 256 so blocks
+        stay tile-aligned).  One NCCL all-gather of the packed records, then this rank evaluates its own
+        rows against all columns; per-row outputs stay with the owner."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        assert n_local % 256 == 0, "shard size must be a multiple of the 256-aircraft tile"
+        allrec = self._get("allrec", (n_local * world, 8), torch.float32)
+        dist.all_gather_into_tensor(allrec, rec_local[:n_local].contiguous(), group=group)
+        return self.detect_packed(allrec, n_local * world, row0=rank * n_local, n_rows=n_local,
+                                  lon_wrap=lon_wrap, want_pairs=want_pairs)
+
+
+def shard_rows(n_all, world, rank):
+    """Block partition used by ``detect_sharded`` and its CPU (gloo) tests: [row0, row0 + n_rows)."""
+    per = n_all // world
+    return rank * per, per

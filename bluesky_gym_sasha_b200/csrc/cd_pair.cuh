@@ -1,0 +1,77 @@
+// cd_pair.cuh -- one ordered aircraft pair of state-based conflict detection, float32.
+// Restates the per-element arithmetic of bluesky/traffic/asas/statebased.py::StateBased.detect
+// (see oracle/statebased.py for the float64 restatement this is checked against; the reference never
+// enables ASAS -- merge_env.py:157 only issues `reso off` -- BASELINE.json's north_star adds it).
+//
+// CD record (32 B, two float4):  A = (x, y, ch, sh)   B = (u, v, alt, vs)
+//   x = Re*rad(lon - lon0), y = Re*rad(lat - lat0)   [m of arc from the airspace origin]
+//   ch, sh = cos, sin of lat/2                       (cos of the pair's mean latitude = chi*chj - shi*shj)
+//   u = gs sin(trk), v = gs cos(trk)                 [m/s east, north]
+// Algebra used (identical to upstream's, fewer special-function ops):
+//   dist sin(qdr) = x-difference * cos(mean lat), dist cos(qdr) = y-difference  (no atan2/sin/cos),
+//   dcpa^2 = |d x w|^2 / |w|^2  (Lagrange identity for dist^2 - tcpa^2 |w|^2; no cancellation),
+//   dxinhor / vrel = sqrt((R^2 - dcpa^2) / |w|^2)    (one MUFU.RCP shared with tcpa),
+//   min/max(tcrosshi, tcrosslo) = t0 -+ |hpz / dvs|.
+// 3 MUFU (rcp, sqrt, rcp) + ~45 FMA/ALU-pipe instructions per ordered pair.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace bsg {
+
+constexpr float kTwoPiRe = 6.283185307179586f * 6371000.0f;
+constexpr float kInvTwoPiRe = 1.0f / (6.283185307179586f * 6371000.0f);
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+struct CdPair {
+    bool conf, los;
+    float tcpa;
+};
+
+// (i) = own row, (j) = intruder column.  `same` marks the diagonal (upstream adds 1e9*eye).
+template <bool WRAP>
+__device__ __forceinline__ CdPair cd_pair_eval(const float4 Ai, const float4 Bi, const float4 Aj,
+                                               const float4 Bj, float R2, float hpz, float dtlook,
+                                               bool same) {
+    float dy = Aj.y - Ai.y;
+    float dxl = Aj.x - Ai.x;
+    if (WRAP) dxl -= kTwoPiRe * rintf(dxl * kInvTwoPiRe);
+    float cav = fmaf(-Ai.w, Aj.w, Ai.z * Aj.z);
+    float dx = dxl * cav;
+    float du = Bj.x - Bi.x, dv = Bj.y - Bi.y;
+    float dv2 = fmaxf(fmaf(du, du, dv * dv), 1e-6f);
+    float dot = fmaf(du, dx, dv * dy);
+    float crs = fmaf(dx, dv, -dy * du);
+    float inv = rcp_approx(dv2);
+    float tcpa = -dot * inv;
+    float dcpa2 = crs * crs * inv;
+    float dist2 = fmaf(dx, dx, dy * dy);
+    bool swhor = dcpa2 < R2;
+    float dtin = sqrt_approx((R2 - dcpa2) * inv);
+    float tinhor = swhor ? tcpa - dtin : 1e8f;
+    float touthor = swhor ? tcpa + dtin : -1e8f;
+    float dalt = Bj.z - Bi.z;
+    float dvs = Bj.w - Bi.w;
+    dvs = fabsf(dvs) < 1e-6f ? 1e-6f : dvs;
+    float ninv = -rcp_approx(dvs);
+    float t0 = dalt * ninv;
+    float hw = fabsf(hpz * ninv);
+    float tinconf = fmaxf(t0 - hw, tinhor);
+    float toutconf = fminf(t0 + hw, touthor);
+    CdPair o;
+    o.conf = swhor && (tinconf <= toutconf) && (toutconf > 0.0f) && (tinconf < dtlook) && !same;
+    o.los = (dist2 < R2) && (fabsf(dalt) < hpz) && !same;
+    o.tcpa = tcpa;
+    return o;
+}
+
+}  // namespace bsg

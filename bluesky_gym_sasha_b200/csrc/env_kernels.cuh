@@ -1,0 +1,298 @@
+// env_kernels.cuh -- K1/K3/K4/K5/K6: the batched BlueSky-Gym step as one kernel launch.
+//
+// One group of G lanes (G = 1, 8, 16 or 32; lane = aircraft slot) owns one env instance; aircraft
+// state lives in registers for all n_sub simulator substeps of an env step and is read / written
+// once per step as coalesced float4 / double2 (slot index fastest, so a warp touches 512 contiguous
+// bytes per array).  Inside a substep: autopilot (select modes, LNAV/FMS for MergeEnv's routes) ->
+// in-group all-pairs state-based CD (records staged in shared memory, broadcast LDS.128; K3) ->
+// OpenAP-lite limits -> airspeed / heading / vertical-speed response -> flat-earth lat/lon
+// integration in float64 (K1).  Then observation + reward + termination (K4), the TimeLimit cap and
+// vector autoreset with a Philox-keyed scenario generator (K5).
+//
+// Replaces, per env step: Env.step of the reference (e.g. horizontal_cr_env.py:103-125 ->
+// n_sub x bs.sim.step() -> _get_obs :150-213 -> _get_reward :225-270), i.e. upstream
+// Simulation.step / Traffic.update / Autopilot.update / perfoap.limits / StateBased.detect as
+// restated in oracle/traffic.py, oracle/perf.py, oracle/statebased.py, oracle/envs.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bsg_internal.h"
+#include "bsg_math.cuh"
+#include "cd_pair.cuh"
+#include "rng.cuh"
+
+namespace bsg {
+
+constexpr int kEnvThreads = 128;
+constexpr uint32_t kFlAlive = 1u, kFlLnav = 2u, kFlLastWp = 4u, kFlWpShift = 8u;
+enum { kModeStep = 0, kModeReset = 1, kModeTraf = 2 };
+
+// bluesky.traffic.performance.openap.phase constants
+enum { PH_NA = 0, PH_TO = 1, PH_IC = 2, PH_CL = 3, PH_CR = 4, PH_DE = 5, PH_AP = 6, PH_LD = 7, PH_GD = 8 };
+
+struct EnvParams {
+    int env_type, E, n_int, cd_enabled, autoreset, max_steps, hdg_random, n_sub, fms_rel_freq, mode;
+    int obs_dim, act_dim, info_dim;
+    float simdt, R2, hpz, dtlook;
+    double fix_lat, fix_lon;      // MergeEnv FIX (merge_env.py:43-46), evaluated on the host in double
+    uint64_t seed;
+    long long gid0;
+    bsg_perf perf;
+    double2* pos; float4* kin; float4* cmd; float4* aux; uint32_t* flags;
+    float* tcpamax; uint8_t* inconf;
+    double* ef64; float* ef32; int32_t* ei32; double* poly;
+    float* obs; float* final_obs; float* reward; uint8_t* term; uint8_t* trunc; float* info;
+    const float* actions; const uint8_t* reset_mask;
+};
+
+struct Ac {
+    double lat, lon;
+    float alt, tas, hdg, vs;
+    float selspd, selalt, selvs, aptrk;
+    float ax, curlegdir, cas;
+    uint32_t flags;
+    float gsn, gse;           // cached tas*cos(hdg), tas*sin(hdg) of the last groundspeed update
+    float tcpamax; bool inconf;
+};
+
+struct EnvS {
+    double wpt_lat, wpt_lon, target_alt, poly_area;
+    float total_reward, drift_sum, final_alt;
+    int step, episode, simk, wpt_reach, drift_n, intrusions, num_ac, nvert, needs_reset, faf, nconf, nlos, rflags;
+};
+
+// ---- MergeEnv constants: merge_env.py:40-46 (FIX = get_point_at_distance(RWY, 200 km, 0 deg)) ----
+constexpr double kRwyLat = 52.36239301495972, kRwyLon = 4.713195734579777;
+constexpr double kSectorLat0 = 51.990426702297746, kSectorLon0 = 4.376124857109851;   // sector_cr_env.py:16
+
+// ---- float64 helpers used only by the (rare) scenario generators -----------------------------------
+__device__ inline void d_atmos(double h, double& p, double& rho, double& T) {
+    T = fmax(288.15 - 0.0065 * h, 216.65);
+    double rhotrop = 1.225 * pow(T / 288.15, 4.256848030018761);
+    rho = rhotrop * exp(-fmax(0.0, h - 11000.0) / 6341.552161);
+    p = rho * 287.05287 * T;
+}
+__device__ inline double d_cas2tas(double cas, double h) {
+    double p, rho, T;
+    d_atmos(h, p, rho, T);
+    double q = 101325.0 * (pow(1.0 + 1.225 * cas * cas / (7.0 * 101325.0), 3.5) - 1.0);
+    double t = sqrt(7.0 * p / rho * (pow(q / p + 1.0, 2.0 / 7.0) - 1.0));
+    return cas < 0 ? -t : t;
+}
+__device__ inline double d_tas2cas(double tas, double h) {
+    double p, rho, T;
+    d_atmos(h, p, rho, T);
+    double q = p * (pow(1.0 + rho * tas * tas / (7.0 * p), 3.5) - 1.0);
+    double c = sqrt(7.0 * 101325.0 / 1.225 * (pow(q / 101325.0 + 1.0, 2.0 / 7.0) - 1.0));
+    return tas < 0 ? -c : c;
+}
+// functions.py:24-42
+__device__ inline void d_point_at_distance(double lat1, double lon1, double d_km, double brg, double& lat2, double& lon2) {
+    double la = lat1 * kDeg2RadD, lo = lon1 * kDeg2RadD, a = brg * kDeg2RadD, ang = d_km / 6371.0;
+    double l2 = asin(sin(la) * cos(ang) + cos(la) * sin(ang) * cos(a));
+    double o2 = lo + atan2(sin(a) * sin(ang) * cos(la), cos(ang) - sin(la) * sin(l2));
+    lat2 = l2 * kRad2DegD; lon2 = o2 * kRad2DegD;
+}
+
+// Traffic.cre with SI arguments (oracle/traffic.py::Traffic.cre)
+__device__ inline void ac_create(Ac& a, double lat, double lon, double hdg, double alt, double cas_cmd) {
+    a.lat = lat; a.lon = lon > 180.0 ? lon - 360.0 : (lon < -180.0 ? lon + 360.0 : lon);
+    double tas = d_cas2tas(cas_cmd, alt);        // the reference never passes a Mach number to cre
+    a.alt = (float)alt; a.tas = (float)tas; a.hdg = (float)hdg; a.vs = 0.0f;
+    a.selspd = (float)cas_cmd; a.selalt = (float)alt; a.selvs = 0.0f; a.aptrk = (float)hdg;
+    a.ax = 0.0f; a.curlegdir = -999.0f; a.cas = (float)cas_cmd;
+    a.flags = kFlAlive;
+    double hr = hdg * kDeg2RadD;
+    a.gsn = (float)(tas * cos(hr)); a.gse = (float)(tas * sin(hr));
+    a.tcpamax = 0.0f; a.inconf = false;
+}
+__device__ inline void ac_clear(Ac& a) {
+    a.lat = 0.0; a.lon = 0.0; a.alt = 0.0f; a.tas = 0.0f; a.hdg = 0.0f; a.vs = 0.0f;
+    a.selspd = 0.0f; a.selalt = 0.0f; a.selvs = 0.0f; a.aptrk = 0.0f; a.ax = 0.0f; a.curlegdir = -999.0f;
+    a.cas = 0.0f; a.flags = 0u; a.gsn = 0.0f; a.gse = 0.0f; a.tcpamax = 0.0f; a.inconf = false;
+}
+
+// ---- state I/O (coalesced: consecutive lanes -> consecutive float4 / double2) ----------------------
+__device__ __forceinline__ void ac_load(Ac& a, const EnvParams& P, long long idx) {
+    double2 p = P.pos[idx];
+    float4 k = P.kin[idx], c = P.cmd[idx], x = P.aux[idx];
+    a.lat = p.x; a.lon = p.y;
+    a.alt = k.x; a.tas = k.y; a.hdg = k.z; a.vs = k.w;
+    a.selspd = c.x; a.selalt = c.y; a.selvs = c.z; a.aptrk = c.w;
+    a.ax = x.x; a.curlegdir = x.y; a.cas = x.z;
+    a.flags = P.flags[idx];
+    float s, co;
+    sincosf(a.hdg * kDeg2Rad, &s, &co);
+    a.gsn = a.tas * co; a.gse = a.tas * s;
+    a.tcpamax = 0.0f; a.inconf = false;
+}
+__device__ __forceinline__ void ac_store(const Ac& a, const EnvParams& P, long long idx) {
+    P.pos[idx] = make_double2(a.lat, a.lon);
+    P.kin[idx] = make_float4(a.alt, a.tas, a.hdg, a.vs);
+    P.cmd[idx] = make_float4(a.selspd, a.selalt, a.selvs, a.aptrk);
+    P.aux[idx] = make_float4(a.ax, a.curlegdir, a.cas, 0.0f);
+    P.flags[idx] = a.flags;
+    if (P.cd_enabled) {
+        P.tcpamax[idx] = a.tcpamax;
+        P.inconf[idx] = a.inconf ? 1 : 0;
+    }
+}
+__device__ __forceinline__ void env_load(EnvS& s, const EnvParams& P, long long e) {
+    const double* d = P.ef64 + e * BSG_F64_COUNT;
+    const float* f = P.ef32 + e * BSG_F32_COUNT;
+    const int32_t* i = P.ei32 + e * BSG_I32_COUNT;
+    s.wpt_lat = d[BSG_F64_WPT_LAT]; s.wpt_lon = d[BSG_F64_WPT_LON]; s.target_alt = d[BSG_F64_TARGET_ALT];
+    s.poly_area = d[BSG_F64_POLY_AREA];
+    s.total_reward = f[BSG_F32_TOTAL_REWARD]; s.drift_sum = f[BSG_F32_DRIFT_SUM]; s.final_alt = f[BSG_F32_FINAL_ALT];
+    s.step = i[BSG_I32_STEP]; s.episode = i[BSG_I32_EPISODE]; s.simk = i[BSG_I32_SIMK];
+    s.wpt_reach = i[BSG_I32_WPT_REACH]; s.drift_n = i[BSG_I32_DRIFT_N]; s.intrusions = i[BSG_I32_INTRUSIONS];
+    s.num_ac = i[BSG_I32_NUM_AC]; s.nvert = i[BSG_I32_NVERT]; s.needs_reset = i[BSG_I32_NEEDS_RESET];
+    s.faf = i[BSG_I32_FAF]; s.nconf = i[BSG_I32_NCONF]; s.nlos = i[BSG_I32_NLOS]; s.rflags = i[BSG_I32_RESET_FLAGS];
+}
+__device__ __forceinline__ void env_store(const EnvS& s, const EnvParams& P, long long e) {
+    double* d = P.ef64 + e * BSG_F64_COUNT;
+    float* f = P.ef32 + e * BSG_F32_COUNT;
+    int32_t* i = P.ei32 + e * BSG_I32_COUNT;
+    d[BSG_F64_WPT_LAT] = s.wpt_lat; d[BSG_F64_WPT_LON] = s.wpt_lon; d[BSG_F64_TARGET_ALT] = s.target_alt;
+    d[BSG_F64_POLY_AREA] = s.poly_area;
+    f[BSG_F32_TOTAL_REWARD] = s.total_reward; f[BSG_F32_DRIFT_SUM] = s.drift_sum; f[BSG_F32_FINAL_ALT] = s.final_alt;
+    i[BSG_I32_STEP] = s.step; i[BSG_I32_EPISODE] = s.episode; i[BSG_I32_SIMK] = s.simk;
+    i[BSG_I32_WPT_REACH] = s.wpt_reach; i[BSG_I32_DRIFT_N] = s.drift_n; i[BSG_I32_INTRUSIONS] = s.intrusions;
+    i[BSG_I32_NUM_AC] = s.num_ac; i[BSG_I32_NVERT] = s.nvert; i[BSG_I32_NEEDS_RESET] = s.needs_reset;
+    i[BSG_I32_FAF] = s.faf; i[BSG_I32_NCONF] = s.nconf; i[BSG_I32_NLOS] = s.nlos; i[BSG_I32_RESET_FLAGS] = s.rflags;
+}
+
+// ====================================================================================================
+// K1: one simulator substep of one aircraft (Traffic.update minus ASAS).  oracle/traffic.py::update
+// ====================================================================================================
+template <int ENV>
+__device__ __forceinline__ void ac_autopilot(Ac& a, const EnvParams& P, bool fms_ready, const Atmos& at,
+                                             float& ap_tas) {
+    if (ENV == BSG_ENV_MERGE) {
+        if (a.flags & kFlLnav) {         // Autopilot.update LNAV + update_fms (2-waypoint route FIX -> RWY)
+            double wlat, wlon;
+            int iwp = (int)(a.flags >> kFlWpShift);
+            if (iwp == 0) { wlat = P.fix_lat; wlon = P.fix_lon; } else { wlat = kRwyLat; wlon = kRwyLon; }
+            float qdr, dist;
+            qdrdist_wgs(a.lat, a.lon, wlat, wlon, qdr, dist);
+            if (fms_ready) {
+                // ActiveWaypoint.reached: next_qdr is -999 for both legs of this route => turndist = 0
+                bool close2wp = dist / fmaxf(0.0001f, fabsf(a.tas)) < 4.0f;
+                bool tooclose = close2wp && fabsf(degto180(mod360(a.hdg) - mod360(qdr))) > 90.0f;
+                bool passed = fabsf(degto180(qdr - a.curlegdir)) > 90.0f;
+                if (tooclose || passed) {
+                    if ((a.flags & kFlLastWp) || iwp >= 1) {
+                        a.flags &= ~kFlLnav;
+                    } else {
+                        a.flags = (a.flags & 0xffu) | (1u << kFlWpShift) | kFlLastWp;
+                        qdrdist_wgs(a.lat, a.lon, kRwyLat, kRwyLon, qdr, dist);
+                        a.curlegdir = qdr;
+                    }
+                }
+            }
+            if (a.flags & kFlLnav) a.aptrk = mod360(qdr);
+        }
+    }
+    ap_tas = casormach2tas(a.selspd, at);
+}
+
+__device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const Atmos& at, float ap_tas) {
+    const float dt = P.simdt;
+    const bsg_perf& pf = P.perf;
+    // ---- Autopilot select modes + APorASAS.update (resolution off, no wind)
+    float selvs_eff = fabsf(a.selvs) > 0.1f ? a.selvs : kVsDef;
+    float p_vs = fabsf(selvs_eff);
+    float p_hdg = mod360(a.aptrk);
+    // ---- perfoap.update: phase.get (later assignments overwrite earlier ones)
+    float alt_ft = a.alt * (1.0f / kFt), roc = a.vs * (1.0f / kFpm);
+    int ph = PH_NA;
+    if (alt_ft <= 75.0f) ph = PH_GD;
+    if (alt_ft >= 75.0f && alt_ft <= 1000.0f && roc >= 150.0f) ph = PH_IC;
+    if (alt_ft >= 75.0f && alt_ft <= 1000.0f && roc <= -150.0f) ph = PH_AP;
+    if (alt_ft >= 1000.0f && roc >= 150.0f) ph = PH_CL;
+    if (alt_ft >= 1000.0f && roc <= -150.0f) ph = PH_DE;
+    if (alt_ft >= 10000.0f && roc <= 150.0f && roc >= -150.0f) ph = PH_CR;
+    float vmin = pf.vminer, vmax = pf.vmaxer;
+    if (ph == PH_AP) { vmin = pf.vminap; vmax = pf.vmaxap; }
+    if (ph == PH_GD) { vmin = 0.0f; vmax = pf.vmaxic; }
+    float amax = (ph == PH_GD) ? pf.axmax_gd : pf.axmax_air;
+    // ---- perfoap.limits (CAS round trip evaluated at the allowed commanded altitude)
+    float allow_h = a.selalt > pf.hmax ? pf.hmax : a.selalt;
+    Atmos ah = (allow_h == a.alt) ? at : vatmos(allow_h);
+    float intent_cas = tas2cas(ap_tas, ah);
+    float allow_tas = ap_tas;                           // vcas2tas(vtas2cas(x)) == x when not clamped
+    if (intent_cas < vmin) allow_tas = cas2tas(vmin, ah);
+    if (intent_cas > vmax) allow_tas = cas2tas(vmax, ah);
+    float snd = vsound(ah);
+    if (allow_tas > pf.mmo * snd) allow_tas = pf.mmo * snd;
+    float vs_max_acc = (1.0f - a.ax / amax) * pf.vsmax;
+    float allow_vs = p_vs;
+    if (p_vs > 0.0f && p_vs > pf.vsmax) allow_vs = vs_max_acc;
+    if (p_vs < 0.0f && p_vs < pf.vsmin) allow_vs = vs_max_acc;
+    if (ph == PH_GD && a.tas < pf.vminto) allow_vs = 0.0f;
+    // ---- update_airspeed
+    float dspd = allow_tas - a.tas;
+    bool need_ax = fabsf(dspd) > fabsf(dt * amax);
+    a.ax = need_ax ? copysignf(amax, dspd) : 0.0f;
+    a.tas = need_ax ? a.tas + a.ax * dt : allow_tas;
+    a.cas = tas2cas(a.tas, at);
+    float turnrate = kRad2Deg * (kG0 * kTanBankDef) / fmaxf(a.tas, 0.01f);
+    float delhdg = degto180(p_hdg - a.hdg);
+    bool swhdgsel = fabsf(delhdg) > fabsf(dt * turnrate);
+    a.hdg = mod360(swhdgsel ? a.hdg + copysignf(dt * turnrate, delhdg) : p_hdg);
+    float delta_alt = allow_h - a.alt;
+    bool swaltsel = fabsf(delta_alt) > 1.05f * fmaxf(fabsf(dt * allow_vs), fabsf(dt * a.vs));
+    float target_vs = swaltsel ? copysignf(fabsf(allow_vs), delta_alt) : 0.0f;
+    float delta_vs = target_vs - a.vs;
+    bool need_az = fabsf(delta_vs) > kAzMax;
+    a.vs = need_az ? a.vs + copysignf(kAzMax, delta_vs) * dt : target_vs;
+    if (!isfinite(a.vs)) a.vs = 0.0f;
+    // ---- update_groundspeed (no wind: gs = tas, trk = hdg)
+    float sh, ch;
+    sincosf(a.hdg * kDeg2Rad, &sh, &ch);
+    a.gsn = a.tas * ch; a.gse = a.tas * sh;
+    // ---- update_pos (lat/lon accumulate in float64)
+    a.alt = swaltsel ? a.alt + a.vs * dt : allow_h;
+    a.lat += (double)(kRad2Deg * (dt * a.gsn * (1.0f / kRearth)));
+    float coslat = cosf((float)a.lat * kDeg2Rad);
+    a.lon += (double)(kRad2Deg * (dt * a.gse / coslat * (1.0f / kRearth)));
+}
+
+// ====================================================================================================
+// K3: in-group all-pairs CD.  Lane i keeps its own record, reads record j from shared memory (broadcast).
+// ====================================================================================================
+template <int G>
+__device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvParams& P, float4* s_rec,
+                                         int& nconf_env, int& nlos_env) {
+    const int lane_g = threadIdx.x & (G - 1);
+    const int gbase = threadIdx.x - lane_g;
+    double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);
+    float sh, ch;
+    sincosf((float)a.lat * (0.5f * kDeg2Rad), &sh, &ch);
+    double dl = a.lon - lon0;
+    dl = dl > 180.0 ? dl - 360.0 : (dl < -180.0 ? dl + 360.0 : dl);
+    float4 Ai = make_float4((float)(kRearthD * kDeg2RadD * dl), (float)(kRearthD * kDeg2RadD * (a.lat - lat0)), ch, sh);
+    float4 Bi = make_float4(a.gse, a.gsn, a.alt, a.vs);
+    s_rec[2 * threadIdx.x] = Ai;
+    s_rec[2 * threadIdx.x + 1] = Bi;
+    __syncwarp(group_mask<G>());
+    int nc = 0, nl = 0;
+    float tmax = 0.0f;
+    for (int j = 0; j < nac; ++j) {
+        float4 Aj = s_rec[2 * (gbase + j)], Bj = s_rec[2 * (gbase + j) + 1];
+        CdPair p = cd_pair_eval<false>(Ai, Bi, Aj, Bj, P.R2, P.hpz, P.dtlook, j == lane_g);
+        if (alive) {
+            nc += p.conf ? 1 : 0;
+            nl += p.los ? 1 : 0;
+            if (p.conf) tmax = fmaxf(tmax, p.tcpa);
+        }
+    }
+    __syncwarp(group_mask<G>());
+    a.inconf = nc > 0;
+    a.tcpamax = tmax;
+    nconf_env = group_sum<G>(nc);
+    nlos_env = group_sum<G>(nl);
+}
+
+}  // namespace bsg

@@ -1,0 +1,586 @@
+// env_step.cu -- K4/K5/K6: per-env scenario generators, action mapping, observation / reward /
+// termination, and the env-step megakernel that strings them around the substep loop of
+// env_kernels.cuh.  Every function cites the reference lines it restates; the float64 CPU
+// restatement these are parity-tested against is oracle/envs.py.
+#include "env_kernels.cuh"
+
+namespace bsg {
+
+struct StepOut { float reward; int terminated; int truncated; };
+
+// rank (0..K-1) of this lane among the K nearest candidates of its group, else -1
+template <int G>
+__device__ __forceinline__ int nearest_rank(float dist, bool cand, int K) {
+    const unsigned lane_g = threadIdx.x & (G - 1);
+    unsigned long long key = cand ? (((unsigned long long)__float_as_uint(dist)) << 32) | lane_g : ~0ULL;
+    int rank = -1;
+    for (int r = 0; r < K; ++r) {
+        unsigned long long m = group_min_u64<G>(key);
+        if (m == key && key != ~0ULL) { rank = r; key = ~0ULL; }
+    }
+    return rank;
+}
+
+// =====================================================================================================
+// DescentEnv (descent_env.py) -- 1 aircraft, G = 1
+// =====================================================================================================
+template <int G>
+__device__ inline void descent_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot) {
+    Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);      // descent_env.py:162-182
+    int alt_init = rng.randint(0, 2000, 4000);
+    s.target_alt = (double)(alt_init + rng.randint(1, -500, 500));
+    double hdg = P.hdg_random ? (double)rng.randint(2, 1, 360) : 0.0;
+    if (slot == 0) ac_create(a, 52.0, 4.0, hdg, (double)alt_init, 150.0); else ac_clear(a);
+    s.total_reward = 0.0f; s.final_alt = 0.0f; s.num_ac = 1;
+}
+template <int G>
+__device__ inline void descent_action(Ac& a, const EnvParams& P, const float* act, int slot) {
+    float vs_cmd = act[0] * 12.5f;                                          // descent_env.py:146-160
+    if (slot == 0) { a.selalt = vs_cmd >= 0.0f ? 1000000.0f : 0.0f; a.selvs = vs_cmd; }
+}
+template <int G>
+__device__ inline StepOut descent_obs_reward(const Ac& a, EnvS& s, const EnvParams& P, float* obs, int slot,
+                                             bool with_reward) {
+    float q, dnm;                                                           // descent_env.py:89-117
+    kwikqdrdist(52.0, 4.0, a.lat, a.lon, q, dnm);
+    float rwy = 200.0f - dnm * 1.852f;
+    float tgt = (float)s.target_alt;
+    if (slot == 0) {
+        obs[0] = (a.alt - 1500.0f) * (1.0f / 3000.0f);
+        obs[1] = a.vs * 0.2f;
+        obs[2] = (tgt - 1500.0f) * (1.0f / 3000.0f);
+        obs[3] = (rwy - 100.0f) * (1.0f / 200.0f);
+    }
+    StepOut o = {0.0f, 0, 0};
+    if (!with_reward) return o;
+    if (rwy > 0.0f && a.alt > 0.0f) {                                       // descent_env.py:128-144
+        o.reward = fabsf(tgt - a.alt) * (-5.0f / 3000.0f);
+    } else if (a.alt <= 0.0f) {
+        o.reward = -100.0f; o.terminated = 1; s.final_alt = -100.0f;
+    } else {
+        o.reward = a.alt * (-50.0f / 3000.0f); o.terminated = 1; s.final_alt = a.alt;
+    }
+    s.total_reward += o.reward;
+    return o;
+}
+__device__ inline void descent_info(const EnvS& s, float* info) {           // descent_env.py:119-126
+    info[0] = s.total_reward; info[1] = s.final_alt; info[2] = 0.0f; info[3] = 0.0f;
+}
+
+// =====================================================================================================
+// HorizontalCREnv (horizontal_cr_env.py) -- slot 0 = ownship, slots 1..n = creconfs intruders
+// =====================================================================================================
+template <int G>
+__device__ inline void horizontal_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot) {
+    Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);      // horizontal_cr_env.py:82-101
+    const int n = P.n_int;
+    const double hdg0 = P.hdg_random ? (double)rng.randint(0, 1, 360) : 0.0;
+    const double lat0 = 52.0, lon0 = 4.0, alt0 = 0.0;
+    const double tas0 = d_cas2tas(150.0, alt0);
+    if (slot == 0) {
+        ac_create(a, lat0, lon0, hdg0, alt0, 150.0);
+    } else if (slot <= n) {
+        // Traffic.creconfs (oracle/traffic.py::creconfs), horizontal_cr_env.py:127-133
+        const uint32_t d = 1u + 3u * (uint32_t)(slot - 1);
+        double dpsi = (double)rng.randint(d, 45, 315);
+        double cpa = (double)rng.randint(d + 1, 0, 5) * 1852.0;
+        double tlosh = (double)rng.randint(d + 2, 100, 1000);
+        const double pzr = 5.0 * 1852.0;
+        double trkref = hdg0 * kDeg2RadD, gsref = tas0;
+        double trk = trkref + dpsi * kDeg2RadD;
+        double gsn = gsref * cos(trk), gse = gsref * sin(trk);
+        double vreln = gsref * cos(trkref) - gsn, vrele = gsref * sin(trkref) - gse;
+        double vrel = sqrt(vreln * vreln + vrele * vrele);
+        double drelcpa = tlosh * vrel + (cpa > pzr ? 0.0 : sqrt(pzr * pzr - cpa * cpa));
+        double dist = sqrt(drelcpa * drelcpa + cpa * cpa);
+        double rd = drelcpa / dist, rx = cpa / dist;
+        double brn = kRad2DegD * atan2(-rx * vreln + rd * vrele, rd * vreln + rx * vrele);
+        // geo.kwikpos
+        double dnm = dist / 1852.0;
+        double lat = lat0 + dnm * cos(brn * kDeg2RadD) / 60.0;
+        double lon = lon0 + dnm * sin(brn * kDeg2RadD) / fmax(0.01, 60.0 * cos(lat0 * kDeg2RadD));
+        lon = fmod(lon + 180.0, 360.0); if (lon < 0.0) lon += 360.0; lon -= 180.0;
+        double acspd = d_tas2cas(sqrt(gsn * gsn + gse * gse), alt0);
+        double achdg = kRad2DegD * atan2(gse, gsn);
+        ac_create(a, lat, lon, achdg, alt0, acspd);
+    } else {
+        ac_clear(a);
+    }
+    int wpt_dis = rng.randint(1u + 3u * (uint32_t)n, 100, 150);             // horizontal_cr_env.py:135-148
+    d_point_at_distance(lat0, lon0, (double)wpt_dis, 0.0, s.wpt_lat, s.wpt_lon);
+    s.wpt_reach = 0; s.total_reward = 0.0f; s.intrusions = 0; s.drift_sum = 0.0f; s.drift_n = 0;
+    s.num_ac = n + 1;
+}
+template <int G>
+__device__ inline void horizontal_action(Ac& a, const EnvParams& P, const float* act, int slot) {
+    if (slot == 0) {                                                        // horizontal_cr_env.py:272-275
+        a.aptrk = a.hdg + act[0] * 45.0f;          // un-wrapped, like the reference's "HDG KL001 x"
+        a.flags &= ~kFlLnav;
+    }
+}
+template <int G>
+__device__ inline StepOut horizontal_obs_reward(const Ac& a, EnvS& s, const EnvParams& P, float* obs, int slot,
+                                                bool with_reward) {
+    const int n = P.n_int;                                                  // horizontal_cr_env.py:150-213
+    const double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);
+    const float hdg0 = group_bcast<G>(a.hdg, 0), gs0 = group_bcast<G>(a.tas, 0);
+    const bool intr = slot >= 1 && slot <= n;
+    float qdr = 0.0f, dis = 1e9f;
+    if (intr) {
+        kwikqdrdist(lat0, lon0, a.lat, a.lon, qdr, dis);
+        float sb, cb, sd, cd;
+        sincosf(wrap180_fold(hdg0 - qdr) * kDeg2Rad, &sb, &cb);
+        sincosf((hdg0 - a.hdg) * kDeg2Rad, &sd, &cd);
+        const int k = slot - 1;
+        obs[k] = dis * (1.852f / 150.0f);
+        obs[n + k] = cb;
+        obs[2 * n + k] = sb;
+        obs[3 * n + k] = -cd * a.tas * (1.0f / 150.0f);
+        obs[4 * n + k] = (gs0 - sd * a.tas) * (1.0f / 150.0f);
+    }
+    float wq, wd;
+    kwikqdrdist(lat0, lon0, s.wpt_lat, s.wpt_lon, wq, wd);
+    const float wkm = wd * 1.852f;
+    const float drift = wrap180_fold(hdg0 - wq);
+    if (slot == 0) {
+        float sd, cd;
+        sincosf(drift * kDeg2Rad, &sd, &cd);
+        obs[5 * n] = wkm * (1.0f / 150.0f);
+        obs[5 * n + 1] = cd;
+        obs[5 * n + 2] = sd;
+    }
+    StepOut o = {0.0f, 0, 0};
+    if (!with_reward) return o;
+    const int nintr = group_sum<G>((intr && dis < 5.0f) ? 1 : 0);           // horizontal_cr_env.py:225-270
+    float r = 0.0f;
+    if (wkm < 5.0f && s.wpt_reach != 1) { s.wpt_reach = 1; r += 1.0f; }
+    const float dr = fabsf(drift * kDeg2Rad);
+    s.drift_sum += dr; s.drift_n += 1;
+    r += dr * -0.1f;
+    s.intrusions += nintr;
+    r += -1.0f * (float)nintr;
+    s.total_reward += r;
+    o.reward = r; o.terminated = s.wpt_reach ? 1 : 0;
+    return o;
+}
+__device__ inline void drift_info(const EnvS& s, float* info) {             // horizontal_cr_env.py:215-223
+    info[0] = s.total_reward; info[1] = (float)s.intrusions;
+    info[2] = s.drift_sum / (float)s.drift_n;       // 0/0 = NaN before the first step, like np.mean([])
+    info[3] = 0.0f;
+}
+
+// =====================================================================================================
+// SectorCREnv (sector_cr_env.py) -- G = 32, variable aircraft count, polygon airspace
+// =====================================================================================================
+__device__ inline bool d_inside_poly(double px, double py, const double* poly, int nv) {
+    // areafilter.checkInside -> even-odd crossing in the (lat, lon) plane (oracle/geo.py::point_in_polygon)
+    int c = 0;
+    for (int k = 0; k < nv; ++k) {
+        int k2 = (k + 1 == nv) ? 0 : k + 1;
+        double x1 = poly[2 * k], y1 = poly[2 * k + 1], x2 = poly[2 * k2], y2 = poly[2 * k2 + 1];
+        if ((y1 > py) != (y2 > py)) {
+            double xint = x1 + (py - y1) * (x2 - x1) / (y2 - y1);
+            c += px < xint ? 1 : 0;
+        }
+    }
+    return (c & 1) == 1;
+}
+
+constexpr int kSectorMaxV = 32, kSectorMaxAc = 32, kSectorMaxTries = 4096;
+
+// scratch per env for the serial generator: [0..31] lat, [32..63] lon, [64..95] hdg
+template <int G>
+__device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot, double* scratch) {
+    double* poly = P.poly + e * (2 * kSectorMaxV);
+    int num_ac = 0, nv = 0, rflags = 0;
+    double area = 0.0, w0lat = 0.0, w0lon = 0.0;
+    if (slot == 0) {                                                        // sector_cr_env.py:87-115
+        Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);
+        uint32_t d = 0;
+        double vx[kSectorMaxV], vy[kSectorMaxV], va[kSectorMaxV];
+        const double R = sqrt(3750.0 / 3.141592653589793);
+        auto shoelace = [&](int n) {
+            double acc = 0.0;
+            for (int i = 0; i < n; ++i) { int j = (i + 1 == n) ? 0 : i + 1; acc += vx[i] * vy[j] - vy[i] * vx[j]; }
+            return fabs(acc) / 2.0;
+        };
+        auto insert_point = [&]() {         // random_point_on_circle + sort by atan2(y, x) (functions.py:44-75)
+            double al = 6.283185307179586 * rng.u01(d++);
+            double x = R * cos(al), y = R * sin(al), ang = atan2(y, x);
+            int k = nv;
+            while (k > 0 && va[k - 1] > ang) { vx[k] = vx[k - 1]; vy[k] = vy[k - 1]; va[k] = va[k - 1]; --k; }
+            vx[k] = x; vy[k] = y; va[k] = ang; ++nv;
+        };
+        insert_point(); insert_point(); insert_point();                     // sector_cr_env.py:141-160
+        area = shoelace(nv);
+        while (area < 2400.0 && nv < kSectorMaxV) { insert_point(); area = shoelace(nv); }
+        if (area < 2400.0) rflags |= 1;
+        const double coslat0 = cos(kSectorLat0 * kDeg2RadD);
+        for (int i = 0; i < nv; ++i) {                                      // nm_to_latlong: x north, y east
+            poly[2 * i] = kSectorLat0 + vx[i] / 60.0;
+            poly[2 * i + 1] = kSectorLon0 + vy[i] / (60.0 * coslat0);
+        }
+        double rho = rng.normal(d, 0.005, 0.001); d += 2;                   // sector_cr_env.py:98-100
+        double nraw = fmax(ceil(rho * area), 5.0);
+        if (nraw > (double)kSectorMaxAc) { nraw = (double)kSectorMaxAc; rflags |= 2; }
+        num_ac = (int)nraw;
+        // _generate_waypoints: num_ac sorted draws along the perimeter      sector_cr_env.py:162-188
+        double elen[kSectorMaxV], perim = 0.0;
+        for (int i = 0; i < nv; ++i) {
+            int j = (i + 1 == nv) ? 0 : i + 1;
+            double ex = vx[j] - vx[i], ey = vy[j] - vy[i];
+            elen[i] = sqrt(ex * ex + ey * ey);
+            perim += elen[i];
+        }
+        double dl[kSectorMaxAc];
+        for (int i = 0; i < num_ac; ++i) {
+            double v = rng.uniform(d++, 0.0, perim);
+            int k = i;
+            while (k > 0 && dl[k - 1] > v) { dl[k] = dl[k - 1]; --k; }
+            dl[k] = v;
+        }
+        double wx[kSectorMaxAc], wy[kSectorMaxAc];
+        {
+            double cur = 0.0; int k = 0;
+            for (int i = 0; i < num_ac; ++i) {
+                while (dl[i] > cur + elen[k] && k < nv - 1) { cur += elen[k]; ++k; }
+                int j = (k + 1 == nv) ? 0 : k + 1;
+                double frac = (dl[i] - cur) / elen[k];
+                wx[i] = vx[k] + frac * (vx[j] - vx[k]);
+                wy[i] = vy[k] + frac * (vy[j] - vy[k]);
+            }
+        }
+        // _generate_ac: rejection sampling in the bounding box              sector_cr_env.py:190-217
+        double minx = vx[0], maxx = vx[0], miny = vy[0], maxy = vy[0];
+        for (int i = 1; i < nv; ++i) { minx = fmin(minx, vx[i]); maxx = fmax(maxx, vx[i]); miny = fmin(miny, vy[i]); maxy = fmax(maxy, vy[i]); }
+        int got = 0, tries = 0;
+        while (got < num_ac && tries < kSectorMaxTries) {
+            ++tries;
+            double x = rng.uniform(d++, minx, maxx), y = rng.uniform(d++, miny, maxy);
+            double la = kSectorLat0 + x / 60.0, lo = kSectorLon0 + y / (60.0 * coslat0);
+            if (d_inside_poly(la, lo, poly, nv)) {
+                double wla = kSectorLat0 + wx[got] / 60.0, wlo = kSectorLon0 + wy[got] / (60.0 * coslat0);
+                // fn.get_hdg: great-circle initial bearing, functions.py:150-178
+                double l1 = la * kDeg2RadD, l2 = wla * kDeg2RadD, dlo = (wlo - lo) * kDeg2RadD;
+                double hx = sin(dlo) * cos(l2), hy = cos(l1) * sin(l2) - sin(l1) * cos(l2) * cos(dlo);
+                double h = fmod(kRad2DegD * atan2(hx, hy) + 360.0, 360.0);
+                scratch[got] = la; scratch[32 + got] = lo; scratch[64 + got] = h;
+                if (got == 0) { w0lat = wla; w0lon = wlo; }
+                ++got;
+            }
+        }
+        if (got < num_ac) { rflags |= 4; num_ac = got > 0 ? got : 1; }
+    }
+    __syncwarp(group_mask<G>());
+    num_ac = group_bcast<G>(num_ac, 0); nv = group_bcast<G>(nv, 0); rflags = group_bcast<G>(rflags, 0);
+    area = group_bcast<G>(area, 0); w0lat = group_bcast<G>(w0lat, 0); w0lon = group_bcast<G>(w0lon, 0);
+    if (slot < num_ac) ac_create(a, scratch[slot], scratch[32 + slot], scratch[64 + slot], 350.0, 150.0);
+    else ac_clear(a);
+    __syncwarp(group_mask<G>());
+    s.num_ac = num_ac; s.nvert = nv; s.rflags = rflags; s.poly_area = area;
+    s.wpt_lat = w0lat; s.wpt_lon = w0lon;
+    s.total_reward = 0.0f; s.intrusions = 0; s.drift_sum = 0.0f; s.drift_n = 0; s.wpt_reach = 0;
+}
+template <int G>
+__device__ inline void sector_action(Ac& a, const EnvParams& P, const float* act, int slot) {
+    if (slot == 0) {                                                        // sector_cr_env.py:315-322
+        a.aptrk = wrap180_fold(a.hdg + act[0] * 22.5f);
+        a.flags &= ~kFlLnav;
+        float kt = (a.cas + act[1] * (20.0f / 3.0f)) * 1.94384f;            // "SPD KL001 x": knots -> m/s
+        a.selspd = (kt > 0.1f && kt < 1.0f) ? kt : kt * kKts;
+    }
+}
+template <int G>
+__device__ inline StepOut sector_obs_reward(const Ac& a, EnvS& s, const EnvParams& P, float* obs, int slot,
+                                            long long e, bool with_reward) {
+    const double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);     // sector_cr_env.py:237-313
+    const float hdg0 = group_bcast<G>(a.hdg, 0), tas0 = group_bcast<G>(a.tas, 0);
+    const float vx0 = group_bcast<G>(a.gsn, 0), vy0 = group_bcast<G>(a.gse, 0);
+    float wq, wd;
+    kwikqdrdist(lat0, lon0, s.wpt_lat, s.wpt_lon, wq, wd);
+    const float drift = wrap180_fold(hdg0 - wq);
+    if (slot == 0) {
+        float sd, cd;
+        sincosf(drift * kDeg2Rad, &sd, &cd);
+        obs[0] = cd; obs[1] = sd; obs[2] = (tas0 - 150.0f) * (1.0f / 6.0f);
+    }
+    const bool other = slot >= 1 && slot < s.num_ac;
+    const double coslat0 = cos(kSectorLat0 * kDeg2RadD);
+    float dxm = (float)((a.lat - lat0) * (60.0 * 1852.0));                  // latlong_to_nm * NM2KM * 1000
+    float dym = (float)((a.lon - lon0) * (60.0 * 1852.0) * coslat0);
+    float dist = sqrtf(dxm * dxm + dym * dym);
+    int rank = nearest_rank<G>(dist, other, 4);
+    if (rank >= 0) {
+        float dvx = a.gsn - vx0, dvy = a.gse - vy0;
+        float hyp = sqrtf(dvx * dvx + dvy * dvy);
+        float ct = hyp > 0.0f ? dvx / hyp : 1.0f, st = hyp > 0.0f ? dvy / hyp : 0.0f;
+        obs[3 + rank] = dxm * (1.0f / 13000.0f);
+        obs[7 + rank] = dym * (1.0f / 13000.0f);
+        obs[11 + rank] = dvx * (1.0f / 32.0f);
+        obs[15 + rank] = dvy * (1.0f / 66.0f);
+        obs[19 + rank] = ct;
+        obs[23 + rank] = st;
+        obs[27 + rank] = (dist - 50000.0f) * (1.0f / 15000.0f);
+    }
+    StepOut o = {0.0f, 0, 0};
+    if (!with_reward) return o;
+    float q, dnm = 1e9f;                                                    // sector_cr_env.py:227-235,324-339
+    if (other) kwikqdrdist(lat0, lon0, a.lat, a.lon, q, dnm);
+    const int nintr = group_sum<G>((other && dnm < 5.0f) ? 1 : 0);
+    const float dr = fabsf(drift * kDeg2Rad);
+    s.drift_sum += dr; s.drift_n += 1;
+    s.intrusions += nintr;
+    o.reward = dr * -0.1f - (float)nintr;
+    s.total_reward += o.reward;
+    // truncation: ownship left the polygon (sector_cr_env.py:134-139); one edge per lane
+    const double* poly = P.poly + e * (2 * kSectorMaxV);
+    int cross = 0;
+    if (slot < s.nvert) {
+        int k2 = (slot + 1 == s.nvert) ? 0 : slot + 1;
+        double x1 = poly[2 * slot], y1 = poly[2 * slot + 1], x2 = poly[2 * k2], y2 = poly[2 * k2 + 1];
+        if ((y1 > lon0) != (y2 > lon0)) cross = lat0 < x1 + (lon0 - y1) * (x2 - x1) / (y2 - y1) ? 1 : 0;
+    }
+    o.truncated = (group_sum<G>(cross) & 1) ? 0 : 1;
+    return o;
+}
+
+// =====================================================================================================
+// MergeEnv (merge_env.py) -- G = 32, slot 0 ownship + 19 FMS-guided intruders (FIX -> RWY)
+// =====================================================================================================
+template <int G>
+__device__ inline void merge_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot) {
+    Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);      // merge_env.py:103-130,148-158
+    const int nac = 20;
+    if (slot < nac) {
+        double brg = rng.uniform(2u * slot, -15.0, 15.0);
+        double dist = slot == 0 ? rng.uniform(1u, 50.0, 200.0) : rng.uniform(2u * slot + 1u, 20.0, 500.0);
+        double lat, lon;
+        d_point_at_distance(P.fix_lat, P.fix_lon, dist, brg, lat, lon);
+        ac_create(a, lat, lon, brg - 180.0, 10000.0, 100.0);
+        if (slot > 0) {     // "INTi addwpt FIX" -> Route.direct + LNAV on; "INTi dest RWY" appends the last wp
+            float q, dm;
+            qdrdist_wgs(a.lat, a.lon, P.fix_lat, P.fix_lon, q, dm);
+            a.curlegdir = q;
+            a.flags |= kFlLnav;
+        }
+    } else {
+        ac_clear(a);
+    }
+    s.wpt_reach = 0; s.faf = 0; s.total_reward = 0.0f; s.intrusions = 0; s.drift_sum = 0.0f; s.drift_n = 0;
+    s.num_ac = nac;
+}
+template <int G>
+__device__ inline void merge_action(Ac& a, const EnvParams& P, const float* act, int slot) {
+    if (slot == 0) {                                                        // merge_env.py:286-293
+        a.aptrk = wrap180_fold(a.hdg + act[0] * 15.0f);
+        a.flags &= ~kFlLnav;
+        float kt = (a.cas + act[1] * 20.0f) * 1.94384f;
+        a.selspd = (kt > 0.1f && kt < 1.0f) ? kt : kt * kKts;
+    }
+}
+template <int G>
+__device__ inline StepOut merge_obs_reward(const Ac& a, EnvS& s, const EnvParams& P, float* obs, int slot,
+                                           bool with_reward) {
+    const double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);     // merge_env.py:160-236
+    const float hdg0 = group_bcast<G>(a.hdg, 0), tas0 = group_bcast<G>(a.tas, 0);
+    const float vx0 = group_bcast<G>(a.gsn, 0), vy0 = group_bcast<G>(a.gse, 0);
+    float wq, wd;
+    if (s.wpt_reach == 0) kwikqdrdist(lat0, lon0, P.fix_lat, P.fix_lon, wq, wd);
+    else kwikqdrdist(lat0, lon0, kRwyLat, kRwyLon, wq, wd);
+    const float drift = wrap180_fold(hdg0 - wq);
+    if (slot == 0) {
+        float sd, cd;
+        sincosf(drift * kDeg2Rad, &sd, &cd);
+        obs[0] = cd; obs[1] = sd; obs[2] = tas0; obs[3] = wd * (1.0f / 250.0f); obs[4] = (float)s.wpt_reach;
+    }
+    const bool other = slot >= 1 && slot < s.num_ac;
+    float brg = 0.0f, dnm = 1e9f;
+    if (other) kwikqdrdist(lat0, lon0, a.lat, a.lon, brg, dnm);
+    int rank = nearest_rank<G>(dnm, other, 5);
+    if (rank >= 0) {
+        float sb, cb;
+        sincosf(brg * kDeg2Rad, &sb, &cb);
+        float dm = dnm * 1852.0f;
+        float dvx = a.gsn - vx0, dvy = a.gse - vy0;
+        float hyp = sqrtf(dvx * dvx + dvy * dvy);
+        float ct = hyp > 0.0f ? dvx / hyp : 1.0f, st = hyp > 0.0f ? dvy / hyp : 0.0f;
+        obs[5 + rank] = dm * cb * 1e-6f;
+        obs[10 + rank] = dm * sb * 1e-6f;
+        obs[15 + rank] = dvx * (1.0f / 150.0f);
+        obs[20 + rank] = dvy * (1.0f / 150.0f);
+        obs[25 + rank] = ct;
+        obs[30 + rank] = st;
+        obs[35 + rank] = dnm * (1.0f / 250.0f);
+    }
+    StepOut o = {0.0f, 0, 0};
+    if (!with_reward) return o;
+    float r = 0.0f;                                                         // merge_env.py:246-284
+    if (wd < 10.0f && s.wpt_reach != 1) { s.wpt_reach = 1; s.faf = 1; r += 1.0f; }
+    else if (wd < 20.0f && s.wpt_reach == 1) { s.faf = 2; o.terminated = 1; }
+    const float dr = fabsf(drift * kDeg2Rad);
+    s.drift_sum += dr; s.drift_n += 1;
+    r += dr * -0.1f;
+    const int nintr = group_sum<G>((other && dnm < 4.0f) ? 1 : 0);
+    s.intrusions += nintr;
+    r -= (float)nintr;
+    s.total_reward += r;
+    o.reward = r;
+    return o;
+}
+__device__ inline void merge_info(const EnvS& s, float* info) {             // merge_env.py:238-244
+    info[0] = s.total_reward; info[1] = (float)s.faf; info[2] = s.drift_sum / (float)s.drift_n; info[3] = (float)s.intrusions;
+}
+
+// =====================================================================================================
+// dispatch helpers
+// =====================================================================================================
+template <int ENV, int G>
+__device__ __forceinline__ void do_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot, double* scratch) {
+    if (ENV == BSG_ENV_DESCENT) descent_reset<G>(a, s, P, e, slot);
+    if (ENV == BSG_ENV_HORIZONTAL_CR) horizontal_reset<G>(a, s, P, e, slot);
+    if (ENV == BSG_ENV_SECTOR_CR) sector_reset<G>(a, s, P, e, slot, scratch);
+    if (ENV == BSG_ENV_MERGE) merge_reset<G>(a, s, P, e, slot);
+    s.step = 0; s.needs_reset = 0; s.episode += 1; s.nconf = 0; s.nlos = 0;
+}
+template <int ENV, int G>
+__device__ __forceinline__ StepOut do_obs(const Ac& a, EnvS& s, const EnvParams& P, float* obs, int slot, long long e,
+                                          bool with_reward) {
+    if (ENV == BSG_ENV_DESCENT) return descent_obs_reward<G>(a, s, P, obs, slot, with_reward);
+    if (ENV == BSG_ENV_HORIZONTAL_CR) return horizontal_obs_reward<G>(a, s, P, obs, slot, with_reward);
+    if (ENV == BSG_ENV_SECTOR_CR) return sector_obs_reward<G>(a, s, P, obs, slot, e, with_reward);
+    return merge_obs_reward<G>(a, s, P, obs, slot, with_reward);
+}
+template <int ENV>
+__device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float* info) {
+    if (ENV == BSG_ENV_DESCENT) descent_info(s, info);
+    else if (ENV == BSG_ENV_MERGE) merge_info(s, info);
+    else drift_info(s, info);
+    info[4] = (float)s.nconf; info[5] = (float)s.nlos;
+}
+
+// =====================================================================================================
+// K6: the env-step megakernel (also serves reset and the kinematics-only parity entry point)
+// =====================================================================================================
+template <int ENV, int G>
+__global__ void __launch_bounds__(kEnvThreads) env_kernel(const EnvParams P) {
+    __shared__ __align__(16) float4 s_rec[kEnvThreads * 2];
+    __shared__ double s_scratch[(ENV == BSG_ENV_SECTOR_CR) ? (kEnvThreads / 32) * 96 : 1];
+    const long long gt = (long long)blockIdx.x * kEnvThreads + threadIdx.x;
+    const long long e = gt / G;
+    const int slot = (int)(gt % G);
+    if (e >= P.E) return;                       // group-uniform (G divides the block size)
+    double* scratch = (ENV == BSG_ENV_SECTOR_CR) ? &s_scratch[(threadIdx.x / 32) * 96] : s_scratch;
+
+    EnvS s;
+    env_load(s, P, e);
+    Ac a;
+    float* obs = P.obs + e * P.obs_dim;
+    float* info = P.info + e * P.info_dim;
+
+    if (P.mode == kModeReset) {
+        if (P.reset_mask && !P.reset_mask[e]) return;
+        do_reset<ENV, G>(a, s, P, e, slot, scratch);
+        do_obs<ENV, G>(a, s, P, obs, slot, e, false);
+        if (slot == 0) {
+            do_info<ENV>(s, P, info);
+            P.reward[e] = 0.0f; P.term[e] = 0; P.trunc[e] = 0;
+            env_store(s, P, e);
+        }
+        ac_store(a, P, gt);
+        return;
+    }
+
+    if (P.mode == kModeStep && P.autoreset == BSG_AUTORESET_NEXT_STEP && s.needs_reset) {
+        do_reset<ENV, G>(a, s, P, e, slot, scratch);
+        do_obs<ENV, G>(a, s, P, obs, slot, e, false);
+        if (slot == 0) {
+            do_info<ENV>(s, P, info);
+            P.reward[e] = 0.0f; P.term[e] = 0; P.trunc[e] = 0;
+            env_store(s, P, e);
+        }
+        ac_store(a, P, gt);
+        return;
+    }
+
+    ac_load(a, P, gt);
+    const bool alive = (a.flags & kFlAlive) != 0;
+    if (P.mode == kModeStep) {
+        const float* act = P.actions + e * P.act_dim;
+        if (ENV == BSG_ENV_DESCENT) descent_action<G>(a, P, act, slot);
+        if (ENV == BSG_ENV_HORIZONTAL_CR) horizontal_action<G>(a, P, act, slot);
+        if (ENV == BSG_ENV_SECTOR_CR) sector_action<G>(a, P, act, slot);
+        if (ENV == BSG_ENV_MERGE) merge_action<G>(a, P, act, slot);
+    }
+
+    int nconf = s.nconf, nlos = s.nlos;
+    for (int k = 0; k < P.n_sub; ++k) {                 // n_sub x bs.sim.step()
+        s.simk += 1;
+        const bool fms_ready = (s.simk % P.fms_rel_freq) == 0;
+        Atmos at = vatmos(a.alt);
+        float ap_tas = 0.0f;
+        if (alive) ac_autopilot<ENV>(a, P, fms_ready, at, ap_tas);
+        if (G > 1 && P.cd_enabled) group_cd<G>(a, alive, s.num_ac, P, s_rec, nconf, nlos);
+        if (alive) ac_kinematics(a, P, at, ap_tas);
+    }
+    s.nconf = nconf; s.nlos = nlos;
+
+    if (P.mode == kModeTraf) {
+        ac_store(a, P, gt);
+        if (slot == 0) env_store(s, P, e);
+        return;
+    }
+
+    StepOut o = do_obs<ENV, G>(a, s, P, obs, slot, e, true);
+    s.step += 1;
+    if (P.max_steps > 0 && s.step >= P.max_steps) o.truncated = 1;      // gymnasium TimeLimit
+    const bool done = o.terminated || o.truncated;
+    if (slot == 0) {
+        P.reward[e] = o.reward; P.term[e] = (uint8_t)o.terminated; P.trunc[e] = (uint8_t)o.truncated;
+        do_info<ENV>(s, P, info);
+    }
+    if (done) {
+        if (P.autoreset == BSG_AUTORESET_SAME_STEP) {
+            if (P.final_obs) {                  // the terminal observation survives in final_obs
+                __syncwarp(group_mask<G>());
+                float* fo = P.final_obs + e * P.obs_dim;
+                for (int i = slot; i < P.obs_dim; i += G) fo[i] = obs[i];
+                __syncwarp(group_mask<G>());
+            }
+            do_reset<ENV, G>(a, s, P, e, slot, scratch);
+            do_obs<ENV, G>(a, s, P, obs, slot, e, false);
+        } else if (P.autoreset == BSG_AUTORESET_NEXT_STEP) {
+            s.needs_reset = 1;
+        }
+    }
+    ac_store(a, P, gt);
+    if (slot == 0) env_store(s, P, e);
+}
+
+}  // namespace bsg
+
+using namespace bsg;
+
+template <int ENV, int G>
+static int launch_env_t(const EnvParams& P, cudaStream_t st) {
+    long long threads = (long long)P.E * G;
+    int blocks = (int)((threads + kEnvThreads - 1) / kEnvThreads);
+    if (blocks == 0) return BSG_OK;
+    env_kernel<ENV, G><<<blocks, kEnvThreads, 0, st>>>(P);
+    return bsg_cuda_check(cudaGetLastError(), "env_kernel launch");
+}
+
+int bsg_launch_env(const EnvParams& P, int slots, cudaStream_t st) {
+    switch (P.env_type) {
+        case BSG_ENV_DESCENT:
+            return launch_env_t<BSG_ENV_DESCENT, 1>(P, st);
+        case BSG_ENV_HORIZONTAL_CR:
+            if (slots == 8) return launch_env_t<BSG_ENV_HORIZONTAL_CR, 8>(P, st);
+            if (slots == 16) return launch_env_t<BSG_ENV_HORIZONTAL_CR, 16>(P, st);
+            return launch_env_t<BSG_ENV_HORIZONTAL_CR, 32>(P, st);
+        case BSG_ENV_SECTOR_CR:
+            return launch_env_t<BSG_ENV_SECTOR_CR, 32>(P, st);
+        case BSG_ENV_MERGE:
+            return launch_env_t<BSG_ENV_MERGE, 32>(P, st);
+    }
+    return bsg_fail(BSG_EINVAL, "unknown env_type");
+}

@@ -1,0 +1,94 @@
+"""Scalar ``gymnasium.Env`` views of the batched simulator: the classes ``gym.make(id)`` returns.
+
+Same constructor keywords, spaces, return types and info keys as the reference classes
+(bluesky_gym/envs/{descent,horizontal_cr,sector_cr,merge}_env.py); each is a ``num_envs=1``
+BlueSkyVectorEnv with autoreset disabled, so ``reset`` / ``step`` follow the single-env contract
+(float64 numpy observations, python scalars for reward / terminated / truncated).
+"""
+import numpy as np
+
+from .gym_compat import Env
+from .spec import SPECS
+from .vector_env import BlueSkyVectorEnv
+
+
+class _ScalarEnv(Env):
+    ENV_ID = None
+    metadata = {"render_modes": ["rgb_array", "human"], "render_fps": 120}   # e.g. horizontal_cr_env.py:39
+
+    def __init__(self, render_mode=None, device=0, seed=0, cd_enabled=False, **kwargs):
+        assert render_mode is None or render_mode in self.metadata["render_modes"]   # horizontal_cr_env.py:64
+        if render_mode is not None:
+            raise NotImplementedError("rendering is out of scope of the batched simulator (render_mode=None only)")
+        self.render_mode = None
+        self._seed = seed
+        self._kw = dict(device=device, cd_enabled=cd_enabled, **kwargs)
+        self._make(seed)
+
+    def _make(self, seed):
+        # the registration's TimeLimit is applied by gym.make's wrapper, exactly like the reference
+        self.vec = BlueSkyVectorEnv(self.ENV_ID, 1, seed=seed, autoreset_mode="disabled",
+                                    max_episode_steps=0, **self._kw)
+        self.observation_space = self.vec.single_observation_space
+        self.action_space = self.vec.single_action_space
+
+    def _info(self, infos):
+        return {k: (float(v[0]) if np.issubdtype(np.asarray(v).dtype, np.floating) else int(v[0]))
+                for k, v in infos.items() if not k.startswith("_") and k != "final_obs"}
+
+    def reset(self, seed=None, options=None):
+        if seed is not None and seed != self._seed:          # re-key the Philox stream
+            self.vec.close()
+            self._seed = seed
+            self._make(seed)
+        obs, infos = self.vec.reset()
+        return {k: v[0].copy() for k, v in obs.items()}, self._info(infos)
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float64).reshape(1, -1)
+        obs, rew, term, trunc, infos = self.vec.step(a)
+        return ({k: v[0].copy() for k, v in obs.items()}, float(rew[0]), bool(term[0]), bool(trunc[0]),
+                self._info(infos))
+
+    def render(self):
+        return None
+
+    def close(self):
+        self.vec.close()
+
+
+class DescentEnv(_ScalarEnv):
+    ENV_ID = "DescentEnv-v0"
+
+
+class HorizontalCREnv(_ScalarEnv):
+    ENV_ID = "HorizontalCREnv-v0"
+
+
+class SectorCREnv(_ScalarEnv):
+    ENV_ID = "SectorCREnv-v0"
+
+    def __init__(self, render_mode=None, ac_density_mode="normal", **kw):      # sector_cr_env.py:45
+        if ac_density_mode != "normal":
+            raise NotImplementedError("only ac_density_mode='normal' is on the accelerated path")
+        super().__init__(render_mode=render_mode, **kw)
+
+
+class MergeEnv(_ScalarEnv):
+    ENV_ID = "MergeEnv-v0"
+
+
+def _not_accelerated(env_id):
+    class _Stub(Env):
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"{env_id} is registered by the reference but is not on the accelerated "
+                                      "path yet (SURVEY.md section 8f)")
+    _Stub.__name__ = env_id.split("-")[0]
+    return _Stub
+
+
+PlanWaypointEnv = _not_accelerated("PlanWaypointEnv-v0")
+VerticalCREnv = _not_accelerated("VerticalCREnv-v0")
+StaticObstacleEnv = _not_accelerated("StaticObstacleEnv-v0")
+
+__all__ = [s.entry_point.split(":")[1] for s in SPECS.values()]

@@ -1,0 +1,234 @@
+"""BlueSkyVectorEnv -- the batched, device-resident front-end of the accelerated step path.
+
+API boundary mirrored: ``gymnasium.vector.VectorEnv`` over the reference's env classes
+(``Env.reset`` / ``Env.step`` of bluesky_gym/envs/*.py, registered in bluesky_gym/__init__.py:4-46).
+PyTorch is plumbing only: it owns the device tensors (structure-of-arrays aircraft state, per-env
+records, obs / reward / flag outputs) and the pinned host mirrors; every computation is a call into
+libbsg_b200.so through the C ABI of include/bsg.h.  There is no CPU path.
+
+Two ways to drive it:
+  * ``reset()`` / ``step(actions)``      -- numpy in / numpy float64 out (gymnasium, SB3, RLlib);
+    each step copies actions host->device and obs / reward / flags / info device->host
+    (``bsg_step_host``).
+  * ``reset_torch()`` / ``step_torch(a)`` -- CUDA float32 tensors in / out, no host sync.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from .gym_compat import VectorEnv, batch_space, spaces
+from .spec import A320_PERF, AUTORESET, NOT_ACCELERATED, SPECS
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class BlueSkyVectorEnv(VectorEnv):
+    metadata = {"render_modes": [], "autoreset_mode": "next_step"}
+
+    def __init__(self, env_id, num_envs, device=0, seed=0, cd_enabled=False, n_intruders=None,
+                 autoreset_mode="next_step", env_id_offset=0, max_episode_steps=None, perf=None,
+                 default_hdg="random", rpz=0.0, hpz=0.0, dtlookahead=0.0, render_mode=None):
+        if env_id in NOT_ACCELERATED:
+            raise NotImplementedError(f"{env_id} is registered by the reference but is not on the accelerated "
+                                      "path yet (SURVEY.md section 8f)")
+        if env_id not in SPECS:
+            raise KeyError(f"unknown env id {env_id!r}")
+        assert render_mode is None, "the batched simulator has no renderer (render_mode=None only)"
+        if not torch.cuda.is_available():
+            raise _lib.BsgError("BlueSkyVectorEnv needs a CUDA device: there is no CPU fallback")
+        self.spec_b200 = SPECS[env_id]
+        self.env_id = env_id
+        self.num_envs = int(num_envs)
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.render_mode = None
+        self.autoreset_mode = autoreset_mode
+        self.metadata = dict(self.metadata, autoreset_mode=autoreset_mode)
+        n_int = n_intruders if n_intruders is not None else self.spec_b200.default_kwargs.get("n_intruders", 0)
+        self.n_intruders = n_int
+
+        lib = _lib.load()
+        pf = _lib.Perf(**{**A320_PERF, **(perf or {})})
+        self.cfg = _lib.Config(
+            env_type=self.spec_b200.env_type, num_envs=self.num_envs, n_intruders=n_int,
+            cd_enabled=int(bool(cd_enabled)), autoreset_mode=AUTORESET[autoreset_mode],
+            max_episode_steps=self.spec_b200.max_episode_steps if max_episode_steps is None else int(max_episode_steps),
+            default_hdg_random=1 if default_hdg == "random" else 0, device=self.device.index,
+            seed=int(seed) & (2 ** 64 - 1), env_id_offset=int(env_id_offset), rpz=rpz, hpz=hpz,
+            dtlookahead=dtlookahead, perf=pf)
+        self.layout = _lib.query_layout(self.cfg)
+        L, E, G = self.layout, self.num_envs, self.layout.slots
+        self.slots = G
+
+        # ---- spaces (identical keys / shapes / dtype to the reference declarations)
+        self.obs_layout, obs_dim = self.spec_b200.obs_layout(n_int)
+        assert obs_dim == L.obs_dim, (obs_dim, L.obs_dim)
+        self.single_observation_space = spaces.Dict(OrderedDict(
+            (k, spaces.Box(lo, hi, shape=(w,), dtype=np.float64)) for k, (off, w, lo, hi) in self.obs_layout.items()))
+        self.single_action_space = spaces.Box(-1, 1, shape=(L.act_dim,), dtype=np.float64)
+        self.observation_space = batch_space(self.single_observation_space, E)
+        self.action_space = batch_space(self.single_action_space, E)
+
+        # ---- device state (torch owns the memory; the library only borrows pointers)
+        dev = self.device
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        self.t = OrderedDict(
+            pos=z((E, G, 2), torch.float64), kin=z((E, G, 4), torch.float32), cmd=z((E, G, 4), torch.float32),
+            aux=z((E, G, 4), torch.float32), flags=z((E, G), torch.int32),
+            tcpamax=z((E, G), torch.float32), inconf=z((E, G), torch.uint8),
+            env_f64=z((E, L.env_f64), torch.float64), env_f32=z((E, L.env_f32), torch.float32),
+            env_i32=z((E, L.env_i32), torch.int32),
+            poly=z((E, max(L.poly_f64, 1)), torch.float64) if L.poly_f64 else None,
+            obs=z((E, L.obs_dim), torch.float32), final_obs=z((E, L.obs_dim), torch.float32),
+            reward=z((E,), torch.float32), terminated=z((E,), torch.uint8), truncated=z((E,), torch.uint8),
+            info=z((E, L.info_dim), torch.float32), actions_staging=z((E, L.act_dim), torch.float32))
+        # pinned host mirrors for the numpy API
+        ph = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
+        self.h = dict(actions=ph((E, L.act_dim), torch.float32), obs=ph((E, L.obs_dim), torch.float32),
+                      reward=ph((E,), torch.float32), terminated=ph((E,), torch.uint8),
+                      truncated=ph((E,), torch.uint8), info=ph((E, L.info_dim), torch.float32),
+                      final_obs=ph((E, L.obs_dim), torch.float32))
+
+        self._h = C.c_void_p(0)
+        with torch.cuda.device(dev):
+            _lib.check(lib.bsg_create(C.byref(self.cfg), C.byref(self._h)))
+            tt = _lib.TensorTable(**{k: _ptr(v) for k, v in self.t.items()})
+            _lib.check(lib.bsg_bind_state(self._h, C.byref(tt)))
+        self._lib = lib
+        self.gpu_launches = 0
+        self.closed = False
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _obs_dict_np(self, flat):
+        f = flat.astype(np.float64)
+        return OrderedDict((k, f[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
+
+    def _obs_dict_torch(self, flat):
+        return OrderedDict((k, flat[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
+
+    def _infos_np(self, info):
+        out = {}
+        for i, k in enumerate(self.spec_b200.info_keys):
+            out[k] = info[:, i].astype(np.float64)
+        if self.cfg.cd_enabled:
+            out["asas_nconf"] = info[:, 4].astype(np.int64)
+            out["asas_nlos"] = info[:, 5].astype(np.int64)
+        return out
+
+    # ------------------------------------------------------------------ device-tensor API (no host sync)
+    def reset_torch(self, mask=None):
+        """Resets every env (or those where ``mask`` is non-zero); returns the obs dict of CUDA tensors."""
+        m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.bsg_reset(self._h, _ptr(m), self._stream()))
+        self.gpu_launches += 1
+        return self._obs_dict_torch(self.t["obs"])
+
+    def step_torch(self, actions):
+        """actions: CUDA float32 [E, act_dim].  Returns (obs dict, reward, terminated, truncated) as views
+        of the bound device tensors (overwritten by the next call)."""
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        assert a.shape == (self.num_envs, self.layout.act_dim), a.shape
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.bsg_step(self._h, _ptr(a), self._stream()))
+        self.gpu_launches += 1
+        return self._obs_dict_torch(self.t["obs"]), self.t["reward"], self.t["terminated"], self.t["truncated"]
+
+    def traf_update(self, n_sub):
+        """n_sub x bs.sim.step() only (kinematics + autopilot, no obs / reward); parity-test entry point."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.bsg_traf_update(self._h, int(n_sub), self._stream()))
+        self.gpu_launches += 1
+
+    # ------------------------------------------------------------------ gymnasium VectorEnv API (numpy)
+    def reset(self, *, seed=None, options=None):
+        if seed is not None:
+            raise ValueError("the Philox seed is fixed at construction (seed=...); per-reset seeds are not supported")
+        self.reset_torch()
+        torch.cuda.synchronize(self.device)
+        obs = self.t["obs"].cpu().numpy()
+        info = self.t["info"].cpu().numpy()
+        return self._obs_dict_np(obs), self._infos_np(info)
+
+    def step(self, actions):
+        a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, self.layout.act_dim)
+        h = self.h
+        h["actions"].numpy()[...] = a
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.bsg_step_host(self._h, _ptr(h["actions"]), _ptr(h["obs"]), _ptr(h["reward"]),
+                                               _ptr(h["terminated"]), _ptr(h["truncated"]), _ptr(h["info"]),
+                                               self._stream()))
+        self.gpu_launches += 1
+        obs = self._obs_dict_np(h["obs"].numpy())
+        rew = h["reward"].numpy().astype(np.float64)
+        term = h["terminated"].numpy().astype(bool)
+        trunc = h["truncated"].numpy().astype(bool)
+        infos = self._infos_np(h["info"].numpy())
+        if self.autoreset_mode == "same_step":
+            done = term | trunc
+            if done.any():
+                fo = self.t["final_obs"].cpu().numpy()
+                infos["final_obs"] = self._obs_dict_np(fo)
+                infos["_final_obs"] = done
+        return obs, rew, term, trunc, infos
+
+    # ------------------------------------------------------------------ state access (parity tests, checkpoints)
+    def state_dict(self):
+        return {k: v for k, v in self.t.items() if v is not None}
+
+    def load_state(self, e, lat, lon, alt, tas, hdg, vs, selspd, selalt, selvs, ap_trk, cas, ax=None,
+                   lnav=None, iactwp=None, curlegdir=None, env_f64=None, env_i32=None, env_f32=None, poly=None):
+        """Injects a (reference / oracle) post-reset traffic state into env ``e`` (bsg_load_state of SURVEY 8b)."""
+        n, G = len(lat), self.slots
+        assert n <= G
+        dev = self.device
+        f32 = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float32), device=dev)
+        pos = torch.zeros((G, 2), dtype=torch.float64, device=dev)
+        pos[:n, 0] = torch.as_tensor(np.asarray(lat, dtype=np.float64), device=dev)
+        pos[:n, 1] = torch.as_tensor(np.asarray(lon, dtype=np.float64), device=dev)
+        kin = torch.zeros((G, 4), dtype=torch.float32, device=dev)
+        cmd = torch.zeros((G, 4), dtype=torch.float32, device=dev)
+        aux = torch.zeros((G, 4), dtype=torch.float32, device=dev)
+        for c, v in enumerate((alt, tas, hdg, vs)):
+            kin[:n, c] = f32(v)
+        for c, v in enumerate((selspd, selalt, selvs, ap_trk)):
+            cmd[:n, c] = f32(v)
+        aux[:n, 0] = f32(np.zeros(n) if ax is None else ax)
+        aux[:n, 1] = f32(np.full(n, -999.0) if curlegdir is None else curlegdir)
+        aux[:n, 2] = f32(cas)
+        fl = np.zeros(G, dtype=np.int32)
+        fl[:n] = _lib.FL_ALIVE
+        if lnav is not None:
+            fl[:n] |= np.where(np.asarray(lnav, dtype=bool), _lib.FL_LNAV, 0).astype(np.int32)
+        if iactwp is not None:
+            ia = np.maximum(np.asarray(iactwp, dtype=np.int32), 0)
+            fl[:n] |= (ia << _lib.FL_WPSHIFT) | np.where(ia >= 1, _lib.FL_LASTWP, 0).astype(np.int32)
+        self.t["pos"][e], self.t["kin"][e], self.t["cmd"][e], self.t["aux"][e] = pos, kin, cmd, aux
+        self.t["flags"][e] = torch.as_tensor(fl, device=dev)
+        for name, vals in (("env_f64", env_f64), ("env_i32", env_i32), ("env_f32", env_f32)):
+            if vals:
+                for idx, v in vals.items():
+                    self.t[name][e, idx] = v
+        if poly is not None:
+            p = np.zeros(self.layout.poly_f64)
+            p[:len(poly)] = poly
+            self.t["poly"][e] = torch.as_tensor(p, device=dev)
+
+    def close(self, **kwargs):
+        if not self.closed and self._h:
+            self._lib.bsg_destroy(self._h)
+            self._h = C.c_void_p(0)
+        self.closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,170 @@
+/* include/bsg.h -- C ABI of libbsg_b200.so: the B200-native batched BlueSky-Gym step path.
+ *
+ * The reference (svlaskin/bluesky-gym-sasha) is pure Python and has no FFI of its own; the boundary
+ * its hot path sits behind is the gymnasium Env API (bluesky_gym/__init__.py:4-46 registration,
+ * Env.reset / Env.step in bluesky_gym/envs/*.py).  Each entry point below therefore cites the
+ * reference *Python* interface it replaces; INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions: extern "C", plain pointers and sizes, no torch / CUDA types in the signatures
+ * (streams travel as void* = cudaStream_t).  Every function returns 0 on success or a negative
+ * BSG_E* code; bsg_last_error() returns a thread-local message.  No exceptions cross the boundary,
+ * there is no global state, and one handle serves one (process, device).  Memory is owned by the
+ * caller (torch tensors in the Python host); the library holds raw device pointers only between
+ * bsg_bind_state() and bsg_destroy() and never frees them.  Calls on one handle are not
+ * thread-safe; different handles may be driven from different threads or processes.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with BSG_ECUDA.
+ */
+#ifndef BSG_H_
+#define BSG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSG_ABI_VERSION 1
+
+enum { BSG_OK = 0, BSG_EINVAL = -1, BSG_ECUDA = -2, BSG_ESTATE = -3, BSG_ENOMEM = -4 };
+
+/* gym ids of bluesky_gym/__init__.py:7-46 that are on the accelerated path */
+enum {
+    BSG_ENV_DESCENT = 0,        /* DescentEnv-v0       descent_env.py       */
+    BSG_ENV_HORIZONTAL_CR = 1,  /* HorizontalCREnv-v0  horizontal_cr_env.py */
+    BSG_ENV_SECTOR_CR = 2,      /* SectorCREnv-v0      sector_cr_env.py     */
+    BSG_ENV_MERGE = 3           /* MergeEnv-v0         merge_env.py         */
+};
+
+/* vector autoreset behaviour (gymnasium.vector.AutoresetMode) */
+enum { BSG_AUTORESET_DISABLED = 0, BSG_AUTORESET_NEXT_STEP = 1, BSG_AUTORESET_SAME_STEP = 2 };
+
+/* OpenAP-lite envelope of the one aircraft type the reference flies ("A320", e.g.
+ * horizontal_cr_env.py:91).  Data, not code: see oracle/perf.py::PerfTable. */
+typedef struct bsg_perf {
+    float vminto, vmaxic, vminer, vmaxer, vminap, vmaxap;   /* m/s CAS */
+    float vsmin, vsmax;                                     /* m/s     */
+    float hmax;                                             /* m       */
+    float mmo;
+    float axmax_gd, axmax_air;                              /* m/s^2   */
+} bsg_perf;
+
+typedef struct bsg_config {
+    int32_t env_type;           /* BSG_ENV_*                                                        */
+    int32_t num_envs;           /* E: env instances on this device                                   */
+    int32_t n_intruders;        /* HorizontalCR only: reference 5 (horizontal_cr_env.py:17)          */
+    int32_t cd_enabled;         /* run StateBased.detect every substep (off in the reference)        */
+    int32_t autoreset_mode;     /* BSG_AUTORESET_*                                                   */
+    int32_t max_episode_steps;  /* TimeLimit of the registration, bluesky_gym/__init__.py:9-45       */
+    int32_t default_hdg_random; /* Traffic.cre(achdg=None) draws randint(1,360) when 1, else 0 deg   */
+    int32_t device;             /* CUDA ordinal                                                      */
+    uint64_t seed;              /* Philox key part; stream = (seed, env_id_offset + e, episode)      */
+    int64_t env_id_offset;      /* global id of env 0 on this device (sharding is placement-free)    */
+    float rpz, hpz, dtlookahead;/* ASAS zone [m], [m], [s]; <= 0 selects 5 NM / 1000 ft / 300 s      */
+    bsg_perf perf;
+} bsg_config;
+
+/* What the caller must allocate (all device memory, zero-initialised) for a given config. */
+typedef struct bsg_layout {
+    int32_t slots;              /* G: aircraft slots per env (1, 8, 16 or 32), slot index fastest    */
+    int32_t obs_dim;            /* floats per env in obs / final_obs                                 */
+    int32_t act_dim;            /* floats per env in actions                                         */
+    int32_t info_dim;           /* floats per env in info                                            */
+    int32_t n_sub;              /* simulator substeps per env step (ACTION_FREQUENCY)                */
+    int32_t env_f64, env_f32, env_i32; /* per-env scalar record widths                               */
+    int32_t poly_f64;           /* per-env polygon doubles (SectorCR: 2*32), else 0                  */
+    float simdt;
+} bsg_layout;
+
+/* Device pointers of caller-owned tensors.  Per-aircraft arrays have E*G elements.                 */
+typedef struct bsg_tensor_table {
+    double *pos;        /* [E*G] double2 (lat, lon) deg            bs.traf.lat / lon                 */
+    float *kin;         /* [E*G] float4  (alt m, tas m/s, hdg deg, vs m/s)    bs.traf.alt/tas/hdg/vs  */
+    float *cmd;         /* [E*G] float4  (selspd, selalt, selvs, ap.trk)      bs.traf.sel*, ap.trk    */
+    float *aux;         /* [E*G] float4  (ax, curlegdir, cas, reserved)                              */
+    uint32_t *flags;    /* [E*G] bit0 alive, bit1 swlnav, bit2 swlastwp, bits 8.. active wp index    */
+    float *tcpamax;     /* [E*G] ASAS tcpamax per aircraft (cd_enabled)                              */
+    uint8_t *inconf;    /* [E*G] ASAS inconf per aircraft  (cd_enabled)                              */
+    double *env_f64;    /* [E*env_f64]                                                               */
+    float *env_f32;     /* [E*env_f32]                                                               */
+    int32_t *env_i32;   /* [E*env_i32]                                                               */
+    double *poly;       /* [E*poly_f64] or NULL                                                      */
+    float *obs;         /* [E*obs_dim]   Env._get_obs, keys concatenated in declaration order        */
+    float *final_obs;   /* [E*obs_dim]   terminal observation (SAME_STEP autoreset), may be NULL     */
+    float *reward;      /* [E]                                                                       */
+    uint8_t *terminated;/* [E]                                                                       */
+    uint8_t *truncated; /* [E]                                                                       */
+    float *info;        /* [E*info_dim]  Env._get_info values at the end of the step (pre-autoreset) */
+    float *actions_staging; /* [E*act_dim] device staging buffer used by bsg_step_host, may be NULL  */
+} bsg_tensor_table;
+
+/* indices into the per-env records (shared by all env types; unused slots stay zero) */
+enum { BSG_F64_WPT_LAT = 0, BSG_F64_WPT_LON = 1, BSG_F64_TARGET_ALT = 2, BSG_F64_POLY_AREA = 3, BSG_F64_COUNT = 4 };
+enum { BSG_F32_TOTAL_REWARD = 0, BSG_F32_DRIFT_SUM = 1, BSG_F32_FINAL_ALT = 2, BSG_F32_LAST_HDG = 3, BSG_F32_COUNT = 4 };
+enum {
+    BSG_I32_STEP = 0, BSG_I32_EPISODE = 1, BSG_I32_SIMK = 2, BSG_I32_WPT_REACH = 3, BSG_I32_DRIFT_N = 4,
+    BSG_I32_INTRUSIONS = 5, BSG_I32_NUM_AC = 6, BSG_I32_NVERT = 7, BSG_I32_NEEDS_RESET = 8,
+    BSG_I32_FAF = 9, BSG_I32_NCONF = 10, BSG_I32_NLOS = 11, BSG_I32_RESET_FLAGS = 12, BSG_I32_COUNT = 16
+};
+
+typedef struct bsg_handle bsg_handle;
+
+int bsg_abi_version(void);
+const char *bsg_last_error(void);
+int bsg_device_count(void);
+
+/* Fills the allocation plan for cfg.  Pure host logic: works without a GPU. */
+int bsg_query_layout(const bsg_config *cfg, bsg_layout *out);
+
+/* replaces: Env.__init__ (bs.init + 'DT n;FF'), e.g. horizontal_cr_env.py:41-80 */
+int bsg_create(const bsg_config *cfg, bsg_handle **out);
+void bsg_destroy(bsg_handle *h);
+int bsg_bind_state(bsg_handle *h, const bsg_tensor_table *t);
+
+/* replaces: Env.reset, e.g. horizontal_cr_env.py:82-101, sector_cr_env.py:87-115, merge_env.py:103-130,
+ * descent_env.py:162-182.  d_mask: E bytes on the device, non-zero = reset that env; NULL = all. */
+int bsg_reset(bsg_handle *h, const uint8_t *d_mask, void *stream);
+
+/* replaces: Env.step, e.g. horizontal_cr_env.py:103-125 (action -> n_sub x bs.sim.step() -> obs ->
+ * reward -> terminated/truncated -> info), plus the TimeLimit wrapper and vector autoreset.
+ * d_actions: [E*act_dim] float32 on the device.  Asynchronous on `stream`. */
+int bsg_step(bsg_handle *h, const float *d_actions, void *stream);
+
+/* End-to-end form of bsg_step for host callers (SB3 / numpy): copies h_actions (pinned or pageable)
+ * to the device, steps, copies obs / reward / terminated / truncated / info back and synchronises. */
+int bsg_step_host(bsg_handle *h, const float *h_actions, float *h_obs, float *h_reward,
+                  uint8_t *h_terminated, uint8_t *h_truncated, float *h_info, void *stream);
+
+/* replaces: n_sub x bs.sim.step() alone (Traffic.update kinematics + autopilot, no obs/reward);
+ * used by the trajectory parity tests. */
+int bsg_traf_update(bsg_handle *h, int32_t n_sub, void *stream);
+
+/* ---- single-airspace state-based conflict detection (StateBased.detect; CD record = 32 B) -------- */
+
+/* Packs float64 SoA aircraft state (bs.traf.lat/lon/trk/gs/alt/vs) into the 32-byte float CD record
+ * (x, y metres from (lat0, lon0); cos/sin of half latitude; u, v; alt; vs).  d_rec must hold
+ * bsg_cd_padded(n) records; the padding is filled with inert aircraft. */
+int64_t bsg_cd_padded(int64_t n);
+int bsg_cd_pack(const double *d_lat, const double *d_lon, const double *d_trk, const double *d_gs,
+                const double *d_alt, const double *d_vs, int64_t n, double lat0, double lon0,
+                float *d_rec, void *stream);
+
+enum { BSG_CD_LON_WRAP = 1,     /* pairs may straddle the +-180 deg meridian relative to lon0        */
+       BSG_CD_SYMMETRIC = 2 };  /* evaluate each unordered pair once (needs n_rows == n_all)         */
+
+/* Rows [row0, row0+n_rows) of d_rec against all n_all aircraft (row sharding for multi-GPU).
+ * Outputs (caller-owned, device): per-row nconf / nlos counts and tcpamax, inconf flags, and a pair
+ * list of capacity `cap` ordered pairs (i, j) with its true length in d_npairs[0] (conflicts) and
+ * d_npairs[1] (LoS pairs found; only counted).  Any output pointer except d_nconf_row may be NULL. */
+int bsg_cd_detect(const float *d_rec, int64_t n_all, int64_t row0, int64_t n_rows,
+                  float rpz, float hpz, float dtlookahead, uint32_t flags,
+                  uint32_t *d_nconf_row, uint32_t *d_nlos_row, float *d_tcpamax, uint8_t *d_inconf,
+                  int32_t *d_pairs, int64_t cap, unsigned long long *d_npairs, void *stream);
+
+/* ---- roofline denominators measured on the spot (bench.py) ------------------------------------- */
+/* Dense FP32 FMA throughput [FLOP/s] of this device, timed with CUDA events. */
+int bsg_probe_fp32(int32_t device, double *flops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSG_H_ */

@@ -1,0 +1,218 @@
+"""K1/K3/K4/K5/K6 parity: the batched env step (through the C ABI) against the float64 oracle envs.
+
+Two families, per SURVEY.md section 0.6:
+  * state injection -- the oracle env is reset with the *reference's* draw source (global np.random /
+    random, seeded), its post-reset state is loaded into the device sim, and both are stepped with the
+    same actions: trajectories, observations, rewards and termination flags must agree;
+  * device reset -- the device's Philox-keyed scenario generator against the oracle env driven by the
+    same Philox stream (oracle/philox.py).
+Tolerances (float32 kernels vs float64 oracle; stated here as the north_star requires):
+  lat/lon 2e-5 deg (~2 m), alt 0.5 m, tas / vs 2e-2 m/s, hdg 5e-3 deg, observations rtol 1e-3 + atol 5e-4,
+  reward atol 1e-3, terminated / truncated sequences identical.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from bluesky_gym_sasha_b200 import _lib
+from oracle import envs as oenvs
+from oracle import geo as ogeo
+from oracle.philox import PhiloxDraws
+from tests.common import angdiff, device_traffic, inject_oracle_env
+
+pytestmark = pytest.mark.gpu
+
+TOL = dict(pos=2e-5, alt=0.5, tas=2e-2, vs=2e-2, hdg=5e-3)
+
+
+def _make_oracle(env_id, draws=None, cd=False, n_int=5):
+    if env_id == "HorizontalCREnv-v0":
+        return oenvs.HorizontalCREnv(n_intruders=n_int, draws=draws, cd_enabled=cd)
+    if env_id == "DescentEnv-v0":
+        return oenvs.DescentEnv(draws=draws)
+    if env_id == "SectorCREnv-v0":
+        return oenvs.SectorCREnv(draws=draws, cd_enabled=cd)
+    return oenvs.MergeEnv(draws=draws, cd_enabled=cd)
+
+
+def _inject(venv, e, oenv, env_id):
+    t = oenv.traf
+    for cmd in t.queue:             # MergeEnv: the queued addwpt/dest run at the start of the first sim step
+        cmd()
+    t.queue = []
+    f64, i32, poly = {}, {}, None
+    if env_id == "HorizontalCREnv-v0":
+        f64 = {_lib.F64_WPT_LAT: oenv.wpt_lat, _lib.F64_WPT_LON: oenv.wpt_lon}
+    elif env_id == "DescentEnv-v0":
+        f64 = {_lib.F64_TARGET_ALT: float(oenv.target_alt)}
+    elif env_id == "SectorCREnv-v0":
+        w = ogeo.nm_to_latlong(oenvs.SECTOR_CENTER, oenv.wpts[0])
+        f64 = {_lib.F64_WPT_LAT: float(w[0]), _lib.F64_WPT_LON: float(w[1])}
+        i32 = {_lib.I32_NVERT: len(oenv.poly_lat)}
+        poly = np.stack([oenv.poly_lat, oenv.poly_lon], axis=1).reshape(-1)
+    inject_oracle_env(venv, e, oenv, extra_f64=f64, extra_i32=i32, poly=poly)
+
+
+def _compare_traffic(venv, oracles, alive_mask, step):
+    d = device_traffic(venv)
+    for e, o in enumerate(oracles):
+        if not alive_mask[e]:
+            continue
+        t = o.traf
+        n = t.ntraf
+        assert np.max(np.abs(d["lat"][e, :n] - t.lat)) < TOL["pos"], (step, e, "lat")
+        assert np.max(np.abs(d["lon"][e, :n] - t.lon)) < TOL["pos"], (step, e, "lon")
+        assert np.max(np.abs(d["alt"][e, :n] - t.alt)) < TOL["alt"], (step, e, "alt")
+        assert np.max(np.abs(d["tas"][e, :n] - t.tas)) < TOL["tas"], (step, e, "tas")
+        assert np.max(np.abs(d["vs"][e, :n] - t.vs)) < TOL["vs"], (step, e, "vs")
+        assert np.max(angdiff(d["hdg"][e, :n], t.hdg)) < TOL["hdg"], (step, e, "hdg")
+
+
+def _compare_obs(gobs, oobs, e, step):
+    for k, v in oobs.items():
+        np.testing.assert_allclose(gobs[k][e], v, rtol=1e-3, atol=5e-4, err_msg=f"step {step} env {e} key {k}")
+
+
+@pytest.mark.parametrize("env_id,n_int,cd,steps", [
+    ("DescentEnv-v0", 0, False, 45),
+    ("HorizontalCREnv-v0", 5, False, 40),
+    ("HorizontalCREnv-v0", 20, True, 25),
+    ("SectorCREnv-v0", 0, True, 40),
+    ("MergeEnv-v0", 0, False, 50),
+])
+def test_step_parity_injected_state(cuda, env_id, n_int, cd, steps):
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    E = 12
+    np.random.seed(1234)
+    random.seed(1234)
+    kw = dict(n_intruders=n_int) if n_int else {}
+    venv = BlueSkyVectorEnv(env_id, E, seed=7, cd_enabled=cd, autoreset_mode="disabled", max_episode_steps=0, **kw)
+    venv.reset()
+    oracles = [_make_oracle(env_id, cd=cd, n_int=n_int) for _ in range(E)]
+    o_obs = [o.reset()[0] for o in oracles]
+    for e, o in enumerate(oracles):
+        _inject(venv, e, o, env_id)
+    rng = np.random.default_rng(0)
+    alive = np.ones(E, dtype=bool)
+    act_dim = venv.layout.act_dim
+    for step in range(steps):
+        a = rng.uniform(-1.0, 1.0, size=(E, act_dim)).astype(np.float32)
+        gobs, grew, gterm, gtrunc, ginfo = venv.step(a)
+        for e, o in enumerate(oracles):
+            if not alive[e]:
+                continue
+            oobs, orew, oterm, otrunc, oinfo = o.step(a[e].astype(np.float64))
+            _compare_obs(gobs, oobs, e, step)
+            assert abs(grew[e] - orew) < 1e-3, (step, e, grew[e], orew)
+            assert bool(gterm[e]) == bool(oterm), (step, e, "terminated")
+            assert bool(gtrunc[e]) == bool(otrunc), (step, e, "truncated")
+            for k, v in oinfo.items():
+                if not (isinstance(v, float) and np.isnan(v)):
+                    assert abs(ginfo[k][e] - v) < 1e-2 + 1e-4 * abs(v), (step, e, k, ginfo[k][e], v)
+            if cd:
+                d = device_traffic(venv)
+                t = o.traf
+                # in-sim ASAS runs before the kinematics of the last substep; the oracle keeps those results
+                assert ginfo["asas_nconf"][e] == len(t.confpairs), (step, e, "nconf", ginfo["asas_nconf"][e], len(t.confpairs))
+                assert ginfo["asas_nlos"][e] == len(t.lospairs), (step, e, "nlos")
+                assert np.array_equal(d["inconf"][e, :t.ntraf], t.inconf), (step, e, "inconf")
+                np.testing.assert_allclose(d["tcpamax"][e, :t.ntraf], t.tcpamax, rtol=1e-3, atol=0.05)
+            if oterm or otrunc:
+                alive[e] = False
+        _compare_traffic(venv, oracles, alive, step)
+    venv.close()
+
+
+@pytest.mark.parametrize("env_id,n_int", [("DescentEnv-v0", 0), ("HorizontalCREnv-v0", 5), ("HorizontalCREnv-v0", 20),
+                                          ("SectorCREnv-v0", 0), ("MergeEnv-v0", 0)])
+def test_device_reset_matches_philox_oracle(cuda, env_id, n_int):
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    E, seed, off = 16, 99, 1000
+    kw = dict(n_intruders=n_int) if n_int else {}
+    venv = BlueSkyVectorEnv(env_id, E, seed=seed, env_id_offset=off, autoreset_mode="disabled", **kw)
+    for episode in range(2):
+        gobs, ginfo = venv.reset()
+        d = device_traffic(venv)
+        i32 = venv.t["env_i32"].cpu().numpy()
+        for e in range(E):
+            o = _make_oracle(env_id, draws=PhiloxDraws(seed, off + e, episode), n_int=n_int)
+            oobs, _ = o.reset()
+            t = o.traf
+            n = t.ntraf
+            assert i32[e, _lib.I32_NUM_AC] == n, (e, i32[e, _lib.I32_NUM_AC], n)
+            assert np.max(np.abs(d["lat"][e, :n] - t.lat)) < 1e-9
+            assert np.max(np.abs(d["lon"][e, :n] - t.lon)) < 1e-9
+            assert np.max(np.abs(d["tas"][e, :n] - t.tas)) < 1e-3
+            assert np.max(np.abs(d["alt"][e, :n] - t.alt)) < 1e-3
+            assert np.max(angdiff(d["hdg"][e, :n], t.hdg)) < 1e-4
+            assert (d["flags"][e, n:] == 0).all()
+            _compare_obs(gobs, oobs, e, -1)
+    venv.close()
+
+
+def test_time_limit_and_autoreset_modes(cuda):
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    E = 8
+    for mode in ("next_step", "same_step"):
+        venv = BlueSkyVectorEnv("HorizontalCREnv-v0", E, seed=3, autoreset_mode=mode, max_episode_steps=4)
+        venv.reset()
+        a = np.zeros((E, 1), dtype=np.float32)
+        for k in range(3):
+            _, _, term, trunc, _ = venv.step(a)
+            assert not trunc.any()
+        obs4, r4, term, trunc, info4 = venv.step(a)
+        assert trunc.all()                                         # TimeLimit: elapsed == cap
+        ep = venv.t["env_i32"].cpu().numpy()[:, _lib.I32_EPISODE]
+        if mode == "same_step":
+            assert (ep == 2).all() and "final_obs" in info4        # already reset; terminal obs kept aside
+            assert not np.allclose(info4["final_obs"]["waypoint_distance"], obs4["waypoint_distance"])
+        else:
+            assert (ep == 1).all()
+            obs5, r5, term5, trunc5, _ = venv.step(a)              # NEXT_STEP: this call only resets
+            assert (ep + 1 == venv.t["env_i32"].cpu().numpy()[:, _lib.I32_EPISODE]).all()
+            assert (r5 == 0).all() and not term5.any() and not trunc5.any()
+        venv.close()
+
+
+def test_shard_invariance(cuda):
+    """Env e's trajectory is a pure function of (seed, global env id): 1 x 16 envs == 2 x 8 envs."""
+    import torch
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    kw = dict(seed=11, n_intruders=20, cd_enabled=True, autoreset_mode="same_step", max_episode_steps=6)
+    full = BlueSkyVectorEnv("HorizontalCREnv-v0", 16, **kw)
+    halves = [BlueSkyVectorEnv("HorizontalCREnv-v0", 8, env_id_offset=8 * r, **kw) for r in range(2)]
+    full.reset_torch()
+    [h.reset_torch() for h in halves]
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for _ in range(15):
+        a = (torch.rand((16, 1), generator=g) * 2 - 1).cuda()
+        of, rf, tf, uf = full.step_torch(a)
+        for r, h in enumerate(halves):
+            oh, rh, th, uh = h.step_torch(a[8 * r:8 * r + 8])
+            assert torch.equal(rf[8 * r:8 * r + 8], rh)
+            assert torch.equal(full.t["obs"][8 * r:8 * r + 8], h.t["obs"])
+            assert torch.equal(tf[8 * r:8 * r + 8], th) and torch.equal(uf[8 * r:8 * r + 8], uh)
+    full.close()
+    [h.close() for h in halves]
+
+
+def test_scalar_env_api(cuda):
+    """gym.make(id) -> reset/step with the reference's spaces, dtypes, info keys (horizontal_cr_env.py:49-62,215-223)."""
+    import bluesky_gym
+    bluesky_gym.register_envs()
+    env = bluesky_gym.make("HorizontalCREnv-v0", render_mode=None)
+    obs, info = env.reset()
+    assert list(obs.keys()) == ["intruder_distance", "cos_difference_pos", "sin_difference_pos", "x_difference_speed",
+                                "y_difference_speed", "waypoint_distance", "cos_drift", "sin_drift"]
+    assert obs["intruder_distance"].shape == (5,) and obs["cos_drift"].shape == (1,)
+    assert all(v.dtype == np.float64 for v in obs.values())
+    assert set(info) >= {"total_reward", "total_intrusions", "average_drift"} and np.isnan(info["average_drift"])
+    obs, r, term, trunc, info = env.step(env.action_space.sample())
+    assert isinstance(r, float) and isinstance(term, bool) and isinstance(trunc, bool)
+    for _ in range(300):
+        obs, r, term, trunc, info = env.step(np.zeros(1))
+        if term or trunc:
+            break
+    assert term or trunc
+    env.close()
