@@ -47,15 +47,19 @@ __device__ __forceinline__ Atmos vatmos(float h) {
 
 __device__ __forceinline__ float vsound(const Atmos& a) { return sqrtf(kGammaR * a.T); }
 
+// (1 + x)^y - 1 without the cancellation of pow(1 + x, y) - 1: the CAS<->TAS round trips feed back into
+// each other every env step (selspd <- cas + dv <- tas2cas(tas)), so their error must stay ~1 ulp.
+__device__ __forceinline__ float pow1pm1(float x, float y) { return expm1f(y * log1pf(x)); }
+
 __device__ __forceinline__ float tas2cas(float tas, const Atmos& a) {
-    float q = a.p * (powpos(1.0f + a.rho * tas * tas / (7.0f * a.p), 3.5f) - 1.0f);
-    float c = sqrtf(7.0f * kP0 / kRho0 * (powpos(q * (1.0f / kP0) + 1.0f, 2.0f / 7.0f) - 1.0f));
+    float q = a.p * pow1pm1(a.rho * tas * tas / (7.0f * a.p), 3.5f);
+    float c = sqrtf(7.0f * kP0 / kRho0 * pow1pm1(q * (1.0f / kP0), 2.0f / 7.0f));
     return tas < 0.0f ? -c : c;
 }
 
 __device__ __forceinline__ float cas2tas(float cas, const Atmos& a) {
-    float q = kP0 * (powpos(1.0f + kRho0 * cas * cas / (7.0f * kP0), 3.5f) - 1.0f);
-    float t = sqrtf(7.0f * a.p / a.rho * (powpos(q / a.p + 1.0f, 2.0f / 7.0f) - 1.0f));
+    float q = kP0 * pow1pm1(kRho0 * cas * cas / (7.0f * kP0), 3.5f);
+    float t = sqrtf(7.0f * a.p / a.rho * pow1pm1(q / a.p, 2.0f / 7.0f));
     return cas < 0.0f ? -t : t;
 }
 

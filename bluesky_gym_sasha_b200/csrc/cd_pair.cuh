@@ -9,7 +9,8 @@
 //   u = gs sin(trk), v = gs cos(trk)                 [m/s east, north]
 // Algebra used (identical to upstream's, fewer special-function ops):
 //   dist sin(qdr) = x-difference * cos(mean lat), dist cos(qdr) = y-difference  (no atan2/sin/cos),
-//   dcpa^2 = |d x w|^2 / |w|^2  (Lagrange identity for dist^2 - tcpa^2 |w|^2; no cancellation),
+//   dcpa^2 = |d x w|^2 / |w|^2  (Lagrange identity for dist^2 - tcpa^2 |w|^2; no cancellation;
+//            the literal form is kept when |w|^2 is clamped, i.e. for co-moving aircraft),
 //   dxinhor / vrel = sqrt((R^2 - dcpa^2) / |w|^2)    (one MUFU.RCP shared with tcpa),
 //   min/max(tcrosshi, tcrosslo) = t0 -+ |hpz / dvs|.
 // 3 MUFU (rcp, sqrt, rcp) + ~45 FMA/ALU-pipe instructions per ordered pair.
@@ -48,13 +49,17 @@ __device__ __forceinline__ CdPair cd_pair_eval(const float4 Ai, const float4 Bi,
     float cav = fmaf(-Ai.w, Aj.w, Ai.z * Aj.z);
     float dx = dxl * cav;
     float du = Bj.x - Bi.x, dv = Bj.y - Bi.y;
-    float dv2 = fmaxf(fmaf(du, du, dv * dv), 1e-6f);
+    float dv2r = fmaf(du, du, dv * dv);
+    bool clamped = dv2r < 1e-6f;                // upstream: dv2 = where(|dv2| < 1e-6, 1e-6, dv2)
+    float dv2 = clamped ? 1e-6f : dv2r;
     float dot = fmaf(du, dx, dv * dy);
     float crs = fmaf(dx, dv, -dy * du);
     float inv = rcp_approx(dv2);
     float tcpa = -dot * inv;
-    float dcpa2 = crs * crs * inv;
     float dist2 = fmaf(dx, dx, dy * dy);
+    // |dist^2 - tcpa^2 dv2| == |d x w|^2 / |w|^2 only while dv2 is the true |w|^2; keep upstream's
+    // literal form for the (co-moving) clamped case
+    float dcpa2 = clamped ? fabsf(fmaf(-tcpa * tcpa, dv2, dist2)) : crs * crs * inv;
     bool swhor = dcpa2 < R2;
     float dtin = sqrt_approx((R2 - dcpa2) * inv);
     float tinhor = swhor ? tcpa - dtin : 1e8f;

@@ -4,12 +4,17 @@ import numpy as np
 from bluesky_gym_sasha_b200 import _lib
 
 
-def synth_airspace(n, box_deg=40.0, seed=0, lat0=52.0, lon0=4.0):
-    """uniform lat/lon box, FL-snapped altitudes, 80 % level flight."""
+def synth_airspace(n, box_deg=40.0, seed=0, lat0=52.0, lon0=4.0, alt_jitter=20.0):
+    """uniform lat/lon box, flight-level altitudes, 80 % level flight.
+
+    Levels are 1000 ft apart and hpz is 1000 ft, so aircraft snapped *exactly* to levels put every
+    adjacent-level pair on the |dalt| == hpz knife edge, where the float64 reference itself decides by
+    rounding noise.  The parity tests therefore jitter altitudes by +-alt_jitter metres (altimetry
+    scatter); bench.py keeps the exact snapping (it does not change the work)."""
     rng = np.random.default_rng(seed)
     lat = lat0 + box_deg * (rng.random(n) - 0.5)
     lon = lon0 + box_deg * (rng.random(n) - 0.5)
-    alt = np.round(rng.uniform(3000.0, 12000.0, n) / 304.8) * 304.8
+    alt = np.round(rng.uniform(3000.0, 12000.0, n) / 304.8) * 304.8 + rng.uniform(-alt_jitter, alt_jitter, n)
     gs = rng.uniform(150.0, 250.0, n)
     trk = rng.uniform(0.0, 360.0, n)
     vs = np.where(rng.random(n) < 0.8, 0.0, rng.choice([-1.0, 1.0], n) * rng.uniform(5.0, 15.0, n))
