@@ -1,0 +1,82 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/bsg.h declares, answers the
+pure-host queries, and fails loudly (no CPU fallback) when asked to compute without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "bsg.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bsg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    from bluesky_gym_sasha_b200 import _lib
+    names = _header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bsg.h but not exported"
+    assert set(_lib.SYMBOLS) == set(names)
+    assert lib.bsg_abi_version() == 1
+
+
+def test_layout_queries(lib):
+    from bluesky_gym_sasha_b200 import _lib, spec
+    want = {"DescentEnv-v0": (1, 4, 1, 30, 1.0), "HorizontalCREnv-v0": (8, 28, 1, 10, 5.0),
+            "SectorCREnv-v0": (32, 31, 2, 5, 1.0), "MergeEnv-v0": (32, 40, 2, 10, 5.0)}
+    for env_id, s in spec.SPECS.items():
+        lay = _lib.query_layout(_lib.Config(env_type=s.env_type, num_envs=3, n_intruders=5))
+        assert (lay.slots, lay.obs_dim, lay.act_dim, lay.n_sub, lay.simdt) == want[env_id]
+        assert s.obs_layout(5)[1] == lay.obs_dim and lay.info_dim >= len(s.info_keys)
+    lay = _lib.query_layout(_lib.Config(env_type=_lib.ENV_HORIZONTAL_CR, num_envs=1, n_intruders=20))
+    assert lay.slots == 32 and lay.obs_dim == 103
+    with pytest.raises(_lib.BsgError):
+        _lib.query_layout(_lib.Config(env_type=_lib.ENV_HORIZONTAL_CR, num_envs=1, n_intruders=40))
+    with pytest.raises(_lib.BsgError):
+        _lib.query_layout(_lib.Config(env_type=17, num_envs=1))
+    assert lib.bsg_cd_padded(0) == 0 and lib.bsg_cd_padded(1) == 256 and lib.bsg_cd_padded(100000) == 100096
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from bluesky_gym_sasha_b200 import _lib
+    h = C.c_void_p(0)
+    cfg = _lib.Config(env_type=_lib.ENV_DESCENT, num_envs=1)
+    rc = lib.bsg_create(C.byref(cfg), C.byref(h))
+    assert rc == _lib.BSG_ECUDA and b"no CPU fallback" in lib.bsg_last_error()
+    out = C.c_double(0)
+    assert lib.bsg_probe_fp32(0, C.byref(out)) == _lib.BSG_ECUDA
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    with pytest.raises(_lib.BsgError):
+        BlueSkyVectorEnv("HorizontalCREnv-v0", 4)
+    from bluesky_gym_sasha_b200.cd import StateBasedCD
+    with pytest.raises(_lib.BsgError):
+        StateBasedCD()
+
+
+def test_argument_validation(lib):
+    from bluesky_gym_sasha_b200 import _lib
+    assert lib.bsg_cd_detect(None, 10, 5, 10, 0.0, 0.0, 0.0, 0, None, None, None, None, None, 0, None, None) == _lib.BSG_EINVAL
+    assert b"row range" in lib.bsg_last_error()
+    assert lib.bsg_cd_pack(None, None, None, None, None, None, 4, 0.0, 0.0, None, None) == _lib.BSG_EINVAL
+    assert lib.bsg_reset(None, None, None) == _lib.BSG_EINVAL
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through the oracle (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "bluesky_gym_sasha_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+    for f in ("bluesky_gym/__init__.py", "bluesky_gym/envs/__init__.py"):
+        assert "oracle" not in open(os.path.join(ROOT, f)).read()
