@@ -240,7 +240,7 @@ def run_b200(args):
                         "bytes_per_env_step": BYTES_PER_ENV_STEP}}
         # CD at N = 100k on this GPU (BASELINE configs[4], single-GPU share)
         cd = bench_cd(torch, dev, StateBasedCD, fp32)
-        cb = cpu_baseline(budget_s=10.0)
+        cb = None if args.skip_cpu else cpu_baseline(budget_s=10.0)
         line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (lat/lon f64)", "data": "synthetic", "config": workload_config(world),
@@ -298,6 +298,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -250,3 +250,20 @@ def test_scalar_env_api(cuda):
             break
     assert term or trunc
     env.close()
+
+
+def test_sb3_adapter_contract(cuda):
+    """terminal_observation / TimeLimit.truncated / per-env info dicts (bluesky_gym/utils/logger.py:18-33)."""
+    from bluesky_gym_sasha_b200.sb3_vec_env import BlueSkySB3VecEnv
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    E = 6
+    v = BlueSkySB3VecEnv(BlueSkyVectorEnv("DescentEnv-v0", E, seed=1, autoreset_mode="same_step", max_episode_steps=5))
+    obs = v.reset()
+    assert obs["altitude"].shape == (E, 1)
+    for k in range(5):
+        v.step_async(np.full((E, 1), -0.1))
+        obs, rew, dones, infos = v.step_wait()
+    assert rew.dtype == np.float32 and dones.all() and len(infos) == E
+    assert all(i["TimeLimit.truncated"] and "terminal_observation" in i and "total_reward" in i for i in infos)
+    assert not np.allclose(infos[0]["terminal_observation"]["altitude"], obs["altitude"][0])
+    v.close()
