@@ -49,11 +49,11 @@ class StateBasedCD:
 
     # ---------------------------------------------------------------- packing
     def pack(self, lat, lon, trk, gs, alt, vs, lat0, lon0, out=None):
-        """float64 SoA -> [n_pad, 8] float32 CD records (padding rows are inert aircraft)."""
+        """float64 SoA -> tile-blocked float32 CD records [n_pad/256, 8, 256] (padding = inert aircraft)."""
         arrs = [self._as_dev(a) for a in (lat, lon, trk, gs, alt, vs)]
         n = arrs[0].numel()
         n_pad = int(self.lib.bsg_cd_padded(n))
-        rec = out if out is not None else torch.empty((max(n_pad, 1), 8), dtype=torch.float32, device=self.device)
+        rec = out if out is not None else torch.empty((max(n_pad // 256, 1), 8, 256), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.bsg_cd_pack(*[_ptr(a) for a in arrs], n, float(lat0), float(lon0), _ptr(rec),
                                             self._stream()))
@@ -115,8 +115,8 @@ class StateBasedCD:
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
         assert n_local % 256 == 0, "shard size must be a multiple of the 256-aircraft tile"
-        allrec = self._get("allrec", (n_local * world, 8), torch.float32)
-        dist.all_gather_into_tensor(allrec, rec_local[:n_local].contiguous(), group=group)
+        allrec = self._get("allrec", (n_local // 256 * world, 8, 256), torch.float32)
+        dist.all_gather_into_tensor(allrec, rec_local[:n_local // 256].contiguous(), group=group)
         return self.detect_packed(allrec, n_local * world, row0=rank * n_local, n_rows=n_local,
                                   lon_wrap=lon_wrap, want_pairs=want_pairs)
 

@@ -2,13 +2,23 @@
 // Replaces the dense N x N float64 matrices of bluesky/traffic/asas/statebased.py::StateBased.detect
 // (upstream's optional single-threaded C++ twin is `cstatebased`); O(N) memory instead of ~15 N^2.
 //
-// Decomposition: a work item = (row block of 512 aircraft) x (group of 8 column tiles of 256 aircraft).
-// A persistent grid of (SM count x resident CTAs) strides over the items, so the tail is < 1 item.
-// Each thread keeps R = 2 own-rows in registers; the intruder tile (256 x 32 B = 8 KB) is staged in
-// shared memory by the TMA engine (cp.async.bulk + mbarrier complete_tx, two stages) and read back
-// with broadcast LDS.128, so every byte of column data is fetched from L2 once per CTA-tile and the
-// inner loop is pure FP32-pipe work (bound: FP32 issue rate; MUFU is the co-limiter at 3 per pair).
-// Rare events (conflict / LoS found) leave the hot loop through one predicated branch.
+// Bound: FP32 issue rate.  Measured on B200 (scripts/pipe_probe.cu): FFMA and ALU-pipe ops (FMNMX, FSETP,
+// FSEL, LOP3) share one issue port per SM sub-partition at 1 warp-instruction/clk; the packed FFMA2 /
+// FADD2 / FMUL2 (f32x2, new on sm_100) occupy the FMA pipe for 2 clk but only ONE issue slot, so the
+// comparison / select / MUFU work of a pair can issue underneath the packed arithmetic of the next.
+// The hot loop is therefore written in f32x2: one thread owns R = 2 rows and evaluates them against
+// column *pairs* (j, j+1): 26 packed FMA-pipe ops per two pairs + 13 scalar ALU/MUFU ops per pair
+// (~28 issue slots and 26 FMA-pipe clk per ordered pair, vs 56 issue slots for the scalar formulation).
+//
+// Layout: records are tile-blocked SoA -- rec[tile][field 0..7][256] floats (field = x, y, ch, sh, u, v,
+// alt, vs; see cd_pair.cuh) -- so a column tile is one contiguous 8 KB block that the TMA engine copies
+// into shared memory (cp.async.bulk + mbarrier complete_tx, two stages; SASS UBLKCP) and a broadcast
+// LDS.128 yields two ready-made packed operands (j..j+1, j+2..j+3) of one field.
+// Decomposition: work item = (256 own rows) x (8 column tiles); a persistent grid of (SMs x resident
+// CTAs) strides over the items, so the tail is < 1 item.  The hot loop only decides "conflict candidate";
+// candidates (conflicts, LoS pairs, the diagonal, co-moving pairs: ~1e-5 of all pairs) are re-evaluated
+// exactly by the scalar reference routine cd_pair_eval() out of line, which also feeds the per-row
+// counters, tcpamax and the pair list.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -19,21 +29,22 @@
 namespace bsg {
 
 constexpr int kTJ = 256;                 // columns per tile
-constexpr int kNT = 256;                 // threads per CTA
+constexpr int kNT = 128;                 // threads per CTA
 constexpr int kR = 2;                    // rows per thread
-constexpr int kRowsPerCta = kNT * kR;    // 512
+constexpr int kRowsPerCta = kNT * kR;    // 256 = one tile of rows
 constexpr int kTilesPerItem = 8;
-constexpr uint32_t kTileBytes = kTJ * 32;
+constexpr int kTileFloats = 8 * kTJ;
+constexpr uint32_t kTileBytes = kTileFloats * 4;
+enum { FX = 0, FY = 1, FCH = 2, FSH = 3, FU = 4, FV = 5, FALT = 6, FVS = 7 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
+typedef unsigned long long u64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -50,16 +61,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- packed f32x2 arithmetic (SASS FADD2 / FMUL2 / FFMA2) ------------------------------------------
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void up2(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
 }
 
 struct CdArgs {
-    const float4* rec;     // [n_pad * 2] (A, B) interleaved
-    long long n_all, n_pad, row0, n_rows;
+    const float* rec;      // [n_tiles][8][256]
+    int n_all, row0, n_rows;
     float R2, hpz, dtlook;
     uint32_t* nconf_row;
     uint32_t* nlos_row;
@@ -70,43 +105,90 @@ struct CdArgs {
     int n_rowblocks, n_colgroups, n_tiles;
 };
 
-template <bool WRAP, bool DIAG>
-__device__ __forceinline__ void cd_tile(const float4* __restrict__ tile, long long c0, const float4 (&Ai)[kR],
-                                        const float4 (&Bi)[kR], const long long (&ri)[kR],
-                                        const bool (&rvalid)[kR], const CdArgs& a, uint32_t (&nconf)[kR],
-                                        uint32_t (&nlos)[kR], float (&tmax)[kR]) {
-#pragma unroll 4
-    for (int j = 0; j < kTJ; ++j) {
-        const float4 Aj = tile[2 * j];
-        const float4 Bj = tile[2 * j + 1];
-#pragma unroll
-        for (int k = 0; k < kR; ++k) {
-            const bool same = DIAG ? (ri[k] == c0 + j) : false;
-            CdPair p = cd_pair_eval<WRAP>(Ai[k], Bi[k], Aj, Bj, a.R2, a.hpz, a.dtlook, same);
-            if ((p.conf | p.los) && rvalid[k]) {           // rare path
-                if (p.los) nlos[k]++;
-                if (p.conf) {
-                    nconf[k]++;
-                    tmax[k] = fmaxf(tmax[k], p.tcpa);
-                    if (a.pairs) {
-                        unsigned long long s = atomicAdd(a.npairs, 1ULL);
-                        if ((long long)s < a.cap) {
-                            a.pairs[2 * s] = (int32_t)ri[k];
-                            a.pairs[2 * s + 1] = (int32_t)(c0 + j);
-                        }
-                    } else if (a.npairs) {
-                        atomicAdd(a.npairs, 1ULL);
-                    }
-                }
-                if (p.los && a.npairs) atomicAdd(a.npairs + 1, 1ULL);
-            }
-        }
+__device__ __forceinline__ void load_record(const float* __restrict__ rec, int idx, float4& A, float4& B) {
+    const float* t = rec + (size_t)(idx / kTJ) * kTileFloats + (idx % kTJ);
+    A = make_float4(t[FX * kTJ], t[FY * kTJ], t[FCH * kTJ], t[FSH * kTJ]);
+    B = make_float4(t[FU * kTJ], t[FV * kTJ], t[FALT * kTJ], t[FVS * kTJ]);
+}
+
+// Exact (reference-order) evaluation of one candidate pair, out of line.  bit0 = conflict, bit1 = LoS.
+template <bool WRAP>
+__device__ __noinline__ uint32_t cd_candidate(const CdArgs& a, int ri, int cj, float& tcpa) {
+    float4 Ai, Bi, Aj, Bj;
+    load_record(a.rec, ri, Ai, Bi);
+    load_record(a.rec, cj, Aj, Bj);
+    CdPair p = cd_pair_eval<WRAP>(Ai, Bi, Aj, Bj, a.R2, a.hpz, a.dtlook, ri == cj);
+    tcpa = p.tcpa;
+    return (p.conf ? 1u : 0u) | (p.los ? 2u : 0u);
+}
+
+struct RowPack {            // loop-invariant operands of one own-row, duplicated into both f32x2 halves
+    u64 nX, nY, CH, nSH, nU, nV, nALT, nVS;
+};
+
+// true when either column of the packed pair is a conflict candidate for this row
+template <bool WRAP>
+__device__ __forceinline__ bool cd_hot2(const RowPack& r, u64 Xc, u64 Yc, u64 CHc, u64 SHc, u64 Uc, u64 Vc,
+                                            u64 ALTc, u64 VSc, u64 R2P, u64 HPZP, u64 NEG1, float dtl) {
+    u64 dy = add2(Yc, r.nY);
+    u64 dxl = add2(Xc, r.nX);
+    if (WRAP) {
+        float a, b;
+        up2(dxl, a, b);
+        a -= kTwoPiRe * rintf(a * kInvTwoPiRe);
+        b -= kTwoPiRe * rintf(b * kInvTwoPiRe);
+        dxl = pk2(a, b);
     }
+    u64 cav = fma2(SHc, r.nSH, mul2(CHc, r.CH));
+    u64 dx = mul2(dxl, cav);
+    u64 du = add2(Uc, r.nU), dv = add2(Vc, r.nV);
+    u64 dv2 = fma2(du, du, mul2(dv, dv));
+    u64 dot = fma2(du, dx, mul2(dv, dy));
+    u64 crs = fma2(dy, du, mul2(mul2(dx, NEG1), dv));          // dy du - dx dv (only its square is used)
+    float v0, v1;
+    up2(dv2, v0, v1);
+    v0 = fmaxf(v0, 1e-6f);
+    v1 = fmaxf(v1, 1e-6f);
+    u64 NINV = pk2(rcp_approx(-v0), rcp_approx(-v1));          // -1/|w|^2
+    u64 tcpa = mul2(dot, NINV);                                // -dot/|w|^2
+    u64 rem = fma2(mul2(crs, crs), NINV, R2P);                 // R^2 - dcpa^2
+    u64 q = mul2(rem, NINV);                                   // -(R^2 - dcpa^2)/|w|^2
+    float rem0, rem1, q0, q1;
+    up2(rem, rem0, rem1);
+    up2(q, q0, q1);
+    u64 DTIN = pk2(sqrt_approx(-q0), sqrt_approx(-q1));        // NaN when dcpa >= R: max/min drop it, the
+    u64 touthor = add2(tcpa, DTIN);                            // predicate below requires rem > 0 anyway
+    u64 tinhor = fma2(DTIN, NEG1, tcpa);
+    u64 dalt = add2(ALTc, r.nALT), dvs = add2(VSc, r.nVS);
+    float s0, s1, a0, a1;
+    up2(dvs, s0, s1);
+    up2(dalt, a0, a1);
+    s0 = fabsf(s0) < 1e-6f ? 1e-6f : s0;
+    s1 = fabsf(s1) < 1e-6f ? 1e-6f : s1;
+    float r0 = rcp_approx(fabsf(s0)), r1 = rcp_approx(fabsf(s1));
+    // t0 = dalt / -dvs = (-sign(dvs) dalt) / |dvs|
+    a0 = __uint_as_float(__float_as_uint(a0) ^ (~__float_as_uint(s0) & 0x80000000u));
+    a1 = __uint_as_float(__float_as_uint(a1) ^ (~__float_as_uint(s1) & 0x80000000u));
+    u64 RV = pk2(r0, r1);
+    u64 t0 = mul2(pk2(a0, a1), RV);
+    u64 hw = mul2(HPZP, RV);
+    u64 toutver = add2(t0, hw);
+    u64 tinver = fma2(hw, NEG1, t0);
+    float ih0, ih1, oh0, oh1, iv0, iv1, ov0, ov1;
+    up2(tinhor, ih0, ih1);
+    up2(touthor, oh0, oh1);
+    up2(tinver, iv0, iv1);
+    up2(toutver, ov0, ov1);
+    float tin0 = fmaxf(iv0, ih0), tout0 = fminf(ov0, oh0);
+    float tin1 = fmaxf(iv1, ih1), tout1 = fminf(ov1, oh1);
+    bool h0 = (rem0 > 0.0f) && (tin0 <= tout0) && (tout0 > -0.01f) && (tin0 < dtl);
+    bool h1 = (rem1 > 0.0f) && (tin1 <= tout1) && (tout1 > -0.01f) && (tin1 < dtl);
+    return h0 || h1;
 }
 
 template <bool WRAP>
-__global__ void __launch_bounds__(kNT, 2) cd_tiled_kernel(const CdArgs a) {
-    __shared__ __align__(128) float4 s_tile[2][kTJ * 2];
+__global__ void __launch_bounds__(kNT, 4) cd_tiled_kernel(const CdArgs a) {
+    __shared__ __align__(128) float s_tile[2][kTileFloats];
     __shared__ __align__(8) uint64_t s_full[2];
 
     const int tid = threadIdx.x;
@@ -117,6 +199,11 @@ __global__ void __launch_bounds__(kNT, 2) cd_tiled_kernel(const CdArgs a) {
     }
     __syncthreads();
     uint32_t parity[2] = {0u, 0u};
+    // The hot loop must flag a SUPERSET of what the exact routine accepts (it differs from it only by
+    // float rounding), so its zone and look-ahead are inflated slightly; the exact routine decides.
+    const float R2h = a.R2 * 1.0002f, hpzh = a.hpz * 1.0001f + 0.01f, dtlh = a.dtlook + 0.01f;
+    const u64 R2P = pk2(R2h, R2h), HPZP = pk2(hpzh, hpzh), NEG1 = pk2(-1.0f, -1.0f);
+    const int row_end = a.row0 + a.n_rows;
 
     const long long n_items = (long long)a.n_rowblocks * a.n_colgroups;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -125,47 +212,86 @@ __global__ void __launch_bounds__(kNT, 2) cd_tiled_kernel(const CdArgs a) {
         const int t_begin = cg * kTilesPerItem;
         const int t_end = min(t_begin + kTilesPerItem, a.n_tiles);
 
-        // own rows -> registers (clamped loads for the ragged last block; results discarded)
-        float4 Ai[kR], Bi[kR];
-        long long ri[kR];
-        bool rvalid[kR];
+        // own rows -> packed registers.  Rows past the shard end are made inert (alt -3e9: can never be a
+        // candidate), so the hot loop needs no validity test.
+        RowPack rp[kR];
+        int ri[kR];
         uint32_t nconf[kR], nlos[kR];
         float tmax[kR];
-        const long long rbase = a.row0 + (long long)rb * kRowsPerCta;
+        const int rbase = a.row0 + rb * kRowsPerCta;
 #pragma unroll
         for (int k = 0; k < kR; ++k) {
-            long long r = rbase + tid + k * kNT;
-            rvalid[k] = r < a.row0 + a.n_rows;
-            ri[k] = rvalid[k] ? r : (a.row0 + a.n_rows - 1);
-            Ai[k] = __ldg(&a.rec[2 * ri[k]]);
-            Bi[k] = __ldg(&a.rec[2 * ri[k] + 1]);
+            int r = rbase + tid + k * kNT;
+            ri[k] = r;
+            float4 A, B;
+            load_record(a.rec, r < row_end ? r : row_end - 1, A, B);
+            if (r >= row_end) B.z = -3.0e9f;                // inert row (padding columns sit at +3e9)
+            rp[k].nX = pk2(-A.x, -A.x); rp[k].nY = pk2(-A.y, -A.y);
+            rp[k].CH = pk2(A.z, A.z);   rp[k].nSH = pk2(-A.w, -A.w);
+            rp[k].nU = pk2(-B.x, -B.x); rp[k].nV = pk2(-B.y, -B.y);
+            rp[k].nALT = pk2(-B.z, -B.z); rp[k].nVS = pk2(-B.w, -B.w);
             nconf[k] = 0; nlos[k] = 0; tmax[k] = 0.0f;
         }
 
         if (tid == 0) {        // prologue: first tile of the item
             mbar_expect_tx(&s_full[t_begin & 1], kTileBytes);
-            tma_load_1d(&s_tile[t_begin & 1][0], a.rec + 2LL * t_begin * kTJ, kTileBytes, &s_full[t_begin & 1]);
+            tma_load_1d(&s_tile[t_begin & 1][0], a.rec + (size_t)t_begin * kTileFloats, kTileBytes, &s_full[t_begin & 1]);
         }
         for (int t = t_begin; t < t_end; ++t) {
             const int s = t & 1;
             if (tid == 0 && t + 1 < t_end) {     // prefetch the next tile into the other stage
                 mbar_expect_tx(&s_full[s ^ 1], kTileBytes);
-                tma_load_1d(&s_tile[s ^ 1][0], a.rec + 2LL * (t + 1) * kTJ, kTileBytes, &s_full[s ^ 1]);
+                tma_load_1d(&s_tile[s ^ 1][0], a.rec + (size_t)(t + 1) * kTileFloats, kTileBytes, &s_full[s ^ 1]);
             }
             mbar_wait(&s_full[s], parity[s]);
             parity[s] ^= 1u;
-            const long long c0 = (long long)t * kTJ;
-            const bool diag = (c0 < rbase + kRowsPerCta) && (c0 + kTJ > rbase);
-            if (diag)
-                cd_tile<WRAP, true>(s_tile[s], c0, Ai, Bi, ri, rvalid, a, nconf, nlos, tmax);
-            else
-                cd_tile<WRAP, false>(s_tile[s], c0, Ai, Bi, ri, rvalid, a, nconf, nlos, tmax);
+            const float* tile = s_tile[s];
+            const int c0 = t * kTJ;
+#pragma unroll 1
+            for (int j = 0; j < kTJ; j += 4) {
+                // 8 broadcast LDS.128: four consecutive columns of each field = two packed operands
+                const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(tile + FX * kTJ + j);
+                const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(tile + FY * kTJ + j);
+                const ulonglong2 CH = *reinterpret_cast<const ulonglong2*>(tile + FCH * kTJ + j);
+                const ulonglong2 SH = *reinterpret_cast<const ulonglong2*>(tile + FSH * kTJ + j);
+                const ulonglong2 U = *reinterpret_cast<const ulonglong2*>(tile + FU * kTJ + j);
+                const ulonglong2 V = *reinterpret_cast<const ulonglong2*>(tile + FV * kTJ + j);
+                const ulonglong2 AL = *reinterpret_cast<const ulonglong2*>(tile + FALT * kTJ + j);
+                const ulonglong2 VS = *reinterpret_cast<const ulonglong2*>(tile + FVS * kTJ + j);
+                bool hit = false;
+#pragma unroll
+                for (int k = 0; k < kR; ++k) {
+                    hit |= cd_hot2<WRAP>(rp[k], X.x, Y.x, CH.x, SH.x, U.x, V.x, AL.x, VS.x, R2P, HPZP, NEG1, dtlh);
+                    hit |= cd_hot2<WRAP>(rp[k], X.y, Y.y, CH.y, SH.y, U.y, V.y, AL.y, VS.y, R2P, HPZP, NEG1, dtlh);
+                }
+                if (hit) for (int b = 0; b < 4 * kR; ++b) {  // rare: exact re-evaluation of the 8 pairs
+                    const int k = b >> 2, cj = c0 + j + (b & 3);
+                    if (ri[k] >= row_end || cj >= a.n_all) continue;
+                    float tc;
+                    const uint32_t f = cd_candidate<WRAP>(a, ri[k], cj, tc);
+                    if (f & 2u) {
+                        nlos[k]++;
+                        if (a.npairs) atomicAdd(a.npairs + 1, 1ULL);
+                    }
+                    if (f & 1u) {
+                        nconf[k]++;
+                        tmax[k] = fmaxf(tmax[k], tc);
+                        if (a.npairs) {
+                            unsigned long long slot = atomicAdd(a.npairs, 1ULL);
+                            if (a.pairs && (long long)slot < a.cap) {
+                                a.pairs[2 * slot] = ri[k];
+                                a.pairs[2 * slot + 1] = cj;
+                            }
+                        }
+                    }
+                }
+            }
             __syncthreads();     // stage s may be overwritten by the prefetch of iteration t+1
         }
 #pragma unroll
         for (int k = 0; k < kR; ++k) {
-            if (rvalid[k]) {
-                const long long o = ri[k] - a.row0;
+            if (ri[k] < row_end) {
+                const int o = ri[k] - a.row0;
                 if (nconf[k]) {
                     atomicAdd(&a.nconf_row[o], nconf[k]);
                     if (a.tcpamax) atomicMax((int*)&a.tcpamax[o], __float_as_int(tmax[k]));
@@ -181,14 +307,14 @@ __global__ void cd_finalize_kernel(const uint32_t* __restrict__ nconf_row, uint8
     if (i < n) inconf[i] = nconf_row[i] > 0;
 }
 
-// float64 SoA -> 32-byte float record (see cd_pair.cuh); padding rows are inert aircraft.
+// float64 SoA -> tile-blocked float32 records (see cd_pair.cuh); padding entries are inert aircraft.
 __global__ void cd_pack_kernel(const double* __restrict__ lat, const double* __restrict__ lon,
                                const double* __restrict__ trk, const double* __restrict__ gs,
                                const double* __restrict__ alt, const double* __restrict__ vs, long long n,
-                               long long n_pad, double lat0, double lon0, float4* __restrict__ rec) {
+                               long long n_pad, double lat0, double lon0, float* __restrict__ rec) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
-    float4 A, B;
+    float f[8];
     if (i < n) {
         double la = lat[i];
         double dl = fmod((lon[i] - lon0) + 180.0, 360.0);
@@ -197,14 +323,16 @@ __global__ void cd_pack_kernel(const double* __restrict__ lat, const double* __r
         double s, c, st, ct;
         sincos(la * (0.5 * kDeg2RadD), &s, &c);
         sincos(trk[i] * kDeg2RadD, &st, &ct);
-        A = make_float4((float)(kRearthD * kDeg2RadD * dl), (float)(kRearthD * kDeg2RadD * (la - lat0)), (float)c, (float)s);
-        B = make_float4((float)(gs[i] * st), (float)(gs[i] * ct), (float)alt[i], (float)vs[i]);
+        f[FX] = (float)(kRearthD * kDeg2RadD * dl); f[FY] = (float)(kRearthD * kDeg2RadD * (la - lat0));
+        f[FCH] = (float)c; f[FSH] = (float)s;
+        f[FU] = (float)(gs[i] * st); f[FV] = (float)(gs[i] * ct); f[FALT] = (float)alt[i]; f[FVS] = (float)vs[i];
     } else {
-        A = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
-        B = make_float4(0.0f, 0.0f, 3.0e9f, 0.0f);     // |dalt| ~ 3e9: never in conflict nor in LoS
+        f[FX] = 0.0f; f[FY] = 0.0f; f[FCH] = 1.0f; f[FSH] = 0.0f;
+        f[FU] = 0.0f; f[FV] = 0.0f; f[FALT] = 3.0e9f; f[FVS] = 0.0f;   // |dalt| ~ 3e9: never a candidate
     }
-    rec[2 * i] = A;
-    rec[2 * i + 1] = B;
+    float* t = rec + (size_t)(i / kTJ) * kTileFloats + (i % kTJ);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k * kTJ] = f[k];
 }
 
 }  // namespace bsg
@@ -222,7 +350,7 @@ extern "C" int bsg_cd_pack(const double* d_lat, const double* d_lon, const doubl
     if (n_pad == 0) return BSG_OK;
     int blocks = (int)((n_pad + 255) / 256);
     cd_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_lat, d_lon, d_trk, d_gs, d_alt, d_vs, n, n_pad,
-                                                              lat0, lon0, (float4*)d_rec);
+                                                              lat0, lon0, d_rec);
     return bsg_cuda_check(cudaGetLastError(), "bsg_cd_pack launch");
 }
 
@@ -232,7 +360,7 @@ extern "C" int bsg_cd_detect(const float* d_rec, int64_t n_all, int64_t row0, in
                              unsigned long long* d_npairs, void* stream) {
     if (n_all < 0 || row0 < 0 || n_rows < 0 || row0 + n_rows > n_all)
         return bsg_fail(BSG_EINVAL, "bsg_cd_detect: row range outside [0, n_all)");
-    if (n_all > 0x7fffffffLL) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: n_all exceeds int32 pair indices");
+    if (n_all > 0x7fffff00LL) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: n_all exceeds int32 pair indices");
     if (n_rows > 0 && (!d_rec || !d_nconf_row)) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: null d_rec / d_nconf_row");
     if (d_pairs && (!d_npairs || cap < 0)) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: pair list needs d_npairs and cap >= 0");
     if (flags & BSG_CD_SYMMETRIC) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: BSG_CD_SYMMETRIC not implemented yet");
@@ -244,15 +372,15 @@ extern "C" int bsg_cd_detect(const float* d_rec, int64_t n_all, int64_t row0, in
     if (d_tcpamax) BSG_CUDA(cudaMemsetAsync(d_tcpamax, 0, sizeof(float) * n_rows, st));
 
     CdArgs a;
-    a.rec = (const float4*)d_rec;
-    a.n_all = n_all; a.n_pad = bsg_cd_padded(n_all); a.row0 = row0; a.n_rows = n_rows;
+    a.rec = d_rec;
+    a.n_all = (int)n_all; a.row0 = (int)row0; a.n_rows = (int)n_rows;
     if (rpz <= 0.0f) rpz = 5.0f * 1852.0f;
     if (hpz <= 0.0f) hpz = 1000.0f * 0.3048f;
     if (dtlookahead <= 0.0f) dtlookahead = 300.0f;
     a.R2 = rpz * rpz; a.hpz = hpz; a.dtlook = dtlookahead;
     a.nconf_row = d_nconf_row; a.nlos_row = d_nlos_row; a.tcpamax = d_tcpamax;
     a.pairs = d_pairs; a.cap = cap; a.npairs = d_npairs;
-    a.n_tiles = (int)(a.n_pad / kTJ);
+    a.n_tiles = (int)(bsg_cd_padded(n_all) / kTJ);
     a.n_rowblocks = (int)((n_rows + kRowsPerCta - 1) / kRowsPerCta);
     a.n_colgroups = (a.n_tiles + kTilesPerItem - 1) / kTilesPerItem;
 

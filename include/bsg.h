@@ -140,9 +140,10 @@ int bsg_traf_update(bsg_handle *h, int32_t n_sub, void *stream);
 
 /* ---- single-airspace state-based conflict detection (StateBased.detect; CD record = 32 B) -------- */
 
-/* Packs float64 SoA aircraft state (bs.traf.lat/lon/trk/gs/alt/vs) into the 32-byte float CD record
- * (x, y metres from (lat0, lon0); cos/sin of half latitude; u, v; alt; vs).  d_rec must hold
- * bsg_cd_padded(n) records; the padding is filled with inert aircraft. */
+/* Packs float64 SoA aircraft state (bs.traf.lat/lon/trk/gs/alt/vs) into 32-byte float CD records
+ * (x, y metres from (lat0, lon0); cos/sin of half latitude; u, v; alt; vs), stored tile-blocked:
+ * d_rec[tile][field 0..7][256] floats, tile = aircraft index / 256.  d_rec must hold bsg_cd_padded(n)
+ * records (8 floats each); the padding of the last tile is filled with inert aircraft. */
 int64_t bsg_cd_padded(int64_t n);
 int bsg_cd_pack(const double *d_lat, const double *d_lon, const double *d_trk, const double *d_gs,
                 const double *d_alt, const double *d_vs, int64_t n, double lat0, double lon0,
