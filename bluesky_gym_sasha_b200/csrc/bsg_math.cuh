@@ -68,10 +68,11 @@ __device__ __forceinline__ float casormach2tas(float spd, const Atmos& a) {
     return fabsf(spd) < 1.0f ? spd * vsound(a) : cas2tas(spd, a);
 }
 
-// numpy's a % 360 (result in [0, 360))
+// numpy's a % 360 (result in [0, 360)); floor form instead of fmodf (~6 instructions instead of ~40)
 __device__ __forceinline__ float mod360(float a) {
-    float r = fmodf(a, 360.0f);
-    return r < 0.0f ? r + 360.0f : r;
+    float r = fmaf(-360.0f, floorf(a * (1.0f / 360.0f)), a);
+    r = r < 0.0f ? r + 360.0f : r;
+    return r >= 360.0f ? r - 360.0f : r;
 }
 // (a + 180) % 360 - 180
 __device__ __forceinline__ float degto180(float a) { return mod360(a + 180.0f) - 180.0f; }

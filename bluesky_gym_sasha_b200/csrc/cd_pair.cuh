@@ -79,4 +79,49 @@ __device__ __forceinline__ CdPair cd_pair_eval(const float4 Ai, const float4 Bi,
     return o;
 }
 
+// Both orders of one unordered pair at once.  (j, i) mirrors (i, j) exactly -- every difference changes
+// sign, tcpa / dcpa / dist are even in them -- except upstream's clamp of a near-zero relative vertical
+// speed to +1e-6 in BOTH orders, which flips the sign of the (j, i) vertical crossing time.
+struct CdSym {
+    bool conf_ij, conf_ji, los;
+    float tcpa;
+};
+__device__ __forceinline__ CdSym cd_pair_sym(const float4 Ai, const float4 Bi, const float4 Aj, const float4 Bj,
+                                             float R2, float hpz, float dtlook) {
+    float dy = Aj.y - Ai.y;
+    float dxl = Aj.x - Ai.x;
+    float cav = fmaf(-Ai.w, Aj.w, Ai.z * Aj.z);
+    float dx = dxl * cav;
+    float du = Bj.x - Bi.x, dv = Bj.y - Bi.y;
+    float dv2r = fmaf(du, du, dv * dv);
+    bool clamped = dv2r < 1e-6f;
+    float dv2 = clamped ? 1e-6f : dv2r;
+    float dot = fmaf(du, dx, dv * dy);
+    float crs = fmaf(dx, dv, -dy * du);
+    float inv = rcp_approx(dv2);
+    float tcpa = -dot * inv;
+    float dist2 = fmaf(dx, dx, dy * dy);
+    float dcpa2 = clamped ? fabsf(fmaf(-tcpa * tcpa, dv2, dist2)) : crs * crs * inv;
+    bool swhor = dcpa2 < R2;
+    float dtin = sqrt_approx((R2 - dcpa2) * inv);
+    float tinhor = swhor ? tcpa - dtin : 1e8f;
+    float touthor = swhor ? tcpa + dtin : -1e8f;
+    float dalt = Bj.z - Bi.z;
+    float dvs = Bj.w - Bi.w;
+    bool vclamp = fabsf(dvs) < 1e-6f;
+    dvs = vclamp ? 1e-6f : dvs;
+    float ninv = -rcp_approx(dvs);
+    float t0 = dalt * ninv;
+    float hw = fabsf(hpz * ninv);
+    float t0r = vclamp ? -t0 : t0;
+    float tin = fmaxf(t0 - hw, tinhor), tout = fminf(t0 + hw, touthor);
+    float tinr = fmaxf(t0r - hw, tinhor), toutr = fminf(t0r + hw, touthor);
+    CdSym o;
+    o.conf_ij = swhor && (tin <= tout) && (tout > 0.0f) && (tin < dtlook);
+    o.conf_ji = swhor && (tinr <= toutr) && (toutr > 0.0f) && (tinr < dtlook);
+    o.los = (dist2 < R2) && (fabsf(dalt) < hpz);
+    o.tcpa = tcpa;
+    return o;
+}
+
 }  // namespace bsg

@@ -462,8 +462,14 @@ __device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float
 // K6: the env-step megakernel (also serves reset and the kinematics-only parity entry point)
 // =====================================================================================================
 template <int ENV, int G>
-__global__ void __launch_bounds__(kEnvThreads) env_kernel(const EnvParams P) {
+__global__ void __launch_bounds__(kEnvThreads, 6) env_kernel(const EnvParams P) {
     __shared__ __align__(16) float4 s_rec[kEnvThreads * 2];
+    __shared__ int s_tmax[kEnvThreads];
+    __shared__ uint16_t s_pairs[kMaxPairs];
+    if (G > 1 && P.cd_enabled && P.mode != kModeReset) {
+        build_pair_table(s_pairs);
+        __syncthreads();
+    }
     __shared__ double s_scratch[(ENV == BSG_ENV_SECTOR_CR) ? (kEnvThreads / 32) * 96 : 1];
     const long long gt = (long long)blockIdx.x * kEnvThreads + threadIdx.x;
     const long long e = gt / G;
@@ -472,85 +478,82 @@ __global__ void __launch_bounds__(kEnvThreads) env_kernel(const EnvParams P) {
     double* scratch = (ENV == BSG_ENV_SECTOR_CR) ? &s_scratch[(threadIdx.x / 32) * 96] : s_scratch;
 
     EnvS s;
-    env_load(s, P, e);
+    env_load_pre(s, P, e);
     Ac a;
     float* obs = P.obs + e * P.obs_dim;
     float* info = P.info + e * P.info_dim;
 
+    // One control flow for reset / step / autoreset so that the scenario generator and the observation
+    // code exist ONCE in the kernel (they are big; duplicating them blew the instruction cache).
+    bool resetting;
     if (P.mode == kModeReset) {
-        if (P.reset_mask && !P.reset_mask[e]) return;
-        do_reset<ENV, G>(a, s, P, e, slot, scratch);
-        do_obs<ENV, G>(a, s, P, obs, slot, e, false);
-        if (slot == 0) {
-            do_info<ENV>(s, P, info);
-            P.reward[e] = 0.0f; P.term[e] = 0; P.trunc[e] = 0;
-            env_store(s, P, e);
+        resetting = P.reset_mask ? (P.reset_mask[e] != 0) : true;
+        if (!resetting) return;
+    } else {
+        resetting = (P.mode == kModeStep) && (P.autoreset == BSG_AUTORESET_NEXT_STEP) && (s.needs_reset != 0);
+    }
+
+    if (!resetting) {
+        ac_load(a, P, gt);
+        const bool alive = (a.flags & kFlAlive) != 0;
+        if (P.mode == kModeStep) {
+            const float* act = P.actions + e * P.act_dim;
+            if (ENV == BSG_ENV_DESCENT) descent_action<G>(a, P, act, slot);
+            if (ENV == BSG_ENV_HORIZONTAL_CR) horizontal_action<G>(a, P, act, slot);
+            if (ENV == BSG_ENV_SECTOR_CR) sector_action<G>(a, P, act, slot);
+            if (ENV == BSG_ENV_MERGE) merge_action<G>(a, P, act, slot);
         }
-        ac_store(a, P, gt);
-        return;
-    }
-
-    if (P.mode == kModeStep && P.autoreset == BSG_AUTORESET_NEXT_STEP && s.needs_reset) {
-        do_reset<ENV, G>(a, s, P, e, slot, scratch);
-        do_obs<ENV, G>(a, s, P, obs, slot, e, false);
-        if (slot == 0) {
-            do_info<ENV>(s, P, info);
-            P.reward[e] = 0.0f; P.term[e] = 0; P.trunc[e] = 0;
-            env_store(s, P, e);
-        }
-        ac_store(a, P, gt);
-        return;
-    }
-
-    ac_load(a, P, gt);
-    const bool alive = (a.flags & kFlAlive) != 0;
-    if (P.mode == kModeStep) {
-        const float* act = P.actions + e * P.act_dim;
-        if (ENV == BSG_ENV_DESCENT) descent_action<G>(a, P, act, slot);
-        if (ENV == BSG_ENV_HORIZONTAL_CR) horizontal_action<G>(a, P, act, slot);
-        if (ENV == BSG_ENV_SECTOR_CR) sector_action<G>(a, P, act, slot);
-        if (ENV == BSG_ENV_MERGE) merge_action<G>(a, P, act, slot);
-    }
-
-    int nconf = s.nconf, nlos = s.nlos;
-    for (int k = 0; k < P.n_sub; ++k) {                 // n_sub x bs.sim.step()
-        s.simk += 1;
-        const bool fms_ready = (s.simk % P.fms_rel_freq) == 0;
-        Atmos at = vatmos(a.alt);
-        float ap_tas = 0.0f;
-        if (alive) ac_autopilot<ENV>(a, P, fms_ready, at, ap_tas);
-        if (G > 1 && P.cd_enabled) group_cd<G>(a, alive, s.num_ac, P, s_rec, nconf, nlos);
-        if (alive) ac_kinematics(a, P, at, ap_tas);
-    }
-    s.nconf = nconf; s.nlos = nlos;
-
-    if (P.mode == kModeTraf) {
-        ac_store(a, P, gt);
-        if (slot == 0) env_store(s, P, e);
-        return;
-    }
-
-    StepOut o = do_obs<ENV, G>(a, s, P, obs, slot, e, true);
-    s.step += 1;
-    if (P.max_steps > 0 && s.step >= P.max_steps) o.truncated = 1;      // gymnasium TimeLimit
-    const bool done = o.terminated || o.truncated;
-    if (slot == 0) {
-        P.reward[e] = o.reward; P.term[e] = (uint8_t)o.terminated; P.trunc[e] = (uint8_t)o.truncated;
-        do_info<ENV>(s, P, info);
-    }
-    if (done) {
-        if (P.autoreset == BSG_AUTORESET_SAME_STEP) {
-            if (P.final_obs) {                  // the terminal observation survives in final_obs
-                __syncwarp(group_mask<G>());
-                float* fo = P.final_obs + e * P.obs_dim;
-                for (int i = slot; i < P.obs_dim; i += G) fo[i] = obs[i];
-                __syncwarp(group_mask<G>());
+        int nconf = s.nconf, nlos = s.nlos;
+        Targets T;
+        compute_targets(a, P, T);
+#pragma unroll 1
+        for (int k = 0; k < P.n_sub; ++k) {                 // n_sub x bs.sim.step()
+            s.simk += 1;
+            const bool fms_ready = (s.simk % P.fms_rel_freq) == 0;
+            if (alive) {
+                if (a.alt != T.k_alt || a.vs != T.k_vs) compute_targets(a, P, T);
+                ac_autopilot<ENV>(a, P, fms_ready);
             }
-            do_reset<ENV, G>(a, s, P, e, slot, scratch);
-            do_obs<ENV, G>(a, s, P, obs, slot, e, false);
-        } else if (P.autoreset == BSG_AUTORESET_NEXT_STEP) {
-            s.needs_reset = 1;
+            if (G > 1 && P.cd_enabled) group_cd<G>(a, alive, s.num_ac, P, s_rec, s_pairs, s_tmax, nconf, nlos);
+            if (alive) ac_kinematics(a, P, T);
         }
+        // update_airspeed's cas = vtas2cas(tas, alt) uses the altitude from before update_pos: T.at of the last substep
+        if (alive && P.n_sub > 0) a.cas = tas2cas(a.tas, T.at);
+        s.nconf = nconf; s.nlos = nlos;
+        if (P.mode == kModeTraf) {
+            ac_store(a, P, gt);
+            if (slot == 0) env_store_pre(s, P, e);
+            return;
+        }
+        env_load_post(s, P, e);
+    }
+
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool fresh = resetting;                    // this pass starts from a newly generated scenario
+        if (resetting) do_reset<ENV, G>(a, s, P, e, slot, scratch);
+        StepOut o = do_obs<ENV, G>(a, s, P, obs, slot, e, !fresh);
+        if (pass == 1) break;                            // SAME_STEP: the step's reward / flags / info stay
+        if (fresh) {
+            if (slot == 0) { P.reward[e] = 0.0f; P.term[e] = 0; P.trunc[e] = 0; do_info<ENV>(s, P, info); }
+            break;
+        }
+        s.step += 1;
+        if (P.max_steps > 0 && s.step >= P.max_steps) o.truncated = 1;      // gymnasium TimeLimit
+        if (slot == 0) {
+            P.reward[e] = o.reward; P.term[e] = (uint8_t)o.terminated; P.trunc[e] = (uint8_t)o.truncated;
+            do_info<ENV>(s, P, info);
+        }
+        if (!(o.terminated || o.truncated)) break;
+        if (P.autoreset == BSG_AUTORESET_NEXT_STEP) { s.needs_reset = 1; break; }
+        if (P.autoreset != BSG_AUTORESET_SAME_STEP) break;
+        if (P.final_obs) {                               // the terminal observation survives in final_obs
+            __syncwarp(group_mask<G>());
+            float* fo = P.final_obs + e * P.obs_dim;
+            for (int i = slot; i < P.obs_dim; i += G) fo[i] = obs[i];
+            __syncwarp(group_mask<G>());
+        }
+        resetting = true;
     }
     ac_store(a, P, gt);
     if (slot == 0) env_store(s, P, e);
