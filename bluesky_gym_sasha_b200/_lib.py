@@ -43,7 +43,7 @@ class Layout(C.Structure):
 
 
 TENSOR_FIELDS = ("pos", "kin", "cmd", "aux", "flags", "tcpamax", "inconf", "env_f64", "env_f32", "env_i32",
-                 "poly", "obs", "final_obs", "reward", "terminated", "truncated", "info", "actions_staging")
+                 "poly", "obs", "final_obs", "final_ids", "final_count", "reward", "terminated", "truncated", "info", "actions_staging")
 
 
 class TensorTable(C.Structure):
@@ -81,7 +81,7 @@ def load():
     lib.bsg_bind_state.argtypes = [vp, C.POINTER(TensorTable)]
     lib.bsg_reset.argtypes = [vp, vp, vp]
     lib.bsg_step.argtypes = [vp, vp, vp]
-    lib.bsg_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.bsg_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.bsg_traf_update.argtypes = [vp, i32, vp]
     lib.bsg_cd_padded.argtypes = [i64]
     lib.bsg_cd_padded.restype = i64

@@ -113,12 +113,13 @@ extern "C" int bsg_bind_state(bsg_handle* h, const bsg_tensor_table* t) {
         return bsg_fail(BSG_EINVAL, "bsg_bind_state: a required tensor pointer is null");
     if (h->cfg.cd_enabled && (!t->tcpamax || !t->inconf)) return bsg_fail(BSG_EINVAL, "cd_enabled needs tcpamax and inconf");
     if (h->lay.poly_f64 && !t->poly) return bsg_fail(BSG_EINVAL, "this env type needs the poly tensor");
+    if (t->final_obs && (!t->final_ids || !t->final_count)) return bsg_fail(BSG_EINVAL, "final_obs needs final_ids and final_count");
     h->t = *t;
     bsg::EnvParams& P = h->P;
     P.pos = (double2*)t->pos; P.kin = (float4*)t->kin; P.cmd = (float4*)t->cmd; P.aux = (float4*)t->aux;
     P.flags = t->flags; P.tcpamax = t->tcpamax; P.inconf = t->inconf;
     P.ef64 = t->env_f64; P.ef32 = t->env_f32; P.ei32 = t->env_i32; P.poly = t->poly;
-    P.obs = t->obs; P.final_obs = t->final_obs; P.reward = t->reward; P.term = t->terminated; P.trunc = t->truncated;
+    P.obs = t->obs; P.final_obs = t->final_obs; P.final_ids = t->final_ids; P.final_count = t->final_count; P.reward = t->reward; P.term = t->terminated; P.trunc = t->truncated;
     P.info = t->info;
     h->bound = true;
     return BSG_OK;
@@ -131,6 +132,8 @@ static int run_mode(bsg_handle* h, int mode, const float* d_actions, const uint8
     bsg::EnvParams P = h->P;
     P.mode = mode; P.actions = d_actions; P.reset_mask = d_mask;
     if (n_sub > 0) P.n_sub = n_sub;
+    if (mode == bsg::kModeStep && P.final_count)
+        BSG_CUDA(cudaMemsetAsync(P.final_count, 0, sizeof(int32_t), (cudaStream_t)stream));
     return bsg_launch_env(P, h->lay.slots, (cudaStream_t)stream);
 }
 
@@ -148,7 +151,8 @@ extern "C" int bsg_traf_update(bsg_handle* h, int32_t n_sub, void* stream) {
 }
 
 extern "C" int bsg_step_host(bsg_handle* h, const float* h_actions, float* h_obs, float* h_reward,
-                             uint8_t* h_terminated, uint8_t* h_truncated, float* h_info, void* stream) {
+                             uint8_t* h_terminated, uint8_t* h_truncated, float* h_info, int32_t* h_final_count,
+                             void* stream) {
     if (!h || !h_actions) return bsg_fail(BSG_EINVAL, "bsg_step_host: null argument");
     if (!h->bound) return bsg_fail(BSG_ESTATE, "bsg_bind_state has not been called");
     if (!h->t.actions_staging) return bsg_fail(BSG_ESTATE, "bsg_step_host needs tensor_table.actions_staging");
@@ -158,11 +162,33 @@ extern "C" int bsg_step_host(bsg_handle* h, const float* h_actions, float* h_obs
     BSG_CUDA(cudaMemcpyAsync(h->t.actions_staging, h_actions, E * h->lay.act_dim * sizeof(float), cudaMemcpyHostToDevice, st));
     int rc = run_mode(h, bsg::kModeStep, h->t.actions_staging, nullptr, 0, stream);
     if (rc != BSG_OK) return rc;
-    if (h_obs) BSG_CUDA(cudaMemcpyAsync(h_obs, h->t.obs, E * h->lay.obs_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (h_reward) BSG_CUDA(cudaMemcpyAsync(h_reward, h->t.reward, E * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (h_terminated) BSG_CUDA(cudaMemcpyAsync(h_terminated, h->t.terminated, E, cudaMemcpyDeviceToHost, st));
-    if (h_truncated) BSG_CUDA(cudaMemcpyAsync(h_truncated, h->t.truncated, E, cudaMemcpyDeviceToHost, st));
-    if (h_info) BSG_CUDA(cudaMemcpyAsync(h_info, h->t.info, E * h->lay.info_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // Outputs that are laid out in ONE contiguous block on the device (obs | reward | info | final_count[4] |
+    // terminated | truncated, as BlueSkyVectorEnv allocates them) and mirrored with the same offsets on
+    // the host go back in a single copy instead of six.
+    {
+        const char* d0 = (const char*)h->t.obs;
+        char* h0 = (char*)h_obs;
+        const size_t n_obs = E * h->lay.obs_dim * sizeof(float), n_rew = E * sizeof(float);
+        const size_t n_info = E * h->lay.info_dim * sizeof(float), n_cnt = 4 * sizeof(int32_t);
+        const size_t o_rew = n_obs, o_info = o_rew + n_rew, o_cnt = o_info + n_info, o_term = o_cnt + n_cnt, o_trunc = o_term + E;
+        const bool packed = h_obs && h_reward && h_info && h_terminated && h_truncated && h_final_count &&
+                            (const char*)h->t.reward == d0 + o_rew && (char*)h_reward == h0 + o_rew &&
+                            (const char*)h->t.info == d0 + o_info && (char*)h_info == h0 + o_info &&
+                            (const char*)h->t.final_count == d0 + o_cnt && (char*)h_final_count == h0 + o_cnt &&
+                            (const char*)h->t.terminated == d0 + o_term && (char*)h_terminated == h0 + o_term &&
+                            (const char*)h->t.truncated == d0 + o_trunc && (char*)h_truncated == h0 + o_trunc;
+        if (packed) {
+            BSG_CUDA(cudaMemcpyAsync(h0, d0, o_trunc + E, cudaMemcpyDeviceToHost, st));
+        } else {
+            if (h_obs) BSG_CUDA(cudaMemcpyAsync(h_obs, h->t.obs, n_obs, cudaMemcpyDeviceToHost, st));
+            if (h_reward) BSG_CUDA(cudaMemcpyAsync(h_reward, h->t.reward, n_rew, cudaMemcpyDeviceToHost, st));
+            if (h_terminated) BSG_CUDA(cudaMemcpyAsync(h_terminated, h->t.terminated, E, cudaMemcpyDeviceToHost, st));
+            if (h_truncated) BSG_CUDA(cudaMemcpyAsync(h_truncated, h->t.truncated, E, cudaMemcpyDeviceToHost, st));
+            if (h_info) BSG_CUDA(cudaMemcpyAsync(h_info, h->t.info, n_info, cudaMemcpyDeviceToHost, st));
+            if (h_final_count && h->t.final_count)
+                BSG_CUDA(cudaMemcpyAsync(h_final_count, h->t.final_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        }
+    }
     BSG_CUDA(cudaStreamSynchronize(st));
     return BSG_OK;
 }

@@ -42,7 +42,7 @@ struct EnvParams {
     double2* pos; float4* kin; float4* cmd; float4* aux; uint32_t* flags;
     float* tcpamax; uint8_t* inconf;
     double* ef64; float* ef32; int32_t* ei32; double* poly;
-    float* obs; float* final_obs; float* reward; uint8_t* term; uint8_t* trunc; float* info;
+    float* obs; float* final_obs; int32_t* final_ids; int32_t* final_count; float* reward; uint8_t* term; uint8_t* trunc; float* info;
     const float* actions; const uint8_t* reset_mask;
 };
 

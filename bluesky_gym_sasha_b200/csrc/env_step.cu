@@ -462,7 +462,7 @@ __device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float
 // K6: the env-step megakernel (also serves reset and the kinematics-only parity entry point)
 // =====================================================================================================
 template <int ENV, int G>
-__global__ void __launch_bounds__(kEnvThreads, 6) env_kernel(const EnvParams P) {
+__global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) {
     __shared__ __align__(16) float4 s_rec[kEnvThreads * 2];
     __shared__ int s_tmax[kEnvThreads];
     __shared__ uint16_t s_pairs[kMaxPairs];
@@ -547,9 +547,12 @@ __global__ void __launch_bounds__(kEnvThreads, 6) env_kernel(const EnvParams P) 
         if (!(o.terminated || o.truncated)) break;
         if (P.autoreset == BSG_AUTORESET_NEXT_STEP) { s.needs_reset = 1; break; }
         if (P.autoreset != BSG_AUTORESET_SAME_STEP) break;
-        if (P.final_obs) {                               // the terminal observation survives in final_obs
+        if (P.final_obs) {                               // the terminal observation survives, compacted
+            int k = 0;
+            if (slot == 0) { k = atomicAdd(P.final_count, 1); P.final_ids[k] = (int32_t)e; }
+            k = group_bcast<G>(k, 0);
             __syncwarp(group_mask<G>());
-            float* fo = P.final_obs + e * P.obs_dim;
+            float* fo = P.final_obs + (long long)k * P.obs_dim;
             for (int i = slot; i < P.obs_dim; i += G) fo[i] = obs[i];
             __syncwarp(group_mask<G>());
         }

@@ -28,7 +28,7 @@ class _ScalarEnv(Env):
     def _make(self, seed):
         # the registration's TimeLimit is applied by gym.make's wrapper, exactly like the reference
         self.vec = BlueSkyVectorEnv(self.ENV_ID, 1, seed=seed, autoreset_mode="disabled",
-                                    max_episode_steps=0, **self._kw)
+                                    max_episode_steps=0, obs_dtype=np.float64, **self._kw)
         self.observation_space = self.vec.single_observation_space
         self.action_space = self.vec.single_action_space
 

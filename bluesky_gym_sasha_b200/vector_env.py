@@ -32,7 +32,8 @@ class BlueSkyVectorEnv(VectorEnv):
 
     def __init__(self, env_id, num_envs, device=0, seed=0, cd_enabled=False, n_intruders=None,
                  autoreset_mode="next_step", env_id_offset=0, max_episode_steps=None, perf=None,
-                 default_hdg="random", rpz=0.0, hpz=0.0, dtlookahead=0.0, render_mode=None):
+                 default_hdg="random", rpz=0.0, hpz=0.0, dtlookahead=0.0, render_mode=None,
+                 obs_dtype=np.float32, copy=True):
         if env_id in NOT_ACCELERATED:
             raise NotImplementedError(f"{env_id} is registered by the reference but is not on the accelerated "
                                       "path yet (SURVEY.md section 8f)")
@@ -46,6 +47,10 @@ class BlueSkyVectorEnv(VectorEnv):
         self.num_envs = int(num_envs)
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
         self.render_mode = None
+        # float32 arrays are valid members of the reference's float64 Box spaces (gymnasium checks
+        # np.can_cast); the scalar Env classes ask for float64 to be byte-for-byte drop-in.
+        self.obs_dtype = np.dtype(obs_dtype)
+        self.copy = bool(copy)          # False: return views of two rotating pinned buffers (valid for 2 steps)
         self.autoreset_mode = autoreset_mode
         self.metadata = dict(self.metadata, autoreset_mode=autoreset_mode)
         n_int = n_intruders if n_intruders is not None else self.spec_b200.default_kwargs.get("n_intruders", 0)
@@ -76,6 +81,22 @@ class BlueSkyVectorEnv(VectorEnv):
         # ---- device state (torch owns the memory; the library only borrows pointers)
         dev = self.device
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        # step outputs live in ONE block (obs | reward | info | terminated | truncated) so that the host
+        # API brings them back with a single device->host copy (bsg_step_host's packed path)
+        n_obs, n_rew, n_info, n_cnt = E * L.obs_dim * 4, E * 4, E * L.info_dim * 4, 16
+        o_info, o_cnt, o_term = n_obs + n_rew, n_obs + n_rew + n_info, n_obs + n_rew + n_info + n_cnt
+        self._out_bytes = o_term + 2 * E
+
+        def carve(block):
+            o = block[:n_obs].view(torch.float32).view(E, L.obs_dim)
+            r = block[n_obs:o_info].view(torch.float32)
+            i = block[o_info:o_cnt].view(torch.float32).view(E, L.info_dim)
+            c = block[o_cnt:o_term].view(torch.int32)
+            te = block[o_term:o_term + E]
+            tr = block[o_term + E:o_term + 2 * E]
+            return o, r, i, c, te, tr
+        self._out_dev = z((self._out_bytes + 16,), torch.uint8)
+        d_obs, d_rew, d_info, d_cnt, d_term, d_trunc = carve(self._out_dev)
         self.t = OrderedDict(
             pos=z((E, G, 2), torch.float64), kin=z((E, G, 4), torch.float32), cmd=z((E, G, 4), torch.float32),
             aux=z((E, G, 4), torch.float32), flags=z((E, G), torch.int32),
@@ -83,15 +104,21 @@ class BlueSkyVectorEnv(VectorEnv):
             env_f64=z((E, L.env_f64), torch.float64), env_f32=z((E, L.env_f32), torch.float32),
             env_i32=z((E, L.env_i32), torch.int32),
             poly=z((E, max(L.poly_f64, 1)), torch.float64) if L.poly_f64 else None,
-            obs=z((E, L.obs_dim), torch.float32), final_obs=z((E, L.obs_dim), torch.float32),
-            reward=z((E,), torch.float32), terminated=z((E,), torch.uint8), truncated=z((E,), torch.uint8),
-            info=z((E, L.info_dim), torch.float32), actions_staging=z((E, L.act_dim), torch.float32))
-        # pinned host mirrors for the numpy API
+            obs=d_obs, final_obs=z((E, L.obs_dim), torch.float32), final_ids=z((E,), torch.int32), final_count=d_cnt,
+            reward=d_rew, terminated=d_term, truncated=d_trunc,
+            info=d_info, actions_staging=z((E, L.act_dim), torch.float32))
+        # pinned host mirrors for the numpy API: two rotating output blocks with the device block's layout
         ph = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
-        self.h = dict(actions=ph((E, L.act_dim), torch.float32), obs=ph((E, L.obs_dim), torch.float32),
-                      reward=ph((E,), torch.float32), terminated=ph((E,), torch.uint8),
-                      truncated=ph((E,), torch.uint8), info=ph((E, L.info_dim), torch.float32),
-                      final_obs=ph((E, L.obs_dim), torch.float32))
+        self._hbuf = []
+        for _ in range(2):
+            blk = ph((self._out_bytes + 16,), torch.uint8)
+            o, r, i, c, te, tr = carve(blk)
+            self._hbuf.append(dict(obs=o, reward=r, info=i, final_count=c, terminated=te, truncated=tr))
+        self._hsel = 0
+        self.h = dict(actions=ph((E, L.act_dim), torch.float32))
+        self._final_np = np.zeros((E, L.obs_dim), dtype=np.float32)
+        self._h_final = ph((E, L.obs_dim), torch.float32)
+        self._h_final_ids = ph((E,), torch.int32)
 
         self._h = C.c_void_p(0)
         with torch.cuda.device(dev):
@@ -107,7 +134,10 @@ class BlueSkyVectorEnv(VectorEnv):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _obs_dict_np(self, flat):
-        f = flat.astype(np.float64)
+        if flat.dtype != self.obs_dtype:
+            f = flat.astype(self.obs_dtype)
+        else:
+            f = flat.copy() if self.copy else flat
         return OrderedDict((k, f[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
 
     def _obs_dict_torch(self, flat):
@@ -158,13 +188,13 @@ class BlueSkyVectorEnv(VectorEnv):
         return self._obs_dict_np(obs), self._infos_np(info)
 
     def step(self, actions):
-        a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, self.layout.act_dim)
-        h = self.h
-        h["actions"].numpy()[...] = a
+        self.h["actions"].numpy()[...] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, self.layout.act_dim)
+        self._hsel ^= 1
+        h = self._hbuf[self._hsel]
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.bsg_step_host(self._h, _ptr(h["actions"]), _ptr(h["obs"]), _ptr(h["reward"]),
+            _lib.check(self._lib.bsg_step_host(self._h, _ptr(self.h["actions"]), _ptr(h["obs"]), _ptr(h["reward"]),
                                                _ptr(h["terminated"]), _ptr(h["truncated"]), _ptr(h["info"]),
-                                               self._stream()))
+                                               _ptr(h["final_count"]), self._stream()))
         self.gpu_launches += 1
         obs = self._obs_dict_np(h["obs"].numpy())
         rew = h["reward"].numpy().astype(np.float64)
@@ -172,10 +202,15 @@ class BlueSkyVectorEnv(VectorEnv):
         trunc = h["truncated"].numpy().astype(bool)
         infos = self._infos_np(h["info"].numpy())
         if self.autoreset_mode == "same_step":
-            done = term | trunc
-            if done.any():
-                fo = self.t["final_obs"].cpu().numpy()
-                infos["final_obs"] = self._obs_dict_np(fo)
+            n_fin = int(h["final_count"][0])
+            if n_fin:                   # fetch only the (compacted) terminal observations of finished envs
+                done = term | trunc
+                self._h_final[:n_fin].copy_(self.t["final_obs"][:n_fin], non_blocking=True)
+                self._h_final_ids[:n_fin].copy_(self.t["final_ids"][:n_fin], non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                self._final_np[self._h_final_ids.numpy()[:n_fin]] = self._h_final.numpy()[:n_fin]
+                fo = self._final_np.astype(self.obs_dtype) if self.obs_dtype != np.float32 else self._final_np
+                infos["final_obs"] = OrderedDict((k, fo[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
                 infos["_final_obs"] = done
         return obs, rew, term, trunc, infos
 

@@ -89,7 +89,10 @@ typedef struct bsg_tensor_table {
     int32_t *env_i32;   /* [E*env_i32]                                                               */
     double *poly;       /* [E*poly_f64] or NULL                                                      */
     float *obs;         /* [E*obs_dim]   Env._get_obs, keys concatenated in declaration order        */
-    float *final_obs;   /* [E*obs_dim]   terminal observation (SAME_STEP autoreset), may be NULL     */
+    float *final_obs;   /* [E*obs_dim]   SAME_STEP autoreset: terminal observations, COMPACT -- row k is the */
+                        /*               terminal obs of env final_ids[k], k < final_count[0]; may be NULL  */
+    int32_t *final_ids; /* [E]           env index of each compact final_obs row (needed with final_obs)    */
+    int32_t *final_count;/* [4]          [0] = number of envs that finished in the last step                */
     float *reward;      /* [E]                                                                       */
     uint8_t *terminated;/* [E]                                                                       */
     uint8_t *truncated; /* [E]                                                                       */
@@ -132,7 +135,8 @@ int bsg_step(bsg_handle *h, const float *d_actions, void *stream);
 /* End-to-end form of bsg_step for host callers (SB3 / numpy): copies h_actions (pinned or pageable)
  * to the device, steps, copies obs / reward / terminated / truncated / info back and synchronises. */
 int bsg_step_host(bsg_handle *h, const float *h_actions, float *h_obs, float *h_reward,
-                  uint8_t *h_terminated, uint8_t *h_truncated, float *h_info, void *stream);
+                  uint8_t *h_terminated, uint8_t *h_truncated, float *h_info, int32_t *h_final_count,
+                  void *stream);
 
 /* replaces: n_sub x bs.sim.step() alone (Traffic.update kinematics + autopilot, no obs/reward);
  * used by the trajectory parity tests. */
