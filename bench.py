@@ -219,7 +219,19 @@ def run_b200(args):
     h2d = E * L.act_dim * 4
     d2h = E * (L.obs_dim * 4 + 4 + 1 + 1 + L.info_dim * 4)
     e2e = {"value": E * world * K / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "api": "BlueSkyVectorEnv.step (numpy in / numpy out, bsg_step_host)"}
+           "api": "BlueSkyVectorEnv.step, default arguments (numpy in; float32 numpy copies out; bsg_step_host)"}
+    # same call with copy=False (views of two rotating pinned buffers instead of fresh copies), for context
+    venv.copy = False
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        venv.step(host_actions[i])
+    barrier()
+    e2e["value_copy_false"] = E * world * K / max_over_ranks(time.perf_counter() - t0)
+    venv.copy = True
+
+    # single airspace, rows sharded over the ranks after one NCCL all-gather (BASELINE configs[4])
+    cd_sharded = bench_cd_sharded(torch, dist, dev, StateBasedCD, world, rank, max_over_ranks, barrier) if world > 1 else None
 
     peaks = {}
     try:
@@ -246,6 +258,9 @@ def run_b200(args):
                 "dtype": "f32 (lat/lon f64)", "data": "synthetic", "config": workload_config(world),
                 "value_l2_warm": warm_value, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
                 "cpu_baseline": cb, "clocks": clk.summary(), "cd_pairs": cd}
+        if cd_sharded is not None:
+            cd_sharded["roofline_frac_per_gpu"] = cd_sharded["ordered_pairs_per_s"] * F_PAIR / world / fp32
+            line["cd_pairs_sharded"] = cd_sharded
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -290,6 +305,40 @@ def bench_cd(torch, dev, StateBasedCD, fp32_peak, n=CD_N, reps=5):
             "roofline": {"bound": "fp32", "achieved": tf, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
                          "frac": tf / (fp32_peak / 1e12), "flop_per_pair": F_PAIR, "executed_fraction": 1.0,
                          "kernel": "cd_tiled_kernel"}}
+
+
+def bench_cd_sharded(torch, dist, dev, StateBasedCD, world, rank, max_over_ranks, barrier, n=CD_N, reps=5):
+    """N = 100k aircraft block-partitioned over the ranks: pack own block, all-gather the 32 B records over
+    NVLink, evaluate own rows against all columns.  Time = max over ranks of (all-gather + detection)."""
+    per = -(-n // world)
+    per = -(-per // 256) * 256                      # tile-aligned blocks
+    n_tot = per * world
+    rng = np.random.default_rng(1)
+    lat = 52 + 40 * (rng.random(n_tot) - 0.5)
+    lon = 4 + 40 * (rng.random(n_tot) - 0.5)
+    alt = np.round(rng.uniform(3000, 12000, n_tot) / 304.8) * 304.8
+    gs = rng.uniform(150, 250, n_tot)
+    trk = rng.uniform(0, 360, n_tot)
+    vs = np.where(rng.random(n_tot) < 0.8, 0.0, rng.choice([-1.0, 1.0], n_tot) * rng.uniform(5, 15, n_tot))
+    sl = slice(rank * per, (rank + 1) * per)
+    cd = StateBasedCD(device=dev.index)
+    rec, _ = cd.pack(lat[sl], lon[sl], trk[sl], gs[sl], alt[sl], vs[sl], 52.0, 4.0)
+    for _ in range(2):
+        out = cd.detect_sharded(rec, per)
+    barrier()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        out = cd.detect_sharded(rec, per)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        best = min(best, max_over_ranks(e0.elapsed_time(e1) * 1e-3))
+    nconf = torch.tensor([int(out["npairs"][0])], dtype=torch.int64, device=dev)
+    dist.all_reduce(nconf)
+    return {"n_aircraft": n_tot, "rows_per_gpu": per, "ordered_pairs_per_s": n_tot * (n_tot - 1) / best, "ms": best * 1e3,
+            "n_conf": int(nconf.item()), "collective": "ncclAllGather of 32 B records, then row-sharded tiles"}
 
 
 def main():
