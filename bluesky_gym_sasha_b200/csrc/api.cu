@@ -61,6 +61,10 @@ extern "C" int bsg_query_layout(const bsg_config* cfg, bsg_layout* out) {
             out->poly_f64 = 64; break;
         case BSG_ENV_MERGE:              // merge_env.py:34-36,59-76,86
             out->slots = 32; out->obs_dim = 5 + 7 * 5; out->act_dim = 2; out->n_sub = 10; out->simdt = 5.0f; break;
+        case BSG_ENV_PLAN_WAYPOINT:      // plan_waypoint_env.py:15,22,49-58,69
+            out->slots = 1; out->obs_dim = 20; out->act_dim = 1; out->n_sub = 10; out->simdt = 1.0f; break;
+        case BSG_ENV_VERTICAL_CR:        // vertical_cr_env.py:40,42,64-82,95
+            out->slots = 8; out->obs_dim = 4 + 7 * 5; out->act_dim = 1; out->n_sub = 30; out->simdt = 1.0f; break;
         default:
             return bsg_fail(BSG_EINVAL, "unknown env_type");
     }

@@ -432,6 +432,147 @@ __device__ inline void merge_info(const EnvS& s, float* info) {             // m
 }
 
 // =====================================================================================================
+// PlanWaypointEnv (plan_waypoint_env.py) -- 1 aircraft, 5 waypoints, G = 1
+// =====================================================================================================
+template <int G>
+__device__ inline void planwp_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot) {
+    Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);      // plan_waypoint_env.py:157-172,200-213
+    double hdg = P.hdg_random ? (double)rng.randint(0, 1, 360) : 0.0;
+    if (slot == 0) ac_create(a, 52.0, 4.0, hdg, 0.0, 150.0); else ac_clear(a);
+    double* w = P.ef64 + e * BSG_F64_COUNT + BSG_F64_WPTS;
+    for (int k = 0; k < 5; ++k) {
+        int dis = rng.randint(1u + 2u * k, 0, 75), brg = rng.randint(2u + 2u * k, 0, 359);
+        d_point_at_distance(52.0, 4.0, (double)dis, (double)brg, w[2 * k], w[2 * k + 1]);
+    }
+    s.wpt_reach = 0; s.total_reward = 0.0f; s.num_ac = 1;
+}
+template <int G>
+__device__ inline StepOut planwp_obs_reward(const Ac& a, EnvS& s, const EnvParams& P, float* obs, int slot,
+                                            long long e, bool with_reward) {
+    const double* w = P.ef64 + e * BSG_F64_COUNT + BSG_F64_WPTS;            // plan_waypoint_env.py:82-124
+    StepOut o = {0.0f, 0, 0};
+    int reach = s.wpt_reach;
+    for (int k = 0; k < 5; ++k) {
+        float q, dnm;
+        kwikqdrdist(a.lat, a.lon, w[2 * k], w[2 * k + 1], q, dnm);
+        float dkm = dnm * 1.852f, sd, cd;
+        sincosf(wrap180_fold(a.hdg - q) * kDeg2Rad, &sd, &cd);
+        const float live = (s.wpt_reach >> k) & 1 ? 0.0f : 1.0f;           // flags from BEFORE this step's check
+        obs[k] = live * dkm * (1.0f / 75.0f);
+        obs[5 + k] = live * cd;
+        obs[10 + k] = live * sd;
+        obs[15 + k] = 1.0f - live;
+        if (with_reward && dkm < 5.0f && !((reach >> k) & 1)) { reach |= 1 << k; o.reward += 1.0f; }   // :215-228
+    }
+    if (with_reward) {
+        s.wpt_reach = reach;
+        s.total_reward += o.reward;
+        o.terminated = (reach == 31) ? 1 : 0;
+    }
+    return o;
+}
+
+// =====================================================================================================
+// VerticalCREnv (vertical_cr_env.py) -- DescentEnv + 5 creconfs intruders with an altitude offset, G = 8
+// =====================================================================================================
+template <int G>
+__device__ inline void vertical_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot) {
+    Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);      // vertical_cr_env.py:258-281
+    const int alt_init = rng.randint(0, 2000, 4000);
+    const double target = (double)(alt_init + rng.randint(1, -500, 500));
+    const double hdg0 = P.hdg_random ? (double)rng.randint(2, 1, 360) : 0.0;
+    const double lat0 = 52.0, lon0 = 4.0, alt0 = (double)alt_init;
+    const double tas0 = d_cas2tas(150.0, alt0);
+    s.target_alt = target;
+    if (slot == 0) {
+        ac_create(a, lat0, lon0, hdg0, alt0, 150.0);
+    } else if (slot <= 5) {                                                  // _generate_conflicts :185-200
+        const uint32_t d = 3u + 4u * (uint32_t)(slot - 1);
+        double dpsi = (double)rng.randint(d, 45, 315);
+        double cpa = (double)rng.randint(d + 1, 0, 5) * 1852.0;
+        double tlosh = (double)rng.randint(d + 2, 100, (int)((200.0 * 0.9) * 1000.0 / tas0));
+        double average_tod = (200.0 * 1000.0 / tas0) - 2.0 * target / 12.5;
+        int dH;
+        if (tlosh > average_tod) dH = rng.randint(d + 3, (int)(-alt0 + 500.0), (int)((target - alt0) + 100.0));
+        else dH = rng.randint(d + 3, (int)((target - alt0) - 500.0), (int)((target - alt0) + 500.0));
+        // Traffic.creconfs with dH, tlosv = 1e11 (oracle/traffic.py::creconfs)
+        const double pzr = 5.0 * 1852.0, pzh = 1000.0 * 0.3048;
+        double trkref = hdg0 * kDeg2RadD, gsref = tas0;
+        double trk = trkref + dpsi * kDeg2RadD;
+        double acalt = alt0 + (double)dH;
+        double sgn = dH > 0 ? 1.0 : (dH < 0 ? -1.0 : 0.0);
+        double acvs = 0.0 - sgn * (fabs((double)dH) - pzh) / 1e11;
+        double gsn = gsref * cos(trk), gse = gsref * sin(trk);
+        double vreln = gsref * cos(trkref) - gsn, vrele = gsref * sin(trkref) - gse;
+        double vrel = sqrt(vreln * vreln + vrele * vrele);
+        double drelcpa = tlosh * vrel + (cpa > pzr ? 0.0 : sqrt(pzr * pzr - cpa * cpa));
+        double dist = sqrt(drelcpa * drelcpa + cpa * cpa);
+        double rd = drelcpa / dist, rx = cpa / dist;
+        double brn = kRad2DegD * atan2(-rx * vreln + rd * vrele, rd * vreln + rx * vrele);
+        double dnm = dist / 1852.0;
+        double lat = lat0 + dnm * cos(brn * kDeg2RadD) / 60.0;
+        double lon = lon0 + dnm * sin(brn * kDeg2RadD) / fmax(0.01, 60.0 * cos(lat0 * kDeg2RadD));
+        lon = fmod(lon + 180.0, 360.0); if (lon < 0.0) lon += 360.0; lon -= 180.0;
+        double acspd = d_tas2cas(sqrt(gsn * gsn + gse * gse), acalt);
+        ac_create(a, lat, lon, kRad2DegD * atan2(gse, gsn), acalt, acspd);
+        a.vs = (float)acvs;                 // creconfs: vs[-1] = acvs; the env then selaltcmd(alt + dH, 0)
+        a.selalt = (float)acalt; a.selvs = 0.0f;
+    } else {
+        ac_clear(a);
+    }
+    s.total_reward = 0.0f; s.intrusions = 0; s.final_alt = 0.0f; s.num_ac = 6;
+}
+template <int G>
+__device__ inline StepOut vertical_obs_reward(const Ac& a, EnvS& s, const EnvParams& P, float* obs, int slot,
+                                              bool with_reward) {
+    const double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);     // vertical_cr_env.py:114-183
+    const float hdg0 = group_bcast<G>(a.hdg, 0), gs0 = group_bcast<G>(a.tas, 0);
+    const float alt0 = group_bcast<G>(a.alt, 0), vs0 = group_bcast<G>(a.vs, 0);
+    float q, dnm;
+    kwikqdrdist(52.0, 4.0, lat0, lon0, q, dnm);
+    const float rwy = 200.0f - dnm * 1.852f;
+    const float tgt = (float)s.target_alt;
+    if (slot == 0) {
+        obs[0] = (alt0 - 1500.0f) * (1.0f / 3000.0f);
+        obs[1] = vs0 * 0.2f;
+        obs[2] = (tgt - 1500.0f) * (1.0f / 3000.0f);
+        obs[3] = (rwy - 100.0f) * (1.0f / 200.0f);
+    }
+    const bool intr = slot >= 1 && slot <= 5;
+    float dis = 1e9f;
+    if (intr) {
+        float qdr;
+        kwikqdrdist(lat0, lon0, a.lat, a.lon, qdr, dis);
+        float sb, cb, sd, cd;
+        sincosf(wrap180_fold(hdg0 - qdr) * kDeg2Rad, &sb, &cb);
+        sincosf((hdg0 - a.hdg) * kDeg2Rad, &sd, &cd);
+        const int k = slot - 1;
+        obs[4 + k] = dis * (1.852f / 200.0f);
+        obs[9 + k] = cb;
+        obs[14 + k] = sb;
+        obs[19 + k] = (a.alt - alt0) * (1.0f / 3000.0f);
+        obs[24 + k] = -cd * a.tas * (1.0f / 150.0f);
+        obs[29 + k] = (gs0 - sd * a.tas) * (1.0f / 150.0f);
+        obs[34 + k] = a.vs - vs0;
+    }
+    StepOut o = {0.0f, 0, 0};
+    if (!with_reward) return o;
+    const int nintr = group_sum<G>((intr && dis < 5.0f && fabsf(alt0 - a.alt) < 1000.0f * 0.3048f) ? 1 : 0);   // :213-240
+    s.intrusions += nintr;
+    float pen;
+    if (rwy > 0.0f && alt0 > 0.0f) {
+        pen = fabsf(tgt - alt0) * (-5.0f / 3000.0f);
+    } else if (alt0 <= 0.0f) {
+        pen = -100.0f; o.terminated = 1; s.final_alt = -100.0f;
+    } else {
+        pen = alt0 * (-50.0f / 3000.0f); o.terminated = 1; s.final_alt = alt0;
+    }
+    o.reward = pen - 50.0f * (float)nintr;
+    s.total_reward += o.reward;
+    return o;
+}
+
+// =====================================================================================================
 // dispatch helpers
 // =====================================================================================================
 template <int ENV, int G>
@@ -440,6 +581,8 @@ __device__ __forceinline__ void do_reset(Ac& a, EnvS& s, const EnvParams& P, lon
     if (ENV == BSG_ENV_HORIZONTAL_CR) horizontal_reset<G>(a, s, P, e, slot);
     if (ENV == BSG_ENV_SECTOR_CR) sector_reset<G>(a, s, P, e, slot, scratch);
     if (ENV == BSG_ENV_MERGE) merge_reset<G>(a, s, P, e, slot);
+    if (ENV == BSG_ENV_PLAN_WAYPOINT) planwp_reset<G>(a, s, P, e, slot);
+    if (ENV == BSG_ENV_VERTICAL_CR) vertical_reset<G>(a, s, P, e, slot);
     s.step = 0; s.needs_reset = 0; s.episode += 1; s.nconf = 0; s.nlos = 0;
 }
 template <int ENV, int G>
@@ -448,13 +591,19 @@ __device__ __forceinline__ StepOut do_obs(const Ac& a, EnvS& s, const EnvParams&
     if (ENV == BSG_ENV_DESCENT) return descent_obs_reward<G>(a, s, P, obs, slot, with_reward);
     if (ENV == BSG_ENV_HORIZONTAL_CR) return horizontal_obs_reward<G>(a, s, P, obs, slot, with_reward);
     if (ENV == BSG_ENV_SECTOR_CR) return sector_obs_reward<G>(a, s, P, obs, slot, e, with_reward);
+    if (ENV == BSG_ENV_PLAN_WAYPOINT) return planwp_obs_reward<G>(a, s, P, obs, slot, e, with_reward);
+    if (ENV == BSG_ENV_VERTICAL_CR) return vertical_obs_reward<G>(a, s, P, obs, slot, with_reward);
     return merge_obs_reward<G>(a, s, P, obs, slot, with_reward);
 }
 template <int ENV>
 __device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float* info) {
     if (ENV == BSG_ENV_DESCENT) descent_info(s, info);
     else if (ENV == BSG_ENV_MERGE) merge_info(s, info);
-    else drift_info(s, info);
+    else if (ENV == BSG_ENV_PLAN_WAYPOINT) {            // plan_waypoint_env.py:126-133
+        info[0] = s.total_reward; info[1] = (float)__popc((unsigned)s.wpt_reach); info[2] = 0.0f; info[3] = 0.0f;
+    } else if (ENV == BSG_ENV_VERTICAL_CR) {            // vertical_cr_env.py:202-211
+        info[0] = s.total_reward; info[1] = (float)s.intrusions; info[2] = s.final_alt; info[3] = 0.0f;
+    } else drift_info(s, info);
     info[4] = (float)s.nconf; info[5] = (float)s.nlos;
 }
 
@@ -498,7 +647,8 @@ __global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) 
         const bool alive = (a.flags & kFlAlive) != 0;
         if (P.mode == kModeStep) {
             const float* act = P.actions + e * P.act_dim;
-            if (ENV == BSG_ENV_DESCENT) descent_action<G>(a, P, act, slot);
+            if (ENV == BSG_ENV_DESCENT || ENV == BSG_ENV_VERTICAL_CR) descent_action<G>(a, P, act, slot);
+            if (ENV == BSG_ENV_PLAN_WAYPOINT) horizontal_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_HORIZONTAL_CR) horizontal_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_SECTOR_CR) sector_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_MERGE) merge_action<G>(a, P, act, slot);
@@ -587,6 +737,10 @@ int bsg_launch_env(const EnvParams& P, int slots, cudaStream_t st) {
             return launch_env_t<BSG_ENV_SECTOR_CR, 32>(P, st);
         case BSG_ENV_MERGE:
             return launch_env_t<BSG_ENV_MERGE, 32>(P, st);
+        case BSG_ENV_PLAN_WAYPOINT:
+            return launch_env_t<BSG_ENV_PLAN_WAYPOINT, 1>(P, st);
+        case BSG_ENV_VERTICAL_CR:
+            return launch_env_t<BSG_ENV_VERTICAL_CR, 8>(P, st);
     }
     return bsg_fail(BSG_EINVAL, "unknown env_type");
 }

@@ -87,8 +87,14 @@ def _not_accelerated(env_id):
     return _Stub
 
 
-PlanWaypointEnv = _not_accelerated("PlanWaypointEnv-v0")
-VerticalCREnv = _not_accelerated("VerticalCREnv-v0")
+class PlanWaypointEnv(_ScalarEnv):
+    ENV_ID = "PlanWaypointEnv-v0"
+
+
+class VerticalCREnv(_ScalarEnv):
+    ENV_ID = "VerticalCREnv-v0"
+
+
 StaticObstacleEnv = _not_accelerated("StaticObstacleEnv-v0")
 
 __all__ = [s.entry_point.split(":")[1] for s in SPECS.values()]

@@ -2,8 +2,7 @@
 from .gym_compat import register, registry
 from .spec import SPECS
 
-_OTHER = {"PlanWaypointEnv-v0": ("PlanWaypointEnv", 300), "VerticalCREnv-v0": ("VerticalCREnv", 300),
-          "StaticObstacleEnv-v0": ("StaticObstacleEnv", 100)}
+_OTHER = {"StaticObstacleEnv-v0": ("StaticObstacleEnv", 100)}
 
 
 def register_envs():

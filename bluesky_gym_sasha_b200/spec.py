@@ -71,10 +71,24 @@ _add(EnvSpec(                                   # merge_env.py:59-76, :238-244
      ("cos(track)", 5, -INF, INF), ("sin(track)", 5, -INF, INF), ("distances", 5, -INF, INF)),
     ("total_reward", "faf_reach", "average_drift", "total_intrusions")))
 
-# ids the reference registers (bluesky_gym/__init__.py:13-16,25-28,37-40) that are NOT on the
+_add(EnvSpec(                                   # plan_waypoint_env.py:49-58, :126-133
+    "PlanWaypointEnv-v0", _lib.ENV_PLAN_WAYPOINT, "bluesky_gym_sasha_b200.envs:PlanWaypointEnv", 300, 1,
+    (("waypoint_distance", 5, -INF, INF), ("cos_difference", 5, -INF, INF), ("sin_difference", 5, -INF, INF),
+     ("waypoint_reached", 5, 0, 1)),
+    ("total_reward", "waypoints_completed")))
+
+_add(EnvSpec(                                   # vertical_cr_env.py:64-82, :202-211
+    "VerticalCREnv-v0", _lib.ENV_VERTICAL_CR, "bluesky_gym_sasha_b200.envs:VerticalCREnv", 300, 1,
+    (("altitude", 1, -INF, INF), ("vz", 1, -INF, INF), ("target_altitude", 1, -INF, INF),
+     ("runway_distance", 1, -INF, INF), ("intruder_distance", 5, -INF, INF), ("cos_difference_pos", 5, -INF, INF),
+     ("sin_difference_pos", 5, -INF, INF), ("altitude_difference", 5, -INF, INF),
+     ("x_difference_speed", 5, -INF, INF), ("y_difference_speed", 5, -INF, INF), ("z_difference_speed", 5, -INF, INF)),
+    ("total_reward", "total_intrusions", "final_altitude")))
+
+# ids the reference registers (bluesky_gym/__init__.py:37-40) that are NOT on the
 # accelerated path yet.  Asking for them fails loudly rather than silently
 # running something else.
-NOT_ACCELERATED = ("PlanWaypointEnv-v0", "VerticalCREnv-v0", "StaticObstacleEnv-v0")
+NOT_ACCELERATED = ("StaticObstacleEnv-v0",)
 
 # oracle/perf.py::A320 (kept in sync by tests/test_host_logic.py)
 A320_PERF = dict(vminto=73.3, vmaxic=88.5, vminer=64.0, vmaxer=163.0, vminap=64.0, vmaxap=78.0,

@@ -32,7 +32,9 @@ enum {
     BSG_ENV_DESCENT = 0,        /* DescentEnv-v0       descent_env.py       */
     BSG_ENV_HORIZONTAL_CR = 1,  /* HorizontalCREnv-v0  horizontal_cr_env.py */
     BSG_ENV_SECTOR_CR = 2,      /* SectorCREnv-v0      sector_cr_env.py     */
-    BSG_ENV_MERGE = 3           /* MergeEnv-v0         merge_env.py         */
+    BSG_ENV_MERGE = 3,          /* MergeEnv-v0         merge_env.py         */
+    BSG_ENV_PLAN_WAYPOINT = 4,  /* PlanWaypointEnv-v0  plan_waypoint_env.py */
+    BSG_ENV_VERTICAL_CR = 5     /* VerticalCREnv-v0    vertical_cr_env.py   */
 };
 
 /* vector autoreset behaviour (gymnasium.vector.AutoresetMode) */
@@ -101,7 +103,8 @@ typedef struct bsg_tensor_table {
 } bsg_tensor_table;
 
 /* indices into the per-env records (shared by all env types; unused slots stay zero) */
-enum { BSG_F64_WPT_LAT = 0, BSG_F64_WPT_LON = 1, BSG_F64_TARGET_ALT = 2, BSG_F64_POLY_AREA = 3, BSG_F64_COUNT = 4 };
+enum { BSG_F64_WPT_LAT = 0, BSG_F64_WPT_LON = 1, BSG_F64_TARGET_ALT = 2, BSG_F64_POLY_AREA = 3,
+       BSG_F64_WPTS = 4 /* PlanWaypoint: 5 x (lat, lon) */, BSG_F64_COUNT = 16 };
 enum { BSG_F32_TOTAL_REWARD = 0, BSG_F32_DRIFT_SUM = 1, BSG_F32_FINAL_ALT = 2, BSG_F32_LAST_HDG = 3, BSG_F32_COUNT = 4 };
 enum {
     BSG_I32_STEP = 0, BSG_I32_EPISODE = 1, BSG_I32_SIMK = 2, BSG_I32_WPT_REACH = 3, BSG_I32_DRIFT_N = 4,

@@ -177,6 +177,147 @@ class HorizontalCREnv(_Base):
 
 
 # =====================================================================================================
+class PlanWaypointEnv(_Base):
+    """plan_waypoint_env.py.  DT 1 (:69), 10 substeps (:22,178-179), 1 aircraft, 5 waypoints (:15)."""
+    SIMDT = 1.0
+    N_SUB = 10
+    NUM_WAYPOINTS = 5
+
+    def reset(self):                                   # plan_waypoint_env.py:157-172,200-213
+        t = self.traf
+        self.total_reward = 0.0
+        self.waypoints_completed = 0
+        t.reset()                                      # (the reference relies on the delete loop at :190-193)
+        t.cre("KL001", actype="A320", acspd=150.0)
+        self.wpt_lat, self.wpt_lon, self.wpt_reach = [], [], []
+        for _ in range(self.NUM_WAYPOINTS):
+            dis = self.draws.randint(0, 75)
+            hdg = self.draws.randint(0, 359)
+            la, lo = geo.get_point_at_distance(t.lat[0], t.lon[0], dis, hdg)
+            self.wpt_lat.append(float(la))
+            self.wpt_lon.append(float(lo))
+            self.wpt_reach.append(0)
+        return self._get_obs(), self._get_info()
+
+    def _get_obs(self):                                # plan_waypoint_env.py:82-124
+        t = self.traf
+        self.ac_hdg = float(t.hdg[0])
+        q, d = geo.kwikqdrdist(t.lat[0], t.lon[0], np.array(self.wpt_lat), np.array(self.wpt_lon))
+        self.wpt_dis = d * NM2KM
+        drift = np.radians(geo.wrap180_fold(self.ac_hdg - q))
+        live = 1.0 - np.array(self.wpt_reach, dtype=np.float64)
+        return {"waypoint_distance": live * self.wpt_dis / 75.0,
+                "cos_difference": live * np.cos(drift),
+                "sin_difference": live * np.sin(drift),
+                "waypoint_reached": np.array(self.wpt_reach, dtype=np.float64)}
+
+    def _get_info(self):                               # plan_waypoint_env.py:126-133
+        return {"total_reward": self.total_reward, "waypoints_completed": self.waypoints_completed}
+
+    def step(self, action):                            # plan_waypoint_env.py:135-155,174-195,215-228
+        hdg_cmd = self.ac_hdg + float(np.asarray(action).reshape(-1)[0]) * 45.0
+        self.traf.stack_hdg("KL001", hdg_cmd)
+        self._substeps()
+        obs = self._get_obs()                          # built with the reach flags from BEFORE this step's check
+        r = 0.0
+        for k in range(self.NUM_WAYPOINTS):
+            if self.wpt_dis[k] < 5.0 and self.wpt_reach[k] != 1:
+                self.waypoints_completed += 1
+                self.wpt_reach[k] = 1
+                r += 1.0
+        self.total_reward += r
+        terminated = 0 if 0 in self.wpt_reach else 1
+        return obs, r, terminated, False, self._get_info()
+
+
+# =====================================================================================================
+class VerticalCREnv(_Base):
+    """vertical_cr_env.py.  DT 1 (:95), 30 substeps (:40), DescentEnv + 5 creconfs intruders with dH (:42)."""
+    SIMDT = 1.0
+    N_SUB = 30
+    NUM_INTRUDERS = 5
+
+    def reset(self):                                   # vertical_cr_env.py:258-281, 185-200
+        t = self.traf
+        t.reset()
+        self.total_reward = 0.0
+        self.total_intrusions = 0
+        self.final_altitude = 0.0
+        alt_init = self.draws.randint(2000, 4000)
+        self.target_alt = alt_init + self.draws.randint(-500, 500)
+        t.cre("KL001", actype="A320", acalt=float(alt_init), acspd=150.0)
+        t.swvnav[0] = False
+        altitude, spd = float(t.alt[0]), float(t.gs[0])
+        for i in range(self.NUM_INTRUDERS):
+            dpsi = self.draws.randint(45, 315)
+            cpa = self.draws.randint(0, 5)
+            tlosh = self.draws.randint(100, int((200 * 0.9) * 1000 / spd))
+            average_tod = (200 * 1000 / spd) - 2 * self.target_alt / 12.5
+            if tlosh > average_tod:
+                dH = self.draws.randint(int(-altitude + 500), int((self.target_alt - altitude) + 100))
+            else:
+                dH = self.draws.randint(int((self.target_alt - altitude) - 500), int((self.target_alt - altitude) + 500))
+            t.creconfs(acid=str(i), actype="A320", targetidx=0, dpsi=dpsi, dcpa=cpa, tlosh=tlosh, dH=dH, tlosv=1e11)
+            t.alt[i + 1] = t.alt[0] + dH
+            t.selaltcmd(i + 1, t.alt[0] + dH, 0)
+        return self._get_obs(), self._get_info()
+
+    def _get_obs(self):                                # vertical_cr_env.py:114-183
+        t = self.traf
+        n = self.NUM_INTRUDERS
+        self.altitude, self.vz = float(t.alt[0]), float(t.vs[0])
+        hdg0 = float(t.hdg[0])
+        qdr, dis = geo.kwikqdrdist(t.lat[0], t.lon[0], t.lat[1:n + 1], t.lon[1:n + 1])
+        bearing = np.radians(geo.wrap180_fold(hdg0 - qdr))
+        dh = np.radians(t.hdg[0] - t.hdg[1:n + 1])
+        self.runway_distance = 200.0 - float(geo.kwikdist(52.0, 4.0, t.lat[0], t.lon[0])) * NM2KM
+        return {"altitude": _a1((self.altitude - 1500.0) / 3000.0),
+                "vz": _a1(self.vz / 5.0),
+                "target_altitude": _a1((self.target_alt - 1500.0) / 3000.0),
+                "runway_distance": _a1((self.runway_distance - 100.0) / 200.0),
+                "intruder_distance": dis * NM2KM / 200.0,
+                "cos_difference_pos": np.cos(bearing),
+                "sin_difference_pos": np.sin(bearing),
+                "altitude_difference": (t.alt[1:n + 1] - self.altitude) / 3000.0,
+                "x_difference_speed": -np.cos(dh) * t.gs[1:n + 1] / 150.0,
+                "y_difference_speed": (t.gs[0] - np.sin(dh) * t.gs[1:n + 1]) / 150.0,
+                "z_difference_speed": t.vs[1:n + 1] - self.vz}
+
+    def _get_info(self):                               # vertical_cr_env.py:202-211
+        return {"total_reward": self.total_reward, "total_intrusions": self.total_intrusions,
+                "final_altitude": self.final_altitude}
+
+    def _get_reward(self):                             # vertical_cr_env.py:213-240
+        t = self.traf
+        n = self.NUM_INTRUDERS
+        dis = geo.kwikdist(t.lat[0], t.lon[0], t.lat[1:n + 1], t.lon[1:n + 1])
+        vert = np.abs(t.alt[0] - t.alt[1:n + 1])
+        nint = int(np.count_nonzero((dis < 5.0) & (vert < 1000 * 0.3048)))
+        self.total_intrusions += nint
+        done = 0
+        if self.runway_distance > 0 and self.altitude > 0:
+            alt_pen = abs(self.target_alt - self.altitude) * (-5.0 / 3000.0)
+        elif self.altitude <= 0:
+            alt_pen, done = -100.0, 1
+            self.final_altitude = -100.0
+        else:
+            alt_pen, done = self.altitude * (-50.0 / 3000.0), 1
+            self.final_altitude = self.altitude
+        r = alt_pen - 50.0 * nint
+        self.total_reward += r
+        return r, done
+
+    def step(self, action):                            # vertical_cr_env.py:242-256,283-305
+        vs_cmd = float(np.asarray(action).reshape(-1)[0]) * 12.5
+        self.traf.selalt[0] = 1000000.0 if vs_cmd >= 0 else 0.0
+        self.traf.selvs[0] = vs_cmd
+        self._substeps()
+        obs = self._get_obs()
+        reward, terminated = self._get_reward()
+        return obs, reward, terminated, False, self._get_info()
+
+
+# =====================================================================================================
 SECTOR_CENTER = np.array([51.990426702297746, 4.376124857109851])     # sector_cr_env.py:16
 
 
@@ -428,4 +569,5 @@ class MergeEnv(_Base):
 
 
 ENVS = {"DescentEnv-v0": DescentEnv, "HorizontalCREnv-v0": HorizontalCREnv,
-        "SectorCREnv-v0": SectorCREnv, "MergeEnv-v0": MergeEnv}
+        "SectorCREnv-v0": SectorCREnv, "MergeEnv-v0": MergeEnv,
+        "PlanWaypointEnv-v0": PlanWaypointEnv, "VerticalCREnv-v0": VerticalCREnv}

@@ -33,6 +33,10 @@ def _make_oracle(env_id, draws=None, cd=False, n_int=5):
         return oenvs.DescentEnv(draws=draws)
     if env_id == "SectorCREnv-v0":
         return oenvs.SectorCREnv(draws=draws, cd_enabled=cd)
+    if env_id == "PlanWaypointEnv-v0":
+        return oenvs.PlanWaypointEnv(draws=draws)
+    if env_id == "VerticalCREnv-v0":
+        return oenvs.VerticalCREnv(draws=draws, cd_enabled=cd)
     return oenvs.MergeEnv(draws=draws, cd_enabled=cd)
 
 
@@ -44,8 +48,13 @@ def _inject(venv, e, oenv, env_id):
     f64, i32, poly = {}, {}, None
     if env_id == "HorizontalCREnv-v0":
         f64 = {_lib.F64_WPT_LAT: oenv.wpt_lat, _lib.F64_WPT_LON: oenv.wpt_lon}
-    elif env_id == "DescentEnv-v0":
+    elif env_id in ("DescentEnv-v0", "VerticalCREnv-v0"):
         f64 = {_lib.F64_TARGET_ALT: float(oenv.target_alt)}
+    elif env_id == "PlanWaypointEnv-v0":
+        f64 = {}
+        for k in range(5):
+            f64[_lib.F64_WPTS + 2 * k] = oenv.wpt_lat[k]
+            f64[_lib.F64_WPTS + 2 * k + 1] = oenv.wpt_lon[k]
     elif env_id == "SectorCREnv-v0":
         w = ogeo.nm_to_latlong(oenvs.SECTOR_CENTER, oenv.wpts[0])
         f64 = {_lib.F64_WPT_LAT: float(w[0]), _lib.F64_WPT_LON: float(w[1])}
@@ -95,6 +104,8 @@ def _compare_obs(gobs, oobs, e, step, vnorm=None, ownship_only=False):
     ("HorizontalCREnv-v0", 20, True, 25),
     ("SectorCREnv-v0", 0, True, 40),
     ("MergeEnv-v0", 0, False, 50),
+    ("PlanWaypointEnv-v0", 0, False, 60),
+    ("VerticalCREnv-v0", 0, True, 45),
 ])
 def test_step_parity_injected_state(cuda, env_id, n_int, cd, steps):
     from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
@@ -159,7 +170,8 @@ def test_step_parity_injected_state(cuda, env_id, n_int, cd, steps):
 
 
 @pytest.mark.parametrize("env_id,n_int", [("DescentEnv-v0", 0), ("HorizontalCREnv-v0", 5), ("HorizontalCREnv-v0", 20),
-                                          ("SectorCREnv-v0", 0), ("MergeEnv-v0", 0)])
+                                          ("SectorCREnv-v0", 0), ("MergeEnv-v0", 0), ("PlanWaypointEnv-v0", 0),
+                                          ("VerticalCREnv-v0", 0)])
 def test_device_reset_matches_philox_oracle(cuda, env_id, n_int):
     from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
     E, seed, off = 16, 99, 1000

@@ -190,7 +190,8 @@ def test_descent_episode_length_pin():
 def test_env_api_shapes_and_info_keys():
     np.random.seed(1)
     random.seed(1)
-    shapes = {"DescentEnv-v0": 4, "HorizontalCREnv-v0": 8, "SectorCREnv-v0": 10, "MergeEnv-v0": 12}
+    shapes = {"DescentEnv-v0": 4, "HorizontalCREnv-v0": 8, "SectorCREnv-v0": 10, "MergeEnv-v0": 12,
+              "PlanWaypointEnv-v0": 4, "VerticalCREnv-v0": 11}
     for name, cls in envs.ENVS.items():
         e = cls()
         obs, info = e.reset()
