@@ -10,13 +10,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbsg_b200.so")
 
 BSG_OK, BSG_EINVAL, BSG_ECUDA, BSG_ESTATE, BSG_ENOMEM = 0, -1, -2, -3, -4
-ENV_DESCENT, ENV_HORIZONTAL_CR, ENV_SECTOR_CR, ENV_MERGE, ENV_PLAN_WAYPOINT, ENV_VERTICAL_CR = 0, 1, 2, 3, 4, 5
+ENV_DESCENT, ENV_HORIZONTAL_CR, ENV_SECTOR_CR, ENV_MERGE, ENV_PLAN_WAYPOINT, ENV_VERTICAL_CR, ENV_STATIC_OBSTACLE = 0, 1, 2, 3, 4, 5, 6
 AUTORESET_DISABLED, AUTORESET_NEXT_STEP, AUTORESET_SAME_STEP = 0, 1, 2
 CD_LON_WRAP, CD_SYMMETRIC = 1, 2
 
 # indices into the per-env records (include/bsg.h)
 F64_WPT_LAT, F64_WPT_LON, F64_TARGET_ALT, F64_POLY_AREA, F64_WPTS, F64_COUNT = 0, 1, 2, 3, 4, 16
-F32_TOTAL_REWARD, F32_DRIFT_SUM, F32_FINAL_ALT, F32_LAST_HDG, F32_COUNT = 0, 1, 2, 3, 4
+F32_TOTAL_REWARD, F32_DRIFT_SUM, F32_FINAL_ALT, F32_LAST_HDG, F32_LAST_WDIST, F32_LAST_DRIFT, F32_COUNT = 0, 1, 2, 3, 4, 5, 8
 (I32_STEP, I32_EPISODE, I32_SIMK, I32_WPT_REACH, I32_DRIFT_N, I32_INTRUSIONS, I32_NUM_AC, I32_NVERT,
  I32_NEEDS_RESET, I32_FAF, I32_NCONF, I32_NLOS, I32_RESET_FLAGS) = range(13)
 I32_COUNT = 16

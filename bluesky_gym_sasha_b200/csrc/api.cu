@@ -65,6 +65,9 @@ extern "C" int bsg_query_layout(const bsg_config* cfg, bsg_layout* out) {
             out->slots = 1; out->obs_dim = 20; out->act_dim = 1; out->n_sub = 10; out->simdt = 1.0f; break;
         case BSG_ENV_VERTICAL_CR:        // vertical_cr_env.py:40,42,64-82,95
             out->slots = 8; out->obs_dim = 4 + 7 * 5; out->act_dim = 1; out->n_sub = 30; out->simdt = 1.0f; break;
+        case BSG_ENV_STATIC_OBSTACLE:    // static_obstacle_env.py:31,33,45-55,83
+            out->slots = 16; out->obs_dim = 3 + 4 * 10; out->act_dim = 2; out->n_sub = 10; out->simdt = 1.0f;
+            out->poly_f64 = 360; break;
         default:
             return bsg_fail(BSG_EINVAL, "unknown env_type");
     }

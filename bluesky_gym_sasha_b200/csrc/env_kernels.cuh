@@ -58,7 +58,8 @@ struct Ac {
 
 struct EnvS {
     double wpt_lat, wpt_lon, target_alt, poly_area;
-    float total_reward, drift_sum, final_alt;
+    float total_reward, drift_sum, final_alt, last_wdist, last_drift;
+    float step_reward; int step_done;      // StaticObstacle: outcome of the per-substep checks (not persisted)
     int step, episode, simk, wpt_reach, drift_n, intrusions, num_ac, nvert, needs_reset, faf, nconf, nlos, rflags;
 };
 
@@ -145,6 +146,7 @@ __device__ __forceinline__ void env_load(EnvS& s, const EnvParams& P, long long 
     s.wpt_lat = d[BSG_F64_WPT_LAT]; s.wpt_lon = d[BSG_F64_WPT_LON]; s.target_alt = d[BSG_F64_TARGET_ALT];
     s.poly_area = d[BSG_F64_POLY_AREA];
     s.total_reward = f[BSG_F32_TOTAL_REWARD]; s.drift_sum = f[BSG_F32_DRIFT_SUM]; s.final_alt = f[BSG_F32_FINAL_ALT];
+    s.last_wdist = f[BSG_F32_LAST_WDIST]; s.last_drift = f[BSG_F32_LAST_DRIFT]; s.step_reward = 0.0f; s.step_done = 0;
     s.step = i[BSG_I32_STEP]; s.episode = i[BSG_I32_EPISODE]; s.simk = i[BSG_I32_SIMK];
     s.wpt_reach = i[BSG_I32_WPT_REACH]; s.drift_n = i[BSG_I32_DRIFT_N]; s.intrusions = i[BSG_I32_INTRUSIONS];
     s.num_ac = i[BSG_I32_NUM_AC]; s.nvert = i[BSG_I32_NVERT]; s.needs_reset = i[BSG_I32_NEEDS_RESET];
@@ -157,7 +159,8 @@ __device__ __forceinline__ void env_load_pre(EnvS& s, const EnvParams& P, long l
     s.needs_reset = i[BSG_I32_NEEDS_RESET]; s.nconf = i[BSG_I32_NCONF]; s.nlos = i[BSG_I32_NLOS];
     s.nvert = i[BSG_I32_NVERT]; s.rflags = i[BSG_I32_RESET_FLAGS];
     s.wpt_lat = 0.0; s.wpt_lon = 0.0; s.target_alt = 0.0; s.poly_area = 0.0;
-    s.total_reward = 0.0f; s.drift_sum = 0.0f; s.final_alt = 0.0f;
+    s.total_reward = 0.0f; s.drift_sum = 0.0f; s.final_alt = 0.0f; s.last_wdist = 0.0f; s.last_drift = 0.0f;
+    s.step_reward = 0.0f; s.step_done = 0;
     s.step = 0; s.wpt_reach = 0; s.drift_n = 0; s.intrusions = 0; s.faf = 0;
 }
 __device__ __forceinline__ void env_load_post(EnvS& s, const EnvParams& P, long long e) {
@@ -167,6 +170,7 @@ __device__ __forceinline__ void env_load_post(EnvS& s, const EnvParams& P, long 
     s.wpt_lat = d[BSG_F64_WPT_LAT]; s.wpt_lon = d[BSG_F64_WPT_LON]; s.target_alt = d[BSG_F64_TARGET_ALT];
     s.poly_area = d[BSG_F64_POLY_AREA];
     s.total_reward = f[BSG_F32_TOTAL_REWARD]; s.drift_sum = f[BSG_F32_DRIFT_SUM]; s.final_alt = f[BSG_F32_FINAL_ALT];
+    s.last_wdist = f[BSG_F32_LAST_WDIST]; s.last_drift = f[BSG_F32_LAST_DRIFT];
     s.step = i[BSG_I32_STEP]; s.wpt_reach = i[BSG_I32_WPT_REACH]; s.drift_n = i[BSG_I32_DRIFT_N];
     s.intrusions = i[BSG_I32_INTRUSIONS]; s.faf = i[BSG_I32_FAF];
 }
@@ -181,6 +185,7 @@ __device__ __forceinline__ void env_store(const EnvS& s, const EnvParams& P, lon
     d[BSG_F64_WPT_LAT] = s.wpt_lat; d[BSG_F64_WPT_LON] = s.wpt_lon; d[BSG_F64_TARGET_ALT] = s.target_alt;
     d[BSG_F64_POLY_AREA] = s.poly_area;
     f[BSG_F32_TOTAL_REWARD] = s.total_reward; f[BSG_F32_DRIFT_SUM] = s.drift_sum; f[BSG_F32_FINAL_ALT] = s.final_alt;
+    f[BSG_F32_LAST_WDIST] = s.last_wdist; f[BSG_F32_LAST_DRIFT] = s.last_drift;
     i[BSG_I32_STEP] = s.step; i[BSG_I32_EPISODE] = s.episode; i[BSG_I32_SIMK] = s.simk;
     i[BSG_I32_WPT_REACH] = s.wpt_reach; i[BSG_I32_DRIFT_N] = s.drift_n; i[BSG_I32_INTRUSIONS] = s.intrusions;
     i[BSG_I32_NUM_AC] = s.num_ac; i[BSG_I32_NVERT] = s.nvert; i[BSG_I32_NEEDS_RESET] = s.needs_reset;

@@ -573,6 +573,144 @@ __device__ inline StepOut vertical_obs_reward(const Ac& a, EnvS& s, const EnvPar
 }
 
 // =====================================================================================================
+// StaticObstacleEnv (static_obstacle_env.py) -- G = 16: lane 0 flies the aircraft, lanes 0..9 each own one
+// polygon no-fly area.  poly record per env (doubles): [0,320) vertices [10][16][lat,lon]; [320,340) centres;
+// [340,350) radius NM; [350,360) vertex counts.
+// =====================================================================================================
+constexpr int kObsN = 10, kObsMaxV = 16, kObsCentre = 320, kObsRadius = 340, kObsNv = 350, kObsPoly = 360;
+
+__device__ inline void d_kwikqdrdist(double lata, double lona, double latb, double lonb, double& qdr, double& dnm) {
+    double dlat = (latb - lata) * kDeg2RadD;
+    double dlon = (dmod360((lonb - lona) + 180.0) - 180.0) * kDeg2RadD;
+    double cav = cos((lata + latb) * (0.5 * kDeg2RadD));
+    dnm = 6371000.0 * sqrt(dlat * dlat + dlon * dlon * cav * cav) / 1852.0;
+    qdr = dmod360(kRad2DegD * atan2(dlon * cav, dlat));
+}
+template <int G>
+__device__ inline int obstacles_hit(double lat, double lon, const double* pe, int slot) {
+    int inside = 0;                                   // areafilter.checkInside, one obstacle per lane
+    if (slot < kObsN) inside = d_inside_poly(lat, lon, pe + slot * (2 * kObsMaxV), (int)pe[kObsNv + slot]) ? 1 : 0;
+    return group_sum<G>(inside);
+}
+template <int G>
+__device__ inline void static_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot) {
+    double* pe = P.poly + e * kObsPoly;
+    double hdg = 0.0, wlat = 0.0, wlon = 0.0;
+    int rflags = 0;
+    const double lat0 = 52.0, lon0 = 4.0;
+    if (slot == 0) {                                                        // static_obstacle_env.py:96-131
+        Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);
+        uint32_t d = 0;
+        if (P.hdg_random) (void)rng.randint(d++, 1, 360);                   // cre's heading draw (overwritten below)
+        for (int i = 0; i < kObsN; ++i) {                                   // :221-232
+            int dis = rng.randint(d++, 20, 150), brg = rng.randint(d++, 0, 360);
+            d_point_at_distance(lat0, lon0, (double)dis, (double)brg, pe[kObsCentre + 2 * i], pe[kObsCentre + 2 * i + 1]);
+        }
+        for (int i = 0; i < kObsN; ++i) {                                   // _generate_polygon :156-169
+            const double R = sqrt((double)rng.randint(d++, 100, 1000) / 3.141592653589793);
+            double vx[kObsMaxV], vy[kObsMaxV], va[kObsMaxV];
+            int nv = 0;
+            auto insert_point = [&]() {
+                double al = 6.283185307179586 * rng.u01(d++);
+                double x = R * cos(al), y = R * sin(al), ang = atan2(y, x);
+                int k = nv;
+                while (k > 0 && va[k - 1] > ang) { vx[k] = vx[k - 1]; vy[k] = vy[k - 1]; va[k] = va[k - 1]; --k; }
+                vx[k] = x; vy[k] = y; va[k] = ang; ++nv;
+            };
+            auto shoelace = [&]() {
+                double acc = 0.0;
+                for (int q = 0; q < nv; ++q) { int r = (q + 1 == nv) ? 0 : q + 1; acc += vx[q] * vy[r] - vy[q] * vx[r]; }
+                return fabs(acc) / 2.0;
+            };
+            insert_point(); insert_point(); insert_point();
+            double area = shoelace();
+            while (area < 50.0 && nv < kObsMaxV) { insert_point(); area = shoelace(); }
+            if (area < 50.0) rflags |= 1;
+            const double clat = pe[kObsCentre + 2 * i], clon = pe[kObsCentre + 2 * i + 1];
+            const double cc = cos(clat * kDeg2RadD);
+            for (int q = 0; q < nv; ++q) {                                  // nm_to_latlong(centre, point)
+                pe[i * (2 * kObsMaxV) + 2 * q] = clat + vx[q] / 60.0;
+                pe[i * (2 * kObsMaxV) + 2 * q + 1] = clon + vy[q] / (60.0 * cc);
+            }
+            pe[kObsRadius + i] = R;
+            pe[kObsNv + i] = (double)nv;
+        }
+        int loops = 0;                                                      // _generate_waypoint :198-219
+        while (true) {
+            ++loops;
+            int dis = rng.randint(d++, 100, 170), brg = rng.randint(d++, 0, 360);
+            d_point_at_distance(lat0, lon0, (double)dis, (double)brg, wlat, wlon);
+            bool in = false;
+            for (int i = 0; i < kObsN; ++i) in |= d_inside_poly(wlat, wlon, pe + i * (2 * kObsMaxV), (int)pe[kObsNv + i]);
+            if (!in) break;
+            if (loops > 1000) { rflags |= 4; break; }
+        }
+        double dnm;
+        d_kwikqdrdist(lat0, lon0, wlat, wlon, hdg, dnm);                    // hdg = ap.trk = initial_wpt_qdr
+    }
+    __syncwarp(group_mask<G>());
+    rflags = group_bcast<G>(rflags, 0); wlat = group_bcast<G>(wlat, 0); wlon = group_bcast<G>(wlon, 0);
+    if (slot == 0) ac_create(a, lat0, lon0, hdg, 350.0, 150.0); else ac_clear(a);
+    s.wpt_lat = wlat; s.wpt_lon = wlon; s.rflags = rflags;
+    s.wpt_reach = 0; s.intrusions = 0; s.total_reward = 0.0f; s.drift_sum = 0.0f; s.drift_n = 0; s.num_ac = 1;
+}
+// static_obstacle_env.py:294-341 after every bs.sim.step(); returns true when the episode ends
+template <int G>
+__device__ inline bool static_substep_check(const Ac& a, EnvS& s, const EnvParams& P, long long e, int slot) {
+    const double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);
+    const int nin = obstacles_hit<G>(lat0, lon0, P.poly + e * kObsPoly, slot);
+    float r = 0.0f;
+    if (s.last_wdist < 5.0f && s.wpt_reach != 1) { s.wpt_reach = 1; r += 1.0f; }      // distance / drift of the last _get_obs
+    const float dr = fabsf(s.last_drift * kDeg2Rad);
+    s.drift_sum += dr; s.drift_n += 1;
+    r += dr * -0.01f;
+    if (nin) { r += -5.0f * (float)nin; s.intrusions = 1; }
+    s.step_reward = r;
+    s.step_done = (s.wpt_reach == 1 || nin) ? 1 : 0;
+    return s.step_done != 0;
+}
+template <int G>
+__device__ inline void static_action(Ac& a, const EnvParams& P, const float* act, int slot) {
+    if (slot == 0) {                                                        // static_obstacle_env.py:343-350
+        a.aptrk = wrap180_fold(a.hdg + act[0] * 45.0f);
+        a.flags &= ~kFlLnav;
+        float kt = (a.cas + act[1] * (20.0f / 3.0f)) * 1.94384f;
+        a.selspd = (kt > 0.1f && kt < 1.0f) ? kt : kt * kKts;
+    }
+}
+template <int G>
+__device__ inline StepOut static_obs_reward(const Ac& a, EnvS& s, const EnvParams& P, float* obs, int slot,
+                                            long long e, bool with_reward) {
+    const double* pe = P.poly + e * kObsPoly;                               // static_obstacle_env.py:234-283
+    const double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);
+    const float hdg0 = group_bcast<G>(a.hdg, 0);
+    float wq, wd;
+    kwikqdrdist(lat0, lon0, s.wpt_lat, s.wpt_lon, wq, wd);
+    s.last_wdist = wd * 1.852f;
+    s.last_drift = wrap180_fold(hdg0 - wq);
+    if (slot == 0) {
+        float sd, cd;
+        sincosf(s.last_drift * kDeg2Rad, &sd, &cd);
+        obs[0] = s.last_wdist * (1.0f / 170.0f); obs[1] = cd; obs[2] = sd;
+    }
+    if (slot < kObsN) {
+        float q, dnm, sb, cb;
+        kwikqdrdist(lat0, lon0, pe[kObsCentre + 2 * slot], pe[kObsCentre + 2 * slot + 1], q, dnm);
+        sincosf(wrap180_fold(hdg0 - q) * kDeg2Rad, &sb, &cb);
+        obs[3 + slot] = (float)pe[kObsRadius + slot] * (1.0f / 50.0f);
+        obs[13 + slot] = dnm * (1.852f / 170.0f);
+        obs[23 + slot] = cb;
+        obs[33 + slot] = sb;
+    }
+    StepOut o = {0.0f, 0, 0};
+    if (!with_reward) return o;
+    o.reward = s.step_reward;                          // the LAST substep's reward (static_obstacle_env.py:139-152)
+    o.terminated = s.step_done;
+    s.total_reward += o.reward;
+    return o;
+}
+
+// =====================================================================================================
 // dispatch helpers
 // =====================================================================================================
 template <int ENV, int G>
@@ -583,6 +721,7 @@ __device__ __forceinline__ void do_reset(Ac& a, EnvS& s, const EnvParams& P, lon
     if (ENV == BSG_ENV_MERGE) merge_reset<G>(a, s, P, e, slot);
     if (ENV == BSG_ENV_PLAN_WAYPOINT) planwp_reset<G>(a, s, P, e, slot);
     if (ENV == BSG_ENV_VERTICAL_CR) vertical_reset<G>(a, s, P, e, slot);
+    if (ENV == BSG_ENV_STATIC_OBSTACLE) static_reset<G>(a, s, P, e, slot);
     s.step = 0; s.needs_reset = 0; s.episode += 1; s.nconf = 0; s.nlos = 0;
 }
 template <int ENV, int G>
@@ -593,6 +732,7 @@ __device__ __forceinline__ StepOut do_obs(const Ac& a, EnvS& s, const EnvParams&
     if (ENV == BSG_ENV_SECTOR_CR) return sector_obs_reward<G>(a, s, P, obs, slot, e, with_reward);
     if (ENV == BSG_ENV_PLAN_WAYPOINT) return planwp_obs_reward<G>(a, s, P, obs, slot, e, with_reward);
     if (ENV == BSG_ENV_VERTICAL_CR) return vertical_obs_reward<G>(a, s, P, obs, slot, with_reward);
+    if (ENV == BSG_ENV_STATIC_OBSTACLE) return static_obs_reward<G>(a, s, P, obs, slot, e, with_reward);
     return merge_obs_reward<G>(a, s, P, obs, slot, with_reward);
 }
 template <int ENV>
@@ -603,6 +743,9 @@ __device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float
         info[0] = s.total_reward; info[1] = (float)__popc((unsigned)s.wpt_reach); info[2] = 0.0f; info[3] = 0.0f;
     } else if (ENV == BSG_ENV_VERTICAL_CR) {            // vertical_cr_env.py:202-211
         info[0] = s.total_reward; info[1] = (float)s.intrusions; info[2] = s.final_alt; info[3] = 0.0f;
+    } else if (ENV == BSG_ENV_STATIC_OBSTACLE) {        // static_obstacle_env.py:285-292
+        info[0] = s.total_reward; info[1] = (float)s.wpt_reach; info[2] = (float)s.intrusions;
+        info[3] = s.drift_sum / (float)s.drift_n;
     } else drift_info(s, info);
     info[4] = (float)s.nconf; info[5] = (float)s.nlos;
 }
@@ -649,6 +792,7 @@ __global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) 
             const float* act = P.actions + e * P.act_dim;
             if (ENV == BSG_ENV_DESCENT || ENV == BSG_ENV_VERTICAL_CR) descent_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_PLAN_WAYPOINT) horizontal_action<G>(a, P, act, slot);
+            if (ENV == BSG_ENV_STATIC_OBSTACLE) static_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_HORIZONTAL_CR) horizontal_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_SECTOR_CR) sector_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_MERGE) merge_action<G>(a, P, act, slot);
@@ -666,6 +810,10 @@ __global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) 
             }
             if (G > 1 && P.cd_enabled) group_cd<G>(a, alive, s.num_ac, P, s_rec, s_pairs, s_tmax, nconf, nlos);
             if (alive) ac_kinematics(a, P, T);
+            if (ENV == BSG_ENV_STATIC_OBSTACLE && P.mode == kModeStep) {   // per-substep reward / termination
+                if (k == 0) env_load_post(s, P, e);
+                if (static_substep_check<G>(a, s, P, e, slot)) break;
+            }
         }
         // update_airspeed's cas = vtas2cas(tas, alt) uses the altitude from before update_pos: T.at of the last substep
         if (alive && P.n_sub > 0) a.cas = tas2cas(a.tas, T.at);
@@ -675,7 +823,7 @@ __global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) 
             if (slot == 0) env_store_pre(s, P, e);
             return;
         }
-        env_load_post(s, P, e);
+        if (ENV != BSG_ENV_STATIC_OBSTACLE) env_load_post(s, P, e);
     }
 
 #pragma unroll 1
@@ -741,6 +889,8 @@ int bsg_launch_env(const EnvParams& P, int slots, cudaStream_t st) {
             return launch_env_t<BSG_ENV_PLAN_WAYPOINT, 1>(P, st);
         case BSG_ENV_VERTICAL_CR:
             return launch_env_t<BSG_ENV_VERTICAL_CR, 8>(P, st);
+        case BSG_ENV_STATIC_OBSTACLE:
+            return launch_env_t<BSG_ENV_STATIC_OBSTACLE, 16>(P, st);
     }
     return bsg_fail(BSG_EINVAL, "unknown env_type");
 }

@@ -78,23 +78,8 @@ class MergeEnv(_ScalarEnv):
     ENV_ID = "MergeEnv-v0"
 
 
-def _not_accelerated(env_id):
-    class _Stub(Env):
-        def __init__(self, *a, **k):
-            raise NotImplementedError(f"{env_id} is registered by the reference but is not on the accelerated "
-                                      "path yet (SURVEY.md section 8f)")
-    _Stub.__name__ = env_id.split("-")[0]
-    return _Stub
+class StaticObstacleEnv(_ScalarEnv):
+    ENV_ID = "StaticObstacleEnv-v0"
 
-
-class PlanWaypointEnv(_ScalarEnv):
-    ENV_ID = "PlanWaypointEnv-v0"
-
-
-class VerticalCREnv(_ScalarEnv):
-    ENV_ID = "VerticalCREnv-v0"
-
-
-StaticObstacleEnv = _not_accelerated("StaticObstacleEnv-v0")
 
 __all__ = [s.entry_point.split(":")[1] for s in SPECS.values()]

@@ -2,7 +2,7 @@
 from .gym_compat import register, registry
 from .spec import SPECS
 
-_OTHER = {"StaticObstacleEnv-v0": ("StaticObstacleEnv", 100)}
+_OTHER = {}
 
 
 def register_envs():

@@ -85,10 +85,16 @@ _add(EnvSpec(                                   # vertical_cr_env.py:64-82, :202
      ("x_difference_speed", 5, -INF, INF), ("y_difference_speed", 5, -INF, INF), ("z_difference_speed", 5, -INF, INF)),
     ("total_reward", "total_intrusions", "final_altitude")))
 
-# ids the reference registers (bluesky_gym/__init__.py:37-40) that are NOT on the
-# accelerated path yet.  Asking for them fails loudly rather than silently
-# running something else.
-NOT_ACCELERATED = ("StaticObstacleEnv-v0",)
+_add(EnvSpec(                                   # static_obstacle_env.py:45-55, :285-292
+    "StaticObstacleEnv-v0", _lib.ENV_STATIC_OBSTACLE, "bluesky_gym_sasha_b200.envs:StaticObstacleEnv", 100, 2,
+    (("destination_waypoint_distance", 1, -INF, INF), ("destination_waypoint_cos_drift", 1, -INF, INF),
+     ("destination_waypoint_sin_drift", 1, -INF, INF), ("restricted_area_radius", 10, 0, 1),
+     ("restricted_area_distance", 10, -INF, INF), ("cos_difference_restricted_area_pos", 10, -INF, INF),
+     ("sin_difference_restricted_area_pos", 10, -INF, INF)),
+    ("total_reward", "waypoint_reached", "crashed", "average_drift")))
+
+# every id the reference registers (bluesky_gym/__init__.py:7-46) is on the accelerated path
+NOT_ACCELERATED = ()
 
 # oracle/perf.py::A320 (kept in sync by tests/test_host_logic.py)
 A320_PERF = dict(vminto=73.3, vmaxic=88.5, vminer=64.0, vmaxer=163.0, vminap=64.0, vmaxap=78.0,

@@ -34,7 +34,8 @@ enum {
     BSG_ENV_SECTOR_CR = 2,      /* SectorCREnv-v0      sector_cr_env.py     */
     BSG_ENV_MERGE = 3,          /* MergeEnv-v0         merge_env.py         */
     BSG_ENV_PLAN_WAYPOINT = 4,  /* PlanWaypointEnv-v0  plan_waypoint_env.py */
-    BSG_ENV_VERTICAL_CR = 5     /* VerticalCREnv-v0    vertical_cr_env.py   */
+    BSG_ENV_VERTICAL_CR = 5,    /* VerticalCREnv-v0    vertical_cr_env.py   */
+    BSG_ENV_STATIC_OBSTACLE = 6 /* StaticObstacleEnv-v0 static_obstacle_env.py */
 };
 
 /* vector autoreset behaviour (gymnasium.vector.AutoresetMode) */
@@ -73,7 +74,7 @@ typedef struct bsg_layout {
     int32_t info_dim;           /* floats per env in info                                            */
     int32_t n_sub;              /* simulator substeps per env step (ACTION_FREQUENCY)                */
     int32_t env_f64, env_f32, env_i32; /* per-env scalar record widths                               */
-    int32_t poly_f64;           /* per-env polygon doubles (SectorCR: 2*32), else 0                  */
+    int32_t poly_f64;           /* per-env polygon doubles (SectorCR: 2*32; StaticObstacle: 360), else 0 */
     float simdt;
 } bsg_layout;
 
@@ -105,7 +106,8 @@ typedef struct bsg_tensor_table {
 /* indices into the per-env records (shared by all env types; unused slots stay zero) */
 enum { BSG_F64_WPT_LAT = 0, BSG_F64_WPT_LON = 1, BSG_F64_TARGET_ALT = 2, BSG_F64_POLY_AREA = 3,
        BSG_F64_WPTS = 4 /* PlanWaypoint: 5 x (lat, lon) */, BSG_F64_COUNT = 16 };
-enum { BSG_F32_TOTAL_REWARD = 0, BSG_F32_DRIFT_SUM = 1, BSG_F32_FINAL_ALT = 2, BSG_F32_LAST_HDG = 3, BSG_F32_COUNT = 4 };
+enum { BSG_F32_TOTAL_REWARD = 0, BSG_F32_DRIFT_SUM = 1, BSG_F32_FINAL_ALT = 2, BSG_F32_LAST_HDG = 3,
+       BSG_F32_LAST_WDIST = 4, BSG_F32_LAST_DRIFT = 5 /* StaticObstacle: values of the last _get_obs */, BSG_F32_COUNT = 8 };
 enum {
     BSG_I32_STEP = 0, BSG_I32_EPISODE = 1, BSG_I32_SIMK = 2, BSG_I32_WPT_REACH = 3, BSG_I32_DRIFT_N = 4,
     BSG_I32_INTRUSIONS = 5, BSG_I32_NUM_AC = 6, BSG_I32_NVERT = 7, BSG_I32_NEEDS_RESET = 8,

@@ -568,6 +568,130 @@ class MergeEnv(_Base):
         return obs, reward, terminated, False, info
 
 
+# =====================================================================================================
+class StaticObstacleEnv(_Base):
+    """static_obstacle_env.py.  DT 1 (:83), 10 substeps (:31), 1 aircraft, 10 polygon no-fly areas (:33).
+    ``max_vertices`` mirrors the device's per-obstacle vertex cap."""
+    SIMDT = 1.0
+    N_SUB = 10
+    NUM_OBSTACLES = 10
+
+    def __init__(self, max_vertices=16, **kw):
+        super().__init__(**kw)
+        self.max_vertices = max_vertices
+
+    def _generate_polygon(self, centre):               # static_obstacle_env.py:156-169
+        poly_area = self.draws.randint(100, 1000)
+        R = np.sqrt(poly_area / np.pi)
+
+        def pt():
+            al = 2.0 * np.pi * self.draws.uniform(0.0, 1.0)
+            return np.array([R * np.cos(al), R * np.sin(al)])
+        p = geo.sort_points_by_angle([pt() for _ in range(3)])
+        area = geo.polygon_area(p)
+        while area < 50.0 and len(p) < self.max_vertices:
+            p.append(pt())
+            p = geo.sort_points_by_angle(p)
+            area = geo.polygon_area(p)
+        return area, [geo.nm_to_latlong(centre, q) for q in p], R
+
+    def _inside_any(self, lat, lon):
+        return [bool(geo.point_in_polygon(lat, lon, v[:, 0], v[:, 1])) for v in self.obstacle_vertices]
+
+    def reset(self):                                   # static_obstacle_env.py:96-131
+        t = self.traf
+        t.reset()
+        self.total_reward = 0.0
+        self.waypoint_reached = 0
+        self.crashed = 0
+        self.drift_hist = []
+        t.cre("KL001", actype="A320", acspd=150.0, acalt=350.0)
+        lat0, lon0 = float(t.lat[0]), float(t.lon[0])
+        self.obstacle_centre_lat, self.obstacle_centre_lon = [], []
+        for _ in range(self.NUM_OBSTACLES):            # :221-232
+            dis = self.draws.randint(20, 150)
+            hdg = self.draws.randint(0, 360)
+            la, lo = geo.get_point_at_distance(lat0, lon0, dis, hdg)
+            self.obstacle_centre_lat.append(float(la))
+            self.obstacle_centre_lon.append(float(lo))
+        self.obstacle_vertices, self.obstacle_radius = [], []
+        for i in range(self.NUM_OBSTACLES):            # :171-196
+            _, p, R = self._generate_polygon((self.obstacle_centre_lat[i], self.obstacle_centre_lon[i]))
+            self.obstacle_vertices.append(np.array(p))
+            self.obstacle_radius.append(R)
+        loops = 0                                      # _generate_waypoint :198-219
+        while True:
+            loops += 1
+            dis = self.draws.randint(100, 170)
+            hdg = self.draws.randint(0, 360)
+            la, lo = geo.get_point_at_distance(lat0, lon0, dis, hdg)
+            if not any(self._inside_any(float(la), float(lo))):
+                break
+            if loops > 1000:
+                raise Exception("No waypoints can be generated outside the obstacles.")
+        self.wpt_lat, self.wpt_lon, self.wpt_reach = float(la), float(lo), 0
+        q, _ = geo.kwikqdrdist(lat0, lon0, self.wpt_lat, self.wpt_lon)
+        t.hdg[0] = float(q)
+        t.ap_trk[0] = float(q)
+        return self._get_obs(), self._get_info()
+
+    def _get_obs(self):                                # static_obstacle_env.py:234-283
+        t = self.traf
+        hdg = float(t.hdg[0])
+        wq, wd = geo.kwikqdrdist(t.lat[0], t.lon[0], self.wpt_lat, self.wpt_lon)
+        self.wpt_dis_km = float(wd) * NM2KM
+        self.drift = float(geo.wrap180_fold(hdg - float(wq)))
+        oq, od = geo.kwikqdrdist(t.lat[0], t.lon[0], np.array(self.obstacle_centre_lat), np.array(self.obstacle_centre_lon))
+        brg = np.radians(geo.wrap180_fold(hdg - oq))
+        return {"destination_waypoint_distance": _a1(self.wpt_dis_km / 170.0),
+                "destination_waypoint_cos_drift": _a1(np.cos(np.radians(self.drift))),
+                "destination_waypoint_sin_drift": _a1(np.sin(np.radians(self.drift))),
+                "restricted_area_radius": np.array(self.obstacle_radius) / 50.0,
+                "restricted_area_distance": od * NM2KM / 170.0,
+                "cos_difference_restricted_area_pos": np.cos(brg),
+                "sin_difference_restricted_area_pos": np.sin(brg)}
+
+    def _get_info(self):                               # static_obstacle_env.py:285-292
+        return {"total_reward": self.total_reward, "waypoint_reached": self.waypoint_reached, "crashed": self.crashed,
+                "average_drift": float(np.mean(self.drift_hist)) if self.drift_hist else float("nan")}
+
+    def _get_reward(self):                             # static_obstacle_env.py:294-341
+        # NB the waypoint distance and drift are the ones of the LAST _get_obs (not refreshed per substep)
+        r = 0.0
+        if self.wpt_dis_km < 5.0 and self.wpt_reach != 1:
+            self.waypoint_reached = 1
+            self.wpt_reach = 1
+            r += 1.0
+        d = abs(np.radians(self.drift))
+        self.drift_hist.append(d)
+        r += d * -0.01
+        t = self.traf
+        nin = sum(self._inside_any(float(t.lat[0]), float(t.lon[0])))
+        if nin:
+            r += -5.0 * nin
+            self.crashed = 1
+        done = 1 if (self.wpt_reach == 1 or nin) else 0
+        return r, done
+
+    def step(self, action):                            # static_obstacle_env.py:133-154,343-350
+        a = np.asarray(action, dtype=np.float64).reshape(-1)
+        t = self.traf
+        hdg_new = float(geo.wrap180_fold(t.hdg[0] + a[0] * 45.0))
+        spd_new = (t.cas[0] + a[1] * (20.0 / 3.0)) * MpS2Kt
+        t.stack_hdg("KL001", hdg_new)
+        t.stack_spd("KL001", spd_new)
+        reward, done = 0.0, 0
+        for _ in range(self.N_SUB):
+            t.simstep()
+            reward, done = self._get_reward()          # per substep; only the last one is returned
+            if done:
+                break
+        obs = self._get_obs()
+        self.total_reward += reward
+        return obs, reward, done, False, self._get_info()
+
+
 ENVS = {"DescentEnv-v0": DescentEnv, "HorizontalCREnv-v0": HorizontalCREnv,
         "SectorCREnv-v0": SectorCREnv, "MergeEnv-v0": MergeEnv,
-        "PlanWaypointEnv-v0": PlanWaypointEnv, "VerticalCREnv-v0": VerticalCREnv}
+        "PlanWaypointEnv-v0": PlanWaypointEnv, "VerticalCREnv-v0": VerticalCREnv,
+        "StaticObstacleEnv-v0": StaticObstacleEnv}

@@ -21,7 +21,7 @@ def synth_airspace(n, box_deg=40.0, seed=0, lat0=52.0, lon0=4.0, alt_jitter=20.0
     return lat, lon, trk, gs, alt, vs
 
 
-def inject_oracle_env(venv, e, oenv, extra_f64=None, extra_i32=None, poly=None):
+def inject_oracle_env(venv, e, oenv, extra_f64=None, extra_i32=None, poly=None, extra_f32=None):
     """Copies an oracle env's post-reset traffic into slot e of a BlueSkyVectorEnv (bsg_load_state)."""
     t = oenv.traf
     lnav = t.swlnav.copy()
@@ -30,6 +30,7 @@ def inject_oracle_env(venv, e, oenv, extra_f64=None, extra_i32=None, poly=None):
            _lib.I32_FAF: 0}
     i32.update(extra_i32 or {})
     f32 = {_lib.F32_TOTAL_REWARD: 0.0, _lib.F32_DRIFT_SUM: 0.0, _lib.F32_FINAL_ALT: 0.0}
+    f32.update(extra_f32 or {})
     venv.load_state(e, t.lat, t.lon, t.alt, t.tas, t.hdg, t.vs, t.selspd, t.selalt, t.selvs, t.ap_trk, t.cas,
                     ax=t.ax, lnav=lnav, iactwp=np.array(t.iactwp), curlegdir=t.curlegdir,
                     env_f64=extra_f64, env_i32=i32, env_f32=f32, poly=poly)

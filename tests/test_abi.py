@@ -30,7 +30,8 @@ def test_layout_queries(lib):
     from bluesky_gym_sasha_b200 import _lib, spec
     want = {"DescentEnv-v0": (1, 4, 1, 30, 1.0), "HorizontalCREnv-v0": (8, 28, 1, 10, 5.0),
             "SectorCREnv-v0": (32, 31, 2, 5, 1.0), "MergeEnv-v0": (32, 40, 2, 10, 5.0),
-            "PlanWaypointEnv-v0": (1, 20, 1, 10, 1.0), "VerticalCREnv-v0": (8, 39, 1, 30, 1.0)}
+            "PlanWaypointEnv-v0": (1, 20, 1, 10, 1.0), "VerticalCREnv-v0": (8, 39, 1, 30, 1.0),
+            "StaticObstacleEnv-v0": (16, 43, 2, 10, 1.0)}
     for env_id, s in spec.SPECS.items():
         lay = _lib.query_layout(_lib.Config(env_type=s.env_type, num_envs=3, n_intruders=5))
         assert (lay.slots, lay.obs_dim, lay.act_dim, lay.n_sub, lay.simdt) == want[env_id]

@@ -37,6 +37,8 @@ def _make_oracle(env_id, draws=None, cd=False, n_int=5):
         return oenvs.PlanWaypointEnv(draws=draws)
     if env_id == "VerticalCREnv-v0":
         return oenvs.VerticalCREnv(draws=draws, cd_enabled=cd)
+    if env_id == "StaticObstacleEnv-v0":
+        return oenvs.StaticObstacleEnv(draws=draws)
     return oenvs.MergeEnv(draws=draws, cd_enabled=cd)
 
 
@@ -45,7 +47,7 @@ def _inject(venv, e, oenv, env_id):
     for cmd in t.queue:             # MergeEnv: the queued addwpt/dest run at the start of the first sim step
         cmd()
     t.queue = []
-    f64, i32, poly = {}, {}, None
+    f64, i32, poly, f32 = {}, {}, None, {}
     if env_id == "HorizontalCREnv-v0":
         f64 = {_lib.F64_WPT_LAT: oenv.wpt_lat, _lib.F64_WPT_LON: oenv.wpt_lon}
     elif env_id in ("DescentEnv-v0", "VerticalCREnv-v0"):
@@ -60,7 +62,16 @@ def _inject(venv, e, oenv, env_id):
         f64 = {_lib.F64_WPT_LAT: float(w[0]), _lib.F64_WPT_LON: float(w[1])}
         i32 = {_lib.I32_NVERT: len(oenv.poly_lat)}
         poly = np.stack([oenv.poly_lat, oenv.poly_lon], axis=1).reshape(-1)
-    inject_oracle_env(venv, e, oenv, extra_f64=f64, extra_i32=i32, poly=poly)
+    elif env_id == "StaticObstacleEnv-v0":
+        f64 = {_lib.F64_WPT_LAT: oenv.wpt_lat, _lib.F64_WPT_LON: oenv.wpt_lon}
+        f32 = {_lib.F32_LAST_WDIST: oenv.wpt_dis_km, _lib.F32_LAST_DRIFT: oenv.drift}
+        poly = np.zeros(360)
+        for k, v in enumerate(oenv.obstacle_vertices):
+            poly[k * 32:k * 32 + 2 * len(v)] = np.asarray(v).reshape(-1)
+            poly[350 + k] = len(v)
+        poly[320:340] = np.stack([oenv.obstacle_centre_lat, oenv.obstacle_centre_lon], axis=1).reshape(-1)
+        poly[340:350] = oenv.obstacle_radius
+    inject_oracle_env(venv, e, oenv, extra_f64=f64, extra_i32=i32, poly=poly, extra_f32=f32)
 
 
 def _compare_traffic(venv, oracles, alive_mask, step, exempt=None):
@@ -106,6 +117,7 @@ def _compare_obs(gobs, oobs, e, step, vnorm=None, ownship_only=False):
     ("MergeEnv-v0", 0, False, 50),
     ("PlanWaypointEnv-v0", 0, False, 60),
     ("VerticalCREnv-v0", 0, True, 45),
+    ("StaticObstacleEnv-v0", 0, False, 100),
 ])
 def test_step_parity_injected_state(cuda, env_id, n_int, cd, steps):
     from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
@@ -171,7 +183,7 @@ def test_step_parity_injected_state(cuda, env_id, n_int, cd, steps):
 
 @pytest.mark.parametrize("env_id,n_int", [("DescentEnv-v0", 0), ("HorizontalCREnv-v0", 5), ("HorizontalCREnv-v0", 20),
                                           ("SectorCREnv-v0", 0), ("MergeEnv-v0", 0), ("PlanWaypointEnv-v0", 0),
-                                          ("VerticalCREnv-v0", 0)])
+                                          ("VerticalCREnv-v0", 0), ("StaticObstacleEnv-v0", 0)])
 def test_device_reset_matches_philox_oracle(cuda, env_id, n_int):
     from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
     E, seed, off = 16, 99, 1000

@@ -20,11 +20,9 @@ def test_register_envs_ids_and_caps():
         assert k in registry and registry[k].max_episode_steps == v
 
 
-def test_not_accelerated_ids_fail_loudly():
-    import bluesky_gym
-    bluesky_gym.register_envs()
-    with pytest.raises(NotImplementedError):
-        bluesky_gym.make("StaticObstacleEnv-v0")
+def test_all_reference_ids_are_accelerated():
+    from bluesky_gym_sasha_b200.spec import NOT_ACCELERATED, SPECS
+    assert NOT_ACCELERATED == () and len(SPECS) == 7
 
 
 def test_obs_layout_matches_reference_declarations():

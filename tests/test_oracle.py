@@ -191,12 +191,12 @@ def test_env_api_shapes_and_info_keys():
     np.random.seed(1)
     random.seed(1)
     shapes = {"DescentEnv-v0": 4, "HorizontalCREnv-v0": 8, "SectorCREnv-v0": 10, "MergeEnv-v0": 12,
-              "PlanWaypointEnv-v0": 4, "VerticalCREnv-v0": 11}
+              "PlanWaypointEnv-v0": 4, "VerticalCREnv-v0": 11, "StaticObstacleEnv-v0": 7}
     for name, cls in envs.ENVS.items():
         e = cls()
         obs, info = e.reset()
         assert len(obs) == shapes[name] and all(v.dtype == np.float64 and v.ndim == 1 for v in obs.values())
-        obs, r, term, trunc, info = e.step(np.zeros(2) if name in ("SectorCREnv-v0", "MergeEnv-v0") else np.zeros(1))
+        obs, r, term, trunc, info = e.step(np.zeros(2) if name in ("SectorCREnv-v0", "MergeEnv-v0", "StaticObstacleEnv-v0") else np.zeros(1))
         assert "total_reward" in info and np.isfinite(r)
     assert envs.MAX_EPISODE_STEPS["MergeEnv-v0"] == 50 and envs.MAX_EPISODE_STEPS["SectorCREnv-v0"] == 200
 
