@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbsg_b200.so")
+LIB_PATH = os.environ.get("BSG_B200_LIB", os.path.join(_HERE, "libbsg_b200.so"))    # override: A/B builds
 
 BSG_OK, BSG_EINVAL, BSG_ECUDA, BSG_ESTATE, BSG_ENOMEM = 0, -1, -2, -3, -4
 ENV_DESCENT, ENV_HORIZONTAL_CR, ENV_SECTOR_CR, ENV_MERGE, ENV_PLAN_WAYPOINT, ENV_VERTICAL_CR, ENV_STATIC_OBSTACLE = 0, 1, 2, 3, 4, 5, 6

@@ -94,18 +94,21 @@ __device__ __forceinline__ CdSym cd_pair_sym(const float4 Ai, const float4 Bi, c
     float dx = dxl * cav;
     float du = Bj.x - Bi.x, dv = Bj.y - Bi.y;
     float dv2r = fmaf(du, du, dv * dv);
-    bool clamped = dv2r < 1e-6f;
-    float dv2 = clamped ? 1e-6f : dv2r;
+    float dv2 = fmaxf(dv2r, 1e-6f);
     float dot = fmaf(du, dx, dv * dy);
     float crs = fmaf(dx, dv, -dy * du);
     float inv = rcp_approx(dv2);
     float tcpa = -dot * inv;
-    float dist2 = fmaf(dx, dx, dy * dy);
-    float dcpa2 = clamped ? fabsf(fmaf(-tcpa * tcpa, dv2, dist2)) : crs * crs * inv;
+    float dcpa2 = crs * crs * inv;
+    if (dv2r < 1e-6f) {            // co-moving pair (rare): upstream's literal |dist^2 - tcpa^2 dv2| with the clamp
+        float dist2 = fmaf(dx, dx, dy * dy);
+        dcpa2 = fabsf(fmaf(-tcpa * tcpa, dv2, dist2));
+    }
     bool swhor = dcpa2 < R2;
+    // sqrt of a negative number is NaN when dcpa >= R; fmaxf / fminf drop the NaN operand and the
+    // predicates below require swhor anyway, so no select is needed for the 1e8 / -1e8 sentinels
     float dtin = sqrt_approx((R2 - dcpa2) * inv);
-    float tinhor = swhor ? tcpa - dtin : 1e8f;
-    float touthor = swhor ? tcpa + dtin : -1e8f;
+    float tinhor = tcpa - dtin, touthor = tcpa + dtin;
     float dalt = Bj.z - Bi.z;
     float dvs = Bj.w - Bi.w;
     bool vclamp = fabsf(dvs) < 1e-6f;
@@ -119,7 +122,8 @@ __device__ __forceinline__ CdSym cd_pair_sym(const float4 Ai, const float4 Bi, c
     CdSym o;
     o.conf_ij = swhor && (tin <= tout) && (tout > 0.0f) && (tin < dtlook);
     o.conf_ji = swhor && (tinr <= toutr) && (toutr > 0.0f) && (tinr < dtlook);
-    o.los = (dist2 < R2) && (fabsf(dalt) < hpz);
+    // LoS (dist < R and |dalt| < hpz) implies dcpa < R: only looked at under swhor
+    o.los = swhor && (fmaf(dx, dx, dy * dy) < R2) && (fabsf(dalt) < hpz);
     o.tcpa = tcpa;
     return o;
 }

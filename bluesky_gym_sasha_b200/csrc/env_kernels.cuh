@@ -53,6 +53,7 @@ struct Ac {
     float ax, curlegdir, cas;
     uint32_t flags;
     float gsn, gse;           // cached tas*cos(hdg), tas*sin(hdg) of the last groundspeed update
+    float coslat;             // cached cos(lat) of the last position update
     float tcpamax; bool inconf;
 };
 
@@ -106,12 +107,13 @@ __device__ inline void ac_create(Ac& a, double lat, double lon, double hdg, doub
     a.flags = kFlAlive;
     double hr = hdg * kDeg2RadD;
     a.gsn = (float)(tas * cos(hr)); a.gse = (float)(tas * sin(hr));
+    a.coslat = (float)cos(a.lat * kDeg2RadD);
     a.tcpamax = 0.0f; a.inconf = false;
 }
 __device__ inline void ac_clear(Ac& a) {
     a.lat = 0.0; a.lon = 0.0; a.alt = 0.0f; a.tas = 0.0f; a.hdg = 0.0f; a.vs = 0.0f;
     a.selspd = 0.0f; a.selalt = 0.0f; a.selvs = 0.0f; a.aptrk = 0.0f; a.ax = 0.0f; a.curlegdir = -999.0f;
-    a.cas = 0.0f; a.flags = 0u; a.gsn = 0.0f; a.gse = 0.0f; a.tcpamax = 0.0f; a.inconf = false;
+    a.cas = 0.0f; a.flags = 0u; a.gsn = 0.0f; a.gse = 0.0f; a.coslat = 1.0f; a.tcpamax = 0.0f; a.inconf = false;
 }
 
 // ---- state I/O (coalesced: consecutive lanes -> consecutive float4 / double2) ----------------------
@@ -126,6 +128,7 @@ __device__ __forceinline__ void ac_load(Ac& a, const EnvParams& P, long long idx
     float s, co;
     sincosf(a.hdg * kDeg2Rad, &s, &co);
     a.gsn = a.tas * co; a.gse = a.tas * s;
+    a.coslat = cosf((float)a.lat * kDeg2Rad);
     a.tcpamax = 0.0f; a.inconf = false;
 }
 __device__ __forceinline__ void ac_store(const Ac& a, const EnvParams& P, long long idx) {
@@ -298,14 +301,16 @@ __device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const T
     a.vs = need_az ? a.vs + copysignf(kAzMax, delta_vs) * dt : target_vs;
     if (!isfinite(a.vs)) a.vs = 0.0f;
     // ---- update_groundspeed (no wind: gs = tas, trk = hdg)
+    // hdg is in [0, 360): evaluate at hdg - 180 in [-pi, pi) where the MUFU sin/cos are accurate to ~5e-7,
+    // and flip the signs (sin(x + pi) = -sin x, cos(x + pi) = -cos x)
     float sh, ch;
-    sincosf(a.hdg * kDeg2Rad, &sh, &ch);
-    a.gsn = a.tas * ch; a.gse = a.tas * sh;
+    __sincosf((a.hdg - 180.0f) * kDeg2Rad, &sh, &ch);
+    a.gsn = -a.tas * ch; a.gse = -a.tas * sh;
     // ---- update_pos (lat/lon accumulate in float64)
     a.alt = swaltsel ? a.alt + a.vs * dt : allow_h;
     a.lat += (double)(kRad2Deg * (dt * a.gsn * (1.0f / kRearth)));
-    float coslat = cosf((float)a.lat * kDeg2Rad);
-    a.lon += (double)(kRad2Deg * (dt * a.gse / coslat * (1.0f / kRearth)));
+    a.coslat = __cosf((float)a.lat * kDeg2Rad);          // |lat| <= 90 deg: MUFU.COS is accurate to ~3e-7 here
+    a.lon += (double)(kRad2Deg * (dt * a.gse / a.coslat * (1.0f / kRearth)));
 }
 
 // ====================================================================================================
@@ -335,8 +340,9 @@ __device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvPa
     const int gbase = threadIdx.x - lane_g;           // first thread of this group in the block
     const int wbase = lane - lane_g;                  // first lane of this group in the warp
     double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);
-    float sh, ch;
-    sincosf((float)a.lat * (0.5f * kDeg2Rad), &sh, &ch);
+    // cos / sin of lat/2 from the cached cos(lat): half-angle identities (absolute error ~1e-7)
+    const float ch = sqrtf(fmaf(0.5f, a.coslat, 0.5f));
+    const float sh = copysignf(sqrtf(fmaxf(fmaf(-0.5f, a.coslat, 0.5f), 0.0f)), (float)a.lat);
     double dl = a.lon - lon0;
     dl = dl > 180.0 ? dl - 360.0 : (dl < -180.0 ? dl + 360.0 : dl);
     s_rec[2 * threadIdx.x] = make_float4((float)(kRearthD * kDeg2RadD * dl), (float)(kRearthD * kDeg2RadD * (a.lat - lat0)), ch, sh);
@@ -346,8 +352,10 @@ __device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvPa
     const int npairs = nac * (nac - 1) / 2;
     unsigned confmask = 0u;       // bit = warp lane of an aircraft that is in conflict (this lane's pairs only)
     int nc = 0, nl = 0;           // ordered conflict pairs / ordered LoS pairs found by this lane
+    unsigned ij_next = lane_g < npairs ? s_pairs[lane_g] : 0u;
     for (int p = lane_g; p < npairs; p += G) {
-        const unsigned ij = s_pairs[p];
+        const unsigned ij = ij_next;
+        if (p + G < npairs) ij_next = s_pairs[p + G];      // next round's pair: off the critical path
         const int i = (int)(ij >> 8), j = (int)(ij & 0xffu);
         CdSym r = cd_pair_sym(s_rec[2 * (gbase + i)], s_rec[2 * (gbase + i) + 1], s_rec[2 * (gbase + j)],
                               s_rec[2 * (gbase + j) + 1], P.R2, P.hpz, P.dtlook);

@@ -816,7 +816,9 @@ __global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) 
             }
         }
         // update_airspeed's cas = vtas2cas(tas, alt) uses the altitude from before update_pos: T.at of the last substep
-        if (alive && P.n_sub > 0) a.cas = tas2cas(a.tas, T.at);
+        // (only the envs whose action reads traf.cas need it: Sector, Merge, StaticObstacle)
+        if ((ENV == BSG_ENV_SECTOR_CR || ENV == BSG_ENV_MERGE || ENV == BSG_ENV_STATIC_OBSTACLE || P.mode == kModeTraf) &&
+            alive && P.n_sub > 0) a.cas = tas2cas(a.tas, T.at);
         s.nconf = nconf; s.nlos = nlos;
         if (P.mode == kModeTraf) {
             ac_store(a, P, gt);
