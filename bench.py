@@ -99,23 +99,46 @@ def workload_config(n_gpus):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML every ~2 ms (an nvidia-smi process
+    per sample would be slower than the whole region), nvidia-smi only when NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         self.samples, self.stop, self.index = [], False, index
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                         pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
         self.th = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
         while not self.stop:
             try:
+                if self.nvml is not None:
+                    mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+                    r = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    self.samples.append([mhz, self.max_mhz] + [bool(r & b) for b in self.bits])
+                    time.sleep(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                    f = [x.strip() for x in out.split(",")]
+                    self.samples.append([float(f[0]), float(f[1])] + [x.lower().startswith("active") for x in f[2:6]])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def __enter__(self):
         self.th.start()
@@ -128,11 +151,10 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2 + i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -243,8 +265,15 @@ def run_b200(args):
         fp32 = C_double_probe(lib, local)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         achieved_tf = FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        try:        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["env_kernel<1, 32>"]
+            traffic, traffic_src = tr["dram_bytes_read"] + tr["dram_bytes_write"], "profiles/ncu_traffic.json <- " + tr["source"]
+        except Exception:
+            pass
         roof = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32 / 1e12, "unit": "TFLOP/s",
-                "frac": achieved_tf / (fp32 / 1e12), "traffic": None, "kernel": "env_kernel<HorizontalCR,32>",
+                "frac": achieved_tf / (fp32 / 1e12), "traffic": traffic, "traffic_unit": "bytes per launch (DRAM)",
+                "traffic_source": traffic_src, "kernel": "env_kernel<HorizontalCR,32>",
                 "peak_source": "bsg_probe_fp32 (dense FFMA, measured in this run)",
                 "flop_per_env_step": FLOP_PER_ENV_STEP,
                 "hbm": {"achieved": BYTES_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -252,7 +281,7 @@ def run_b200(args):
                         "bytes_per_env_step": BYTES_PER_ENV_STEP}}
         # CD at N = 100k on this GPU (BASELINE configs[4], single-GPU share)
         cd = bench_cd(torch, dev, StateBasedCD, fp32)
-        cb = None if args.skip_cpu else cpu_baseline(budget_s=10.0)
+        cb = None if (args.skip_cpu or world > 1) else cpu_baseline(budget_s=10.0)
         line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (lat/lon f64)", "data": "synthetic", "config": workload_config(world),

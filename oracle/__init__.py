@@ -8,7 +8,13 @@ golden vectors or fixtures.  Everything tagged [UPSTREAM-RECALL] below is a rest
 sites (cited per function).  The in-tree parts (env reset / action / obs / reward logic,
 ``common/functions.py``) are restated from the reference files directly and cited file:line.
 
-What pins exist (tests/test_oracle_*.py): closed-form geo/aero cases, the ISA ``vcas2tas`` table,
+PARTIAL PIN (tests/golden/, tests/test_golden.py): the in-tree half of the path IS pinned -- the
+reference's own env files and ``common/functions.py`` are executed unmodified in the build container
+(``oracle/bs_shim.py`` stands in for the absent ``bluesky`` package, backed by oracle/traffic.py) and
+their reset / step outputs are committed as golden vectors; oracle/envs.py reproduces them to 1e-9 and
+the CUDA path to the stated float32 tolerances.  The simulator core under ``bs.*`` stays unpinned.
+
+Other pins (tests/test_oracle.py): closed-form geo/aero cases, the ISA ``vcas2tas`` table,
 ``creconfs`` -> ``detect`` round trips, and the distribution-level episode-length pins derived from
 the reference's shipped training logs.
 

@@ -1,0 +1,188 @@
+"""Golden fixtures produced by the REFERENCE's own code (tests/golden/make_golden.py, run in the build container):
+
+* ``ref_functions.npz``: ``bluesky_gym/envs/common/functions.py`` imported as is;
+* ``ref_<EnvId>.npz``: the reference's env classes executed over ``oracle/bs_shim.py`` (reference env logic on
+  the oracle's restated BlueSky core), 3 seeds x 100-120 rows of reset / step outputs each, episodes run to
+  termination / TimeLimit truncation and continue with un-reseeded resets.
+
+CPU tests pin oracle/geo.py and oracle/envs.py to those vectors (float64, 1e-9); the GPU test steps the CUDA
+path through the C ABI on the same actions from the same post-reset state and compares it with the GOLDEN rows
+(float32 kernels: tolerances of tests/test_gpu_env.py).  Nothing here reads /root/reference.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import envs as oenvs
+from oracle import geo as ogeo
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ENV_IDS = ["DescentEnv-v0", "PlanWaypointEnv-v0", "HorizontalCREnv-v0", "VerticalCREnv-v0", "SectorCREnv-v0",
+           "StaticObstacleEnv-v0", "MergeEnv-v0"]
+TRAF_FIELDS = ("lat", "lon", "alt", "hdg", "tas", "vs")
+
+
+def _oracle(env_id):
+    return {"DescentEnv-v0": oenvs.DescentEnv, "PlanWaypointEnv-v0": oenvs.PlanWaypointEnv,
+            "HorizontalCREnv-v0": oenvs.HorizontalCREnv, "VerticalCREnv-v0": oenvs.VerticalCREnv,
+            "SectorCREnv-v0": oenvs.SectorCREnv, "StaticObstacleEnv-v0": oenvs.StaticObstacleEnv,
+            "MergeEnv-v0": oenvs.MergeEnv}[env_id]()
+
+
+def _rows(g, seed):
+    p = f"s{seed}_"
+    obs_keys = [k[len(p) + 4:] for k in g.files if k.startswith(p + "obs_")]
+    info_keys = [k[len(p) + 5:] for k in g.files if k.startswith(p + "info_")]
+    return p, obs_keys, info_keys
+
+
+# ----------------------------------------------------------------------------------------------- CPU pins
+def test_functions_match_reference_golden():
+    g = np.load(os.path.join(GOLD, "ref_functions.npz"))
+    np.testing.assert_allclose([ogeo.wrap180_fold(a) for a in g["wrap_in"]], g["wrap_out"], rtol=0, atol=1e-12)
+    out = np.array([ogeo.get_point_at_distance(*r) for r in g["gpad_in"]])
+    np.testing.assert_allclose(out, g["gpad_out"], rtol=0, atol=1e-11)
+    c = g["center"]
+    ll = np.array([ogeo.nm_to_latlong(c, p) for p in g["nm_in"]])
+    np.testing.assert_allclose(ll, g["nm2ll_out"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose([ogeo.latlong_to_nm(c, q) for q in g["nm2ll_out"]], g["ll2nm_out"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose([ogeo.get_hdg(a, b) for a, b in zip(g["hdg_in_a"], g["hdg_in_b"])], g["hdg_out"],
+                               rtol=0, atol=1e-9)
+    for v, s, area in zip(g["poly_in"], g["poly_sorted"], g["poly_area"]):
+        n = int(np.sum(np.isfinite(v[:, 0])))
+        mine = np.array(ogeo.sort_points_by_angle(list(v[:n])))
+        np.testing.assert_allclose(mine, s[:n], rtol=0, atol=0)
+        assert abs(ogeo.polygon_area(list(mine)) - area) < 1e-9
+
+
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_oracle_env_matches_reference_golden(env_id):
+    g = np.load(os.path.join(GOLD, f"ref_{env_id}.npz"))
+    cap = int(g["cap"])
+    n_rows = n_term = n_trunc = 0
+    for seed in g["seeds"]:
+        p, obs_keys, info_keys = _rows(g, seed)
+        np.random.seed(int(seed))
+        random.seed(int(seed))
+        env = _oracle(env_id)
+        t = 0
+        for r in range(len(g[p + "is_reset"])):
+            if g[p + "is_reset"][r]:
+                obs, info = env.reset()
+                rew, term, trunc, t = 0.0, False, False, 0
+            else:
+                obs, rew, term, trunc, info = env.step(g[p + "action"][r].copy())
+                t += 1
+                trunc = bool(trunc) or t >= cap
+            where = (env_id, int(seed), r)
+            for k in obs_keys:
+                np.testing.assert_allclose(np.asarray(obs[k], dtype=np.float64).reshape(-1), g[p + "obs_" + k][r],
+                                           rtol=0, atol=1e-9, err_msg=str(where + (k,)))
+            assert abs(rew - g[p + "reward"][r]) < 1e-9, where
+            assert bool(term) == bool(g[p + "terminated"][r]) and bool(trunc) == bool(g[p + "truncated"][r]), where
+            for k in info_keys:
+                a, b = float(info[k]), float(g[p + "info_" + k][r])
+                assert (np.isnan(a) and np.isnan(b)) or abs(a - b) < 1e-9, where + (k, a, b)
+            n = int(g[p + "ntraf"][r])
+            if not (term and env_id in ("DescentEnv-v0", "PlanWaypointEnv-v0", "HorizontalCREnv-v0", "VerticalCREnv-v0")):
+                # (after a terminal step the reference has run its delete loop; the oracle resets instead)
+                assert env.traf.ntraf == n, where
+                for f in TRAF_FIELDS:
+                    np.testing.assert_allclose(getattr(env.traf, f)[:n], g[p + "traf_" + f][r, :n], rtol=0, atol=1e-9,
+                                               err_msg=str(where + (f,)))
+            n_rows += 1
+            n_term += bool(term)
+            n_trunc += bool(trunc)
+    assert n_rows >= 300
+    print(f"{env_id}: {n_rows} golden rows, {n_term} terminations, {n_trunc} truncations reproduced")
+
+
+def test_golden_covers_terminal_branches():
+    """The fixtures exercise the branches they are meant to pin (goal reached, crash, TimeLimit, sector exit)."""
+    tot = {}
+    for env_id in ENV_IDS:
+        g = np.load(os.path.join(GOLD, f"ref_{env_id}.npz"))
+        tot[env_id] = (sum(int(g[f"s{s}_terminated"].sum()) for s in g["seeds"]),
+                       sum(int(g[f"s{s}_truncated"].sum()) for s in g["seeds"]))
+    assert tot["DescentEnv-v0"][0] >= 3 and tot["VerticalCREnv-v0"][0] >= 3
+    assert tot["MergeEnv-v0"][1] >= 2 and tot["MergeEnv-v0"][0] >= 1          # 50-step cap and runway reached
+    assert tot["SectorCREnv-v0"][1] >= 2                                          # left the sector polygon
+    assert tot["StaticObstacleEnv-v0"][0] >= 3
+
+
+# ----------------------------------------------------------------------------------------------- GPU parity
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_cuda_env_matches_reference_golden(cuda, env_id):
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    from tests.common import angdiff, device_traffic
+    from tests.test_gpu_env import TOL, _compare_obs, _inject
+    g = np.load(os.path.join(GOLD, f"ref_{env_id}.npz"))
+    seeds = [int(s) for s in g["seeds"]]
+    E, cap = len(seeds), int(g["cap"])
+    venv = BlueSkyVectorEnv(env_id, E, seed=7, cd_enabled=False, autoreset_mode="disabled", max_episode_steps=cap)
+    venv.reset()
+    # the oracle runs in lockstep only to provide the post-reset state to inject (proved equal to the golden rows
+    # by the CPU test above) and to detect the documented Merge exemption; expected values come from the fixture
+    oracles, rstate = [], []
+    for s in seeds:
+        np.random.seed(s)
+        random.seed(s)
+        oracles.append(_oracle(env_id))
+        rstate.append((np.random.get_state(), random.getstate()))
+    n_rows = len(g[f"s{seeds[0]}_is_reset"])
+    act_dim = venv.layout.act_dim
+    vnorm = {"SectorCREnv-v0": (32.0, 66.0), "MergeEnv-v0": (150.0, 150.0)}.get(env_id)
+    exempt = [set() for _ in range(E)]
+    compared = 0
+    for r in range(n_rows):
+        a = np.zeros((E, act_dim), dtype=np.float32)
+        is_reset = [bool(g[f"s{s}_is_reset"][r]) for s in seeds]
+        for e, s in enumerate(seeds):
+            if not is_reset[e]:
+                a[e] = g[f"s{s}_action"][r]
+        gobs, grew, gterm, gtrunc, ginfo = venv.step(a)
+        d = device_traffic(venv)
+        for e, s in enumerate(seeds):
+            p, obs_keys, info_keys = _rows(g, s)
+            o = oracles[e]
+            np.random.set_state(rstate[e][0])          # each seed owns its global-RNG stream, like its own process
+            random.setstate(rstate[e][1])
+            if is_reset[e]:
+                o.reset()
+                _inject(venv, e, o, env_id)
+                exempt[e] = set()
+            else:
+                lnav_before = o.traf.swlnav.copy()
+                o.step(g[p + "action"][r].copy())
+                if len(lnav_before) == o.traf.ntraf:   # MergeEnv: aircraft whose LNAV switched off at the last waypoint
+                    exempt[e] |= set(np.where(lnav_before & ~o.traf.swlnav)[0].tolist())
+                gold_obs = {k: g[p + "obs_" + k][r] for k in obs_keys}
+                _compare_obs(gobs, gold_obs, e, r, vnorm, ownship_only=bool(exempt[e]))
+                if not exempt[e]:
+                    compared += 1
+                    assert abs(grew[e] - g[p + "reward"][r]) < 1e-3, (env_id, s, r, grew[e], g[p + "reward"][r])
+                    assert bool(gterm[e]) == bool(g[p + "terminated"][r]), (env_id, s, r, "terminated")
+                    assert bool(gtrunc[e]) == bool(g[p + "truncated"][r]), (env_id, s, r, "truncated")
+                    for k in info_keys:
+                        v = float(g[p + "info_" + k][r])
+                        if not np.isnan(v):
+                            assert abs(ginfo[k][e] - v) < 1e-2 + 1e-4 * abs(v), (env_id, s, r, k, ginfo[k][e], v)
+                    n = int(g[p + "ntraf"][r])
+                    if n and not g[p + "terminated"][r]:
+                        gt = {f: g[p + "traf_" + f][r, :n] for f in TRAF_FIELDS}
+                        lnav_wp = np.asarray(o.traf.iactwp[:n]) >= 1 if o.traf.ntraf == n else np.zeros(n, bool)
+                        pos_tol = np.where(lnav_wp, 5.0 * TOL["pos"], TOL["pos"])
+                        assert np.all(np.abs(d["lat"][e, :n] - gt["lat"]) < pos_tol), (env_id, s, r, "lat")
+                        assert np.all(np.abs(d["lon"][e, :n] - gt["lon"]) < pos_tol), (env_id, s, r, "lon")
+                        assert np.max(np.abs(d["alt"][e, :n] - gt["alt"])) < TOL["alt"], (env_id, s, r, "alt")
+                        assert np.max(np.abs(d["tas"][e, :n] - gt["tas"])) < TOL["tas"], (env_id, s, r, "tas")
+                        assert np.max(np.abs(d["vs"][e, :n] - gt["vs"])) < TOL["vs"], (env_id, s, r, "vs")
+                        if env_id != "MergeEnv-v0":        # (LNAV bearing tolerance is handled in test_gpu_env.py)
+                            assert np.max(angdiff(d["hdg"][e, :n], gt["hdg"])) < TOL["hdg"], (env_id, s, r, "hdg")
+            rstate[e] = (np.random.get_state(), random.getstate())
+    print(f"{env_id}: {compared} golden step rows matched by the CUDA path")
+    assert compared >= n_rows * E // 3
+    venv.close()
