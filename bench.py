@@ -239,9 +239,9 @@ def run_b200(args):
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     L = venv.layout
     h2d = E * L.act_dim * 4
-    d2h = E * (L.obs_dim * 4 + 4 + 1 + 1 + L.info_dim * 4)
+    d2h = venv._out_bytes          # the mirrored head of the output block: obs, reward, info, flags, terminal-obs window
     e2e = {"value": E * world * K / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "api": "BlueSkyVectorEnv.step, default arguments (numpy in; float32 numpy copies out; bsg_step_host)"}
+           "api": "BlueSkyVectorEnv.step, default arguments (numpy in; fresh float32 numpy arrays out; bsg_step_host_block)"}
     # same call with copy=False (views of two rotating pinned buffers instead of fresh copies), for context
     venv.copy = False
     barrier()

@@ -51,7 +51,7 @@ class TensorTable(C.Structure):
 
 
 SYMBOLS = ("bsg_abi_version", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
-           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_traf_update",
+           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_host_copy", "bsg_traf_update",
            "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_probe_fp32")
 
 _lib = None
@@ -82,13 +82,17 @@ def load():
     lib.bsg_reset.argtypes = [vp, vp, vp]
     lib.bsg_step.argtypes = [vp, vp, vp]
     lib.bsg_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.bsg_step_host_block.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    lib.bsg_host_copy.argtypes = [vp, vp, C.c_size_t]
+    lib.bsg_host_copy.restype = C.c_int
+    lib.bsg_step_host_copy.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp]
     lib.bsg_traf_update.argtypes = [vp, i32, vp]
     lib.bsg_cd_padded.argtypes = [i64]
     lib.bsg_cd_padded.restype = i64
     lib.bsg_cd_pack.argtypes = [vp, vp, vp, vp, vp, vp, i64, f64, f64, vp, vp]
     lib.bsg_cd_detect.argtypes = [vp, i64, i64, i64, f32, f32, f32, u32, vp, vp, vp, vp, vp, i64, vp, vp]
     lib.bsg_probe_fp32.argtypes = [i32, C.POINTER(f64)]
-    for name in ("bsg_query_layout", "bsg_create", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host",
+    for name in ("bsg_query_layout", "bsg_create", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy",
                  "bsg_traf_update", "bsg_cd_pack", "bsg_cd_detect", "bsg_probe_fp32"):
         getattr(lib, name).restype = C.c_int
     _lib = lib

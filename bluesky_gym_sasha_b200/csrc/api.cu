@@ -4,12 +4,14 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <new>
 #include <string.h>
 
 #include "env_kernels.cuh"
 
 int bsg_launch_env(const bsg::EnvParams& P, int slots, cudaStream_t st);   // env_step.cu
+namespace bsg { void host_copy_mt(void* dst, const void* src, size_t n); void host_pool_prewake(); }   // host_pool.cu
 
 static thread_local char g_err[512] = "";
 
@@ -29,6 +31,8 @@ struct bsg_handle {
     bsg_tensor_table t;
     bool bound;
     bsg::EnvParams P;
+    cudaEvent_t ev[4];      // chunk-arrival events of bsg_step_host_copy (created on first use)
+    bool have_ev;
 };
 
 extern "C" int bsg_abi_version(void) { return BSG_ABI_VERSION; }
@@ -111,7 +115,14 @@ extern "C" int bsg_create(const bsg_config* cfg, bsg_handle** out) {
     return BSG_OK;
 }
 
-extern "C" void bsg_destroy(bsg_handle* h) { delete h; }
+extern "C" void bsg_destroy(bsg_handle* h) {
+    if (!h) return;
+    if (h->have_ev) {
+        cudaSetDevice(h->cfg.device);
+        for (int k = 0; k < 4; ++k) cudaEventDestroy(h->ev[k]);
+    }
+    delete h;
+}
 
 extern "C" int bsg_bind_state(bsg_handle* h, const bsg_tensor_table* t) {
     if (!h || !t) return bsg_fail(BSG_EINVAL, "bsg_bind_state: null argument");
@@ -197,6 +208,75 @@ extern "C" int bsg_step_host(bsg_handle* h, const float* h_actions, float* h_obs
         }
     }
     BSG_CUDA(cudaStreamSynchronize(st));
+    return BSG_OK;
+}
+
+// Single-mirror form: the caller laid the step outputs out as ONE contiguous device block starting at
+// tensor_table.obs (obs | reward | info | final_count[4] | terminated | truncated | pad | final_ids |
+// final_obs rows ...) and mirrors its first `nbytes` bytes in pinned host memory.  One H2D copy, one
+// launch, one D2H copy, one synchronise per env step.
+extern "C" int bsg_step_host_block(bsg_handle* h, const float* h_actions, void* h_block, size_t nbytes, void* stream) {
+    if (!h || !h_actions || !h_block) return bsg_fail(BSG_EINVAL, "bsg_step_host_block: null argument");
+    if (!h->bound) return bsg_fail(BSG_ESTATE, "bsg_bind_state has not been called");
+    if (!h->t.actions_staging) return bsg_fail(BSG_ESTATE, "bsg_step_host_block needs tensor_table.actions_staging");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t E = (size_t)h->cfg.num_envs;
+    BSG_CUDA(cudaSetDevice(h->cfg.device));
+    BSG_CUDA(cudaMemcpyAsync(h->t.actions_staging, h_actions, E * h->lay.act_dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = run_mode(h, bsg::kModeStep, h->t.actions_staging, nullptr, 0, stream);
+    if (rc != BSG_OK) return rc;
+    BSG_CUDA(cudaMemcpyAsync(h_block, h->t.obs, nbytes, cudaMemcpyDeviceToHost, st));
+    BSG_CUDA(cudaStreamSynchronize(st));
+    return BSG_OK;
+}
+
+// bsg_step_host_block + the copy of the block's first `dst_bytes` bytes (the observations) into the caller's
+// own result array, pipelined: the device->host transfer is issued in chunks, and while chunk k+1 is still
+// crossing PCIe the host threads (host_pool.cu) move chunk k from the pinned mirror into `dst`.
+extern "C" int bsg_step_host_copy(bsg_handle* h, const float* h_actions, void* h_block, size_t nbytes,
+                                  void* dst, size_t dst_bytes, void* stream) {
+    if (!h || !h_actions || !h_block) return bsg_fail(BSG_EINVAL, "bsg_step_host_copy: null argument");
+    if (!h->bound) return bsg_fail(BSG_ESTATE, "bsg_bind_state has not been called");
+    if (!h->t.actions_staging) return bsg_fail(BSG_ESTATE, "bsg_step_host_copy needs tensor_table.actions_staging");
+    if (dst_bytes > nbytes) return bsg_fail(BSG_EINVAL, "bsg_step_host_copy: dst_bytes exceeds the mirrored block");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t E = (size_t)h->cfg.num_envs;
+    BSG_CUDA(cudaSetDevice(h->cfg.device));
+    if (!h->have_ev) {
+        for (int k = 0; k < 4; ++k) BSG_CUDA(cudaEventCreateWithFlags(&h->ev[k], cudaEventDisableTiming));
+        h->have_ev = true;
+    }
+    BSG_CUDA(cudaMemcpyAsync(h->t.actions_staging, h_actions, E * h->lay.act_dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = run_mode(h, bsg::kModeStep, h->t.actions_staging, nullptr, 0, stream);
+    if (rc != BSG_OK) return rc;
+    const char* d0 = (const char*)h->t.obs;
+    char* h0 = (char*)h_block;
+    if (dst) bsg::host_pool_prewake();     // the copy threads wake up while the GPU is busy
+    // chunks: small transfers go in one piece; otherwise 4 pieces of the copied region, the tail with the last
+    static const int want = [] { const char* e = getenv("BSG_D2H_CHUNKS"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
+    const int nchunk = (dst && dst_bytes >= (512u << 10)) ? want : 1;
+    size_t bounds[5];
+    for (int k = 0; k <= nchunk; ++k) bounds[k] = (dst_bytes * k / nchunk) & ~(size_t)255;
+    bounds[0] = 0;
+    bounds[nchunk] = nbytes;
+    for (int k = 0; k < nchunk; ++k) {
+        BSG_CUDA(cudaMemcpyAsync(h0 + bounds[k], d0 + bounds[k], bounds[k + 1] - bounds[k], cudaMemcpyDeviceToHost, st));
+        BSG_CUDA(cudaEventRecord(h->ev[k], st));
+    }
+    for (int k = 0; k < nchunk; ++k) {
+        BSG_CUDA(cudaEventSynchronize(h->ev[k]));
+        if (dst) {
+            size_t lo = bounds[k], hi = bounds[k + 1] < dst_bytes ? bounds[k + 1] : dst_bytes;
+            if (hi > lo) bsg::host_copy_mt((char*)dst + lo, h0 + lo, hi - lo);
+        }
+    }
+    return BSG_OK;
+}
+
+extern "C" int bsg_host_copy(void* dst, const void* src, size_t nbytes) {
+    if ((!dst || !src) && nbytes) return bsg_fail(BSG_EINVAL, "bsg_host_copy: null argument");
+    bsg::host_pool_prewake();
+    bsg::host_copy_mt(dst, src, nbytes);
     return BSG_OK;
 }
 

@@ -81,22 +81,30 @@ class BlueSkyVectorEnv(VectorEnv):
         # ---- device state (torch owns the memory; the library only borrows pointers)
         dev = self.device
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
-        # step outputs live in ONE block (obs | reward | info | terminated | truncated) so that the host
-        # API brings them back with a single device->host copy (bsg_step_host's packed path)
+        # step outputs live in ONE block (obs | reward | info | final_count | terminated | truncated | pad |
+        # final_ids | final_obs rows) so that the host API brings them back with a single device->host copy
+        # of the block's head (bsg_step_host_block): everything up to and including the first `_final_cap`
+        # compacted terminal observations, which covers all envs that finish in a typical step
         n_obs, n_rew, n_info, n_cnt = E * L.obs_dim * 4, E * 4, E * L.info_dim * 4, 16
         o_info, o_cnt, o_term = n_obs + n_rew, n_obs + n_rew + n_info, n_obs + n_rew + n_info + n_cnt
-        self._out_bytes = o_term + 2 * E
+        o_fids = (o_term + 2 * E + 15) // 16 * 16
+        o_fobs = o_fids + 4 * E
+        self._final_cap = min(E, max(8, E // 32))
+        self._out_bytes = o_fobs + self._final_cap * L.obs_dim * 4       # mirrored on the host every step
+        dev_bytes = o_fobs + E * L.obs_dim * 4
 
-        def carve(block):
+        def carve(block, n_final):
             o = block[:n_obs].view(torch.float32).view(E, L.obs_dim)
             r = block[n_obs:o_info].view(torch.float32)
             i = block[o_info:o_cnt].view(torch.float32).view(E, L.info_dim)
             c = block[o_cnt:o_term].view(torch.int32)
             te = block[o_term:o_term + E]
             tr = block[o_term + E:o_term + 2 * E]
-            return o, r, i, c, te, tr
-        self._out_dev = z((self._out_bytes + 16,), torch.uint8)
-        d_obs, d_rew, d_info, d_cnt, d_term, d_trunc = carve(self._out_dev)
+            fi = block[o_fids:o_fobs].view(torch.int32)
+            fo = block[o_fobs:o_fobs + n_final * L.obs_dim * 4].view(torch.float32).view(n_final, L.obs_dim)
+            return o, r, i, c, te, tr, fi, fo
+        self._out_dev = z((dev_bytes,), torch.uint8)
+        d_obs, d_rew, d_info, d_cnt, d_term, d_trunc, d_fids, d_fobs = carve(self._out_dev, E)
         self.t = OrderedDict(
             pos=z((E, G, 2), torch.float64), kin=z((E, G, 4), torch.float32), cmd=z((E, G, 4), torch.float32),
             aux=z((E, G, 4), torch.float32), flags=z((E, G), torch.int32),
@@ -104,21 +112,24 @@ class BlueSkyVectorEnv(VectorEnv):
             env_f64=z((E, L.env_f64), torch.float64), env_f32=z((E, L.env_f32), torch.float32),
             env_i32=z((E, L.env_i32), torch.int32),
             poly=z((E, max(L.poly_f64, 1)), torch.float64) if L.poly_f64 else None,
-            obs=d_obs, final_obs=z((E, L.obs_dim), torch.float32), final_ids=z((E,), torch.int32), final_count=d_cnt,
+            obs=d_obs, final_obs=d_fobs, final_ids=d_fids, final_count=d_cnt,
             reward=d_rew, terminated=d_term, truncated=d_trunc,
             info=d_info, actions_staging=z((E, L.act_dim), torch.float32))
-        # pinned host mirrors for the numpy API: two rotating output blocks with the device block's layout
+        # pinned host mirrors for the numpy API: two rotating blocks with the device block's layout; the numpy
+        # views are made once (torch -> numpy conversion per step costs more than the small copies themselves)
         ph = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
         self._hbuf = []
         for _ in range(2):
-            blk = ph((self._out_bytes + 16,), torch.uint8)
-            o, r, i, c, te, tr = carve(blk)
-            self._hbuf.append(dict(obs=o, reward=r, info=i, final_count=c, terminated=te, truncated=tr))
+            blk = ph((self._out_bytes,), torch.uint8)
+            names = ("obs", "reward", "info", "final_count", "terminated", "truncated", "final_ids", "final_obs")
+            hb = {k: v.numpy() for k, v in zip(names, carve(blk, self._final_cap))}
+            hb["block"], hb["ptr"] = blk, _ptr(blk)
+            self._hbuf.append(hb)
         self._hsel = 0
         self.h = dict(actions=ph((E, L.act_dim), torch.float32))
+        self._act_np, self._act_ptr = self.h["actions"].numpy(), _ptr(self.h["actions"])
         self._final_np = np.zeros((E, L.obs_dim), dtype=np.float32)
-        self._h_final = ph((E, L.obs_dim), torch.float32)
-        self._h_final_ids = ph((E,), torch.int32)
+        self._h_final = ph((E, L.obs_dim), torch.float32)          # overflow beyond `_final_cap` rows (rare)
 
         self._h = C.c_void_p(0)
         with torch.cuda.device(dev):
@@ -188,30 +199,40 @@ class BlueSkyVectorEnv(VectorEnv):
         return self._obs_dict_np(obs), self._infos_np(info)
 
     def step(self, actions):
-        self.h["actions"].numpy()[...] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, self.layout.act_dim)
+        E = self.num_envs
+        self._act_np[...] = np.asarray(actions, dtype=np.float32).reshape(E, self.layout.act_dim)
         self._hsel ^= 1
         h = self._hbuf[self._hsel]
+        fresh = self.copy and self.obs_dtype == np.float32
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.bsg_step_host(self._h, _ptr(self.h["actions"]), _ptr(h["obs"]), _ptr(h["reward"]),
-                                               _ptr(h["terminated"]), _ptr(h["truncated"]), _ptr(h["info"]),
-                                               _ptr(h["final_count"]), self._stream()))
+            if fresh:       # the result array is filled by the library's host threads while the transfer is in flight
+                flat = np.empty((E, self.layout.obs_dim), dtype=np.float32)
+                _lib.check(self._lib.bsg_step_host_copy(self._h, self._act_ptr, h["ptr"], self._out_bytes,
+                                                        C.c_void_p(flat.ctypes.data), flat.nbytes, self._stream()))
+            else:
+                _lib.check(self._lib.bsg_step_host_block(self._h, self._act_ptr, h["ptr"], self._out_bytes, self._stream()))
         self.gpu_launches += 1
-        obs = self._obs_dict_np(h["obs"].numpy())
-        rew = h["reward"].numpy().astype(np.float64)
-        term = h["terminated"].numpy().astype(bool)
-        trunc = h["truncated"].numpy().astype(bool)
-        infos = self._infos_np(h["info"].numpy())
+        if fresh:
+            obs = OrderedDict((k, flat[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
+        else:
+            obs = self._obs_dict_np(h["obs"])
+        rew = h["reward"].astype(np.float64)
+        term = h["terminated"].astype(bool)
+        trunc = h["truncated"].astype(bool)
+        infos = self._infos_np(h["info"])
         if self.autoreset_mode == "same_step":
             n_fin = int(h["final_count"][0])
-            if n_fin:                   # fetch only the (compacted) terminal observations of finished envs
-                done = term | trunc
-                self._h_final[:n_fin].copy_(self.t["final_obs"][:n_fin], non_blocking=True)
-                self._h_final_ids[:n_fin].copy_(self.t["final_ids"][:n_fin], non_blocking=True)
-                torch.cuda.current_stream(self.device).synchronize()
-                self._final_np[self._h_final_ids.numpy()[:n_fin]] = self._h_final.numpy()[:n_fin]
+            if n_fin:                   # compacted terminal observations of the envs that finished in this step
+                ids = h["final_ids"][:n_fin]
+                cap = self._final_cap
+                self._final_np[ids[:cap]] = h["final_obs"][:min(n_fin, cap)]
+                if n_fin > cap:         # more finished than the mirrored window holds: fetch the rest
+                    self._h_final[cap:n_fin].copy_(self.t["final_obs"][cap:n_fin], non_blocking=True)
+                    torch.cuda.current_stream(self.device).synchronize()
+                    self._final_np[ids[cap:]] = self._h_final.numpy()[cap:n_fin]
                 fo = self._final_np.astype(self.obs_dtype) if self.obs_dtype != np.float32 else self._final_np
                 infos["final_obs"] = OrderedDict((k, fo[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
-                infos["_final_obs"] = done
+                infos["_final_obs"] = term | trunc
         return obs, rew, term, trunc, infos
 
     # ------------------------------------------------------------------ state access (parity tests, checkpoints)

@@ -17,6 +17,7 @@
 #ifndef BSG_H_
 #define BSG_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -142,6 +143,22 @@ int bsg_step(bsg_handle *h, const float *d_actions, void *stream);
 int bsg_step_host(bsg_handle *h, const float *h_actions, float *h_obs, float *h_reward,
                   uint8_t *h_terminated, uint8_t *h_truncated, float *h_info, int32_t *h_final_count,
                   void *stream);
+
+/* Same as bsg_step_host for callers that allocated the step outputs as ONE contiguous device block that
+ * starts at tensor_table.obs and keep a pinned host mirror of it: copies h_actions in, steps, copies the
+ * first `nbytes` bytes of that block to h_block and synchronises (one copy each way per env step).
+ * Replaces the same reference call as bsg_step (Env.step, e.g. horizontal_cr_env.py:103-125). */
+int bsg_step_host_block(bsg_handle *h, const float *h_actions, void *h_block, size_t nbytes, void *stream);
+
+/* bsg_step_host_block that additionally copies the first `dst_bytes` bytes of the mirrored block (the
+ * observations) from the pinned mirror into `dst`, the caller's own (pageable) result array, using the
+ * library's host threads (BSG_HOST_THREADS, default 4) and overlapping that copy with the device->host
+ * transfer chunk by chunk.  dst may be NULL (then identical to bsg_step_host_block). */
+int bsg_step_host_copy(bsg_handle *h, const float *h_actions, void *h_block, size_t nbytes,
+                       void *dst, size_t dst_bytes, void *stream);
+
+/* The host-thread copy bsg_step_host_copy uses, on its own (pure host code; works without a GPU). */
+int bsg_host_copy(void *dst, const void *src, size_t nbytes);
 
 /* replaces: n_sub x bs.sim.step() alone (Traffic.update kinematics + autopilot, no obs/reward);
  * used by the trajectory parity tests. */

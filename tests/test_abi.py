@@ -82,3 +82,20 @@ def test_product_does_not_import_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
     for f in ("bluesky_gym/__init__.py", "bluesky_gym/envs/__init__.py"):
         assert "oracle" not in open(os.path.join(ROOT, f)).read()
+
+
+def test_host_thread_copy(lib):
+    """bsg_host_copy (the pooled memcpy behind bsg_step_host_copy) is byte-exact for ragged sizes and offsets."""
+    import ctypes as C
+    import numpy as np
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, 256, 5_000_003, dtype=np.uint8)
+    for n, off in [(0, 0), (1, 3), (4096, 1), (262_144, 0), (262_145, 7), (1_687_552, 0), (4_999_990, 13)]:
+        dst = np.zeros(n + 64, dtype=np.uint8)
+        assert lib.bsg_host_copy(C.c_void_p(dst.ctypes.data + 32), C.c_void_p(src.ctypes.data + off), n) == 0
+        assert np.array_equal(dst[32:32 + n], src[off:off + n])
+        assert not dst[:32].any() and not dst[32 + n:].any()
+    for _ in range(50):                                   # repeated calls reuse the sleeping workers
+        dst = np.empty(1_687_552, dtype=np.uint8)
+        lib.bsg_host_copy(C.c_void_p(dst.ctypes.data), C.c_void_p(src.ctypes.data), dst.nbytes)
+        assert np.array_equal(dst, src[:dst.nbytes])
