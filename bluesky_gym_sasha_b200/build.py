@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libbsg_b200.so")
+LIB = os.environ.get("BSG_LIB_OUT") or os.path.join(HERE, "libbsg_b200.so")      # BSG_LIB_OUT: A/B builds
 SOURCES = ["api.cu", "env_step.cu", "cd_tiled.cu", "host_pool.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr"]
@@ -29,6 +29,10 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    flags += os.environ.get("BSG_EXTRA_NVCC_FLAGS", "").split()
+    if os.environ.get("BSG_LIB_OUT"):
+        objdir = os.path.join(HERE, "build", "ab_" + os.path.basename(LIB))
+        os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:                       # one nvcc per translation unit, in parallel
         obj = os.path.join(objdir, src.replace(".cu", ".o"))

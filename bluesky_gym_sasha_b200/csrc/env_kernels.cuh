@@ -314,16 +314,29 @@ __device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const T
 }
 
 // ====================================================================================================
-// K3: in-group all-pairs CD.  The group's records are staged in shared memory; its P = n(n-1)/2
-// UNORDERED pairs are spread over the G lanes (pair p -> lane p % G), each evaluated once for both
-// orders (cd_pair_sym), and the per-aircraft results are scattered back through shared-memory
-// atomics that only fire for the (few) conflicting pairs.  7 rounds instead of 21 for 21 aircraft.
+// K3: in-group all-pairs CD in two phases.
+//   Hot phase (packed f32x2): lane i tests the n/2 unordered pairs {i, (i + k) mod n}, k = 1 .. n/2, two
+//   offsets per iteration, for the ONLY condition every conflict or LoS needs: dcpa < R, evaluated without
+//   a division as |d x w|^2 < R^2 |w|^2 (inflated by 2e-4 and by an absolute term that lets co-moving pairs
+//   through, so the filter is a superset of what the exact routine accepts; ~11 % of the pairs of a
+//   HorizontalCR-20 env pass).  The group's records are staged as a structure of arrays written twice,
+//   n apart, so (i + k) mod n is a plain offset and consecutive lanes read consecutive words.
+//   Exact phase: the candidates (i, k) are compacted into a per-group queue in shared memory, spread over
+//   the lanes, and evaluated by cd_pair_sym() -- the same routine as before, so results are bit-identical
+//   to evaluating every pair -- with per-aircraft results scattered through shared-memory atomics that
+//   only fire for conflicting pairs.
 // ====================================================================================================
-constexpr int kMaxPairs = 32 * 31 / 2;
+enum { HX = 0, HY = 1, HCH = 2, HSH = 3, HU = 4, HV = 5, kHotFields = 6 };
+constexpr int kQueuePerThread = 16;      // G/2 candidates per lane at most
+#ifndef BSG_HOT_UNROLL
+#define BSG_HOT_UNROLL 1
+#endif
+constexpr int kHotUnroll = BSG_HOT_UNROLL;
 
+constexpr int kSmallPairs = 8 * 7 / 2;
 // pair p (ordered by j, then i < j) -> (i, j); the first n(n-1)/2 entries cover exactly the aircraft < n
 __device__ __forceinline__ void build_pair_table(uint16_t* s_pairs) {
-    for (int p = threadIdx.x; p < kMaxPairs; p += blockDim.x) {
+    for (int p = threadIdx.x; p < kSmallPairs; p += blockDim.x) {
         int j = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
         while (j * (j - 1) / 2 > p) --j;
         while ((j + 1) * j / 2 <= p) ++j;
@@ -334,47 +347,125 @@ __device__ __forceinline__ void build_pair_table(uint16_t* s_pairs) {
 
 template <int G>
 __device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvParams& P, float4* s_rec,
-                                         const uint16_t* s_pairs, int* s_tmax, int& nconf_env, int& nlos_env) {
+                                         float* s_hot, uint16_t* s_queue, int* s_tmax, int* s_cnt,
+                                         const uint16_t* s_pairs, int& nconf_env, int& nlos_env) {
     const int lane = threadIdx.x & 31;
     const int lane_g = threadIdx.x & (G - 1);
     const int gbase = threadIdx.x - lane_g;           // first thread of this group in the block
     const int wbase = lane - lane_g;                  // first lane of this group in the warp
+    const int grp = threadIdx.x / G;
     double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);
     // cos / sin of lat/2 from the cached cos(lat): half-angle identities (absolute error ~1e-7)
     const float ch = sqrtf(fmaf(0.5f, a.coslat, 0.5f));
     const float sh = copysignf(sqrtf(fmaxf(fmaf(-0.5f, a.coslat, 0.5f), 0.0f)), (float)a.lat);
     double dl = a.lon - lon0;
     dl = dl > 180.0 ? dl - 360.0 : (dl < -180.0 ? dl + 360.0 : dl);
-    s_rec[2 * threadIdx.x] = make_float4((float)(kRearthD * kDeg2RadD * dl), (float)(kRearthD * kDeg2RadD * (a.lat - lat0)), ch, sh);
+    const float x = (float)(kRearthD * kDeg2RadD * dl), y = (float)(kRearthD * kDeg2RadD * (a.lat - lat0));
+    s_rec[2 * threadIdx.x] = make_float4(x, y, ch, sh);
     s_rec[2 * threadIdx.x + 1] = make_float4(a.gse, a.gsn, a.alt, a.vs);
+    float* hot = s_hot + gbase * (2 * kHotFields);    // [field][2G] for this group
+    if (lane_g < nac) {
+        float* w = hot + lane_g;
+        w[HX * 2 * G] = -x; w[HY * 2 * G] = y;  w[HCH * 2 * G] = ch;      // (x is stored negated: see crs below)
+        w[HSH * 2 * G] = sh; w[HU * 2 * G] = a.gse; w[HV * 2 * G] = a.gsn;
+        w += nac;
+        w[HX * 2 * G] = -x; w[HY * 2 * G] = y;  w[HCH * 2 * G] = ch;
+        w[HSH * 2 * G] = sh; w[HU * 2 * G] = a.gse; w[HV * 2 * G] = a.gsn;
+    }
     s_tmax[threadIdx.x] = 0;
+    if (G > 8 && lane_g == 0) s_cnt[grp] = 0;
     __syncwarp(group_mask<G>());
-    const int npairs = nac * (nac - 1) / 2;
     unsigned confmask = 0u;       // bit = warp lane of an aircraft that is in conflict (this lane's pairs only)
-    int nc = 0, nl = 0;           // ordered conflict pairs / ordered LoS pairs found by this lane
-    unsigned ij_next = lane_g < npairs ? s_pairs[lane_g] : 0u;
-    for (int p = lane_g; p < npairs; p += G) {
-        const unsigned ij = ij_next;
-        if (p + G < npairs) ij_next = s_pairs[p + G];      // next round's pair: off the critical path
-        const int i = (int)(ij >> 8), j = (int)(ij & 0xffu);
+    int counts = 0;               // ordered conflict pairs (low half) / ordered LoS pairs (high half) found by this lane
+    auto exact_pair = [&](int i, int j) {
         CdSym r = cd_pair_sym(s_rec[2 * (gbase + i)], s_rec[2 * (gbase + i) + 1], s_rec[2 * (gbase + j)],
                               s_rec[2 * (gbase + j) + 1], P.R2, P.hpz, P.dtlook);
-        nc += (r.conf_ij ? 1 : 0) + (r.conf_ji ? 1 : 0);
-        nl += r.los ? 2 : 0;
+        counts += (r.conf_ij ? 1 : 0) + (r.conf_ji ? 1 : 0) + (r.los ? (2 << 16) : 0);
         confmask |= (r.conf_ij ? 1u << (wbase + i) : 0u) | (r.conf_ji ? 1u << (wbase + j) : 0u);
         if (r.conf_ij | r.conf_ji) {               // tcpamax = max over the row of tcpa * swconfl (>= 0)
             const int tb = __float_as_int(fmaxf(r.tcpa, 0.0f));
             if (r.conf_ij) atomicMax(&s_tmax[gbase + i], tb);
             if (r.conf_ji) atomicMax(&s_tmax[gbase + j], tb);
         }
+    };
+    const int kmax = nac >> 1;
+    if (G <= 8) {
+        // small groups (<= 8 aircraft, <= 28 pairs): the filter + queue cost more than they save; the
+        // unordered pairs are dealt to the lanes from a table (pair p -> lane p % G) and evaluated exactly
+        const int npairs = nac * (nac - 1) / 2;
+        for (int p = lane_g; p < npairs; p += G) {
+            const unsigned ij = s_pairs[p];
+            exact_pair((int)(ij >> 8), (int)(ij & 0xffu));
+        }
+    } else {
+    // ---- hot phase ---------------------------------------------------------------------------------
+    unsigned cand = 0u;
+    {
+        const u64 pX = pk2(x, x), nY = pk2(-y, -y), CH = pk2(ch, ch), nSH = pk2(-sh, -sh);
+        const u64 nU = pk2(-a.gse, -a.gse), nV = pk2(-a.gsn, -a.gsn);
+        const float R2h = P.R2 * 1.0002f;
+        const float* q = hot + lane_g + 1;
+#pragma unroll kHotUnroll
+        for (int kk = 0; kk < kmax; kk += 2, q += 2) {        // offsets k = kk + 1 and kk + 2
+            const u64 nX = pk2(q[HX * 2 * G], q[HX * 2 * G + 1]);
+            const u64 Y = pk2(q[HY * 2 * G], q[HY * 2 * G + 1]);
+            const u64 CHc = pk2(q[HCH * 2 * G], q[HCH * 2 * G + 1]);
+            const u64 SHc = pk2(q[HSH * 2 * G], q[HSH * 2 * G + 1]);
+            const u64 U = pk2(q[HU * 2 * G], q[HU * 2 * G + 1]);
+            const u64 V = pk2(q[HV * 2 * G], q[HV * 2 * G + 1]);
+            const u64 dy = add2(Y, nY);
+            const u64 cav = fma2(SHc, nSH, mul2(CHc, CH));
+            const u64 ndx = mul2(add2(nX, pX), cav);              // -(x_j - x_i) cos(mean lat)
+            const u64 du = add2(U, nU), dv = add2(V, nV);
+            const u64 dv2 = fma2(du, du, mul2(dv, dv));
+            const u64 crs = fma2(ndx, dv, mul2(dy, du));          // -(dx dv - dy du): only its square is used
+            const u64 lhs = mul2(crs, crs);
+            float l0, l1, w0, w1;
+            up2(lhs, l0, l1);
+            up2(dv2, w0, w1);
+            cand |= ((l0 < fmaf(w0, R2h, 2.0e6f) ? 1u : 0u) | (l1 < fmaf(w1, R2h, 2.0e6f) ? 2u : 0u)) << kk;
+        }
+        // offsets 1 .. n/2 only; for even n the offset n/2 names each pair twice: the lower half keeps it
+        unsigned valid = (1u << kmax) - 1u;
+        if (!(nac & 1) && lane_g >= kmax) valid >>= 1;
+        cand = (lane_g < nac) ? (cand & valid) : 0u;
     }
-    // one REDUX.OR over the warp merges every lane's findings; each aircraft then reads its own bit
-    confmask = __reduce_or_sync(0xffffffffu, confmask);
+
+    // ---- compaction: (i, k) entries into the group's queue -------------------------------------------
+    uint16_t* queue = s_queue + gbase * kQueuePerThread;
+    {
+        const int cnt = __popc(cand);
+        int pos = 0;
+        if (cnt) pos = atomicAdd(&s_cnt[grp], cnt);
+        uint16_t* qp = queue + pos;
+        unsigned val = ((unsigned)lane_g << 8) | 1u, c = cand;
+#pragma unroll 1
+        for (int b = 0; b < kmax; b += 4, c >>= 4, val += 4u) {
+            if (c & 1u) *qp++ = (uint16_t)val;
+            if (c & 2u) *qp++ = (uint16_t)(val + 1u);
+            if (c & 4u) *qp++ = (uint16_t)(val + 2u);
+            if (c & 8u) *qp++ = (uint16_t)(val + 3u);
+        }
+    }
     __syncwarp(group_mask<G>());
+    const int ncand = s_cnt[grp];
+
+    // ---- exact phase -------------------------------------------------------------------------------
+    for (int p = lane_g; p < ncand; p += G) {
+        const unsigned e = queue[p];
+        const int i = (int)(e >> 8);
+        int j = i + (int)(e & 0xffu);
+        j = j >= nac ? j - nac : j;
+        exact_pair(i, j);
+    }
+    }
+    // one REDUX.OR over the group merges every lane's findings; each aircraft then reads its own bit
+    confmask = __reduce_or_sync(group_mask<G>(), confmask);
+    counts = (int)__reduce_add_sync(group_mask<G>(), (unsigned)counts);
     a.inconf = alive && ((confmask >> lane) & 1u);
     a.tcpamax = __int_as_float(s_tmax[threadIdx.x]);
-    nconf_env = group_sum<G>(nc);
-    nlos_env = group_sum<G>(nl);
+    nconf_env = counts & 0xffff;
+    nlos_env = counts >> 16;
     __syncwarp(group_mask<G>());
 }
 

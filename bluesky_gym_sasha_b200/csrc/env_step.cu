@@ -755,10 +755,13 @@ __device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float
 // =====================================================================================================
 template <int ENV, int G>
 __global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) {
-    __shared__ __align__(16) float4 s_rec[kEnvThreads * 2];
-    __shared__ int s_tmax[kEnvThreads];
-    __shared__ uint16_t s_pairs[kMaxPairs];
-    if (G > 1 && P.cd_enabled && P.mode != kModeReset) {
+    __shared__ __align__(16) float4 s_rec[(G > 1) ? kEnvThreads * 2 : 1];
+    __shared__ float s_hot[(G > 8) ? kEnvThreads * 2 * kHotFields : 1];
+    __shared__ uint16_t s_queue[(G > 8) ? kEnvThreads * kQueuePerThread : 1];
+    __shared__ int s_tmax[(G > 1) ? kEnvThreads : 1];
+    __shared__ int s_cnt[(G > 8) ? kEnvThreads / G : 1];
+    __shared__ uint16_t s_pairs[(G > 1 && G <= 8) ? kSmallPairs : 1];
+    if (G > 1 && G <= 8 && P.cd_enabled && P.mode != kModeReset) {
         build_pair_table(s_pairs);
         __syncthreads();
     }
@@ -808,7 +811,7 @@ __global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) 
                 if (a.alt != T.k_alt || a.vs != T.k_vs) compute_targets(a, P, T);
                 ac_autopilot<ENV>(a, P, fms_ready);
             }
-            if (G > 1 && P.cd_enabled) group_cd<G>(a, alive, s.num_ac, P, s_rec, s_pairs, s_tmax, nconf, nlos);
+            if (G > 1 && P.cd_enabled) group_cd<G>(a, alive, s.num_ac, P, s_rec, s_hot, s_queue, s_tmax, s_cnt, s_pairs, nconf, nlos);
             if (alive) ac_kinematics(a, P, T);
             if (ENV == BSG_ENV_STATIC_OBSTACLE && P.mode == kModeStep) {   // per-substep reward / termination
                 if (k == 0) env_load_post(s, P, e);
