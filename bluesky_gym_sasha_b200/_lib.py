@@ -51,7 +51,7 @@ class TensorTable(C.Structure):
 
 
 SYMBOLS = ("bsg_abi_version", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
-           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_host_copy", "bsg_traf_update",
+           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_host_copy", "bsg_set_obs_noise", "bsg_traf_update",
            "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_probe_fp32")
 
 _lib = None
@@ -83,6 +83,8 @@ def load():
     lib.bsg_step.argtypes = [vp, vp, vp]
     lib.bsg_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.bsg_step_host_block.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    lib.bsg_set_obs_noise.argtypes = [vp, f32]
+    lib.bsg_set_obs_noise.restype = C.c_int
     lib.bsg_host_copy.argtypes = [vp, vp, C.c_size_t]
     lib.bsg_host_copy.restype = C.c_int
     lib.bsg_step_host_copy.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp]

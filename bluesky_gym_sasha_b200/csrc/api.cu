@@ -11,6 +11,7 @@
 #include "env_kernels.cuh"
 
 int bsg_launch_env(const bsg::EnvParams& P, int slots, cudaStream_t st);   // env_step.cu
+int bsg_launch_obs_noise(const bsg::EnvParams& P, float sigma, uint32_t call, bool with_final, cudaStream_t st);   // obs_noise.cu
 namespace bsg { void host_copy_mt(void* dst, const void* src, size_t n); void host_pool_prewake(); }   // host_pool.cu
 
 static thread_local char g_err[512] = "";
@@ -33,6 +34,8 @@ struct bsg_handle {
     bsg::EnvParams P;
     cudaEvent_t ev[4];      // chunk-arrival events of bsg_step_host_copy (created on first use)
     bool have_ev;
+    float obs_noise;        // NoisyObservationWrapper sigma (0 = off)
+    uint32_t noise_calls;   // reset / step calls so far: the noise stream's call index
 };
 
 extern "C" int bsg_abi_version(void) { return BSG_ABI_VERSION; }
@@ -152,7 +155,16 @@ static int run_mode(bsg_handle* h, int mode, const float* d_actions, const uint8
     if (n_sub > 0) P.n_sub = n_sub;
     if (mode == bsg::kModeStep && P.final_count)
         BSG_CUDA(cudaMemsetAsync(P.final_count, 0, sizeof(int32_t), (cudaStream_t)stream));
-    return bsg_launch_env(P, h->lay.slots, (cudaStream_t)stream);
+    int rc = bsg_launch_env(P, h->lay.slots, (cudaStream_t)stream);
+    if (rc != BSG_OK || mode == bsg::kModeTraf || !(h->obs_noise > 0.0f)) return rc;
+    return bsg_launch_obs_noise(P, h->obs_noise, h->noise_calls++, mode == bsg::kModeStep, (cudaStream_t)stream);
+}
+
+extern "C" int bsg_set_obs_noise(bsg_handle* h, float sigma) {
+    if (!h) return bsg_fail(BSG_EINVAL, "null handle");
+    if (!(sigma >= 0.0f)) return bsg_fail(BSG_EINVAL, "bsg_set_obs_noise: noise level must be >= 0");
+    h->obs_noise = sigma;
+    return BSG_OK;
 }
 
 extern "C" int bsg_reset(bsg_handle* h, const uint8_t* d_mask, void* stream) {

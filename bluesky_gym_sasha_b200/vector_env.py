@@ -33,7 +33,7 @@ class BlueSkyVectorEnv(VectorEnv):
     def __init__(self, env_id, num_envs, device=0, seed=0, cd_enabled=False, n_intruders=None,
                  autoreset_mode="next_step", env_id_offset=0, max_episode_steps=None, perf=None,
                  default_hdg="random", rpz=0.0, hpz=0.0, dtlookahead=0.0, render_mode=None,
-                 obs_dtype=np.float32, copy=True):
+                 obs_dtype=np.float32, copy=True, obs_noise=0.0):
         if env_id in NOT_ACCELERATED:
             raise NotImplementedError(f"{env_id} is registered by the reference but is not on the accelerated "
                                       "path yet (SURVEY.md section 8f)")
@@ -139,8 +139,17 @@ class BlueSkyVectorEnv(VectorEnv):
         self._lib = lib
         self.gpu_launches = 0
         self.closed = False
+        self.obs_noise = 0.0
+        if obs_noise:
+            self.set_obs_noise(obs_noise)
 
     # ------------------------------------------------------------------ helpers
+    def set_obs_noise(self, noise_level):
+        """NoisyObservationWrapper on the device (bluesky_gym/wrappers/uncertainty.py): N(0, noise_level) on every
+        observation element returned from now on; 0 switches it off."""
+        _lib.check(self._lib.bsg_set_obs_noise(self._h, float(noise_level)))
+        self.obs_noise = float(noise_level)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

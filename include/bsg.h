@@ -160,6 +160,12 @@ int bsg_step_host_copy(bsg_handle *h, const float *h_actions, void *h_block, siz
 /* The host-thread copy bsg_step_host_copy uses, on its own (pure host code; works without a GPU). */
 int bsg_host_copy(void *dst, const void *src, size_t nbytes);
 
+/* replaces: NoisyObservationWrapper (bluesky_gym/wrappers/uncertainty.py:4-31): from now on every observation
+ * written by bsg_reset / bsg_step* (terminal observations of same-step autoreset included) carries independent
+ * Gaussian noise N(0, sigma) per element, drawn from a Philox stream keyed by (seed, global env id, call index).
+ * sigma = 0 switches it off.  One extra elementwise kernel per call while it is on. */
+int bsg_set_obs_noise(bsg_handle *h, float sigma);
+
 /* replaces: n_sub x bs.sim.step() alone (Traffic.update kinematics + autopilot, no obs/reward);
  * used by the trajectory parity tests. */
 int bsg_traf_update(bsg_handle *h, int32_t n_sub, void *stream);

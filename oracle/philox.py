@@ -84,3 +84,19 @@ class GlobalStdlibDraws(GlobalNumpyDraws):
 
     def uniform(self, a, b):
         return _pyrandom.uniform(a, b)
+
+
+def noise_normals(seed, env_gid, call_index, n, terminal=False):
+    """The N(0, 1) sequence the device observation-noise kernel (csrc/obs_noise.cu) adds to the n elements of env
+    ``env_gid``'s observation at reset/step call number ``call_index``: block m of the Philox stream tagged 'NOIS'
+    ('NOIT' for terminal observations), Box-Muller on words 0 and 1 -> elements 2m (cos) and 2m+1 (sin)."""
+    tag = 0x4e4f4954 if terminal else 0x4e4f4953
+    key = (seed & MASK, env_gid & MASK)
+    out = []
+    for m in range((n + 1) // 2):
+        w = philox4x32_10((m, call_index & MASK, tag, (seed >> 32) & MASK), key)
+        u1 = ((w[0] >> 8) + 1) * (1.0 / 16777216.0)
+        u2 = (w[1] >> 8) * (1.0 / 16777216.0)
+        r = math.sqrt(-2.0 * math.log(u1))
+        out += [r * math.cos(2.0 * math.pi * u2), r * math.sin(2.0 * math.pi * u2)]
+    return np.array(out[:n])
