@@ -206,7 +206,7 @@ __device__ __forceinline__ void env_store(const EnvS& s, const EnvParams& P, lon
 // between env steps).  This removes 7 of the 9 pow-type evaluations from the steady-state substep.
 struct Targets {
     Atmos at;               // atmosphere at the aircraft altitude
-    float allow_tas, allow_h, amax;
+    float allow_tas, allow_h, amax, inv_amax;
     float k_alt, k_vs;      // inputs the cache was computed for
     int ph;
 };
@@ -230,6 +230,7 @@ __device__ __forceinline__ void compute_targets(const Ac& a, const EnvParams& P,
     if (ph == PH_AP) { vmin = pf.vminap; vmax = pf.vmaxap; }
     if (ph == PH_GD) { vmin = 0.0f; vmax = pf.vmaxic; }
     T.amax = (ph == PH_GD) ? pf.axmax_gd : pf.axmax_air;
+    T.inv_amax = 1.0f / T.amax;
     // ---- perfoap.limits (CAS round trip evaluated at the allowed commanded altitude)
     T.allow_h = a.selalt > pf.hmax ? pf.hmax : a.selalt;
     Atmos ah = (T.allow_h == a.alt) ? T.at : vatmos(T.allow_h);
@@ -279,7 +280,7 @@ __device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const T
     float p_vs = fabsf(selvs_eff);
     float p_hdg = mod360(a.aptrk);
     const float amax = T.amax, allow_tas = T.allow_tas, allow_h = T.allow_h;
-    float vs_max_acc = (1.0f - a.ax / amax) * pf.vsmax;
+    float vs_max_acc = (1.0f - a.ax * T.inv_amax) * pf.vsmax;
     float allow_vs = p_vs;
     if (p_vs > 0.0f && p_vs > pf.vsmax) allow_vs = vs_max_acc;
     if (p_vs < 0.0f && p_vs < pf.vsmin) allow_vs = vs_max_acc;
@@ -289,7 +290,7 @@ __device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const T
     bool need_ax = fabsf(dspd) > fabsf(dt * amax);
     a.ax = need_ax ? copysignf(amax, dspd) : 0.0f;
     a.tas = need_ax ? a.tas + a.ax * dt : allow_tas;
-    float turnrate = kRad2Deg * (kG0 * kTanBankDef) / fmaxf(a.tas, 0.01f);
+    float turnrate = (kRad2Deg * (kG0 * kTanBankDef)) * rcp_approx(fmaxf(a.tas, 0.01f));
     float delhdg = degto180(p_hdg - a.hdg);
     bool swhdgsel = fabsf(delhdg) > fabsf(dt * turnrate);
     a.hdg = mod360(swhdgsel ? a.hdg + copysignf(dt * turnrate, delhdg) : p_hdg);
@@ -310,7 +311,7 @@ __device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const T
     a.alt = swaltsel ? a.alt + a.vs * dt : allow_h;
     a.lat += (double)(kRad2Deg * (dt * a.gsn * (1.0f / kRearth)));
     a.coslat = __cosf((float)a.lat * kDeg2Rad);          // |lat| <= 90 deg: MUFU.COS is accurate to ~3e-7 here
-    a.lon += (double)(kRad2Deg * (dt * a.gse / a.coslat * (1.0f / kRearth)));
+    a.lon += (double)(kRad2Deg * (dt * a.gse * rcp_approx(a.coslat) * (1.0f / kRearth)));
 }
 
 // ====================================================================================================
@@ -356,8 +357,8 @@ __device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvPa
     const int grp = threadIdx.x / G;
     double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);
     // cos / sin of lat/2 from the cached cos(lat): half-angle identities (absolute error ~1e-7)
-    const float ch = sqrtf(fmaf(0.5f, a.coslat, 0.5f));
-    const float sh = copysignf(sqrtf(fmaxf(fmaf(-0.5f, a.coslat, 0.5f), 0.0f)), (float)a.lat);
+    const float ch = sqrt_approx(fmaf(0.5f, a.coslat, 0.5f));
+    const float sh = copysignf(sqrt_approx(fmaxf(fmaf(-0.5f, a.coslat, 0.5f), 0.0f)), (float)a.lat);
     double dl = a.lon - lon0;
     dl = dl > 180.0 ? dl - 360.0 : (dl < -180.0 ? dl + 360.0 : dl);
     const float x = (float)(kRearthD * kDeg2RadD * dl), y = (float)(kRearthD * kDeg2RadD * (a.lat - lat0));
