@@ -320,7 +320,8 @@ __device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const T
 //   offsets per iteration, for the ONLY condition every conflict or LoS needs: dcpa < R, evaluated without
 //   a division as |d x w|^2 < R^2 |w|^2 (inflated by 2e-4 and by an absolute term that lets co-moving pairs
 //   through, so the filter is a superset of what the exact routine accepts; ~11 % of the pairs of a
-//   HorizontalCR-20 env pass).  The group's records are staged as a structure of arrays written twice,
+//   HorizontalCR-20 env pass).  (Also dropping pairs that move apart outside the zone was tried: it removes
+//   most candidates late in an episode but costs more in the filter than it saves while traffic converges.)  The group's records are staged as a structure of arrays written twice,
 //   n apart, so (i + k) mod n is a plain offset and consecutive lanes read consecutive words.
 //   Exact phase: the candidates (i, k) are compacted into a per-group queue in shared memory, spread over
 //   the lanes, and evaluated by cd_pair_sym() -- the same routine as before, so results are bit-identical
@@ -432,9 +433,10 @@ __device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvPa
         cand = (lane_g < nac) ? (cand & valid) : 0u;
     }
 
-    // ---- compaction: (i, k) entries into the group's queue -------------------------------------------
+    // ---- compaction: (i, k) entries into the group's queue (skipped when the whole group found nothing) --------
     uint16_t* queue = s_queue + gbase * kQueuePerThread;
-    {
+    int ncand = 0;
+    if (__any_sync(group_mask<G>(), cand != 0u)) {
         const int cnt = __popc(cand);
         int pos = 0;
         if (cnt) pos = atomicAdd(&s_cnt[grp], cnt);
@@ -447,9 +449,9 @@ __device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvPa
             if (c & 4u) *qp++ = (uint16_t)(val + 2u);
             if (c & 8u) *qp++ = (uint16_t)(val + 3u);
         }
+        __syncwarp(group_mask<G>());
+        ncand = s_cnt[grp];
     }
-    __syncwarp(group_mask<G>());
-    const int ncand = s_cnt[grp];
 
     // ---- exact phase -------------------------------------------------------------------------------
     for (int p = lane_g; p < ncand; p += G) {
