@@ -281,12 +281,15 @@ def run_b200(args):
                         "bytes_per_env_step": BYTES_PER_ENV_STEP}}
         # CD at N = 100k on this GPU (BASELINE configs[4], single-GPU share)
         cd = bench_cd(torch, dev, StateBasedCD, fp32)
+        other = bench_other_envs(torch, dev, BlueSkyVectorEnv) if world == 1 else None
         cb = None if (args.skip_cpu or world > 1) else cpu_baseline(budget_s=10.0)
         line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (lat/lon f64)", "data": "synthetic", "config": workload_config(world),
                 "value_l2_warm": warm_value, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
                 "cpu_baseline": cb, "clocks": clk.summary(), "cd_pairs": cd}
+        if other is not None:
+            line["other_envs"] = other
         if cd_sharded is not None:
             cd_sharded["roofline_frac_per_gpu"] = cd_sharded["ordered_pairs_per_s"] * F_PAIR / world / fp32
             line["cd_pairs_sharded"] = cd_sharded
@@ -295,6 +298,32 @@ def run_b200(args):
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line))
+
+
+def bench_other_envs(torch, dev, BlueSkyVectorEnv, steps=60):
+    """Device time per batched step of the other BASELINE configs on this GPU (context only; not the headline)."""
+    out = {}
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    for name, env_id, E, kw in (("SectorCREnv-v0 (configs[2] per-GPU share)", "SectorCREnv-v0", 8192, dict(cd_enabled=True)),
+                                ("MergeEnv-v0 (configs[3])", "MergeEnv-v0", 4096, dict(cd_enabled=True)),
+                                ("DescentEnv-v0 (configs[0], batched)", "DescentEnv-v0", 65536, {}),
+                                ("HorizontalCREnv-v0 reference default (5 intruders, no CD)", "HorizontalCREnv-v0", 65536, {})):
+        v = BlueSkyVectorEnv(env_id, E, device=dev.index, seed=0, autoreset_mode="same_step", **kw)
+        v.reset_torch()
+        a = torch.rand((steps + 5, E, v.layout.act_dim), device=dev) * 2.0 - 1.0
+        for i in range(5):
+            v.step_torch(a[i])
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            flush.fill_(float(i))
+            ev[i][0].record()
+            v.step_torch(a[5 + i])
+            ev[i][1].record()
+        torch.cuda.synchronize(dev)
+        ms = sum(x.elapsed_time(y) for x, y in ev) / steps
+        out[name] = {"envs": E, "ms_per_step": ms, "env_steps_per_s": E / ms * 1e3}
+        v.close()
+    return out
 
 
 def C_double_probe(lib, device):

@@ -26,6 +26,18 @@ int bsg_cuda_check(cudaError_t e, const char* what) {
     return BSG_ECUDA;
 }
 
+// Entry points run on the handle's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+    int prev = -1, dev;
+    explicit DeviceGuard(int d) : dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
+
 struct bsg_handle {
     bsg_config cfg;
     bsg_layout lay;
@@ -149,7 +161,7 @@ extern "C" int bsg_bind_state(bsg_handle* h, const bsg_tensor_table* t) {
 static int run_mode(bsg_handle* h, int mode, const float* d_actions, const uint8_t* d_mask, int n_sub, void* stream) {
     if (!h) return bsg_fail(BSG_EINVAL, "null handle");
     if (!h->bound) return bsg_fail(BSG_ESTATE, "bsg_bind_state has not been called");
-    BSG_CUDA(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     bsg::EnvParams P = h->P;
     P.mode = mode; P.actions = d_actions; P.reset_mask = d_mask;
     if (n_sub > 0) P.n_sub = n_sub;
@@ -188,7 +200,7 @@ extern "C" int bsg_step_host(bsg_handle* h, const float* h_actions, float* h_obs
     if (!h->t.actions_staging) return bsg_fail(BSG_ESTATE, "bsg_step_host needs tensor_table.actions_staging");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t E = (size_t)h->cfg.num_envs;
-    BSG_CUDA(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     BSG_CUDA(cudaMemcpyAsync(h->t.actions_staging, h_actions, E * h->lay.act_dim * sizeof(float), cudaMemcpyHostToDevice, st));
     int rc = run_mode(h, bsg::kModeStep, h->t.actions_staging, nullptr, 0, stream);
     if (rc != BSG_OK) return rc;
@@ -233,7 +245,7 @@ extern "C" int bsg_step_host_block(bsg_handle* h, const float* h_actions, void* 
     if (!h->t.actions_staging) return bsg_fail(BSG_ESTATE, "bsg_step_host_block needs tensor_table.actions_staging");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t E = (size_t)h->cfg.num_envs;
-    BSG_CUDA(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     BSG_CUDA(cudaMemcpyAsync(h->t.actions_staging, h_actions, E * h->lay.act_dim * sizeof(float), cudaMemcpyHostToDevice, st));
     int rc = run_mode(h, bsg::kModeStep, h->t.actions_staging, nullptr, 0, stream);
     if (rc != BSG_OK) return rc;
@@ -253,7 +265,7 @@ extern "C" int bsg_step_host_copy(bsg_handle* h, const float* h_actions, void* h
     if (dst_bytes > nbytes) return bsg_fail(BSG_EINVAL, "bsg_step_host_copy: dst_bytes exceeds the mirrored block");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t E = (size_t)h->cfg.num_envs;
-    BSG_CUDA(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     if (!h->have_ev) {
         for (int k = 0; k < 4; ++k) BSG_CUDA(cudaEventCreateWithFlags(&h->ev[k], cudaEventDisableTiming));
         h->have_ev = true;

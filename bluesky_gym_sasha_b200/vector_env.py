@@ -164,12 +164,11 @@ class BlueSkyVectorEnv(VectorEnv):
         return OrderedDict((k, flat[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
 
     def _infos_np(self, info):
-        out = {}
-        for i, k in enumerate(self.spec_b200.info_keys):
-            out[k] = info[:, i].astype(np.float64)
+        t = info.T.astype(np.float64)               # [info_dim, E]: one conversion, contiguous rows per key
+        out = {k: t[i] for i, k in enumerate(self.spec_b200.info_keys)}
         if self.cfg.cd_enabled:
-            out["asas_nconf"] = info[:, 4].astype(np.int64)
-            out["asas_nlos"] = info[:, 5].astype(np.int64)
+            out["asas_nconf"] = t[4].astype(np.int64)
+            out["asas_nlos"] = t[5].astype(np.int64)
         return out
 
     # ------------------------------------------------------------------ device-tensor API (no host sync)
@@ -186,8 +185,9 @@ class BlueSkyVectorEnv(VectorEnv):
         of the bound device tensors (overwritten by the next call)."""
         a = actions.to(device=self.device, dtype=torch.float32).contiguous()
         assert a.shape == (self.num_envs, self.layout.act_dim), a.shape
-        with torch.cuda.device(self.device):
-            _lib.check(self._lib.bsg_step(self._h, _ptr(a), self._stream()))
+        rc = self._lib.bsg_step(self._h, a.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _lib.check(rc)
         self.gpu_launches += 1
         return self._obs_dict_torch(self.t["obs"]), self.t["reward"], self.t["terminated"], self.t["truncated"]
 
@@ -213,13 +213,16 @@ class BlueSkyVectorEnv(VectorEnv):
         self._hsel ^= 1
         h = self._hbuf[self._hsel]
         fresh = self.copy and self.obs_dtype == np.float32
-        with torch.cuda.device(self.device):
-            if fresh:       # the result array is filled by the library's host threads while the transfer is in flight
-                flat = np.empty((E, self.layout.obs_dim), dtype=np.float32)
-                _lib.check(self._lib.bsg_step_host_copy(self._h, self._act_ptr, h["ptr"], self._out_bytes,
-                                                        C.c_void_p(flat.ctypes.data), flat.nbytes, self._stream()))
-            else:
-                _lib.check(self._lib.bsg_step_host_block(self._h, self._act_ptr, h["ptr"], self._out_bytes, self._stream()))
+        # (the library sets the device itself; the stream is looked up per call because callers may switch streams)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if fresh:           # the result array is filled by the library's host threads while the transfer is in flight
+            flat = np.empty((E, self.layout.obs_dim), dtype=np.float32)
+            rc = self._lib.bsg_step_host_copy(self._h, self._act_ptr, h["ptr"], self._out_bytes,
+                                              flat.ctypes.data, flat.nbytes, stream)
+        else:
+            rc = self._lib.bsg_step_host_block(self._h, self._act_ptr, h["ptr"], self._out_bytes, stream)
+        if rc:
+            _lib.check(rc)
         self.gpu_launches += 1
         if fresh:
             obs = OrderedDict((k, flat[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
