@@ -33,7 +33,13 @@ class Config(C.Structure):
                 ("cd_enabled", C.c_int32), ("autoreset_mode", C.c_int32), ("max_episode_steps", C.c_int32),
                 ("default_hdg_random", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64),
                 ("env_id_offset", C.c_int64), ("rpz", C.c_float), ("hpz", C.c_float),
-                ("dtlookahead", C.c_float), ("perf", Perf)]
+                ("dtlookahead", C.c_float), ("perf", Perf), ("wind_obs", C.c_int32)]
+
+
+class Wind(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("n_alt", C.c_int32), ("alt_step", C.c_float),
+                ("d_lat", C.c_void_p), ("d_lon", C.c_void_p), ("d_vn", C.c_void_p), ("d_ve", C.c_void_p),
+                ("d_gs", C.c_void_p)]
 
 
 class Layout(C.Structure):
@@ -51,7 +57,7 @@ class TensorTable(C.Structure):
 
 
 SYMBOLS = ("bsg_abi_version", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
-           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_host_copy", "bsg_set_obs_noise", "bsg_traf_update",
+           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_host_copy", "bsg_set_obs_noise", "bsg_set_wind", "bsg_traf_update",
            "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_probe_fp32")
 
 _lib = None
@@ -85,6 +91,9 @@ def load():
     lib.bsg_step_host_block.argtypes = [vp, vp, vp, C.c_size_t, vp]
     lib.bsg_set_obs_noise.argtypes = [vp, f32]
     lib.bsg_set_obs_noise.restype = C.c_int
+    if hasattr(lib, "bsg_set_wind"):            # (absent only in older A/B builds loaded through BSG_B200_LIB)
+        lib.bsg_set_wind.argtypes = [vp, C.POINTER(Wind)]
+        lib.bsg_set_wind.restype = C.c_int
     lib.bsg_host_copy.argtypes = [vp, vp, C.c_size_t]
     lib.bsg_host_copy.restype = C.c_int
     lib.bsg_step_host_copy.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp]

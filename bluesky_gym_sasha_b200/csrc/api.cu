@@ -90,6 +90,7 @@ extern "C" int bsg_query_layout(const bsg_config* cfg, bsg_layout* out) {
         default:
             return bsg_fail(BSG_EINVAL, "unknown env_type");
     }
+    if (cfg->wind_obs) out->obs_dim += 2;        // wrappers/wind.py:17-23: wind_u, wind_v appended
     return BSG_OK;
 }
 
@@ -113,7 +114,7 @@ extern "C" int bsg_create(const bsg_config* cfg, bsg_handle** out) {
     P.n_sub = lay.n_sub; P.simdt = lay.simdt;
     int rel = (int)floor(10.5 / (double)lay.simdt);          // settings.fms_dt // simdt  (core/simtime.py Timer)
     P.fms_rel_freq = rel < 1 ? 1 : rel;
-    P.obs_dim = lay.obs_dim; P.act_dim = lay.act_dim; P.info_dim = lay.info_dim;
+    P.obs_dim = lay.obs_dim; P.act_dim = lay.act_dim; P.info_dim = lay.info_dim; P.wind_obs = cfg->wind_obs;
     float rpz = cfg->rpz > 0.0f ? cfg->rpz : 5.0f * 1852.0f;
     P.R2 = rpz * rpz;
     P.hpz = cfg->hpz > 0.0f ? cfg->hpz : 1000.0f * 0.3048f;
@@ -170,6 +171,22 @@ static int run_mode(bsg_handle* h, int mode, const float* d_actions, const uint8
     int rc = bsg_launch_env(P, h->lay.slots, (cudaStream_t)stream);
     if (rc != BSG_OK || mode == bsg::kModeTraf || !(h->obs_noise > 0.0f)) return rc;
     return bsg_launch_obs_noise(P, h->obs_noise, h->noise_calls++, mode == bsg::kModeStep, (cudaStream_t)stream);
+}
+
+extern "C" int bsg_set_wind(bsg_handle* h, const bsg_wind* w) {
+    if (!h) return bsg_fail(BSG_EINVAL, "null handle");
+    bsg::EnvParams& P = h->P;
+    if (!w || w->n_points == 0) {
+        P.wind_n = 0; P.wind_nalt = 0; P.wind_lat = P.wind_lon = P.wind_vn = P.wind_ve = nullptr; P.gsv = nullptr;
+        return BSG_OK;
+    }
+    if (w->n_points < 0 || w->n_points > 64) return bsg_fail(BSG_EINVAL, "bsg_set_wind: n_points must be in [0, 64]");
+    if (w->n_alt < 1 || (w->n_alt > 1 && !(w->alt_step > 0.0f))) return bsg_fail(BSG_EINVAL, "bsg_set_wind: bad altitude axis");
+    if (!w->d_lat || !w->d_lon || !w->d_vn || !w->d_ve || !w->d_gs) return bsg_fail(BSG_EINVAL, "bsg_set_wind: null pointer");
+    P.wind_n = w->n_points; P.wind_nalt = w->n_alt; P.wind_altstep = w->alt_step;
+    P.wind_lat = w->d_lat; P.wind_lon = w->d_lon; P.wind_vn = w->d_vn; P.wind_ve = w->d_ve;
+    P.gsv = (float2*)w->d_gs;
+    return BSG_OK;
 }
 
 extern "C" int bsg_set_obs_noise(bsg_handle* h, float sigma) {

@@ -44,6 +44,11 @@ struct EnvParams {
     double* ef64; float* ef32; int32_t* ei32; double* poly;
     float* obs; float* final_obs; int32_t* final_ids; int32_t* final_count; float* reward; uint8_t* term; uint8_t* trunc; float* info;
     const float* actions; const uint8_t* reset_mask;
+    // WindFieldWrapper (bsg_set_wind): wind_n == 0 <=> no wind
+    int wind_n, wind_nalt, wind_obs;
+    float wind_altstep;
+    const float* wind_lat; const float* wind_lon; const float* wind_vn; const float* wind_ve;
+    float2* gsv;
 };
 
 struct Ac {
@@ -116,6 +121,43 @@ __device__ inline void ac_clear(Ac& a) {
     a.cas = 0.0f; a.flags = 0u; a.gsn = 0.0f; a.gse = 0.0f; a.coslat = 1.0f; a.tcpamax = 0.0f; a.inconf = false;
 }
 
+// ---- wind field: upstream windfield.py::getdata (oracle/windfield.py) -------------------------------
+// inverse-distance-squared weights on the flat-earth metric in degrees (longitude scaled by the cosine of the
+// mean latitude), linear interpolation between the two bracketing altitude rows
+__device__ __forceinline__ void wind_at(const EnvParams& P, double latd, double lond, float alt, float& vn, float& ve) {
+    const int n = P.wind_n;
+    int ia = 0;
+    float fa = 0.0f;
+    if (P.wind_nalt > 1) {
+        float idx = fmaxf(0.0f, fminf(P.wind_altstep * (float)(P.wind_nalt - 1), alt) / P.wind_altstep);
+        ia = min((int)floorf(idx), P.wind_nalt - 2);
+        fa = idx - (float)ia;
+    }
+    float wsum = 0.0f, sn = 0.0f, se = 0.0f;
+    for (int k = 0; k < n; ++k) {
+        const float plat = P.wind_lat[k], plon = P.wind_lon[k];
+        const float dy = (float)(latd - (double)plat), dxl = (float)(lond - (double)plon);
+        const float cav = __cosf(0.5f * ((float)latd + plat) * kDeg2Rad);
+        const float dx = cav * dxl;
+        const float w = 1.0f / fmaxf(fmaf(dx, dx, dy * dy), 1e-20f);
+        float vnk = P.wind_vn[ia * n + k], vek = P.wind_ve[ia * n + k];
+        if (P.wind_nalt > 1) {
+            vnk = fmaf(fa, P.wind_vn[(ia + 1) * n + k] - vnk, vnk);
+            vek = fmaf(fa, P.wind_ve[(ia + 1) * n + k] - vek, vek);
+        }
+        wsum += w; sn = fmaf(w, vnk, sn); se = fmaf(w, vek, se);
+    }
+    vn = n ? sn / wsum : 0.0f;
+    ve = n ? se / wsum : 0.0f;
+}
+// bs.traf.gs: equals tas without wind (and below 50 ft)
+__device__ __forceinline__ float ac_gs(const Ac& a, const EnvParams& P) {
+    return P.wind_n > 0 ? sqrtf(fmaf(a.gsn, a.gsn, a.gse * a.gse)) : a.tas;
+}
+__device__ __forceinline__ float ac_trk(const Ac& a, const EnvParams& P) {
+    return P.wind_n > 0 ? mod360(kRad2Deg * atan2f(a.gse, a.gsn)) : a.hdg;
+}
+
 // ---- state I/O (coalesced: consecutive lanes -> consecutive float4 / double2) ----------------------
 __device__ __forceinline__ void ac_load(Ac& a, const EnvParams& P, long long idx) {
     double2 p = P.pos[idx];
@@ -128,6 +170,7 @@ __device__ __forceinline__ void ac_load(Ac& a, const EnvParams& P, long long idx
     float s, co;
     sincosf(a.hdg * kDeg2Rad, &s, &co);
     a.gsn = a.tas * co; a.gse = a.tas * s;
+    if (P.gsv) { float2 g = P.gsv[idx]; a.gsn = g.x; a.gse = g.y; }      // with wind the ground speed is state
     a.coslat = cosf((float)a.lat * kDeg2Rad);
     a.tcpamax = 0.0f; a.inconf = false;
 }
@@ -137,6 +180,7 @@ __device__ __forceinline__ void ac_store(const Ac& a, const EnvParams& P, long l
     P.cmd[idx] = make_float4(a.selspd, a.selalt, a.selvs, a.aptrk);
     P.aux[idx] = make_float4(a.ax, a.curlegdir, a.cas, 0.0f);
     P.flags[idx] = a.flags;
+    if (P.gsv) P.gsv[idx] = make_float2(a.gsn, a.gse);
     if (P.cd_enabled) {
         P.tcpamax[idx] = a.tcpamax;
         P.inconf[idx] = a.inconf ? 1 : 0;
@@ -254,8 +298,8 @@ __device__ __forceinline__ void ac_autopilot(Ac& a, const EnvParams& P, bool fms
             qdrdist_wgs(a.lat, a.lon, wlat, wlon, qdr, dist);
             if (fms_ready) {
                 // ActiveWaypoint.reached: next_qdr is -999 for both legs of this route => turndist = 0
-                bool close2wp = dist / fmaxf(0.0001f, fabsf(a.tas)) < 4.0f;
-                bool tooclose = close2wp && fabsf(degto180(mod360(a.hdg) - mod360(qdr))) > 90.0f;
+                bool close2wp = dist / fmaxf(0.0001f, fabsf(ac_gs(a, P))) < 4.0f;
+                bool tooclose = close2wp && fabsf(degto180(mod360(ac_trk(a, P)) - mod360(qdr))) > 90.0f;
                 bool passed = fabsf(degto180(qdr - a.curlegdir)) > 90.0f;
                 if (tooclose || passed) {
                     if ((a.flags & kFlLastWp) || iwp >= 1) {
@@ -272,13 +316,25 @@ __device__ __forceinline__ void ac_autopilot(Ac& a, const EnvParams& P, bool fms
     }
 }
 
+template <bool WIND>
 __device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const Targets& T) {
     const float dt = P.simdt;
     const bsg_perf& pf = P.perf;
-    // ---- Autopilot select modes + APorASAS.update (resolution off, no wind)
+    // ---- Autopilot select modes + APorASAS.update (resolution off)
     float selvs_eff = fabsf(a.selvs) > 0.1f ? a.selvs : kVsDef;
     float p_vs = fabsf(selvs_eff);
     float p_hdg = mod360(a.aptrk);
+    float wn = 0.0f, we = 0.0f;
+    if (WIND) {
+        // APorASAS.update with wind: the heading that makes good the commanded track (crab angle), from the
+        // wind at the aircraft's position before this substep's update_pos
+        wind_at(P, a.lat, a.lon, a.alt, wn, we);
+        const float vw = sqrtf(fmaf(wn, wn, we * we));
+        const float drift = a.aptrk * kDeg2Rad - atan2f(we, wn);
+        const float steer = asinf(fminf(1.0f, fmaxf(-1.0f, vw * sinf(drift) / fmaxf(0.001f, a.tas))));
+        p_hdg = mod360(a.aptrk + kRad2Deg * steer);
+        if (!(a.alt > 50.0f * kFt)) { wn = 0.0f; we = 0.0f; }       // update_groundspeed: wind only when airborne
+    }
     const float amax = T.amax, allow_tas = T.allow_tas, allow_h = T.allow_h;
     float vs_max_acc = (1.0f - a.ax * T.inv_amax) * pf.vsmax;
     float allow_vs = p_vs;
@@ -301,12 +357,13 @@ __device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const T
     bool need_az = fabsf(delta_vs) > kAzMax;
     a.vs = need_az ? a.vs + copysignf(kAzMax, delta_vs) * dt : target_vs;
     if (!isfinite(a.vs)) a.vs = 0.0f;
-    // ---- update_groundspeed (no wind: gs = tas, trk = hdg)
+    // ---- update_groundspeed (no wind: gs = tas, trk = hdg; WIND: + the wind vector when above 50 ft)
     // hdg is in [0, 360): evaluate at hdg - 180 in [-pi, pi) where the MUFU sin/cos are accurate to ~5e-7,
     // and flip the signs (sin(x + pi) = -sin x, cos(x + pi) = -cos x)
     float sh, ch;
     __sincosf((a.hdg - 180.0f) * kDeg2Rad, &sh, &ch);
     a.gsn = -a.tas * ch; a.gse = -a.tas * sh;
+    if (WIND) { a.gsn += wn; a.gse += we; }
     // ---- update_pos (lat/lon accumulate in float64)
     a.alt = swaltsel ? a.alt + a.vs * dt : allow_h;
     a.lat += (double)(kRad2Deg * (dt * a.gsn * (1.0f / kRearth)));

@@ -123,7 +123,8 @@ __device__ inline StepOut horizontal_obs_reward(const Ac& a, EnvS& s, const EnvP
                                                 bool with_reward) {
     const int n = P.n_int;                                                  // horizontal_cr_env.py:150-213
     const double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);
-    const float hdg0 = group_bcast<G>(a.hdg, 0), gs0 = group_bcast<G>(a.tas, 0);
+    const float gs_own = ac_gs(a, P);
+    const float hdg0 = group_bcast<G>(a.hdg, 0), gs0 = group_bcast<G>(gs_own, 0);
     const bool intr = slot >= 1 && slot <= n;
     float qdr = 0.0f, dis = 1e9f;
     if (intr) {
@@ -135,8 +136,8 @@ __device__ inline StepOut horizontal_obs_reward(const Ac& a, EnvS& s, const EnvP
         obs[k] = dis * (1.852f / 150.0f);
         obs[n + k] = cb;
         obs[2 * n + k] = sb;
-        obs[3 * n + k] = -cd * a.tas * (1.0f / 150.0f);
-        obs[4 * n + k] = (gs0 - sd * a.tas) * (1.0f / 150.0f);
+        obs[3 * n + k] = -cd * gs_own * (1.0f / 150.0f);
+        obs[4 * n + k] = (gs0 - sd * gs_own) * (1.0f / 150.0f);
     }
     float wq, wd;
     kwikqdrdist(lat0, lon0, s.wpt_lat, s.wpt_lon, wq, wd);
@@ -295,7 +296,11 @@ __device__ inline StepOut sector_obs_reward(const Ac& a, EnvS& s, const EnvParam
                                             long long e, bool with_reward) {
     const double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);     // sector_cr_env.py:237-313
     const float hdg0 = group_bcast<G>(a.hdg, 0), tas0 = group_bcast<G>(a.tas, 0);
-    const float vx0 = group_bcast<G>(a.gsn, 0), vy0 = group_bcast<G>(a.gse, 0);
+    // cos / sin(hdg) * tas: the cached ground-speed components are exactly that without wind; with wind they carry
+    // the wind vector, which the reference's observation does not include (it uses bs.traf.hdg and bs.traf.tas)
+    float avx = a.gsn, avy = a.gse;
+    if (P.wind_n > 0) { float sh_, ch_; sincosf(a.hdg * kDeg2Rad, &sh_, &ch_); avx = a.tas * ch_; avy = a.tas * sh_; }
+    const float vx0 = group_bcast<G>(avx, 0), vy0 = group_bcast<G>(avy, 0);
     float wq, wd;
     kwikqdrdist(lat0, lon0, s.wpt_lat, s.wpt_lon, wq, wd);
     const float drift = wrap180_fold(hdg0 - wq);
@@ -311,7 +316,7 @@ __device__ inline StepOut sector_obs_reward(const Ac& a, EnvS& s, const EnvParam
     float dist = sqrtf(dxm * dxm + dym * dym);
     int rank = nearest_rank<G>(dist, other, 4);
     if (rank >= 0) {
-        float dvx = a.gsn - vx0, dvy = a.gse - vy0;
+        float dvx = avx - vx0, dvy = avy - vy0;
         float hyp = sqrtf(dvx * dvx + dvy * dvy);
         float ct = hyp > 0.0f ? dvx / hyp : 1.0f, st = hyp > 0.0f ? dvy / hyp : 0.0f;
         obs[3 + rank] = dxm * (1.0f / 13000.0f);
@@ -383,7 +388,11 @@ __device__ inline StepOut merge_obs_reward(const Ac& a, EnvS& s, const EnvParams
                                            bool with_reward) {
     const double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);     // merge_env.py:160-236
     const float hdg0 = group_bcast<G>(a.hdg, 0), tas0 = group_bcast<G>(a.tas, 0);
-    const float vx0 = group_bcast<G>(a.gsn, 0), vy0 = group_bcast<G>(a.gse, 0);
+    // cos / sin(hdg) * tas: the cached ground-speed components are exactly that without wind; with wind they carry
+    // the wind vector, which the reference's observation does not include (it uses bs.traf.hdg and bs.traf.tas)
+    float avx = a.gsn, avy = a.gse;
+    if (P.wind_n > 0) { float sh_, ch_; sincosf(a.hdg * kDeg2Rad, &sh_, &ch_); avx = a.tas * ch_; avy = a.tas * sh_; }
+    const float vx0 = group_bcast<G>(avx, 0), vy0 = group_bcast<G>(avy, 0);
     float wq, wd;
     if (s.wpt_reach == 0) kwikqdrdist(lat0, lon0, P.fix_lat, P.fix_lon, wq, wd);
     else kwikqdrdist(lat0, lon0, kRwyLat, kRwyLon, wq, wd);
@@ -401,7 +410,7 @@ __device__ inline StepOut merge_obs_reward(const Ac& a, EnvS& s, const EnvParams
         float sb, cb;
         sincosf(brg * kDeg2Rad, &sb, &cb);
         float dm = dnm * 1852.0f;
-        float dvx = a.gsn - vx0, dvy = a.gse - vy0;
+        float dvx = avx - vx0, dvy = avy - vy0;
         float hyp = sqrtf(dvx * dvx + dvy * dvy);
         float ct = hyp > 0.0f ? dvx / hyp : 1.0f, st = hyp > 0.0f ? dvy / hyp : 0.0f;
         obs[5 + rank] = dm * cb * 1e-6f;
@@ -526,7 +535,8 @@ template <int G>
 __device__ inline StepOut vertical_obs_reward(const Ac& a, EnvS& s, const EnvParams& P, float* obs, int slot,
                                               bool with_reward) {
     const double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);     // vertical_cr_env.py:114-183
-    const float hdg0 = group_bcast<G>(a.hdg, 0), gs0 = group_bcast<G>(a.tas, 0);
+    const float gs_own = ac_gs(a, P);
+    const float hdg0 = group_bcast<G>(a.hdg, 0), gs0 = group_bcast<G>(gs_own, 0);
     const float alt0 = group_bcast<G>(a.alt, 0), vs0 = group_bcast<G>(a.vs, 0);
     float q, dnm;
     kwikqdrdist(52.0, 4.0, lat0, lon0, q, dnm);
@@ -551,8 +561,8 @@ __device__ inline StepOut vertical_obs_reward(const Ac& a, EnvS& s, const EnvPar
         obs[9 + k] = cb;
         obs[14 + k] = sb;
         obs[19 + k] = (a.alt - alt0) * (1.0f / 3000.0f);
-        obs[24 + k] = -cd * a.tas * (1.0f / 150.0f);
-        obs[29 + k] = (gs0 - sd * a.tas) * (1.0f / 150.0f);
+        obs[24 + k] = -cd * gs_own * (1.0f / 150.0f);
+        obs[29 + k] = (gs0 - sd * gs_own) * (1.0f / 150.0f);
         obs[34 + k] = a.vs - vs0;
     }
     StepOut o = {0.0f, 0, 0};
@@ -753,7 +763,7 @@ __device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float
 // =====================================================================================================
 // K6: the env-step megakernel (also serves reset and the kinematics-only parity entry point)
 // =====================================================================================================
-template <int ENV, int G>
+template <int ENV, int G, bool WIND>
 __global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) {
     __shared__ __align__(16) float4 s_rec[(G > 1) ? kEnvThreads * 2 : 1];
     __shared__ float s_hot[(G > 8) ? kEnvThreads * 2 * kHotFields : 1];
@@ -799,6 +809,13 @@ __global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) 
             if (ENV == BSG_ENV_HORIZONTAL_CR) horizontal_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_SECTOR_CR) sector_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_MERGE) merge_action<G>(a, P, act, slot);
+            if (WIND && ENV != BSG_ENV_DESCENT && ENV != BSG_ENV_VERTICAL_CR && slot == 0 && a.alt > 50.0f * kFt) {
+                // Autopilot.selhdgcmd with wind: the commanded HEADING becomes the track it produces right now
+                float wn, we, sh, ch;
+                wind_at(P, a.lat, a.lon, a.alt, wn, we);
+                sincosf(a.aptrk * kDeg2Rad, &sh, &ch);
+                a.aptrk = mod360(kRad2Deg * atan2f(fmaf(a.tas, sh, we), fmaf(a.tas, ch, wn)));
+            }
         }
         int nconf = s.nconf, nlos = s.nlos;
         Targets T;
@@ -812,7 +829,7 @@ __global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) 
                 ac_autopilot<ENV>(a, P, fms_ready);
             }
             if (G > 1 && P.cd_enabled) group_cd<G>(a, alive, s.num_ac, P, s_rec, s_hot, s_queue, s_tmax, s_cnt, s_pairs, nconf, nlos);
-            if (alive) ac_kinematics(a, P, T);
+            if (alive) ac_kinematics<WIND>(a, P, T);
             if (ENV == BSG_ENV_STATIC_OBSTACLE && P.mode == kModeStep) {   // per-substep reward / termination
                 if (k == 0) env_load_post(s, P, e);
                 if (static_substep_check<G>(a, s, P, e, slot)) break;
@@ -836,6 +853,13 @@ __global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) 
         const bool fresh = resetting;                    // this pass starts from a newly generated scenario
         if (resetting) do_reset<ENV, G>(a, s, P, e, slot, scratch);
         StepOut o = do_obs<ENV, G>(a, s, P, obs, slot, e, !fresh);
+        if (P.wind_obs && slot == 0) {                   // wrappers/wind.py:55-64 (_get_wind_observation)
+            float wn = 0.0f, we = 0.0f, sh, ch;
+            if (WIND) wind_at(P, a.lat, a.lon, a.alt, wn, we);
+            sincosf(a.hdg * kDeg2Rad, &sh, &ch);
+            obs[P.obs_dim - 2] = (wn * ch + we * sh) * (1.0f / 50.0f);
+            obs[P.obs_dim - 1] = (-wn * sh + we * ch) * (1.0f / 50.0f);
+        }
         if (pass == 1) break;                            // SAME_STEP: the step's reward / flags / info stay
         if (fresh) {
             if (slot == 0) { P.reward[e] = 0.0f; P.term[e] = 0; P.trunc[e] = 0; do_info<ENV>(s, P, info); }
@@ -874,7 +898,8 @@ static int launch_env_t(const EnvParams& P, cudaStream_t st) {
     long long threads = (long long)P.E * G;
     int blocks = (int)((threads + kEnvThreads - 1) / kEnvThreads);
     if (blocks == 0) return BSG_OK;
-    env_kernel<ENV, G><<<blocks, kEnvThreads, 0, st>>>(P);
+    if (P.wind_n > 0) env_kernel<ENV, G, true><<<blocks, kEnvThreads, 0, st>>>(P);
+    else env_kernel<ENV, G, false><<<blocks, kEnvThreads, 0, st>>>(P);
     return bsg_cuda_check(cudaGetLastError(), "env_kernel launch");
 }
 

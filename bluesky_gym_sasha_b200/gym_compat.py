@@ -16,6 +16,7 @@ try:                                            # pragma: no cover - not install
     from gymnasium.vector import VectorEnv
     from gymnasium.vector.utils import batch_space
     Env = _gym.Env
+    Wrapper = _gym.Wrapper
     make = _gym.make
     HAVE_GYMNASIUM = True
 except ImportError:
@@ -122,6 +123,48 @@ except ImportError:
         @property
         def unwrapped(self):
             return self
+
+    class Wrapper(Env):
+        """gymnasium.Wrapper: forwards everything to ``env``; spaces can be overridden by assignment."""
+
+        def __init__(self, env):
+            self.env = env
+            self._observation_space = None
+            self._action_space = None
+
+        def __getattr__(self, name):
+            if name.startswith("_"):
+                raise AttributeError(name)
+            return getattr(self.env, name)
+
+        @property
+        def observation_space(self):
+            return self._observation_space if self._observation_space is not None else self.env.observation_space
+
+        @observation_space.setter
+        def observation_space(self, space):
+            self._observation_space = space
+
+        @property
+        def action_space(self):
+            return self._action_space if self._action_space is not None else self.env.action_space
+
+        @action_space.setter
+        def action_space(self, space):
+            self._action_space = space
+
+        def reset(self, **kwargs):
+            return self.env.reset(**kwargs)
+
+        def step(self, action):
+            return self.env.step(action)
+
+        def close(self):
+            return self.env.close()
+
+        @property
+        def unwrapped(self):
+            return self.env.unwrapped
 
     class VectorEnv:
         metadata = {}

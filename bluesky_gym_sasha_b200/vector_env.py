@@ -33,7 +33,7 @@ class BlueSkyVectorEnv(VectorEnv):
     def __init__(self, env_id, num_envs, device=0, seed=0, cd_enabled=False, n_intruders=None,
                  autoreset_mode="next_step", env_id_offset=0, max_episode_steps=None, perf=None,
                  default_hdg="random", rpz=0.0, hpz=0.0, dtlookahead=0.0, render_mode=None,
-                 obs_dtype=np.float32, copy=True, obs_noise=0.0):
+                 obs_dtype=np.float32, copy=True, obs_noise=0.0, wind=None, wind_obs=False):
         if env_id in NOT_ACCELERATED:
             raise NotImplementedError(f"{env_id} is registered by the reference but is not on the accelerated "
                                       "path yet (SURVEY.md section 8f)")
@@ -64,13 +64,18 @@ class BlueSkyVectorEnv(VectorEnv):
             max_episode_steps=self.spec_b200.max_episode_steps if max_episode_steps is None else int(max_episode_steps),
             default_hdg_random=1 if default_hdg == "random" else 0, device=self.device.index,
             seed=int(seed) & (2 ** 64 - 1), env_id_offset=int(env_id_offset), rpz=rpz, hpz=hpz,
-            dtlookahead=dtlookahead, perf=pf)
+            dtlookahead=dtlookahead, perf=pf, wind_obs=int(bool(wind_obs)))
         self.layout = _lib.query_layout(self.cfg)
         L, E, G = self.layout, self.num_envs, self.layout.slots
         self.slots = G
 
         # ---- spaces (identical keys / shapes / dtype to the reference declarations)
         self.obs_layout, obs_dim = self.spec_b200.obs_layout(n_int)
+        self.wind_obs = bool(wind_obs)
+        if self.wind_obs:                       # wrappers/wind.py:17-23: two more keys at the end of the Dict
+            self.obs_layout["wind_u"] = (obs_dim, 1, -np.inf, np.inf)
+            self.obs_layout["wind_v"] = (obs_dim + 1, 1, -np.inf, np.inf)
+            obs_dim += 2
         assert obs_dim == L.obs_dim, (obs_dim, L.obs_dim)
         self.single_observation_space = spaces.Dict(OrderedDict(
             (k, spaces.Box(lo, hi, shape=(w,), dtype=np.float64)) for k, (off, w, lo, hi) in self.obs_layout.items()))
@@ -142,6 +147,9 @@ class BlueSkyVectorEnv(VectorEnv):
         self.obs_noise = 0.0
         if obs_noise:
             self.set_obs_noise(obs_noise)
+        self._wind_t = None
+        if wind is not None:
+            self.set_wind(**wind)
 
     # ------------------------------------------------------------------ helpers
     def set_obs_noise(self, noise_level):
@@ -149,6 +157,46 @@ class BlueSkyVectorEnv(VectorEnv):
         observation element returned from now on; 0 switches it off."""
         _lib.check(self._lib.bsg_set_obs_noise(self._h, float(noise_level)))
         self.obs_noise = float(noise_level)
+
+    ALT_STEP = 100.0 * 0.3048           # upstream windfield altitude axis: 100 ft steps up to 45 000 ft
+    N_ALT = 451
+
+    def set_wind(self, lat=None, lon=None, vnorth=None, veast=None, alt=None):
+        """WindFieldWrapper on the device (bluesky_gym/wrappers/wind.py:28 ``bs.traf.wind.addpointvne``): wind vectors
+        [m/s north / east] at the given lat / lon points; ``vnorth[k, i]`` is point i at ``alt[k]`` (``alt=None`` and one
+        row = no altitude dependence).  ``set_wind()`` without arguments switches the wind off."""
+        if lat is None:
+            _lib.check(self._lib.bsg_set_wind(self._h, None))
+            self._wind_t = None
+            return
+        dev = self.device
+        lat = np.atleast_1d(np.asarray(lat, dtype=np.float64))
+        lon = np.atleast_1d(np.asarray(lon, dtype=np.float64))
+        vn = np.atleast_2d(np.asarray(vnorth, dtype=np.float64))
+        ve = np.atleast_2d(np.asarray(veast, dtype=np.float64))
+        n = len(lat)
+        assert len(lon) == n and vn.shape[1] == n and ve.shape == vn.shape, "one wind vector (column) per point"
+        if alt is None:
+            n_alt, tab_n, tab_e = 1, vn[:1], ve[:1]
+        else:                                   # per-point profile resampled on upstream's altitude axis
+            axis = np.arange(self.N_ALT) * self.ALT_STEP
+            wa = np.atleast_1d(np.asarray(alt, dtype=np.float64))
+            n_alt = self.N_ALT
+            tab_n = np.stack([np.interp(axis, wa, vn[:, i]) for i in range(n)], axis=1)
+            tab_e = np.stack([np.interp(axis, wa, ve[:, i]) for i in range(n)], axis=1)
+        f32 = lambda x: torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32), device=dev)
+        t = dict(lat=f32(lat), lon=f32(lon), vn=f32(tab_n), ve=f32(tab_e))
+        if self._wind_t is None or "gs" not in self._wind_t:
+            # ground speed becomes state: start from the no-wind value of the current aircraft (tas along hdg)
+            kin = self.t["kin"]
+            h = torch.deg2rad(kin[..., 2])
+            t["gs"] = torch.stack([kin[..., 1] * torch.cos(h), kin[..., 1] * torch.sin(h)], dim=-1).contiguous()
+        else:
+            t["gs"] = self._wind_t["gs"]
+        w = _lib.Wind(n_points=n, n_alt=n_alt, alt_step=self.ALT_STEP, d_lat=t["lat"].data_ptr(), d_lon=t["lon"].data_ptr(),
+                      d_vn=t["vn"].data_ptr(), d_ve=t["ve"].data_ptr(), d_gs=t["gs"].data_ptr())
+        _lib.check(self._lib.bsg_set_wind(self._h, C.byref(w)))
+        self._wind_t = t                         # keeps the device arrays alive while the library points at them
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

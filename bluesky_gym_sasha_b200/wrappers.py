@@ -51,3 +51,42 @@ class NoisyObservationWrapper(_Wrapper):
                           if isinstance(value, np.ndarray) else value) for key, value in observation.items()}
         print('observation not an numpy array or dictionary, return observation unaltered')
         return observation
+
+
+class WindFieldWrapper(_Wrapper):
+    """wrappers/wind.py:8-64.  The wind field is handed to the simulator (``BlueSkyVectorEnv.set_wind``): kinematics,
+    autopilot heading and the optional ``wind_u`` / ``wind_v`` observations (wind along / across the ownship heading,
+    divided by MAX_WIND = 50) are all computed on the device.  The reference re-adds the points after every reset
+    because ``bs.traf.reset()`` clears them; here the field simply stays on.
+
+    Around a scalar env (``gym.make(id)``) the env's one-instance simulator is rebuilt with the wind (and, for
+    ``augment_obs=True``, with the two extra observation keys).  A ``BlueSkyVectorEnv`` must have been constructed with
+    ``wind_obs=augment_obs`` because the observation layout is fixed at construction."""
+
+    def __init__(self, env, lat, lon, vnorth, veast, alt=None, augment_obs=False):
+        super().__init__(env)
+        self.lat, self.lon, self.vnorth, self.veast, self.alt = lat, lon, vnorth, veast, alt
+        self.augment_obs = augment_obs
+        wind = dict(lat=lat, lon=lon, vnorth=vnorth, veast=veast, alt=alt)
+        if isinstance(env, BlueSkyVectorEnv):
+            if env.wind_obs != bool(augment_obs):
+                raise ValueError("construct the BlueSkyVectorEnv with wind_obs=%r (the observation layout is fixed at "
+                                 "construction)" % bool(augment_obs))
+            env.set_wind(**wind)
+        else:
+            scalar = getattr(env, "unwrapped", env)
+            if not hasattr(scalar, "_make"):
+                raise TypeError("WindFieldWrapper needs an accelerated bluesky_gym env")
+            scalar._kw.update(wind=wind, wind_obs=bool(augment_obs))
+            scalar.vec.close()
+            scalar._make(scalar._seed)
+
+    @property
+    def observation_space(self):
+        return self.env.observation_space
+
+    def reset(self, **kwargs):
+        return self.env.reset(**kwargs)
+
+    def step(self, action):
+        return self.env.step(action)

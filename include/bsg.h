@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BSG_ABI_VERSION 1
+#define BSG_ABI_VERSION 2
 
 enum { BSG_OK = 0, BSG_EINVAL = -1, BSG_ECUDA = -2, BSG_ESTATE = -3, BSG_ENOMEM = -4 };
 
@@ -65,6 +65,7 @@ typedef struct bsg_config {
     int64_t env_id_offset;      /* global id of env 0 on this device (sharding is placement-free)    */
     float rpz, hpz, dtlookahead;/* ASAS zone [m], [m], [s]; <= 0 selects 5 NM / 1000 ft / 300 s      */
     bsg_perf perf;
+    int32_t wind_obs;           /* WindFieldWrapper(augment_obs=True): append wind_u, wind_v to obs  */
 } bsg_config;
 
 /* What the caller must allocate (all device memory, zero-initialised) for a given config. */
@@ -159,6 +160,22 @@ int bsg_step_host_copy(bsg_handle *h, const float *h_actions, void *h_block, siz
 
 /* The host-thread copy bsg_step_host_copy uses, on its own (pure host code; works without a GPU). */
 int bsg_host_copy(void *dst, const void *src, size_t nbytes);
+
+/* replaces: WindFieldWrapper (bluesky_gym/wrappers/wind.py:8-64) = bs.traf.wind.addpointvne(lat, lon, vnorth,
+ * veast, alt) + the wind terms of upstream Traffic.update_groundspeed / APorASAS.update / Autopilot.selhdgcmd.
+ * Wind vectors at n_points lat/lon points, interpolated with inverse-distance-squared weights; n_alt == 1: no
+ * altitude dependence, else vn/ve hold n_alt rows (row k = altitude k * alt_step, upstream: 100 ft steps to
+ * 45 000 ft) of n_points values.  All pointers are DEVICE memory owned by the caller and must stay valid until
+ * the wind is cleared or the handle destroyed; d_gs is [E * slots * 2] floats (ground-speed north / east per
+ * aircraft, persistent state that only exists with wind).  w == NULL or n_points == 0 switches the wind off. */
+typedef struct bsg_wind {
+    int32_t n_points, n_alt;
+    float alt_step;             /* [m] */
+    const float *d_lat, *d_lon; /* [n_points] deg */
+    const float *d_vn, *d_ve;   /* [n_alt * n_points] m/s */
+    float *d_gs;                /* [E * slots * 2] */
+} bsg_wind;
+int bsg_set_wind(bsg_handle *h, const bsg_wind *w);
 
 /* replaces: NoisyObservationWrapper (bluesky_gym/wrappers/uncertainty.py:4-31): from now on every observation
  * written by bsg_reset / bsg_step* (terminal observations of same-step autoreset included) carries independent

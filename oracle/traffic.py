@@ -19,6 +19,7 @@ Test infrastructure only (see oracle/__init__.py).
 import numpy as np
 
 from . import aero, geo, perf, statebased
+from .windfield import Windfield
 from .aero import fpm, g0, nm, ft, Rearth
 
 FMS_DT = 10.5           # settings.fms_dt
@@ -45,6 +46,7 @@ class Traffic:
         self.nstep = 0                  # sim steps since bs.init (never reset, like simt)
         self.queue = []                 # pending stack commands
         self.fms_rel_freq = max(1, int(FMS_DT // self.simdt))
+        self.wind = Windfield()
         self.reset()
 
     # ------------------------------------------------------------------ bookkeeping
@@ -63,8 +65,10 @@ class Traffic:
         self.tcpamax = np.zeros(0)
         self.confpairs = []
         self.lospairs = []
+        self.wind.clear()               # Traffic.reset(): self.wind.clear()
 
     def id2idx(self, acid):
+        acid = acid.upper()             # upstream upper-cases the call sign (wrappers/wind.py:56 asks for 'kl001')
         return self.id.index(acid) if acid in self.id else -1
 
     def _append(self, **vals):
@@ -96,8 +100,13 @@ class Traffic:
         tas, cas, M = aero.vcasormach(acspd, acalt)
         tas, cas, M = float(tas), float(cas), float(M)
         h = np.radians(achdg)
-        self._append(lat=aclat, lon=aclon, alt=acalt, hdg=achdg, trk=achdg, tas=tas, gs=tas, cas=cas, M=M,
-                     vs=0.0, gsnorth=tas * np.cos(h), gseast=tas * np.sin(h), selspd=cas, selalt=acalt,
+        gsn, gse, gs0, trk0 = tas * np.cos(h), tas * np.sin(h), tas, achdg
+        if self.wind.winddim > 0 and acalt > 50.0 * ft:      # Traffic.cre: wind only changes the initial gs / trk
+            vn, ve = self.wind.getdata(aclat, aclon, acalt)
+            gsn, gse = gsn + vn, gse + ve
+            gs0, trk0 = float(np.hypot(gsn, gse)), float(np.degrees(np.arctan2(gse, gsn)))
+        self._append(lat=aclat, lon=aclon, alt=acalt, hdg=achdg, trk=trk0, tas=tas, gs=gs0, cas=cas, M=M,
+                     vs=0.0, gsnorth=gsn, gseast=gse, selspd=cas, selalt=acalt,
                      selvs=0.0, ap_trk=achdg, ap_tas=tas, ap_alt=acalt, ap_vs=0.0,
                      actwp_lat=ACTWP_LAT0, actwp_lon=ACTWP_LON0, next_qdr=-999.0, curlegdir=-999.0)
         self.id.append(acid)
@@ -137,7 +146,14 @@ class Traffic:
 
     # ------------------------------------------------------------------ autopilot commands
     def selhdgcmd(self, idx, hdg):          # stack "HDG acid hdg"
-        self.ap_trk[idx] = hdg
+        if self.wind.winddim > 0 and self.alt[idx] > 50.0 * ft:
+            # Autopilot.selhdgcmd: with wind the commanded HEADING is turned into the track it produces now
+            vn, ve = self.wind.getdata(self.lat[idx], self.lon[idx], self.alt[idx])
+            gsn = self.tas[idx] * np.cos(np.radians(hdg)) + vn
+            gse = self.tas[idx] * np.sin(np.radians(hdg)) + ve
+            self.ap_trk[idx] = np.degrees(np.arctan2(gse, gsn)) % 360.0
+        else:
+            self.ap_trk[idx] = hdg
         self.swlnav[idx] = False
 
     def selspdcmd(self, idx, casmach):      # stack "SPD acid spd" (spd already in m/s CAS or Mach)
@@ -212,7 +228,15 @@ class Traffic:
         # ---- APorASAS.update --------------------------------------------------------------
         p_trk, p_tas, p_alt = self.ap_trk, self.ap_tas, self.ap_alt
         p_vs = np.abs(self.ap_vs)
-        p_hdg = p_trk % 360.0
+        if self.wind.winddim > 0:                   # APorASAS.update: heading that compensates for the wind
+            vwn, vwe = self.wind.getdata(self.lat, self.lon, self.alt)
+            Vw = np.sqrt(vwn * vwn + vwe * vwe)
+            winddir = np.arctan2(vwe, vwn)
+            drift = np.radians(p_trk) - winddir
+            steer = np.arcsin(np.minimum(1.0, np.maximum(-1.0, Vw * np.sin(drift) / np.maximum(0.001, self.tas))))
+            p_hdg = (p_trk + np.degrees(steer)) % 360.0
+        else:
+            p_hdg = p_trk % 360.0
         # ---- perf.update + limits ---------------------------------------------------------
         self.phase = perf.phase_fixwing(self.tas, self.vs, self.alt)
         amax = perf.axmax(self.phase, tab)
@@ -238,10 +262,18 @@ class Traffic:
         self.vs = np.where(np.isfinite(self.vs), self.vs, 0.0)
         # ---- update_groundspeed (no wind) -------------------------------------------------
         hr = np.radians(self.hdg)
-        self.gsnorth = self.tas * np.cos(hr)
-        self.gseast = self.tas * np.sin(hr)
-        self.gs = self.tas.copy()
-        self.trk = self.hdg.copy()
+        if self.wind.winddim == 0:
+            self.gsnorth = self.tas * np.cos(hr)
+            self.gseast = self.tas * np.sin(hr)
+            self.gs = self.tas.copy()
+            self.trk = self.hdg.copy()
+        else:                                       # Traffic.update_groundspeed with wind (only when airborne)
+            applywind = self.alt > 50.0 * ft
+            vnwnd, vewnd = self.wind.getdata(self.lat, self.lon, self.alt)
+            self.gsnorth = self.tas * np.cos(hr) + vnwnd * applywind
+            self.gseast = self.tas * np.sin(hr) + vewnd * applywind
+            self.gs = np.where(applywind, np.sqrt(self.gsnorth ** 2 + self.gseast ** 2), self.tas)
+            self.trk = np.where(applywind, np.degrees(np.arctan2(self.gseast, self.gsnorth)) % 360.0, self.hdg)
         # ---- update_pos -------------------------------------------------------------------
         self.alt = np.where(self.swaltsel, np.round(self.alt + self.vs * dt, 6), p_alt)
         self.lat = self.lat + np.degrees(dt * self.gsnorth / Rearth)

@@ -14,7 +14,8 @@ Two kinds of fixture:
   unpinned -- see oracle/__init__.py).  Per seed the file holds a flat sequence of rows: a row is either the
   output of ``reset()`` (``is_reset`` = 1, action NaN) or of ``step(action)``; episodes run to termination /
   truncation (TimeLimit cap of the registration applied here, bluesky_gym/__init__.py:9-45) and are followed by
-  a fresh ``reset()`` WITHOUT reseeding, until ``ROWS`` rows exist.  ``traf_*`` is the aircraft state right
+  a fresh ``reset()`` WITHOUT reseeding, until ``ROWS`` rows exist.  ``ref_wind_<EnvId>.npz``: the same envs inside
+  the reference's own ``WindFieldWrapper`` (wrappers/wind.py, ``augment_obs=True``, the README's four-source field).  ``traf_*`` is the aircraft state right
   after the row's call (NaN padded; after a terminal step the reference has already deleted aircraft).
 """
 import importlib
@@ -40,7 +41,7 @@ SPEC = [  # env id, module, class, action dim, TimeLimit cap, rows per seed
     ("MergeEnv-v0", "merge_env", "MergeEnv", 2, 50, 120),
 ]
 SEEDS = (0, 1, 2)
-TRAF_FIELDS = ("lat", "lon", "alt", "hdg", "tas", "vs")
+TRAF_FIELDS = ("lat", "lon", "alt", "hdg", "tas", "vs", "gs", "trk")
 MAX_AC = 32
 
 
@@ -55,13 +56,29 @@ def action_bank(seed, rows, adim, env_id):
     return a
 
 
-def gen_env(bs, env_id, mod, cls, adim, cap, rows):
+# wrappers/README.md example: a static wind field from four sources, no altitude gradient
+WIND = dict(lat=np.array([51.9, 51.9, 52.1, 52.1]), lon=np.array([3.9, 4.1, 3.9, 4.1]),
+            vnorth=np.array([[16.0, 12.0, 14.0, 15.0]]), veast=np.array([[3.0, 7.0, 9.0, 4.0]]))
+# augment_obs: the reference wrapper reads bs.traf.lat[id2idx('kl001')] AFTER the env's step; DescentEnv / VerticalCREnv
+# delete their aircraft on the terminal step, so with augment_obs=True the reference raises IndexError there --
+# those two are recorded with augment_obs=False (wind in the dynamics only)
+WIND_ENVS = {"DescentEnv-v0": False, "VerticalCREnv-v0": False, "SectorCREnv-v0": True, "MergeEnv-v0": True}
+
+
+def gen_env(bs, env_id, mod, cls, adim, cap, rows, wind=False):
     m = importlib.import_module("bluesky_gym.envs." + mod)
     out = {"seeds": np.array(SEEDS), "cap": np.array(cap)}
+    if wind:
+        wmod = importlib.import_module("bluesky_gym.wrappers.wind")     # the reference's WindFieldWrapper, as is
+        for k, v in WIND.items():
+            out["wind_" + k] = v
+        out["augment_obs"] = np.array(WIND_ENVS[env_id])
     for seed in SEEDS:
         np.random.seed(seed)
         random.seed(seed)
         env = getattr(m, cls)()
+        if wind:
+            env = wmod.WindFieldWrapper(env, augment_obs=WIND_ENVS[env_id], **WIND)
         acts = action_bank(seed, rows, adim, env_id)
         rec = {"is_reset": [], "action": [], "reward": [], "terminated": [], "truncated": []}
         obs_rec, info_rec, traf_rec = {}, {}, {f: [] for f in TRAF_FIELDS}
@@ -109,7 +126,7 @@ def gen_env(bs, env_id, mod, cls, adim, cap, rows):
         n_ep = int(np.sum(rec["is_reset"]))
         print(f"{env_id} seed {seed}: {rows} rows, {n_ep} episodes, {int(np.sum(rec['terminated']))} terminated, "
               f"{int(np.sum(rec['truncated']))} truncated, sum reward {np.sum(rec['reward']):.4f}")
-    np.savez_compressed(os.path.join(HERE, f"ref_{env_id}.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, f"ref_{'wind_' if wind else ''}{env_id}.npz"), **out)
 
 
 def gen_functions():
@@ -153,6 +170,9 @@ def main():
     gen_functions()
     for spec in SPEC:
         gen_env(bs, *spec)
+    for spec in SPEC:
+        if spec[0] in WIND_ENVS:
+            gen_env(bs, *spec[:5], 80, wind=True)
 
 
 if __name__ == "__main__":

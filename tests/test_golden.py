@@ -57,16 +57,59 @@ def test_functions_match_reference_golden():
         assert abs(ogeo.polygon_area(list(mine)) - area) < 1e-9
 
 
-@pytest.mark.parametrize("env_id", ENV_IDS)
-def test_oracle_env_matches_reference_golden(env_id):
-    g = np.load(os.path.join(GOLD, f"ref_{env_id}.npz"))
+WIND_IDS = ["DescentEnv-v0", "VerticalCREnv-v0", "SectorCREnv-v0", "MergeEnv-v0"]
+CASES = [(e, False) for e in ENV_IDS] + [(e, True) for e in WIND_IDS]
+
+
+class _OracleWind:
+    """What the reference's WindFieldWrapper (wrappers/wind.py) does, on an oracle env: add the wind points after every
+    reset (the env's reset cleared them) and append wind_u / wind_v (wind along / across the ownship heading / 50)."""
+
+    def __init__(self, env, g):
+        self.env, self.traf_of = env, (lambda: env.traf)
+        self.w = dict(lat=g["wind_lat"], lon=g["wind_lon"], vnorth=g["wind_vnorth"], veast=g["wind_veast"])
+        self.augment = bool(g["augment_obs"])
+
+    @property
+    def traf(self):
+        return self.env.traf
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def _aug(self, obs):
+        if not self.augment:
+            return obs
+        t = self.env.traf
+        wn, we = t.wind.getdata(t.lat[0], t.lon[0], t.alt[0])
+        h = np.radians(t.hdg[0])
+        return {**obs, "wind_u": np.array([(wn * np.cos(h) + we * np.sin(h)) / 50.0]),
+                "wind_v": np.array([(-wn * np.sin(h) + we * np.cos(h)) / 50.0])}
+
+    def reset(self):
+        obs, info = self.env.reset()
+        self.env.traf.wind.addpointvne(self.w["lat"], self.w["lon"], self.w["vnorth"], self.w["veast"], None)
+        return self._aug(obs), info
+
+    def step(self, a):
+        obs, r, te, tr, info = self.env.step(a)
+        return (obs if (te and self.env.traf.ntraf == 0) else self._aug(obs)), r, te, tr, info
+
+
+def _load(env_id, wind):
+    return np.load(os.path.join(GOLD, f"ref_{'wind_' if wind else ''}{env_id}.npz"))
+
+
+@pytest.mark.parametrize("env_id,wind", CASES)
+def test_oracle_env_matches_reference_golden(env_id, wind):
+    g = _load(env_id, wind)
     cap = int(g["cap"])
     n_rows = n_term = n_trunc = 0
     for seed in g["seeds"]:
         p, obs_keys, info_keys = _rows(g, seed)
         np.random.seed(int(seed))
         random.seed(int(seed))
-        env = _oracle(env_id)
+        env = _OracleWind(_oracle(env_id), g) if wind else _oracle(env_id)
         t = 0
         for r in range(len(g[p + "is_reset"])):
             if g[p + "is_reset"][r]:
@@ -95,8 +138,8 @@ def test_oracle_env_matches_reference_golden(env_id):
             n_rows += 1
             n_term += bool(term)
             n_trunc += bool(trunc)
-    assert n_rows >= 300
-    print(f"{env_id}: {n_rows} golden rows, {n_term} terminations, {n_trunc} truncations reproduced")
+    assert n_rows >= 240
+    print(f"{env_id}{' + wind' if wind else ''}: {n_rows} golden rows, {n_term} terminations, {n_trunc} truncations reproduced")
 
 
 def test_golden_covers_terminal_branches():
@@ -114,15 +157,20 @@ def test_golden_covers_terminal_branches():
 
 # ----------------------------------------------------------------------------------------------- GPU parity
 @pytest.mark.gpu
-@pytest.mark.parametrize("env_id", ENV_IDS)
-def test_cuda_env_matches_reference_golden(cuda, env_id):
+@pytest.mark.parametrize("env_id,wind", CASES)
+def test_cuda_env_matches_reference_golden(cuda, env_id, wind):
+    import torch
     from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
     from tests.common import angdiff, device_traffic
     from tests.test_gpu_env import TOL, _compare_obs, _inject
-    g = np.load(os.path.join(GOLD, f"ref_{env_id}.npz"))
+    g = _load(env_id, wind)
     seeds = [int(s) for s in g["seeds"]]
     E, cap = len(seeds), int(g["cap"])
-    venv = BlueSkyVectorEnv(env_id, E, seed=7, cd_enabled=False, autoreset_mode="disabled", max_episode_steps=cap)
+    kw = {}
+    if wind:        # the device form of WindFieldWrapper (wrappers/wind.py): wind in the simulator, wind_u / wind_v in obs
+        kw = dict(wind=dict(lat=g["wind_lat"], lon=g["wind_lon"], vnorth=g["wind_vnorth"], veast=g["wind_veast"]),
+                  wind_obs=bool(g["augment_obs"]))
+    venv = BlueSkyVectorEnv(env_id, E, seed=7, cd_enabled=False, autoreset_mode="disabled", max_episode_steps=cap, **kw)
     venv.reset()
     # the oracle runs in lockstep only to provide the post-reset state to inject (proved equal to the golden rows
     # by the CPU test above) and to detect the documented Merge exemption; expected values come from the fixture
@@ -130,7 +178,7 @@ def test_cuda_env_matches_reference_golden(cuda, env_id):
     for s in seeds:
         np.random.seed(s)
         random.seed(s)
-        oracles.append(_oracle(env_id))
+        oracles.append(_OracleWind(_oracle(env_id), g) if wind else _oracle(env_id))
         rstate.append((np.random.get_state(), random.getstate()))
     n_rows = len(g[f"s{seeds[0]}_is_reset"])
     act_dim = venv.layout.act_dim
@@ -152,7 +200,11 @@ def test_cuda_env_matches_reference_golden(cuda, env_id):
             random.setstate(rstate[e][1])
             if is_reset[e]:
                 o.reset()
-                _inject(venv, e, o, env_id)
+                _inject(venv, e, o.env if wind else o, env_id)
+                if wind:        # ground speed is state once there is wind: the post-reset (no-wind) value
+                    n0 = o.traf.ntraf
+                    venv._wind_t["gs"][e, :n0] = torch.as_tensor(np.stack([o.traf.gsnorth, o.traf.gseast], 1),
+                                                                 dtype=torch.float32, device=venv.device)
                 exempt[e] = set()
             else:
                 lnav_before = o.traf.swlnav.copy()
@@ -183,6 +235,6 @@ def test_cuda_env_matches_reference_golden(cuda, env_id):
                         if env_id != "MergeEnv-v0":        # (LNAV bearing tolerance is handled in test_gpu_env.py)
                             assert np.max(angdiff(d["hdg"][e, :n], gt["hdg"])) < TOL["hdg"], (env_id, s, r, "hdg")
             rstate[e] = (np.random.get_state(), random.getstate())
-    print(f"{env_id}: {compared} golden step rows matched by the CUDA path")
+    print(f"{env_id}{' + wind' if wind else ''}: {compared} golden step rows matched by the CUDA path")
     assert compared >= n_rows * E // 3
     venv.close()
