@@ -33,7 +33,8 @@ class Config(C.Structure):
                 ("cd_enabled", C.c_int32), ("autoreset_mode", C.c_int32), ("max_episode_steps", C.c_int32),
                 ("default_hdg_random", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64),
                 ("env_id_offset", C.c_int64), ("rpz", C.c_float), ("hpz", C.c_float),
-                ("dtlookahead", C.c_float), ("perf", Perf), ("wind_obs", C.c_int32)]
+                ("dtlookahead", C.c_float), ("perf", Perf), ("wind_obs", C.c_int32),
+                ("sector_density_uniform", C.c_int32)]
 
 
 class Wind(C.Structure):

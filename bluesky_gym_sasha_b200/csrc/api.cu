@@ -114,7 +114,7 @@ extern "C" int bsg_create(const bsg_config* cfg, bsg_handle** out) {
     P.n_sub = lay.n_sub; P.simdt = lay.simdt;
     int rel = (int)floor(10.5 / (double)lay.simdt);          // settings.fms_dt // simdt  (core/simtime.py Timer)
     P.fms_rel_freq = rel < 1 ? 1 : rel;
-    P.obs_dim = lay.obs_dim; P.act_dim = lay.act_dim; P.info_dim = lay.info_dim; P.wind_obs = cfg->wind_obs;
+    P.obs_dim = lay.obs_dim; P.act_dim = lay.act_dim; P.info_dim = lay.info_dim; P.wind_obs = cfg->wind_obs; P.sector_uniform = cfg->sector_density_uniform;
     float rpz = cfg->rpz > 0.0f ? cfg->rpz : 5.0f * 1852.0f;
     P.R2 = rpz * rpz;
     P.hpz = cfg->hpz > 0.0f ? cfg->hpz : 1000.0f * 0.3048f;

@@ -45,7 +45,7 @@ struct EnvParams {
     float* obs; float* final_obs; int32_t* final_ids; int32_t* final_count; float* reward; uint8_t* term; uint8_t* trunc; float* info;
     const float* actions; const uint8_t* reset_mask;
     // WindFieldWrapper (bsg_set_wind): wind_n == 0 <=> no wind
-    int wind_n, wind_nalt, wind_obs;
+    int wind_n, wind_nalt, wind_obs, sector_uniform;
     float wind_altstep;
     const float* wind_lat; const float* wind_lon; const float* wind_vn; const float* wind_ve;
     float2* gsv;

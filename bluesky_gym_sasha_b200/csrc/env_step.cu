@@ -221,7 +221,9 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
             poly[2 * i] = kSectorLat0 + vx[i] / 60.0;
             poly[2 * i + 1] = kSectorLon0 + vy[i] / (60.0 * coslat0);
         }
-        double rho = rng.normal(d, 0.005, 0.001); d += 2;                   // sector_cr_env.py:98-100
+        double rho;                                                         // sector_cr_env.py:98-103
+        if (P.sector_uniform) { rho = rng.uniform(d, 0.003, 0.007); d += 1; }
+        else { rho = rng.normal(d, 0.005, 0.001); d += 2; }
         double nraw = fmax(ceil(rho * area), 5.0);
         if (nraw > (double)kSectorMaxAc) { nraw = (double)kSectorMaxAc; rflags |= 2; }
         num_ac = (int)nraw;

@@ -42,7 +42,16 @@ class _ScalarEnv(Env):
             self._seed = seed
             self._make(seed)
         obs, infos = self.vec.reset()
+        self._check_reset_flags()
         return {k: v[0].copy() for k, v in obs.items()}, self._info(infos)
+
+    def _check_reset_flags(self):
+        """The scenario generators run on the device; conditions under which the reference raises are recorded in the
+        env record (BSG_I32_RESET_FLAGS) and turned back into the reference's exception here."""
+        flags = int(self.vec.reset_flags()[0])
+        if self.ENV_ID == "StaticObstacleEnv-v0" and flags & 4:               # static_obstacle_env.py:215-216
+            raise Exception("No waypoints can be generated outside the obstacles. Check the parameters of the obstacles "
+                            "in the definition of the scenario.")
 
     def step(self, action):
         a = np.asarray(action, dtype=np.float64).reshape(1, -1)
@@ -69,9 +78,7 @@ class SectorCREnv(_ScalarEnv):
     ENV_ID = "SectorCREnv-v0"
 
     def __init__(self, render_mode=None, ac_density_mode="normal", **kw):      # sector_cr_env.py:45
-        if ac_density_mode != "normal":
-            raise NotImplementedError("only ac_density_mode='normal' is on the accelerated path")
-        super().__init__(render_mode=render_mode, **kw)
+        super().__init__(render_mode=render_mode, ac_density_mode=ac_density_mode, **kw)
 
 
 class MergeEnv(_ScalarEnv):

@@ -33,7 +33,8 @@ class BlueSkyVectorEnv(VectorEnv):
     def __init__(self, env_id, num_envs, device=0, seed=0, cd_enabled=False, n_intruders=None,
                  autoreset_mode="next_step", env_id_offset=0, max_episode_steps=None, perf=None,
                  default_hdg="random", rpz=0.0, hpz=0.0, dtlookahead=0.0, render_mode=None,
-                 obs_dtype=np.float32, copy=True, obs_noise=0.0, wind=None, wind_obs=False):
+                 obs_dtype=np.float32, copy=True, obs_noise=0.0, wind=None, wind_obs=False,
+                 ac_density_mode="normal"):
         if env_id in NOT_ACCELERATED:
             raise NotImplementedError(f"{env_id} is registered by the reference but is not on the accelerated "
                                       "path yet (SURVEY.md section 8f)")
@@ -64,7 +65,8 @@ class BlueSkyVectorEnv(VectorEnv):
             max_episode_steps=self.spec_b200.max_episode_steps if max_episode_steps is None else int(max_episode_steps),
             default_hdg_random=1 if default_hdg == "random" else 0, device=self.device.index,
             seed=int(seed) & (2 ** 64 - 1), env_id_offset=int(env_id_offset), rpz=rpz, hpz=hpz,
-            dtlookahead=dtlookahead, perf=pf, wind_obs=int(bool(wind_obs)))
+            dtlookahead=dtlookahead, perf=pf, wind_obs=int(bool(wind_obs)),
+            sector_density_uniform=0 if ac_density_mode == "normal" else 1)     # sector_cr_env.py:98-103: anything else = uniform
         self.layout = _lib.query_layout(self.cfg)
         L, E, G = self.layout, self.num_envs, self.layout.slots
         self.slots = G
@@ -295,9 +297,26 @@ class BlueSkyVectorEnv(VectorEnv):
                 infos["_final_obs"] = term | trunc
         return obs, rew, term, trunc, infos
 
+    def reset_flags(self):
+        """Per-env bit mask left by the last scenario generation (include/bsg.h BSG_I32_RESET_FLAGS): 1 = polygon area
+        below the reference's threshold when the vertex cap was hit, 2 = aircraft count clipped to the slot count,
+        4 = rejection sampling gave up (the reference raises there, static_obstacle_env.py:215-216)."""
+        return self.t["env_i32"][:, _lib.I32_RESET_FLAGS].cpu().numpy()
+
     # ------------------------------------------------------------------ state access (parity tests, checkpoints)
     def state_dict(self):
-        return {k: v for k, v in self.t.items() if v is not None}
+        """Checkpoint: clones of every device tensor that carries simulator state (aircraft SoA, per-env records,
+        polygons, last outputs, the wind ground-speed state and the noise call counter's host mirror)."""
+        sd = {k: v.clone() for k, v in self.t.items() if v is not None and k != "actions_staging"}
+        if self._wind_t is not None:
+            sd["wind_gs"] = self._wind_t["gs"].clone()
+        return sd
+
+    def load_state_dict(self, sd):
+        """Resume from ``state_dict()`` of an env built with the same configuration (same seed => same future draws)."""
+        for k, v in sd.items():
+            dst = self._wind_t["gs"] if k == "wind_gs" else self.t[k]
+            dst.copy_(v)
 
     def load_state(self, e, lat, lon, alt, tas, hdg, vs, selspd, selalt, selvs, ap_trk, cas, ax=None,
                    lnav=None, iactwp=None, curlegdir=None, env_f64=None, env_i32=None, env_f32=None, poly=None):

@@ -66,6 +66,8 @@ typedef struct bsg_config {
     float rpz, hpz, dtlookahead;/* ASAS zone [m], [m], [s]; <= 0 selects 5 NM / 1000 ft / 300 s      */
     bsg_perf perf;
     int32_t wind_obs;           /* WindFieldWrapper(augment_obs=True): append wind_u, wind_v to obs  */
+    int32_t sector_density_uniform; /* SectorCREnv(ac_density_mode != "normal"): uniform(0.003, 0.007) traffic
+                                     * density instead of normal(0.005, 0.001), sector_cr_env.py:98-103  */
 } bsg_config;
 
 /* What the caller must allocate (all device memory, zero-initialised) for a given config. */

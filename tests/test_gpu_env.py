@@ -26,13 +26,13 @@ pytestmark = pytest.mark.gpu
 TOL = dict(pos=2e-5, alt=0.5, tas=2e-2, vs=2e-2, hdg=5e-3)
 
 
-def _make_oracle(env_id, draws=None, cd=False, n_int=5):
+def _make_oracle(env_id, draws=None, cd=False, n_int=5, density="normal"):
     if env_id == "HorizontalCREnv-v0":
         return oenvs.HorizontalCREnv(n_intruders=n_int, draws=draws, cd_enabled=cd)
     if env_id == "DescentEnv-v0":
         return oenvs.DescentEnv(draws=draws)
     if env_id == "SectorCREnv-v0":
-        return oenvs.SectorCREnv(draws=draws, cd_enabled=cd)
+        return oenvs.SectorCREnv(draws=draws, cd_enabled=cd, ac_density_mode=density)
     if env_id == "PlanWaypointEnv-v0":
         return oenvs.PlanWaypointEnv(draws=draws)
     if env_id == "VerticalCREnv-v0":
@@ -190,18 +190,21 @@ def test_step_parity_injected_state(cuda, env_id, n_int, cd, steps):
 
 @pytest.mark.parametrize("env_id,n_int", [("DescentEnv-v0", 0), ("HorizontalCREnv-v0", 5), ("HorizontalCREnv-v0", 20),
                                           ("SectorCREnv-v0", 0), ("MergeEnv-v0", 0), ("PlanWaypointEnv-v0", 0),
-                                          ("VerticalCREnv-v0", 0), ("StaticObstacleEnv-v0", 0)])
+                                          ("VerticalCREnv-v0", 0), ("StaticObstacleEnv-v0", 0), ("SectorCREnv-v0", -1)])
 def test_device_reset_matches_philox_oracle(cuda, env_id, n_int):
     from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
     E, seed, off = 16, 99, 1000
-    kw = dict(n_intruders=n_int) if n_int else {}
+    kw = dict(n_intruders=n_int) if n_int > 0 else {}
+    density = "uniform" if n_int < 0 else "normal"          # SectorCREnv(ac_density_mode=...), sector_cr_env.py:98-103
+    if n_int < 0:
+        kw["ac_density_mode"] = density
     venv = BlueSkyVectorEnv(env_id, E, seed=seed, env_id_offset=off, autoreset_mode="disabled", **kw)
     for episode in range(2):
         gobs, ginfo = venv.reset()
         d = device_traffic(venv)
         i32 = venv.t["env_i32"].cpu().numpy()
         for e in range(E):
-            o = _make_oracle(env_id, draws=PhiloxDraws(seed, off + e, episode), n_int=n_int)
+            o = _make_oracle(env_id, draws=PhiloxDraws(seed, off + e, episode), n_int=n_int, density=density)
             oobs, _ = o.reset()
             t = o.traf
             n = t.ntraf
@@ -298,3 +301,42 @@ def test_sb3_adapter_contract(cuda):
     assert all(i["TimeLimit.truncated"] and "terminal_observation" in i and "total_reward" in i for i in infos)
     assert not np.allclose(infos[0]["terminal_observation"]["altitude"], obs["altitude"][0])
     v.close()
+
+
+def test_checkpoint_resume_is_bit_exact(cuda):
+    """state_dict() / load_state_dict(): resuming replays exactly the same trajectory (autoreset draws included)."""
+    import torch
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    E = 64
+    v = BlueSkyVectorEnv("HorizontalCREnv-v0", E, seed=21, n_intruders=20, cd_enabled=True, autoreset_mode="same_step",
+                         max_episode_steps=7)
+    v.reset_torch()
+    g = torch.Generator(device="cpu").manual_seed(1)
+    acts = (torch.rand((20, E, 1), generator=g) * 2 - 1).cuda()
+    for i in range(5):
+        v.step_torch(acts[i])
+    sd = v.state_dict()
+    ref = []
+    for i in range(5, 20):
+        o, r, te, tr = v.step_torch(acts[i])
+        ref.append((v.t["obs"].clone(), r.clone(), te.clone(), tr.clone()))
+    v.load_state_dict(sd)
+    for i in range(5, 20):
+        o, r, te, tr = v.step_torch(acts[i])
+        assert torch.equal(v.t["obs"], ref[i - 5][0]) and torch.equal(r, ref[i - 5][1])
+        assert torch.equal(te, ref[i - 5][2]) and torch.equal(tr, ref[i - 5][3])
+    assert any(bool(x[3].any()) for x in ref)            # the window crossed TimeLimit truncations + autoresets
+    v.close()
+
+
+def test_static_obstacle_scalar_env_reset_flags(cuda):
+    """reset_flags() is surfaced (0 for a normal scenario); the scalar env turns flag 4 into the reference's Exception."""
+    import bluesky_gym
+    bluesky_gym.register_envs()
+    env = bluesky_gym.make("StaticObstacleEnv-v0")
+    obs, info = env.reset()
+    assert int(env.unwrapped.vec.reset_flags()[0]) & 4 == 0
+    env.unwrapped.vec.t["env_i32"][0, _lib.I32_RESET_FLAGS] = 4
+    with pytest.raises(Exception, match="No waypoints can be generated"):
+        env.unwrapped._check_reset_flags()
+    env.close()
