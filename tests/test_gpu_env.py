@@ -120,6 +120,8 @@ def _compare_obs(gobs, oobs, e, step, vnorm=None, ownship_only=False):
     ("DescentEnv-v0", 0, False, 45),
     ("HorizontalCREnv-v0", 5, False, 40),
     ("HorizontalCREnv-v0", 20, True, 25),
+    ("HorizontalCREnv-v0", 12, True, 25),          # 16-lane groups (two-phase in-group CD with G = 16)
+    ("HorizontalCREnv-v0", 31, True, 12),          # a full 32-aircraft group (even n: the doubled offset n/2)
     ("SectorCREnv-v0", 0, True, 40),
     ("MergeEnv-v0", 0, False, 50),
     ("PlanWaypointEnv-v0", 0, False, 60),
