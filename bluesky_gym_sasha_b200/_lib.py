@@ -58,7 +58,7 @@ class TensorTable(C.Structure):
 
 
 SYMBOLS = ("bsg_abi_version", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
-           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_host_copy", "bsg_set_obs_noise", "bsg_set_wind", "bsg_traf_update",
+           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_host_copy", "bsg_set_obs_noise", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
            "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_probe_fp32")
 
 _lib = None
@@ -92,6 +92,9 @@ def load():
     lib.bsg_step_host_block.argtypes = [vp, vp, vp, C.c_size_t, vp]
     lib.bsg_set_obs_noise.argtypes = [vp, f32]
     lib.bsg_set_obs_noise.restype = C.c_int
+    if hasattr(lib, "bsg_set_seed"):
+        lib.bsg_set_seed.argtypes = [vp, C.c_uint64]
+        lib.bsg_set_seed.restype = C.c_int
     if hasattr(lib, "bsg_set_wind"):            # (absent only in older A/B builds loaded through BSG_B200_LIB)
         lib.bsg_set_wind.argtypes = [vp, C.POINTER(Wind)]
         lib.bsg_set_wind.restype = C.c_int

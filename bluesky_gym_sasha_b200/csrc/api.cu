@@ -173,6 +173,13 @@ static int run_mode(bsg_handle* h, int mode, const float* d_actions, const uint8
     return bsg_launch_obs_noise(P, h->obs_noise, h->noise_calls++, mode == bsg::kModeStep, (cudaStream_t)stream);
 }
 
+extern "C" int bsg_set_seed(bsg_handle* h, uint64_t seed) {
+    if (!h) return bsg_fail(BSG_EINVAL, "null handle");
+    h->cfg.seed = seed;
+    h->P.seed = seed;
+    return BSG_OK;
+}
+
 extern "C" int bsg_set_wind(bsg_handle* h, const bsg_wind* w) {
     if (!h) return bsg_fail(BSG_EINVAL, "null handle");
     bsg::EnvParams& P = h->P;

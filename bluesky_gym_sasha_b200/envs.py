@@ -37,11 +37,9 @@ class _ScalarEnv(Env):
                 for k, v in infos.items() if not k.startswith("_") and k != "final_obs"}
 
     def reset(self, seed=None, options=None):
-        if seed is not None and seed != self._seed:          # re-key the Philox stream
-            self.vec.close()
+        if seed is not None:
             self._seed = seed
-            self._make(seed)
-        obs, infos = self.vec.reset()
+        obs, infos = self.vec.reset(seed=seed)               # re-keys the Philox stream when a seed is given
         self._check_reset_flags()
         return {k: v[0].copy() for k, v in obs.items()}, self._info(infos)
 

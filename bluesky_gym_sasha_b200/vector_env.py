@@ -249,8 +249,9 @@ class BlueSkyVectorEnv(VectorEnv):
 
     # ------------------------------------------------------------------ gymnasium VectorEnv API (numpy)
     def reset(self, *, seed=None, options=None):
-        if seed is not None:
-            raise ValueError("the Philox seed is fixed at construction (seed=...); per-reset seeds are not supported")
+        if seed is not None:        # gymnasium: reset(seed=s) re-seeds; here it re-keys every env's Philox stream
+            _lib.check(self._lib.bsg_set_seed(self._h, int(seed) & (2 ** 64 - 1)))
+            self.cfg.seed = int(seed) & (2 ** 64 - 1)
         self.reset_torch()
         torch.cuda.synchronize(self.device)
         obs = self.t["obs"].cpu().numpy()

@@ -163,6 +163,11 @@ int bsg_step_host_copy(bsg_handle *h, const float *h_actions, void *h_block, siz
 /* The host-thread copy bsg_step_host_copy uses, on its own (pure host code; works without a GPU). */
 int bsg_host_copy(void *dst, const void *src, size_t nbytes);
 
+/* replaces: Env.reset(seed=...) (gymnasium seeding, e.g. horizontal_cr_env.py:82-83 super().reset(seed=seed)):
+ * re-keys the Philox streams of the scenario generators and of the observation noise; takes effect at the next
+ * reset of each env (stream = (seed, env_id_offset + e, episode)). */
+int bsg_set_seed(bsg_handle *h, uint64_t seed);
+
 /* replaces: WindFieldWrapper (bluesky_gym/wrappers/wind.py:8-64) = bs.traf.wind.addpointvne(lat, lon, vnorth,
  * veast, alt) + the wind terms of upstream Traffic.update_groundspeed / APorASAS.update / Autopilot.selhdgcmd.
  * Wind vectors at n_points lat/lon points, interpolated with inverse-distance-squared weights; n_alt == 1: no

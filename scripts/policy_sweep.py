@@ -10,9 +10,11 @@ from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
 
 POL = os.path.join(ROOT, "tests", "golden", "policies")
 STATS = json.load(open(os.path.join(POL, "log_stats.json")))
-cases = [("SectorCREnv-v0", "PPO"), ("StaticObstacleEnv-v0", "PPO"), ("HorizontalCREnv-v0", "SAC"), ("VerticalCREnv-v0", "SAC"),
-         ("DescentEnv-v0", "SAC"), ("PlanWaypointEnv-v0", "SAC")]
-variants = [dict(), dict(axmax_air=1.0), dict(axmax_air=2.0), dict(vmaxic=87.5), dict(vmaxic=89.5), dict(vminer=70.0), dict(vmaxer=158.0)]
+cases = [("SectorCREnv-v0", "PPO"), ("StaticObstacleEnv-v0", "PPO"), ("VerticalCREnv-v0", "SAC"), ("DescentEnv-v0", "SAC")]
+variants = [dict(), dict(vmaxer=170.0), dict(vmaxer=180.0), dict(vmaxer=190.0), dict(vmaxer=200.0), dict(vmaxer=180.0, axmax_air=2.0),
+            dict(vminer=90.0), dict(vminer=110.0)]
+if len(sys.argv) > 1:
+    variants = [json.loads(a) for a in sys.argv[1:]]
 for env_id, algo in cases:
     st = STATS[f"{env_id}_{algo}"]
     print(f"{env_id} {algo}: log return {st['total_reward_mean']:.3f} +- {st['total_reward_std']:.3f}, length {st['length_mean']:.1f}, "

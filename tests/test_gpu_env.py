@@ -342,3 +342,18 @@ def test_static_obstacle_scalar_env_reset_flags(cuda):
     with pytest.raises(Exception, match="No waypoints can be generated"):
         env.unwrapped._check_reset_flags()
     env.close()
+
+
+def test_reset_seed_rekeys_streams(cuda):
+    """gymnasium seeding: reset(seed=s) reproduces the scenario of a fresh env built with seed=s."""
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    a = BlueSkyVectorEnv("SectorCREnv-v0", 8, seed=1)
+    b = BlueSkyVectorEnv("SectorCREnv-v0", 8, seed=77)
+    oa, _ = a.reset(seed=77)
+    ob, _ = b.reset()
+    for k in oa:
+        assert np.array_equal(oa[k], ob[k]), k
+    o2, _ = a.reset()                                        # next episode of the same stream differs
+    assert not np.array_equal(o2["x_r"], oa["x_r"])
+    a.close()
+    b.close()
