@@ -59,7 +59,7 @@ class TensorTable(C.Structure):
 
 SYMBOLS = ("bsg_abi_version", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
            "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_host_copy", "bsg_set_obs_noise", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
-           "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_probe_fp32")
+           "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_cd_cull_workspace", "bsg_cd_detect_culled", "bsg_probe_fp32")
 
 _lib = None
 
@@ -106,6 +106,11 @@ def load():
     lib.bsg_cd_padded.restype = i64
     lib.bsg_cd_pack.argtypes = [vp, vp, vp, vp, vp, vp, i64, f64, f64, vp, vp]
     lib.bsg_cd_detect.argtypes = [vp, i64, i64, i64, f32, f32, f32, u32, vp, vp, vp, vp, vp, i64, vp, vp]
+    if hasattr(lib, "bsg_cd_detect_culled"):
+        lib.bsg_cd_cull_workspace.argtypes = [i64, i64]
+        lib.bsg_cd_cull_workspace.restype = i64
+        lib.bsg_cd_detect_culled.argtypes = [vp, i64, i64, i64, f32, f32, f32, u32, vp, vp, vp, vp, vp, i64, vp, vp, i64, vp]
+        lib.bsg_cd_detect_culled.restype = C.c_int
     lib.bsg_probe_fp32.argtypes = [i32, C.POINTER(f64)]
     for name in ("bsg_query_layout", "bsg_create", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy",
                  "bsg_traf_update", "bsg_cd_pack", "bsg_cd_detect", "bsg_probe_fp32"):

@@ -61,8 +61,9 @@ class StateBasedCD:
         return rec, n
 
     # ---------------------------------------------------------------- detection on packed records
-    def detect_packed(self, rec, n_all, row0=0, n_rows=None, lon_wrap=False, want_pairs=True):
-        """Rows [row0, row0+n_rows) x all n_all columns.  Asynchronous; returns device tensors."""
+    def detect_packed(self, rec, n_all, row0=0, n_rows=None, lon_wrap=False, want_pairs=True, cull=False):
+        """Rows [row0, row0+n_rows) x all n_all columns.  Asynchronous; returns device tensors.
+        ``cull=True``: bsg_cd_detect_culled (identical outputs; pays off on spatially sorted records)."""
         n_rows = n_all - row0 if n_rows is None else n_rows
         m = max(n_rows, 1)
         nconf = self._get("nconf", (m,), torch.int32)
@@ -73,17 +74,49 @@ class StateBasedCD:
         pairs = self._get("pairs", (max(self.pair_capacity, 1), 2), torch.int32) if want_pairs else None
         flags = _lib.CD_LON_WRAP if lon_wrap else 0
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.bsg_cd_detect(_ptr(rec), n_all, row0, n_rows, self.rpz, self.hpz, self.dtlookahead,
-                                              flags, _ptr(nconf), _ptr(nlos), _ptr(tcpamax), _ptr(inconf),
-                                              _ptr(pairs), self.pair_capacity if want_pairs else 0, _ptr(npairs),
-                                              self._stream()))
-        self.gpu_launches += 2 if n_rows else 0
+            if cull:
+                nbytes = int(self.lib.bsg_cd_cull_workspace(n_all, n_rows))
+                work = self._get("cull_work", (nbytes,), torch.uint8)
+                _lib.check(self.lib.bsg_cd_detect_culled(_ptr(rec), n_all, row0, n_rows, self.rpz, self.hpz, self.dtlookahead,
+                                                         flags, _ptr(nconf), _ptr(nlos), _ptr(tcpamax), _ptr(inconf),
+                                                         _ptr(pairs), self.pair_capacity if want_pairs else 0, _ptr(npairs),
+                                                         _ptr(work), nbytes, self._stream()))
+                self.gpu_launches += 5 if n_rows else 0
+            else:
+                _lib.check(self.lib.bsg_cd_detect(_ptr(rec), n_all, row0, n_rows, self.rpz, self.hpz, self.dtlookahead,
+                                                  flags, _ptr(nconf), _ptr(nlos), _ptr(tcpamax), _ptr(inconf),
+                                                  _ptr(pairs), self.pair_capacity if want_pairs else 0, _ptr(npairs),
+                                                  self._stream()))
+                self.gpu_launches += 2 if n_rows else 0
         return dict(nconf_row=nconf[:n_rows], nlos_row=nlos[:n_rows], tcpamax=tcpamax[:n_rows],
                     inconf=inconf[:n_rows], pairs=pairs, npairs=npairs)
 
+    # ---------------------------------------------------------------- spatial order for the culled form
+    @staticmethod
+    def spatial_order(lat_d, lon_d, tile=256):
+        """Permutation that makes consecutive records -- hence the kernel's 256-record tiles -- spatially compact,
+        which is what makes tile culling effective: aircraft are cut into latitude strips holding a whole number of
+        tiles each and sorted by longitude within a strip, with the strip count chosen so that a tile's footprint is
+        roughly square.
+        (torch ops: plumbing, O(N log N) on the device.)"""
+        n = lat_d.numel()
+        la0, la1 = float(lat_d.min()), float(lat_d.max())
+        lo0, lo1 = float(lon_d.min()), float(lon_d.max())
+        h = max(la1 - la0, 1e-9)
+        w = max((lo1 - lo0) * np.cos(np.radians(0.5 * (la0 + la1))), 1e-9)
+        n_tiles = max(1, -(-n // tile))
+        strips = int(max(1, round(np.sqrt(n_tiles * h / w))))
+        per_strip = -(-n_tiles // strips) * tile          # whole tiles per strip: no tile straddles two strips
+        rank = torch.empty(n, dtype=torch.int64, device=lat_d.device)
+        rank[torch.argsort(lat_d)] = torch.arange(n, device=lat_d.device)
+        key = (rank // per_strip).to(torch.float64) * 1024.0 + (lon_d - lo0)          # lon span < 360 < 1024
+        return torch.argsort(key)
+
     # ---------------------------------------------------------------- convenience: StateBased.detect
-    def detect(self, lat, lon, trk, gs, alt, vs, lat0=None, lon0=None):
-        """Full N x N detection.  Returns host results shaped like upstream's ``detect`` outputs."""
+    def detect(self, lat, lon, trk, gs, alt, vs, lat0=None, lon0=None, cull=False):
+        """Full N x N detection.  Returns host results shaped like upstream's ``detect`` outputs.
+        ``cull=True`` sorts the aircraft into spatially compact tiles and skips tile pairs that are out of each other's
+        reach (bsg_cd_detect_culled); results are identical, indices are mapped back to the caller's order."""
         lat_d, lon_d = self._as_dev(lat), self._as_dev(lon)
         n = lat_d.numel()
         if n == 0:
@@ -95,22 +128,38 @@ class StateBasedCD:
         if lon0 is None:
             lon0 = float(lon_d[0])
         span = float((((lon_d - lon0) + 180.0) % 360.0 - 180.0).abs().max())
+        cull = cull and span < 90.0                       # (airspaces across the antimeridian: plain form)
+        perm = None
+        if cull:
+            perm = self.spatial_order(lat_d, lon_d)
+            lat_d, lon_d = lat_d[perm], lon_d[perm]
+            trk, gs, alt, vs = (self._as_dev(x)[perm] for x in (trk, gs, alt, vs))
         rec, n = self.pack(lat_d, lon_d, trk, gs, alt, vs, lat0, lon0)
-        out = self.detect_packed(rec, n, lon_wrap=span >= 90.0)
+        out = self.detect_packed(rec, n, lon_wrap=span >= 90.0, cull=cull)
         torch.cuda.synchronize(self.device)
         n_conf, n_los = (int(v) for v in out["npairs"].cpu())
         k = min(n_conf, self.pair_capacity)
-        return dict(confpairs=out["pairs"][:k].cpu().numpy(), inconf=out["inconf"].cpu().numpy().astype(bool),
-                    tcpamax=out["tcpamax"].cpu().numpy().astype(np.float64),
-                    nconf_row=out["nconf_row"].cpu().numpy().astype(np.int64),
-                    nlos_row=out["nlos_row"].cpu().numpy().astype(np.int64),
+        pairs, inconf, tcpamax = out["pairs"][:k], out["inconf"], out["tcpamax"]
+        nconf_row, nlos_row = out["nconf_row"], out["nlos_row"]
+        if perm is not None:                              # back to the caller's aircraft order
+            pairs = perm[pairs.long()].to(torch.int32)
+            def unperm(x):
+                y = torch.empty_like(x)
+                y[perm] = x
+                return y
+            inconf, tcpamax, nconf_row, nlos_row = (unperm(x) for x in (inconf, tcpamax, nconf_row, nlos_row))
+        return dict(confpairs=pairs.cpu().numpy(), inconf=inconf.cpu().numpy().astype(bool),
+                    tcpamax=tcpamax.cpu().numpy().astype(np.float64),
+                    nconf_row=nconf_row.cpu().numpy().astype(np.int64),
+                    nlos_row=nlos_row.cpu().numpy().astype(np.int64),
                     n_conf=n_conf, n_los=n_los, truncated=n_conf > self.pair_capacity)
 
     # ---------------------------------------------------------------- multi-GPU: rows sharded over ranks
-    def detect_sharded(self, rec_local, n_local, group=None, lon_wrap=False, want_pairs=False):
+    def detect_sharded(self, rec_local, n_local, group=None, lon_wrap=False, want_pairs=False, cull=False):
         """Each rank owns ``n_local`` aircraft (the same count on every rank, a multiple of 256 so blocks
         stay tile-aligned).  One NCCL all-gather of the packed records, then this rank evaluates its own
-        rows against all columns; per-row outputs stay with the owner."""
+        rows against all columns; per-row outputs stay with the owner.  ``cull=True`` (bsg_cd_detect_culled) pays off when
+        the global record order is spatially coherent (``spatial_order`` applied before the blocks were dealt out)."""
         import torch.distributed as dist
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
@@ -118,7 +167,7 @@ class StateBasedCD:
         allrec = self._get("allrec", (n_local // 256 * world, 8, 256), torch.float32)
         dist.all_gather_into_tensor(allrec, rec_local[:n_local // 256].contiguous(), group=group)
         return self.detect_packed(allrec, n_local * world, row0=rank * n_local, n_rows=n_local,
-                                  lon_wrap=lon_wrap, want_pairs=want_pairs)
+                                  lon_wrap=lon_wrap, want_pairs=want_pairs, cull=cull)
 
 
 def shard_rows(n_all, world, rank):

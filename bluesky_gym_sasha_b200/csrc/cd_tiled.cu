@@ -33,6 +33,7 @@ constexpr int kNT = 128;                 // threads per CTA
 constexpr int kR = 2;                    // rows per thread
 constexpr int kRowsPerCta = kNT * kR;    // 256 = one tile of rows
 constexpr int kTilesPerItem = 8;
+constexpr int kTilesPerChunk = 2;        // culled form: work item = one row block x up to 2 listed column tiles
 constexpr int kTileFloats = 8 * kTJ;
 constexpr uint32_t kTileBytes = kTileFloats * 4;
 enum { FX = 0, FY = 1, FCH = 2, FSH = 3, FU = 4, FV = 5, FALT = 6, FVS = 7 };
@@ -78,6 +79,12 @@ struct CdArgs {
     long long cap;
     unsigned long long* npairs;
     int n_rowblocks, n_colgroups, n_tiles;
+    // culled form (bsg_cd_detect_culled): per row block the column tiles that can hold a conflict partner
+    const int32_t* tile_list;     // [n_rowblocks][list_stride]
+    const int32_t* list_cnt;      // [n_rowblocks]
+    const int32_t* chunk_off;     // [n_rowblocks + 1] exclusive scan of ceil(list_cnt / kTilesPerChunk)
+    int list_stride;
+    unsigned int* work_counter;   // dynamic item fetch (items differ in size: a static stride leaves a long tail)
 };
 
 __device__ __forceinline__ void load_record(const float* __restrict__ rec, int idx, float4& A, float4& B) {
@@ -161,10 +168,110 @@ __device__ __forceinline__ bool cd_hot2(const RowPack& r, u64 Xc, u64 Yc, u64 CH
     return h0 || h1;
 }
 
-template <bool WRAP>
+// One work item: 256 own rows (2 per thread, in packed registers) against n_t column tiles, which are either
+// consecutive (t_begin ..) or taken from a list (culled form).  Column tiles arrive through the 2-stage TMA ring.
+template <bool WRAP, bool LIST>
+__device__ __forceinline__ void cd_process_item(const CdArgs& a, float (*s_tile)[kTileFloats], uint64_t* s_full, uint32_t* parity,
+                                                const int rb, const int t_begin, const int n_t, const int32_t* __restrict__ list,
+                                                const u64 R2P, const u64 HPZP, const u64 NEG1, const float dtlh, const int row_end) {
+    const int tid = threadIdx.x;
+    auto tile_of = [&](int tt) { return LIST ? (int)list[tt] : t_begin + tt; };
+    // own rows -> packed registers.  Rows past the shard end are made inert (alt -3e9: can never be a
+    // candidate), so the hot loop needs no validity test.
+    RowPack rp[kR];
+    int ri[kR];
+    uint32_t nconf[kR], nlos[kR];
+    float tmax[kR];
+    const int rbase = a.row0 + rb * kRowsPerCta;
+#pragma unroll
+    for (int k = 0; k < kR; ++k) {
+        int r = rbase + tid + k * kNT;
+        ri[k] = r;
+        float4 A, B;
+        load_record(a.rec, r < row_end ? r : row_end - 1, A, B);
+        if (r >= row_end) B.z = -3.0e9f;                // inert row (padding columns sit at +3e9)
+        rp[k].nX = pk2(-A.x, -A.x); rp[k].nY = pk2(-A.y, -A.y);
+        rp[k].CH = pk2(A.z, A.z);   rp[k].nSH = pk2(-A.w, -A.w);
+        rp[k].nU = pk2(-B.x, -B.x); rp[k].nV = pk2(-B.y, -B.y);
+        rp[k].nALT = pk2(-B.z, -B.z); rp[k].nVS = pk2(-B.w, -B.w);
+        nconf[k] = 0; nlos[k] = 0; tmax[k] = 0.0f;
+    }
+
+    if (tid == 0) {        // prologue: first tile of the item
+        mbar_expect_tx(&s_full[0], kTileBytes);
+        tma_load_1d(&s_tile[0][0], a.rec + (size_t)tile_of(0) * kTileFloats, kTileBytes, &s_full[0]);
+    }
+#pragma unroll 1
+    for (int tt = 0; tt < n_t; ++tt) {
+        const int s = tt & 1;
+        const int t = tile_of(tt);
+        if (tid == 0 && tt + 1 < n_t) {     // prefetch the next tile into the other stage
+            mbar_expect_tx(&s_full[s ^ 1], kTileBytes);
+            tma_load_1d(&s_tile[s ^ 1][0], a.rec + (size_t)tile_of(tt + 1) * kTileFloats, kTileBytes, &s_full[s ^ 1]);
+        }
+        mbar_wait(&s_full[s], parity[s]);
+        parity[s] ^= 1u;
+        const float* tile = s_tile[s];
+        const int c0 = t * kTJ;
+#pragma unroll 1
+        for (int j = 0; j < kTJ; j += 4) {
+            // 8 broadcast LDS.128: four consecutive columns of each field = two packed operands
+            const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(tile + FX * kTJ + j);
+            const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(tile + FY * kTJ + j);
+            const ulonglong2 CH = *reinterpret_cast<const ulonglong2*>(tile + FCH * kTJ + j);
+            const ulonglong2 SH = *reinterpret_cast<const ulonglong2*>(tile + FSH * kTJ + j);
+            const ulonglong2 U = *reinterpret_cast<const ulonglong2*>(tile + FU * kTJ + j);
+            const ulonglong2 V = *reinterpret_cast<const ulonglong2*>(tile + FV * kTJ + j);
+            const ulonglong2 AL = *reinterpret_cast<const ulonglong2*>(tile + FALT * kTJ + j);
+            const ulonglong2 VS = *reinterpret_cast<const ulonglong2*>(tile + FVS * kTJ + j);
+            bool hit = false;
+#pragma unroll
+            for (int k = 0; k < kR; ++k) {
+                hit |= cd_hot2<WRAP>(rp[k], X.x, Y.x, CH.x, SH.x, U.x, V.x, AL.x, VS.x, R2P, HPZP, NEG1, dtlh);
+                hit |= cd_hot2<WRAP>(rp[k], X.y, Y.y, CH.y, SH.y, U.y, V.y, AL.y, VS.y, R2P, HPZP, NEG1, dtlh);
+            }
+            if (hit) for (int b = 0; b < 4 * kR; ++b) {  // rare: exact re-evaluation of the 8 pairs
+                const int k = b >> 2, cj = c0 + j + (b & 3);
+                if (ri[k] >= row_end || cj >= a.n_all) continue;
+                float tc;
+                const uint32_t f = cd_candidate<WRAP>(a, ri[k], cj, tc);
+                if (f & 2u) {
+                    nlos[k]++;
+                    if (a.npairs) atomicAdd(a.npairs + 1, 1ULL);
+                }
+                if (f & 1u) {
+                    nconf[k]++;
+                    tmax[k] = fmaxf(tmax[k], tc);
+                    if (a.npairs) {
+                        unsigned long long slot = atomicAdd(a.npairs, 1ULL);
+                        if (a.pairs && (long long)slot < a.cap) {
+                            a.pairs[2 * slot] = ri[k];
+                            a.pairs[2 * slot + 1] = cj;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();     // stage s may be overwritten by the prefetch of iteration t+1
+    }
+#pragma unroll
+    for (int k = 0; k < kR; ++k) {
+        if (ri[k] < row_end) {
+            const int o = ri[k] - a.row0;
+            if (nconf[k]) {
+                atomicAdd(&a.nconf_row[o], nconf[k]);
+                if (a.tcpamax) atomicMax((int*)&a.tcpamax[o], __float_as_int(tmax[k]));
+            }
+            if (nlos[k] && a.nlos_row) atomicAdd(&a.nlos_row[o], nlos[k]);
+        }
+    }
+}
+
+template <bool WRAP, bool LIST>
 __global__ void __launch_bounds__(kNT, 4) cd_tiled_kernel(const CdArgs a) {
     __shared__ __align__(128) float s_tile[2][kTileFloats];
     __shared__ __align__(8) uint64_t s_full[2];
+    __shared__ int s_item[3];
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -180,101 +287,121 @@ __global__ void __launch_bounds__(kNT, 4) cd_tiled_kernel(const CdArgs a) {
     const u64 R2P = pk2(R2h, R2h), HPZP = pk2(hpzh, hpzh), NEG1 = pk2(-1.0f, -1.0f);
     const int row_end = a.row0 + a.n_rows;
 
-    const long long n_items = (long long)a.n_rowblocks * a.n_colgroups;
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int rb = (int)(item / a.n_colgroups);
-        const int cg = (int)(item % a.n_colgroups);
-        const int t_begin = cg * kTilesPerItem;
-        const int t_end = min(t_begin + kTilesPerItem, a.n_tiles);
-
-        // own rows -> packed registers.  Rows past the shard end are made inert (alt -3e9: can never be a
-        // candidate), so the hot loop needs no validity test.
-        RowPack rp[kR];
-        int ri[kR];
-        uint32_t nconf[kR], nlos[kR];
-        float tmax[kR];
-        const int rbase = a.row0 + rb * kRowsPerCta;
-#pragma unroll
-        for (int k = 0; k < kR; ++k) {
-            int r = rbase + tid + k * kNT;
-            ri[k] = r;
-            float4 A, B;
-            load_record(a.rec, r < row_end ? r : row_end - 1, A, B);
-            if (r >= row_end) B.z = -3.0e9f;                // inert row (padding columns sit at +3e9)
-            rp[k].nX = pk2(-A.x, -A.x); rp[k].nY = pk2(-A.y, -A.y);
-            rp[k].CH = pk2(A.z, A.z);   rp[k].nSH = pk2(-A.w, -A.w);
-            rp[k].nU = pk2(-B.x, -B.x); rp[k].nV = pk2(-B.y, -B.y);
-            rp[k].nALT = pk2(-B.z, -B.z); rp[k].nVS = pk2(-B.w, -B.w);
-            nconf[k] = 0; nlos[k] = 0; tmax[k] = 0.0f;
+    if (!LIST) {
+        // all column tiles, 8 per item; a persistent grid strides over the items
+        const long long n_items = (long long)a.n_rowblocks * a.n_colgroups;
+        for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int rb = (int)(item / a.n_colgroups);
+            const int t_begin = (int)(item % a.n_colgroups) * kTilesPerItem;
+            const int n_t = min(kTilesPerItem, a.n_tiles - t_begin);
+            cd_process_item<WRAP, false>(a, s_tile, s_full, parity, rb, t_begin, n_t, nullptr, R2P, HPZP, NEG1, dtlh, row_end);
         }
-
-        if (tid == 0) {        // prologue: first tile of the item
-            mbar_expect_tx(&s_full[t_begin & 1], kTileBytes);
-            tma_load_1d(&s_tile[t_begin & 1][0], a.rec + (size_t)t_begin * kTileFloats, kTileBytes, &s_full[t_begin & 1]);
-        }
-        for (int t = t_begin; t < t_end; ++t) {
-            const int s = t & 1;
-            if (tid == 0 && t + 1 < t_end) {     // prefetch the next tile into the other stage
-                mbar_expect_tx(&s_full[s ^ 1], kTileBytes);
-                tma_load_1d(&s_tile[s ^ 1][0], a.rec + (size_t)(t + 1) * kTileFloats, kTileBytes, &s_full[s ^ 1]);
-            }
-            mbar_wait(&s_full[s], parity[s]);
-            parity[s] ^= 1u;
-            const float* tile = s_tile[s];
-            const int c0 = t * kTJ;
-#pragma unroll 1
-            for (int j = 0; j < kTJ; j += 4) {
-                // 8 broadcast LDS.128: four consecutive columns of each field = two packed operands
-                const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(tile + FX * kTJ + j);
-                const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(tile + FY * kTJ + j);
-                const ulonglong2 CH = *reinterpret_cast<const ulonglong2*>(tile + FCH * kTJ + j);
-                const ulonglong2 SH = *reinterpret_cast<const ulonglong2*>(tile + FSH * kTJ + j);
-                const ulonglong2 U = *reinterpret_cast<const ulonglong2*>(tile + FU * kTJ + j);
-                const ulonglong2 V = *reinterpret_cast<const ulonglong2*>(tile + FV * kTJ + j);
-                const ulonglong2 AL = *reinterpret_cast<const ulonglong2*>(tile + FALT * kTJ + j);
-                const ulonglong2 VS = *reinterpret_cast<const ulonglong2*>(tile + FVS * kTJ + j);
-                bool hit = false;
-#pragma unroll
-                for (int k = 0; k < kR; ++k) {
-                    hit |= cd_hot2<WRAP>(rp[k], X.x, Y.x, CH.x, SH.x, U.x, V.x, AL.x, VS.x, R2P, HPZP, NEG1, dtlh);
-                    hit |= cd_hot2<WRAP>(rp[k], X.y, Y.y, CH.y, SH.y, U.y, V.y, AL.y, VS.y, R2P, HPZP, NEG1, dtlh);
-                }
-                if (hit) for (int b = 0; b < 4 * kR; ++b) {  // rare: exact re-evaluation of the 8 pairs
-                    const int k = b >> 2, cj = c0 + j + (b & 3);
-                    if (ri[k] >= row_end || cj >= a.n_all) continue;
-                    float tc;
-                    const uint32_t f = cd_candidate<WRAP>(a, ri[k], cj, tc);
-                    if (f & 2u) {
-                        nlos[k]++;
-                        if (a.npairs) atomicAdd(a.npairs + 1, 1ULL);
-                    }
-                    if (f & 1u) {
-                        nconf[k]++;
-                        tmax[k] = fmaxf(tmax[k], tc);
-                        if (a.npairs) {
-                            unsigned long long slot = atomicAdd(a.npairs, 1ULL);
-                            if (a.pairs && (long long)slot < a.cap) {
-                                a.pairs[2 * slot] = ri[k];
-                                a.pairs[2 * slot + 1] = cj;
-                            }
-                        }
+    } else {
+        // culled form: items (row block, chunk of its tile list) differ in size and are handed out through a global
+        // counter, so no CTA is left with a long tail
+        const int n_items = a.chunk_off[a.n_rowblocks];
+        for (;;) {
+            if (tid == 0) {
+                const int item = (int)atomicAdd(a.work_counter, 1u);
+                int lo = 0, hi = a.n_rowblocks;
+                if (item < n_items) {              // item -> row block: binary search in the scan of chunk counts
+                    while (hi - lo > 1) {
+                        int mid = (lo + hi) >> 1;
+                        if (a.chunk_off[mid] <= item) lo = mid; else hi = mid;
                     }
                 }
+                s_item[0] = lo;
+                s_item[1] = item < n_items ? item - a.chunk_off[lo] : 0;
+                s_item[2] = item;
             }
-            __syncthreads();     // stage s may be overwritten by the prefetch of iteration t+1
-        }
-#pragma unroll
-        for (int k = 0; k < kR; ++k) {
-            if (ri[k] < row_end) {
-                const int o = ri[k] - a.row0;
-                if (nconf[k]) {
-                    atomicAdd(&a.nconf_row[o], nconf[k]);
-                    if (a.tcpamax) atomicMax((int*)&a.tcpamax[o], __float_as_int(tmax[k]));
-                }
-                if (nlos[k] && a.nlos_row) atomicAdd(&a.nlos_row[o], nlos[k]);
-            }
+            __syncthreads();
+            const int rb = s_item[0], k0 = s_item[1] * kTilesPerChunk, item = s_item[2];
+            __syncthreads();                       // s_item is rewritten for the next item
+            if (item >= n_items) break;
+            cd_process_item<WRAP, true>(a, s_tile, s_full, parity, rb, 0, min(kTilesPerChunk, a.list_cnt[rb] - k0),
+                                        a.tile_list + (size_t)rb * a.list_stride + k0, R2P, HPZP, NEG1, dtlh, row_end);
         }
     }
+}
+
+// ---- culled form: which column tiles can hold a conflict / LoS partner of a row block -----------------
+// Per tile of 256 records: bounding box in the kernel's own metric (x, y metres of arc), the smallest cos(lat)
+// (dx = x-difference * cos(mean lat) >= x-difference * min cos), the largest ground speed, the altitude band
+// and the largest |vs|.  Padding records (index >= n_all) are ignored.
+enum { TB_XMIN = 0, TB_XMAX, TB_YMIN, TB_YMAX, TB_COSMIN, TB_VMAX, TB_AMIN, TB_AMAX, TB_VSMAX, TB_COUNT = 12 };
+
+__global__ void __launch_bounds__(kTJ) cd_tile_bounds_kernel(const float* __restrict__ rec, int n_all, float* __restrict__ bounds) {
+    __shared__ float s_red[9][kTJ / 32];
+    const int tile = blockIdx.x, j = threadIdx.x, idx = tile * kTJ + j;
+    const float* t = rec + (size_t)tile * kTileFloats + j;
+    const bool live = idx < n_all;
+    const float x = t[FX * kTJ], y = t[FY * kTJ], ch = t[FCH * kTJ], sh = t[FSH * kTJ];
+    const float u = t[FU * kTJ], v = t[FV * kTJ], alt = t[FALT * kTJ], vs = t[FVS * kTJ];
+    float m[9];
+    m[TB_XMIN] = live ? x : 3.0e38f;  m[TB_XMAX] = live ? x : -3.0e38f;
+    m[TB_YMIN] = live ? y : 3.0e38f;  m[TB_YMAX] = live ? y : -3.0e38f;
+    m[TB_COSMIN] = live ? fmaf(ch, ch, -sh * sh) : 1.0f;                 // cos(lat) from the half-angle pair
+    m[TB_VMAX] = live ? sqrtf(fmaf(u, u, v * v)) : 0.0f;
+    m[TB_AMIN] = live ? alt : 3.0e38f; m[TB_AMAX] = live ? alt : -3.0e38f;
+    m[TB_VSMAX] = live ? fabsf(vs) : 0.0f;
+    const bool is_min[9] = {true, false, true, false, true, false, true, false, false};
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        float r = m[q];
+        for (int o = 16; o > 0; o >>= 1) {
+            float w = __shfl_xor_sync(0xffffffffu, r, o);
+            r = is_min[q] ? fminf(r, w) : fmaxf(r, w);
+        }
+        if ((j & 31) == 0) s_red[q][j >> 5] = r;
+    }
+    __syncthreads();
+    if (j < 9) {
+        float r = s_red[j][0];
+        for (int w = 1; w < kTJ / 32; ++w) r = is_min[j] ? fminf(r, s_red[j][w]) : fmaxf(r, s_red[j][w]);
+        bounds[tile * TB_COUNT + j] = r;
+    }
+}
+
+// One thread per (row block, column tile): keep the column tile unless NO aircraft pair of the two tiles can be
+// in conflict or LoS -- horizontally closer than R + (v_a + v_b) T at time 0 is necessary for the protected zones
+// to touch within the look-ahead T, and so is a vertical gap below hpz + (|vs_a| + |vs_b|) T.  Margins cover
+// float rounding.  Kept tiles are appended to the row block's list in arbitrary order.
+__global__ void cd_cull_kernel(const float* __restrict__ bounds, int n_tiles, int row_tile0, int n_rowblocks, float R,
+                               float hpz, float T, int32_t* __restrict__ list, int32_t* __restrict__ cnt, int stride) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long long)n_rowblocks * n_tiles) return;
+    const int rb = (int)(p / n_tiles), ct = (int)(p % n_tiles);
+    const float* A = bounds + (size_t)(row_tile0 + rb) * TB_COUNT;
+    const float* B = bounds + (size_t)ct * TB_COUNT;
+    if (A[TB_XMIN] > A[TB_XMAX] || B[TB_XMIN] > B[TB_XMAX]) return;         // a tile of padding only
+    const float gx = fmaxf(0.0f, fmaxf(B[TB_XMIN] - A[TB_XMAX], A[TB_XMIN] - B[TB_XMAX]));
+    const float gy = fmaxf(0.0f, fmaxf(B[TB_YMIN] - A[TB_YMAX], A[TB_YMIN] - B[TB_YMAX]));
+    const float cmin = fmaxf(0.0f, fminf(A[TB_COSMIN], B[TB_COSMIN]) - 1e-6f);
+    const float dmin = sqrtf(fmaf(gx * cmin, gx * cmin, gy * gy));
+    const float reach = (R * 1.001f + 1.0f) + (A[TB_VMAX] + B[TB_VMAX]) * (T + 0.05f) * 1.0001f;
+    const float ga = fmaxf(0.0f, fmaxf(B[TB_AMIN] - A[TB_AMAX], A[TB_AMIN] - B[TB_AMAX]));
+    const float vreach = (hpz * 1.001f + 0.1f) + (A[TB_VSMAX] + B[TB_VSMAX]) * (T + 0.05f) * 1.0001f;
+    if (dmin <= reach && ga <= vreach) list[(size_t)rb * stride + atomicAdd(&cnt[rb], 1)] = ct;
+}
+
+// chunk_off = exclusive scan of ceil(cnt / kTilesPerChunk) over the row blocks (one block, any n)
+__global__ void __launch_bounds__(1024) cd_chunk_scan_kernel(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ chunk_off) {
+    __shared__ int s_part[1024];
+    const int tid = threadIdx.x, per = (n + 1023) / 1024;
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += (cnt[i] + kTilesPerChunk - 1) / kTilesPerChunk;
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                 // inclusive Hillis-Steele scan of the per-thread sums
+        int v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int run = s_part[tid] - sum;
+    for (int i = lo; i < hi; ++i) { chunk_off[i] = run; run += (cnt[i] + kTilesPerChunk - 1) / kTilesPerChunk; }
+    if (tid == 1023) chunk_off[n] = s_part[1023];
 }
 
 __global__ void cd_finalize_kernel(const uint32_t* __restrict__ nconf_row, uint8_t* __restrict__ inconf, long long n) {
@@ -358,18 +485,88 @@ extern "C" int bsg_cd_detect(const float* d_rec, int64_t n_all, int64_t row0, in
     a.n_tiles = (int)(bsg_cd_padded(n_all) / kTJ);
     a.n_rowblocks = (int)((n_rows + kRowsPerCta - 1) / kRowsPerCta);
     a.n_colgroups = (a.n_tiles + kTilesPerItem - 1) / kTilesPerItem;
+    a.tile_list = nullptr; a.list_cnt = nullptr; a.chunk_off = nullptr; a.list_stride = 0; a.work_counter = nullptr;
 
     int dev = 0, sms = 0, occ = 0;
     BSG_CUDA(cudaGetDevice(&dev));
     BSG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const bool wrap = (flags & BSG_CD_LON_WRAP) != 0;
-    if (wrap) BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<true>, kNT, 0));
-    else BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false>, kNT, 0));
+    if (wrap) BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<true, false>, kNT, 0));
+    else BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, false>, kNT, 0));
     if (occ < 1) occ = 1;
     long long n_items = (long long)a.n_rowblocks * a.n_colgroups;
     int grid = (int)((n_items < (long long)sms * occ) ? n_items : (long long)sms * occ);
-    if (wrap) cd_tiled_kernel<true><<<grid, kNT, 0, st>>>(a);
-    else cd_tiled_kernel<false><<<grid, kNT, 0, st>>>(a);
+    if (wrap) cd_tiled_kernel<true, false><<<grid, kNT, 0, st>>>(a);
+    else cd_tiled_kernel<false, false><<<grid, kNT, 0, st>>>(a);
+    BSG_CUDA(cudaGetLastError());
+    if (d_inconf) {
+        cd_finalize_kernel<<<(int)((n_rows + 255) / 256), 256, 0, st>>>(d_nconf_row, d_inconf, n_rows);
+        BSG_CUDA(cudaGetLastError());
+    }
+    return BSG_OK;
+}
+
+extern "C" int64_t bsg_cd_cull_workspace(int64_t n_all, int64_t n_rows) {
+    const int64_t n_tiles = bsg_cd_padded(n_all) / kTJ, n_rb = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
+    // bounds | list_cnt | chunk_off | work counter | tile_list
+    return 16 * ((n_tiles * TB_COUNT * 4 + 15) / 16) + 16 * ((n_rb * 4 + 15) / 16) + 16 * (((n_rb + 1) * 4 + 15) / 16) + 16 +
+           n_rb * n_tiles * 4 + 64;
+}
+
+extern "C" int bsg_cd_detect_culled(const float* d_rec, int64_t n_all, int64_t row0, int64_t n_rows, float rpz, float hpz,
+                                    float dtlookahead, uint32_t flags, uint32_t* d_nconf_row, uint32_t* d_nlos_row,
+                                    float* d_tcpamax, uint8_t* d_inconf, int32_t* d_pairs, int64_t cap,
+                                    unsigned long long* d_npairs, void* d_work, int64_t work_bytes, void* stream) {
+    if (n_all < 0 || row0 < 0 || n_rows < 0 || row0 + n_rows > n_all)
+        return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: row range outside [0, n_all)");
+    if (row0 % kRowsPerCta) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: row0 must be a multiple of 256");
+    if (flags & BSG_CD_LON_WRAP) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: airspaces across the antimeridian use bsg_cd_detect");
+    if (n_all > 0x7fffff00LL) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: n_all exceeds int32 pair indices");
+    if (n_rows > 0 && (!d_rec || !d_nconf_row || !d_work)) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: null pointer");
+    if (work_bytes < bsg_cd_cull_workspace(n_all, n_rows)) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: workspace too small (bsg_cd_cull_workspace)");
+    if (d_pairs && (!d_npairs || cap < 0)) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: pair list needs d_npairs and cap >= 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_npairs) BSG_CUDA(cudaMemsetAsync(d_npairs, 0, 2 * sizeof(unsigned long long), st));
+    if (n_rows == 0) return BSG_OK;
+    BSG_CUDA(cudaMemsetAsync(d_nconf_row, 0, sizeof(uint32_t) * n_rows, st));
+    if (d_nlos_row) BSG_CUDA(cudaMemsetAsync(d_nlos_row, 0, sizeof(uint32_t) * n_rows, st));
+    if (d_tcpamax) BSG_CUDA(cudaMemsetAsync(d_tcpamax, 0, sizeof(float) * n_rows, st));
+
+    CdArgs a;
+    a.rec = d_rec;
+    a.n_all = (int)n_all; a.row0 = (int)row0; a.n_rows = (int)n_rows;
+    if (rpz <= 0.0f) rpz = 5.0f * 1852.0f;
+    if (hpz <= 0.0f) hpz = 1000.0f * 0.3048f;
+    if (dtlookahead <= 0.0f) dtlookahead = 300.0f;
+    a.R2 = rpz * rpz; a.hpz = hpz; a.dtlook = dtlookahead;
+    a.nconf_row = d_nconf_row; a.nlos_row = d_nlos_row; a.tcpamax = d_tcpamax;
+    a.pairs = d_pairs; a.cap = cap; a.npairs = d_npairs;
+    a.n_tiles = (int)(bsg_cd_padded(n_all) / kTJ);
+    a.n_rowblocks = (int)((n_rows + kRowsPerCta - 1) / kRowsPerCta);
+    a.n_colgroups = 0;
+    char* w = (char*)d_work;
+    float* bounds = (float*)w;                       w += 16 * (((size_t)a.n_tiles * TB_COUNT * 4 + 15) / 16);
+    int32_t* cnt = (int32_t*)w;                      w += 16 * (((size_t)a.n_rowblocks * 4 + 15) / 16);
+    int32_t* chunk_off = (int32_t*)w;                w += 16 * (((size_t)(a.n_rowblocks + 1) * 4 + 15) / 16);
+    a.work_counter = (unsigned int*)w;               w += 16;
+    int32_t* list = (int32_t*)w;
+    a.tile_list = list; a.list_cnt = cnt; a.chunk_off = chunk_off; a.list_stride = a.n_tiles;
+
+    BSG_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * a.n_rowblocks, st));
+    BSG_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), st));
+    cd_tile_bounds_kernel<<<a.n_tiles, kTJ, 0, st>>>(d_rec, a.n_all, bounds);
+    const long long n_pairs = (long long)a.n_rowblocks * a.n_tiles;
+    cd_cull_kernel<<<(int)((n_pairs + 255) / 256), 256, 0, st>>>(bounds, a.n_tiles, (int)(row0 / kRowsPerCta), a.n_rowblocks,
+                                                                 rpz, hpz, dtlookahead, list, cnt, a.list_stride);
+    cd_chunk_scan_kernel<<<1, 1024, 0, st>>>(cnt, a.n_rowblocks, chunk_off);
+    BSG_CUDA(cudaGetLastError());
+
+    int dev = 0, sms = 0, occ = 0;
+    BSG_CUDA(cudaGetDevice(&dev));
+    BSG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, true>, kNT, 0));
+    if (occ < 1) occ = 1;
+    cd_tiled_kernel<false, true><<<sms * occ, kNT, 0, st>>>(a);
     BSG_CUDA(cudaGetLastError());
     if (d_inconf) {
         cd_finalize_kernel<<<(int)((n_rows + 255) / 256), 256, 0, st>>>(d_nconf_row, d_inconf, n_rows);

@@ -217,6 +217,19 @@ int bsg_cd_detect(const float *d_rec, int64_t n_all, int64_t row0, int64_t n_row
                   uint32_t *d_nconf_row, uint32_t *d_nlos_row, float *d_tcpamax, uint8_t *d_inconf,
                   int32_t *d_pairs, int64_t cap, unsigned long long *d_npairs, void *stream);
 
+/* bsg_cd_detect with spatial culling: identical outputs, but column tiles that cannot contain a conflict or LoS
+ * partner of a row block (farther apart at time 0 than rpz + (v_a + v_b) * dtlookahead, or vertically beyond
+ * hpz + (|vs_a| + |vs_b|) * dtlookahead, from per-tile bounding boxes) are never evaluated.  It pays off when the
+ * records are spatially coherent (sort the aircraft into compact tiles before bsg_cd_pack, as
+ * StateBasedCD.detect(cull=True) does); on unsorted input every tile pair survives and it degenerates to
+ * bsg_cd_detect plus three tiny kernels.  row0 must be a multiple of 256; no BSG_CD_LON_WRAP.
+ * d_work: device scratch of at least bsg_cd_cull_workspace(n_all, n_rows) bytes. */
+int64_t bsg_cd_cull_workspace(int64_t n_all, int64_t n_rows);
+int bsg_cd_detect_culled(const float *d_rec, int64_t n_all, int64_t row0, int64_t n_rows, float rpz, float hpz,
+                         float dtlookahead, uint32_t flags, uint32_t *d_nconf_row, uint32_t *d_nlos_row,
+                         float *d_tcpamax, uint8_t *d_inconf, int32_t *d_pairs, int64_t cap,
+                         unsigned long long *d_npairs, void *d_work, int64_t work_bytes, void *stream);
+
 /* ---- roofline denominators measured on the spot (bench.py) ------------------------------------- */
 /* Dense FP32 FMA throughput [FLOP/s] of this device, timed with CUDA events. */
 int bsg_probe_fp32(int32_t device, double *flops_out);

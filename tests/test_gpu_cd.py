@@ -125,3 +125,62 @@ def test_full_size_sampled_rows(cuda):
         if abs(int(c["nconf_row"][0]) - int(g["nconf_row"][r])) > 0 or abs(int(c["nlos_row"][0]) - int(g["nlos_row"][r])) > 0:
             o = statebased.detect_rows(np.array([r]), *s, RPZ, HPZ, DTL, with_margins=True)
             assert o["near_conf"].any() or o["near_los"].any(), f"row {r}: counts differ with no banded pair"
+
+
+@pytest.mark.parametrize("n,box,seed", [(20000, 40.0, 3), (5000, 3.0, 4), (1, 1.0, 5), (257, 60.0, 6), (40001, 25.0, 7)])
+def test_culled_form_is_identical_to_plain(cuda, n, box, seed):
+    """bsg_cd_detect_culled (Z-order sorted records, tile culling) == bsg_cd_detect: same conflict pair set, same
+    per-aircraft counts / flags, bit-identical tcpamax -- culling only skips tile pairs that cannot interact."""
+    from bluesky_gym_sasha_b200.cd import StateBasedCD
+    s = synth_airspace(n, box_deg=box, seed=seed)
+    cd = StateBasedCD(device=0, pair_capacity=1 << 22)
+    plain = cd.detect(*s)
+    culled = cd.detect(*s, cull=True)
+    assert plain["n_conf"] == culled["n_conf"] and plain["n_los"] == culled["n_los"]
+    assert set(map(tuple, plain["confpairs"].tolist())) == set(map(tuple, culled["confpairs"].tolist()))
+    assert np.array_equal(plain["nconf_row"], culled["nconf_row"]) and np.array_equal(plain["nlos_row"], culled["nlos_row"])
+    assert np.array_equal(plain["inconf"], culled["inconf"])
+    assert np.array_equal(plain["tcpamax"], culled["tcpamax"])
+    if n >= 5000:
+        assert plain["n_conf"] > 0
+
+
+def test_culled_form_against_oracle(cuda):
+    """and directly against the float64 oracle (dense), like the plain form."""
+    from bluesky_gym_sasha_b200.cd import StateBasedCD
+    s = synth_airspace(3000, box_deg=12.0, seed=11)
+    g = StateBasedCD(device=0).detect(*s, cull=True)
+    n_exempt, n_pairs = _check_against_oracle(s, g)
+    assert n_pairs > 50 and n_exempt <= max(2, n_pairs // 50)
+
+
+def test_cull_fraction_and_speed(cuda):
+    """N = 100k in the 40 x 40 degree box of SURVEY 8d: the culled form evaluates a few percent of the tile pairs."""
+    import torch
+    from bluesky_gym_sasha_b200.cd import StateBasedCD
+    n = 100_000
+    s = synth_airspace(n, box_deg=40.0, seed=1, alt_jitter=0.0)
+    cd = StateBasedCD(device=0)
+    lat_d, lon_d = cd._as_dev(s[0]), cd._as_dev(s[1])
+    perm = cd.spatial_order(lat_d, lon_d)
+    rec, _ = cd.pack(*[cd._as_dev(x)[perm] for x in s], 52.0, 4.0)
+    out = {}
+    for cull in (False, True):
+        for _ in range(2):
+            o = cd.detect_packed(rec, n, cull=cull)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        o = cd.detect_packed(rec, n, cull=cull)
+        e1.record()
+        torch.cuda.synchronize()
+        out[cull] = (e0.elapsed_time(e1), int(o["npairs"][0]), int(o["npairs"][1]), o["nconf_row"].clone())
+    n_tiles = (n + 255) // 256
+    work = cd._buf["cull_work"]
+    cnt_off = 16 * ((n_tiles * 12 * 4 + 15) // 16)          # workspace layout: bounds | list_cnt | ...
+    cnt = work[cnt_off:cnt_off + 4 * n_tiles].view(torch.int32).cpu().numpy()
+    frac = cnt.sum() / float(n_tiles * n_tiles)
+    print(f"plain {out[False][0]:.2f} ms, culled {out[True][0]:.3f} ms, tile pairs evaluated {100 * frac:.2f} %, "
+          f"{out[True][1]} conflicts")
+    assert out[False][1:3] == out[True][1:3] and torch.equal(out[False][3], out[True][3])
+    assert frac < 0.15 and out[True][0] < 0.35 * out[False][0]
