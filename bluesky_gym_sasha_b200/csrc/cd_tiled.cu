@@ -104,6 +104,16 @@ __device__ __noinline__ uint32_t cd_candidate(const CdArgs& a, int ri, int cj, f
     return (p.conf ? 1u : 0u) | (p.los ? 2u : 0u);
 }
 
+// Same, on records already at hand (own row from its packed registers, column from the shared-memory tile): no
+// global loads on the rare path, which matters once culling has concentrated the candidates.
+template <bool WRAP>
+__device__ __noinline__ uint32_t cd_candidate_rec(const float4 Ai, const float4 Bi, const float4 Aj, const float4 Bj,
+                                                  float R2, float hpz, float dtlook, bool same, float& tcpa) {
+    CdPair p = cd_pair_eval<WRAP>(Ai, Bi, Aj, Bj, R2, hpz, dtlook, same);
+    tcpa = p.tcpa;
+    return (p.conf ? 1u : 0u) | (p.los ? 2u : 0u);
+}
+
 struct RowPack {            // loop-invariant operands of one own-row, duplicated into both f32x2 halves
     u64 nX, nY, CH, nSH, nU, nV, nALT, nVS;
 };
@@ -224,17 +234,27 @@ __device__ __forceinline__ void cd_process_item(const CdArgs& a, float (*s_tile)
             const ulonglong2 V = *reinterpret_cast<const ulonglong2*>(tile + FV * kTJ + j);
             const ulonglong2 AL = *reinterpret_cast<const ulonglong2*>(tile + FALT * kTJ + j);
             const ulonglong2 VS = *reinterpret_cast<const ulonglong2*>(tile + FVS * kTJ + j);
-            bool hit = false;
+            bool hit[kR];               // per own row: any of the four columns j .. j+3 flagged
 #pragma unroll
             for (int k = 0; k < kR; ++k) {
-                hit |= cd_hot2<WRAP>(rp[k], X.x, Y.x, CH.x, SH.x, U.x, V.x, AL.x, VS.x, R2P, HPZP, NEG1, dtlh);
-                hit |= cd_hot2<WRAP>(rp[k], X.y, Y.y, CH.y, SH.y, U.y, V.y, AL.y, VS.y, R2P, HPZP, NEG1, dtlh);
+                hit[k] = cd_hot2<WRAP>(rp[k], X.x, Y.x, CH.x, SH.x, U.x, V.x, AL.x, VS.x, R2P, HPZP, NEG1, dtlh);
+                hit[k] |= cd_hot2<WRAP>(rp[k], X.y, Y.y, CH.y, SH.y, U.y, V.y, AL.y, VS.y, R2P, HPZP, NEG1, dtlh);
             }
-            if (hit) for (int b = 0; b < 4 * kR; ++b) {  // rare: exact re-evaluation of the 8 pairs
-                const int k = b >> 2, cj = c0 + j + (b & 3);
-                if (ri[k] >= row_end || cj >= a.n_all) continue;
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < kR; ++k) any |= hit[k];
+            if (any) for (int b = 0; b < 4 * kR; ++b) {  // rare: exact re-evaluation of the flagged rows' four pairs
+                const int k = b >> 2, jc = j + (b & 3), cj = c0 + jc;
+                if (!(k == 0 ? hit[0] : hit[kR - 1]) || ri[k] >= row_end || cj >= a.n_all) continue;
+                float nx, ny, chh, nsh, nu, nv, nal, nvs, dummy;
+                up2(rp[k].nX, nx, dummy); up2(rp[k].nY, ny, dummy); up2(rp[k].CH, chh, dummy); up2(rp[k].nSH, nsh, dummy);
+                up2(rp[k].nU, nu, dummy); up2(rp[k].nV, nv, dummy); up2(rp[k].nALT, nal, dummy); up2(rp[k].nVS, nvs, dummy);
                 float tc;
-                const uint32_t f = cd_candidate<WRAP>(a, ri[k], cj, tc);
+                const uint32_t f = cd_candidate_rec<WRAP>(
+                    make_float4(-nx, -ny, chh, -nsh), make_float4(-nu, -nv, -nal, -nvs),
+                    make_float4(tile[FX * kTJ + jc], tile[FY * kTJ + jc], tile[FCH * kTJ + jc], tile[FSH * kTJ + jc]),
+                    make_float4(tile[FU * kTJ + jc], tile[FV * kTJ + jc], tile[FALT * kTJ + jc], tile[FVS * kTJ + jc]),
+                    a.R2, a.hpz, a.dtlook, ri[k] == cj, tc);
                 if (f & 2u) {
                     nlos[k]++;
                     if (a.npairs) atomicAdd(a.npairs + 1, 1ULL);
