@@ -33,7 +33,9 @@ constexpr int kNT = 128;                 // threads per CTA
 constexpr int kR = 2;                    // rows per thread
 constexpr int kRowsPerCta = kNT * kR;    // 256 = one tile of rows
 constexpr int kTilesPerItem = 8;
-constexpr int kTilesPerChunk = 2;        // culled form: work item = one row block x up to 2 listed column tiles
+// culled form: work item = one row block x up to kTilesPerChunk listed column tiles.  Measured at N = 100k (2.8 % of
+// the tile pairs kept): 1 -> 0.506 ms, 2 -> 0.539, 4 -> 0.574, 8 -> 0.626: balance beats the per-item set-up cost.
+constexpr int kTilesPerChunk = 1;
 constexpr int kTileFloats = 8 * kTJ;
 constexpr uint32_t kTileBytes = kTileFloats * 4;
 enum { FX = 0, FY = 1, FCH = 2, FSH = 3, FU = 4, FV = 5, FALT = 6, FVS = 7 };
