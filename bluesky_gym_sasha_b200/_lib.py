@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("BSG_B200_LIB", os.path.join(_HERE, "libbsg_b200.so"))
 BSG_OK, BSG_EINVAL, BSG_ECUDA, BSG_ESTATE, BSG_ENOMEM = 0, -1, -2, -3, -4
 ENV_DESCENT, ENV_HORIZONTAL_CR, ENV_SECTOR_CR, ENV_MERGE, ENV_PLAN_WAYPOINT, ENV_VERTICAL_CR, ENV_STATIC_OBSTACLE = 0, 1, 2, 3, 4, 5, 6
 AUTORESET_DISABLED, AUTORESET_NEXT_STEP, AUTORESET_SAME_STEP = 0, 1, 2
-CD_LON_WRAP, CD_SYMMETRIC = 1, 2
+CD_LON_WRAP, CD_SYMMETRIC, CD_CULL = 1, 2, 4
 
 # indices into the per-env records (include/bsg.h)
 F64_WPT_LAT, F64_WPT_LON, F64_TARGET_ALT, F64_POLY_AREA, F64_WPTS, F64_COUNT = 0, 1, 2, 3, 4, 16
@@ -59,7 +59,7 @@ class TensorTable(C.Structure):
 
 SYMBOLS = ("bsg_abi_version", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
            "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_host_copy", "bsg_set_obs_noise", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
-           "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_cd_cull_workspace", "bsg_cd_detect_culled", "bsg_probe_fp32")
+           "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_cd_cull_workspace", "bsg_cd_detect_culled", "bsg_cd_detect_peers", "bsg_probe_fp32")
 
 _lib = None
 
@@ -111,6 +111,9 @@ def load():
         lib.bsg_cd_cull_workspace.restype = i64
         lib.bsg_cd_detect_culled.argtypes = [vp, i64, i64, i64, f32, f32, f32, u32, vp, vp, vp, vp, vp, i64, vp, vp, i64, vp]
         lib.bsg_cd_detect_culled.restype = C.c_int
+    if hasattr(lib, "bsg_cd_detect_peers"):
+        lib.bsg_cd_detect_peers.argtypes = [C.POINTER(vp), i32, i32, i64, f32, f32, f32, u32, vp, vp, vp, vp, vp, i64, vp, vp, i64, vp]
+        lib.bsg_cd_detect_peers.restype = C.c_int
     lib.bsg_probe_fp32.argtypes = [i32, C.POINTER(f64)]
     for name in ("bsg_query_layout", "bsg_create", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy",
                  "bsg_traf_update", "bsg_cd_pack", "bsg_cd_detect", "bsg_probe_fp32"):

@@ -170,6 +170,49 @@ class StateBasedCD:
                                   lon_wrap=lon_wrap, want_pairs=want_pairs, cull=cull)
 
 
+    # ---------------------------------------------------------------- multi-GPU without a gather (peer memory)
+    def detect_sharded_p2p(self, rec_local, n_local, group=None, want_pairs=False, cull=False):
+        """Same decomposition as ``detect_sharded`` but with NO collective on the data path: every rank copies its packed
+        block into a symmetric-memory buffer (torch.distributed._symmetric_memory: peer-addressable allocation +
+        device-side barrier; plumbing), and ``bsg_cd_detect_peers`` reads the column tiles it needs straight from the
+        owners over NVLink with the kernel's TMA bulk copies.  With ``cull=True`` only tiles that survive culling
+        ever cross the link."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        assert n_local % 256 == 0 and world <= 8, "shard size must be a multiple of 256; one node (<= 8 GPUs)"
+        st = self._buf.get("symm")
+        if st is None or st[0] != n_local:
+            buf = symm.empty((n_local // 256, 8, 256), dtype=torch.float32, device=self.device)
+            hdl = symm.rendezvous(buf, group)
+            ptrs = (C.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+            st = (n_local, buf, hdl, ptrs)
+            self._buf["symm"] = st
+        _, buf, hdl, ptrs = st
+        buf.copy_(rec_local[:n_local // 256])
+        hdl.barrier(channel=0)                  # every rank's block is in place (device-side, on the current stream)
+        m = n_local
+        nconf = self._get("nconf", (m,), torch.int32)
+        nlos = self._get("nlos", (m,), torch.int32)
+        tcpamax = self._get("tcpamax", (m,), torch.float32)
+        inconf = self._get("inconf", (m,), torch.uint8)
+        npairs = self._get("npairs", (2,), torch.int64)
+        pairs = self._get("pairs", (max(self.pair_capacity, 1), 2), torch.int32) if want_pairs else None
+        work, nbytes = None, 0
+        if cull:
+            nbytes = int(self.lib.bsg_cd_cull_workspace(n_local * world, n_local))
+            work = self._get("cull_work", (nbytes,), torch.uint8)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bsg_cd_detect_peers(ptrs, world, rank, n_local, self.rpz, self.hpz, self.dtlookahead,
+                                                    _lib.CD_CULL if cull else 0, _ptr(nconf), _ptr(nlos), _ptr(tcpamax),
+                                                    _ptr(inconf), _ptr(pairs), self.pair_capacity if want_pairs else 0,
+                                                    _ptr(npairs), _ptr(work), nbytes, self._stream()))
+        hdl.barrier(channel=1)                  # nobody overwrites a block that a peer may still be reading
+        self.gpu_launches += 5 if cull else 2
+        return dict(nconf_row=nconf, nlos_row=nlos, tcpamax=tcpamax, inconf=inconf, pairs=pairs, npairs=npairs)
+
+
 def shard_rows(n_all, world, rank):
     """Block partition used by ``detect_sharded`` and its CPU (gloo) tests: [row0, row0 + n_rows)."""
     per = n_all // world

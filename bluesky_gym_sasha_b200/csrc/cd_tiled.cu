@@ -87,12 +87,24 @@ struct CdArgs {
     const int32_t* chunk_off;     // [n_rowblocks + 1] exclusive scan of ceil(list_cnt / kTilesPerChunk)
     int list_stride;
     unsigned int* work_counter;   // dynamic item fetch (items differ in size: a static stride leaves a long tail)
+    // peer form (bsg_cd_detect_peers): the records stay where each GPU packed them; column tile t is read from
+    // peer_rec[t / tiles_per_peer] over NVLink by the same TMA bulk copies (n_peers == 0: one local buffer, rec)
+    const float* peer_rec[8];
+    int n_peers, tiles_per_peer;
+    const float* rec_rows;        // the buffer holding this call's own rows; its first record has global index rows_base
+    int rows_base;
 };
 
 __device__ __forceinline__ void load_record(const float* __restrict__ rec, int idx, float4& A, float4& B) {
     const float* t = rec + (size_t)(idx / kTJ) * kTileFloats + (idx % kTJ);
     A = make_float4(t[FX * kTJ], t[FY * kTJ], t[FCH * kTJ], t[FSH * kTJ]);
     B = make_float4(t[FU * kTJ], t[FV * kTJ], t[FALT * kTJ], t[FVS * kTJ]);
+}
+
+__device__ __forceinline__ const float* tile_base(const CdArgs& a, int t) {
+    if (a.n_peers == 0) return a.rec + (size_t)t * kTileFloats;
+    const int p = t / a.tiles_per_peer;
+    return a.peer_rec[p] + (size_t)(t - p * a.tiles_per_peer) * kTileFloats;
 }
 
 // Exact (reference-order) evaluation of one candidate pair, out of line.  bit0 = conflict, bit1 = LoS.
@@ -200,7 +212,7 @@ __device__ __forceinline__ void cd_process_item(const CdArgs& a, float (*s_tile)
         int r = rbase + tid + k * kNT;
         ri[k] = r;
         float4 A, B;
-        load_record(a.rec, r < row_end ? r : row_end - 1, A, B);
+        load_record(a.rec_rows, (r < row_end ? r : row_end - 1) - a.rows_base, A, B);
         if (r >= row_end) B.z = -3.0e9f;                // inert row (padding columns sit at +3e9)
         rp[k].nX = pk2(-A.x, -A.x); rp[k].nY = pk2(-A.y, -A.y);
         rp[k].CH = pk2(A.z, A.z);   rp[k].nSH = pk2(-A.w, -A.w);
@@ -211,7 +223,7 @@ __device__ __forceinline__ void cd_process_item(const CdArgs& a, float (*s_tile)
 
     if (tid == 0) {        // prologue: first tile of the item
         mbar_expect_tx(&s_full[0], kTileBytes);
-        tma_load_1d(&s_tile[0][0], a.rec + (size_t)tile_of(0) * kTileFloats, kTileBytes, &s_full[0]);
+        tma_load_1d(&s_tile[0][0], tile_base(a, tile_of(0)), kTileBytes, &s_full[0]);
     }
 #pragma unroll 1
     for (int tt = 0; tt < n_t; ++tt) {
@@ -219,7 +231,7 @@ __device__ __forceinline__ void cd_process_item(const CdArgs& a, float (*s_tile)
         const int t = tile_of(tt);
         if (tid == 0 && tt + 1 < n_t) {     // prefetch the next tile into the other stage
             mbar_expect_tx(&s_full[s ^ 1], kTileBytes);
-            tma_load_1d(&s_tile[s ^ 1][0], a.rec + (size_t)tile_of(tt + 1) * kTileFloats, kTileBytes, &s_full[s ^ 1]);
+            tma_load_1d(&s_tile[s ^ 1][0], tile_base(a, tile_of(tt + 1)), kTileBytes, &s_full[s ^ 1]);
         }
         mbar_wait(&s_full[s], parity[s]);
         parity[s] ^= 1u;
@@ -352,10 +364,10 @@ __global__ void __launch_bounds__(kNT, 4) cd_tiled_kernel(const CdArgs a) {
 // and the largest |vs|.  Padding records (index >= n_all) are ignored.
 enum { TB_XMIN = 0, TB_XMAX, TB_YMIN, TB_YMAX, TB_COSMIN, TB_VMAX, TB_AMIN, TB_AMAX, TB_VSMAX, TB_COUNT = 12 };
 
-__global__ void __launch_bounds__(kTJ) cd_tile_bounds_kernel(const float* __restrict__ rec, int n_all, float* __restrict__ bounds) {
+__global__ void __launch_bounds__(kTJ) cd_tile_bounds_kernel(const CdArgs a, int n_all, float* __restrict__ bounds) {
     __shared__ float s_red[9][kTJ / 32];
     const int tile = blockIdx.x, j = threadIdx.x, idx = tile * kTJ + j;
-    const float* t = rec + (size_t)tile * kTileFloats + j;
+    const float* t = tile_base(a, tile) + j;
     const bool live = idx < n_all;
     const float x = t[FX * kTJ], y = t[FY * kTJ], ch = t[FCH * kTJ], sh = t[FSH * kTJ];
     const float u = t[FU * kTJ], v = t[FV * kTJ], alt = t[FALT * kTJ], vs = t[FVS * kTJ];
@@ -478,25 +490,15 @@ extern "C" int bsg_cd_pack(const double* d_lat, const double* d_lon, const doubl
     return bsg_cuda_check(cudaGetLastError(), "bsg_cd_pack launch");
 }
 
-extern "C" int bsg_cd_detect(const float* d_rec, int64_t n_all, int64_t row0, int64_t n_rows, float rpz, float hpz,
-                             float dtlookahead, uint32_t flags, uint32_t* d_nconf_row, uint32_t* d_nlos_row,
-                             float* d_tcpamax, uint8_t* d_inconf, int32_t* d_pairs, int64_t cap,
-                             unsigned long long* d_npairs, void* stream) {
-    if (n_all < 0 || row0 < 0 || n_rows < 0 || row0 + n_rows > n_all)
-        return bsg_fail(BSG_EINVAL, "bsg_cd_detect: row range outside [0, n_all)");
-    if (n_all > 0x7fffff00LL) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: n_all exceeds int32 pair indices");
-    if (n_rows > 0 && (!d_rec || !d_nconf_row)) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: null d_rec / d_nconf_row");
-    if (d_pairs && (!d_npairs || cap < 0)) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: pair list needs d_npairs and cap >= 0");
-    if (flags & BSG_CD_SYMMETRIC) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: BSG_CD_SYMMETRIC not implemented yet");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (d_npairs) BSG_CUDA(cudaMemsetAsync(d_npairs, 0, 2 * sizeof(unsigned long long), st));
-    if (n_rows == 0) return BSG_OK;
-    BSG_CUDA(cudaMemsetAsync(d_nconf_row, 0, sizeof(uint32_t) * n_rows, st));
-    if (d_nlos_row) BSG_CUDA(cudaMemsetAsync(d_nlos_row, 0, sizeof(uint32_t) * n_rows, st));
-    if (d_tcpamax) BSG_CUDA(cudaMemsetAsync(d_tcpamax, 0, sizeof(float) * n_rows, st));
-
-    CdArgs a;
-    a.rec = d_rec;
+// ---- launch plumbing shared by the three entry points ------------------------------------------------
+static int cd_fill_args(CdArgs& a, int64_t n_all, int64_t row0, int64_t n_rows, float rpz, float hpz, float dtlookahead,
+                        uint32_t* d_nconf_row, uint32_t* d_nlos_row, float* d_tcpamax, int32_t* d_pairs, int64_t cap,
+                        unsigned long long* d_npairs) {
+    if (n_all < 0 || row0 < 0 || n_rows < 0 || row0 + n_rows > n_all) return bsg_fail(BSG_EINVAL, "CD: row range outside [0, n_all)");
+    if (n_all > 0x7fffff00LL) return bsg_fail(BSG_EINVAL, "CD: n_all exceeds int32 pair indices");
+    if (n_rows > 0 && !d_nconf_row) return bsg_fail(BSG_EINVAL, "CD: null d_nconf_row");
+    if (d_pairs && (!d_npairs || cap < 0)) return bsg_fail(BSG_EINVAL, "CD: pair list needs d_npairs and cap >= 0");
+    memset(&a, 0, sizeof(a));
     a.n_all = (int)n_all; a.row0 = (int)row0; a.n_rows = (int)n_rows;
     if (rpz <= 0.0f) rpz = 5.0f * 1852.0f;
     if (hpz <= 0.0f) hpz = 1000.0f * 0.3048f;
@@ -507,25 +509,69 @@ extern "C" int bsg_cd_detect(const float* d_rec, int64_t n_all, int64_t row0, in
     a.n_tiles = (int)(bsg_cd_padded(n_all) / kTJ);
     a.n_rowblocks = (int)((n_rows + kRowsPerCta - 1) / kRowsPerCta);
     a.n_colgroups = (a.n_tiles + kTilesPerItem - 1) / kTilesPerItem;
-    a.tile_list = nullptr; a.list_cnt = nullptr; a.chunk_off = nullptr; a.list_stride = 0; a.work_counter = nullptr;
+    return BSG_OK;
+}
 
+static int cd_launch(CdArgs& a, bool wrap, bool cull, void* d_work, int64_t work_bytes, uint8_t* d_inconf, cudaStream_t st) {
+    if (a.npairs) BSG_CUDA(cudaMemsetAsync(a.npairs, 0, 2 * sizeof(unsigned long long), st));
+    if (a.n_rows == 0) return BSG_OK;
+    BSG_CUDA(cudaMemsetAsync(a.nconf_row, 0, sizeof(uint32_t) * a.n_rows, st));
+    if (a.nlos_row) BSG_CUDA(cudaMemsetAsync(a.nlos_row, 0, sizeof(uint32_t) * a.n_rows, st));
+    if (a.tcpamax) BSG_CUDA(cudaMemsetAsync(a.tcpamax, 0, sizeof(float) * a.n_rows, st));
     int dev = 0, sms = 0, occ = 0;
     BSG_CUDA(cudaGetDevice(&dev));
     BSG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const bool wrap = (flags & BSG_CD_LON_WRAP) != 0;
-    if (wrap) BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<true, false>, kNT, 0));
-    else BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, false>, kNT, 0));
-    if (occ < 1) occ = 1;
-    long long n_items = (long long)a.n_rowblocks * a.n_colgroups;
-    int grid = (int)((n_items < (long long)sms * occ) ? n_items : (long long)sms * occ);
-    if (wrap) cd_tiled_kernel<true, false><<<grid, kNT, 0, st>>>(a);
-    else cd_tiled_kernel<false, false><<<grid, kNT, 0, st>>>(a);
+    if (cull) {
+        if (a.row0 % kRowsPerCta) return bsg_fail(BSG_EINVAL, "culled CD: row0 must be a multiple of 256");
+        if (wrap) return bsg_fail(BSG_EINVAL, "culled CD: airspaces across the antimeridian use the plain form");
+        if (!d_work || work_bytes < bsg_cd_cull_workspace(a.n_all, a.n_rows))
+            return bsg_fail(BSG_EINVAL, "culled CD: workspace missing or too small (bsg_cd_cull_workspace)");
+        char* w = (char*)d_work;
+        float* bounds = (float*)w;                       w += 16 * (((size_t)a.n_tiles * TB_COUNT * 4 + 15) / 16);
+        int32_t* cnt = (int32_t*)w;                      w += 16 * (((size_t)a.n_rowblocks * 4 + 15) / 16);
+        int32_t* chunk_off = (int32_t*)w;                w += 16 * (((size_t)(a.n_rowblocks + 1) * 4 + 15) / 16);
+        a.work_counter = (unsigned int*)w;               w += 16;
+        int32_t* list = (int32_t*)w;
+        a.tile_list = list; a.list_cnt = cnt; a.chunk_off = chunk_off; a.list_stride = a.n_tiles;
+        BSG_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * a.n_rowblocks, st));
+        BSG_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), st));
+        cd_tile_bounds_kernel<<<a.n_tiles, kTJ, 0, st>>>(a, a.n_all, bounds);
+        const long long n_pairs = (long long)a.n_rowblocks * a.n_tiles;
+        cd_cull_kernel<<<(int)((n_pairs + 255) / 256), 256, 0, st>>>(bounds, a.n_tiles, a.row0 / kRowsPerCta, a.n_rowblocks,
+                                                                     sqrtf(a.R2), a.hpz, a.dtlook, list, cnt, a.list_stride);
+        cd_chunk_scan_kernel<<<1, 1024, 0, st>>>(cnt, a.n_rowblocks, chunk_off);
+        BSG_CUDA(cudaGetLastError());
+        BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, true>, kNT, 0));
+        if (occ < 1) occ = 1;
+        cd_tiled_kernel<false, true><<<sms * occ, kNT, 0, st>>>(a);
+    } else {
+        if (wrap) BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<true, false>, kNT, 0));
+        else BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, false>, kNT, 0));
+        if (occ < 1) occ = 1;
+        const long long n_items = (long long)a.n_rowblocks * a.n_colgroups;
+        const int grid = (int)((n_items < (long long)sms * occ) ? n_items : (long long)sms * occ);
+        if (wrap) cd_tiled_kernel<true, false><<<grid, kNT, 0, st>>>(a);
+        else cd_tiled_kernel<false, false><<<grid, kNT, 0, st>>>(a);
+    }
     BSG_CUDA(cudaGetLastError());
     if (d_inconf) {
-        cd_finalize_kernel<<<(int)((n_rows + 255) / 256), 256, 0, st>>>(d_nconf_row, d_inconf, n_rows);
+        cd_finalize_kernel<<<(int)((a.n_rows + 255) / 256), 256, 0, st>>>(a.nconf_row, d_inconf, a.n_rows);
         BSG_CUDA(cudaGetLastError());
     }
     return BSG_OK;
+}
+
+extern "C" int bsg_cd_detect(const float* d_rec, int64_t n_all, int64_t row0, int64_t n_rows, float rpz, float hpz,
+                             float dtlookahead, uint32_t flags, uint32_t* d_nconf_row, uint32_t* d_nlos_row,
+                             float* d_tcpamax, uint8_t* d_inconf, int32_t* d_pairs, int64_t cap,
+                             unsigned long long* d_npairs, void* stream) {
+    if (flags & BSG_CD_SYMMETRIC) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: BSG_CD_SYMMETRIC not implemented yet");
+    CdArgs a;
+    int rc = cd_fill_args(a, n_all, row0, n_rows, rpz, hpz, dtlookahead, d_nconf_row, d_nlos_row, d_tcpamax, d_pairs, cap, d_npairs);
+    if (rc != BSG_OK) return rc;
+    if (n_rows > 0 && !d_rec) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: null d_rec");
+    a.rec = d_rec; a.rec_rows = d_rec; a.rows_base = 0;
+    return cd_launch(a, (flags & BSG_CD_LON_WRAP) != 0, false, nullptr, 0, d_inconf, (cudaStream_t)stream);
 }
 
 extern "C" int64_t bsg_cd_cull_workspace(int64_t n_all, int64_t n_rows) {
@@ -539,60 +585,30 @@ extern "C" int bsg_cd_detect_culled(const float* d_rec, int64_t n_all, int64_t r
                                     float dtlookahead, uint32_t flags, uint32_t* d_nconf_row, uint32_t* d_nlos_row,
                                     float* d_tcpamax, uint8_t* d_inconf, int32_t* d_pairs, int64_t cap,
                                     unsigned long long* d_npairs, void* d_work, int64_t work_bytes, void* stream) {
-    if (n_all < 0 || row0 < 0 || n_rows < 0 || row0 + n_rows > n_all)
-        return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: row range outside [0, n_all)");
-    if (row0 % kRowsPerCta) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: row0 must be a multiple of 256");
-    if (flags & BSG_CD_LON_WRAP) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: airspaces across the antimeridian use bsg_cd_detect");
-    if (n_all > 0x7fffff00LL) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: n_all exceeds int32 pair indices");
-    if (n_rows > 0 && (!d_rec || !d_nconf_row || !d_work)) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: null pointer");
-    if (work_bytes < bsg_cd_cull_workspace(n_all, n_rows)) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: workspace too small (bsg_cd_cull_workspace)");
-    if (d_pairs && (!d_npairs || cap < 0)) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: pair list needs d_npairs and cap >= 0");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (d_npairs) BSG_CUDA(cudaMemsetAsync(d_npairs, 0, 2 * sizeof(unsigned long long), st));
-    if (n_rows == 0) return BSG_OK;
-    BSG_CUDA(cudaMemsetAsync(d_nconf_row, 0, sizeof(uint32_t) * n_rows, st));
-    if (d_nlos_row) BSG_CUDA(cudaMemsetAsync(d_nlos_row, 0, sizeof(uint32_t) * n_rows, st));
-    if (d_tcpamax) BSG_CUDA(cudaMemsetAsync(d_tcpamax, 0, sizeof(float) * n_rows, st));
-
     CdArgs a;
-    a.rec = d_rec;
-    a.n_all = (int)n_all; a.row0 = (int)row0; a.n_rows = (int)n_rows;
-    if (rpz <= 0.0f) rpz = 5.0f * 1852.0f;
-    if (hpz <= 0.0f) hpz = 1000.0f * 0.3048f;
-    if (dtlookahead <= 0.0f) dtlookahead = 300.0f;
-    a.R2 = rpz * rpz; a.hpz = hpz; a.dtlook = dtlookahead;
-    a.nconf_row = d_nconf_row; a.nlos_row = d_nlos_row; a.tcpamax = d_tcpamax;
-    a.pairs = d_pairs; a.cap = cap; a.npairs = d_npairs;
-    a.n_tiles = (int)(bsg_cd_padded(n_all) / kTJ);
-    a.n_rowblocks = (int)((n_rows + kRowsPerCta - 1) / kRowsPerCta);
-    a.n_colgroups = 0;
-    char* w = (char*)d_work;
-    float* bounds = (float*)w;                       w += 16 * (((size_t)a.n_tiles * TB_COUNT * 4 + 15) / 16);
-    int32_t* cnt = (int32_t*)w;                      w += 16 * (((size_t)a.n_rowblocks * 4 + 15) / 16);
-    int32_t* chunk_off = (int32_t*)w;                w += 16 * (((size_t)(a.n_rowblocks + 1) * 4 + 15) / 16);
-    a.work_counter = (unsigned int*)w;               w += 16;
-    int32_t* list = (int32_t*)w;
-    a.tile_list = list; a.list_cnt = cnt; a.chunk_off = chunk_off; a.list_stride = a.n_tiles;
+    int rc = cd_fill_args(a, n_all, row0, n_rows, rpz, hpz, dtlookahead, d_nconf_row, d_nlos_row, d_tcpamax, d_pairs, cap, d_npairs);
+    if (rc != BSG_OK) return rc;
+    if (n_rows > 0 && !d_rec) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: null d_rec");
+    a.rec = d_rec; a.rec_rows = d_rec; a.rows_base = 0;
+    return cd_launch(a, (flags & BSG_CD_LON_WRAP) != 0, true, d_work, work_bytes, d_inconf, (cudaStream_t)stream);
+}
 
-    BSG_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * a.n_rowblocks, st));
-    BSG_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), st));
-    cd_tile_bounds_kernel<<<a.n_tiles, kTJ, 0, st>>>(d_rec, a.n_all, bounds);
-    const long long n_pairs = (long long)a.n_rowblocks * a.n_tiles;
-    cd_cull_kernel<<<(int)((n_pairs + 255) / 256), 256, 0, st>>>(bounds, a.n_tiles, (int)(row0 / kRowsPerCta), a.n_rowblocks,
-                                                                 rpz, hpz, dtlookahead, list, cnt, a.list_stride);
-    cd_chunk_scan_kernel<<<1, 1024, 0, st>>>(cnt, a.n_rowblocks, chunk_off);
-    BSG_CUDA(cudaGetLastError());
-
-    int dev = 0, sms = 0, occ = 0;
-    BSG_CUDA(cudaGetDevice(&dev));
-    BSG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, true>, kNT, 0));
-    if (occ < 1) occ = 1;
-    cd_tiled_kernel<false, true><<<sms * occ, kNT, 0, st>>>(a);
-    BSG_CUDA(cudaGetLastError());
-    if (d_inconf) {
-        cd_finalize_kernel<<<(int)((n_rows + 255) / 256), 256, 0, st>>>(d_nconf_row, d_inconf, n_rows);
-        BSG_CUDA(cudaGetLastError());
-    }
-    return BSG_OK;
+extern "C" int bsg_cd_detect_peers(const float* const* h_peer_rec, int32_t n_peers, int32_t my_rank, int64_t n_per_peer,
+                                   float rpz, float hpz, float dtlookahead, uint32_t flags, uint32_t* d_nconf_row,
+                                   uint32_t* d_nlos_row, float* d_tcpamax, uint8_t* d_inconf, int32_t* d_pairs, int64_t cap,
+                                   unsigned long long* d_npairs, void* d_work, int64_t work_bytes, void* stream) {
+    if (!h_peer_rec || n_peers < 1 || n_peers > 8 || my_rank < 0 || my_rank >= n_peers)
+        return bsg_fail(BSG_EINVAL, "bsg_cd_detect_peers: need 1..8 peer buffers and a rank among them");
+    if (n_per_peer <= 0 || n_per_peer % kTJ) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_peers: n_per_peer must be a positive multiple of 256");
+    for (int p = 0; p < n_peers; ++p)
+        if (!h_peer_rec[p]) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_peers: null peer buffer");
+    CdArgs a;
+    int rc = cd_fill_args(a, n_per_peer * n_peers, n_per_peer * my_rank, n_per_peer, rpz, hpz, dtlookahead, d_nconf_row, d_nlos_row,
+                          d_tcpamax, d_pairs, cap, d_npairs);
+    if (rc != BSG_OK) return rc;
+    a.rec = nullptr;
+    for (int p = 0; p < n_peers; ++p) a.peer_rec[p] = h_peer_rec[p];
+    a.n_peers = n_peers; a.tiles_per_peer = (int)(n_per_peer / kTJ);
+    a.rec_rows = h_peer_rec[my_rank]; a.rows_base = (int)(n_per_peer * my_rank);
+    return cd_launch(a, (flags & BSG_CD_LON_WRAP) != 0, (flags & BSG_CD_CULL) != 0, d_work, work_bytes, d_inconf, (cudaStream_t)stream);
 }

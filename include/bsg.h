@@ -206,7 +206,8 @@ int bsg_cd_pack(const double *d_lat, const double *d_lon, const double *d_trk, c
                 float *d_rec, void *stream);
 
 enum { BSG_CD_LON_WRAP = 1,     /* pairs may straddle the +-180 deg meridian relative to lon0        */
-       BSG_CD_SYMMETRIC = 2 };  /* evaluate each unordered pair once (needs n_rows == n_all)         */
+       BSG_CD_SYMMETRIC = 2,    /* evaluate each unordered pair once (needs n_rows == n_all)         */
+       BSG_CD_CULL = 4 };       /* bsg_cd_detect_peers: use the culled form (needs the workspace)    */
 
 /* Rows [row0, row0+n_rows) of d_rec against all n_all aircraft (row sharding for multi-GPU).
  * Outputs (caller-owned, device): per-row nconf / nlos counts and tcpamax, inconf flags, and a pair
@@ -229,6 +230,20 @@ int bsg_cd_detect_culled(const float *d_rec, int64_t n_all, int64_t row0, int64_
                          float dtlookahead, uint32_t flags, uint32_t *d_nconf_row, uint32_t *d_nlos_row,
                          float *d_tcpamax, uint8_t *d_inconf, int32_t *d_pairs, int64_t cap,
                          unsigned long long *d_npairs, void *d_work, int64_t work_bytes, void *stream);
+
+/* Multi-GPU form without a gather: every GPU of the node packs its block of n_per_peer aircraft (a multiple of 256)
+ * into a buffer that its peers can address (CUDA peer access / symmetric memory: torch.distributed._symmetric_memory
+ * gives the pointers), and this call evaluates rank my_rank's rows against ALL columns, fetching column tile t
+ * from h_peer_rec[t / (n_per_peer / 256)] directly over NVLink with the kernel's own TMA bulk copies -- the transfer
+ * overlaps the pair arithmetic tile by tile and, with BSG_CD_CULL, only the tiles that survive culling ever cross the
+ * link.  h_peer_rec is a HOST array of n_peers (<= 8) DEVICE pointers valid in this process.  The caller must make
+ * sure all peers have finished packing before the call and keep their buffers unchanged until every rank's call has
+ * completed (a barrier on each side; StateBasedCD.detect_sharded_p2p uses the symmetric-memory barrier).
+ * Replaces: ncclAllGather + bsg_cd_detect(row0 = my_rank * n_per_peer, n_rows = n_per_peer). */
+int bsg_cd_detect_peers(const float *const *h_peer_rec, int32_t n_peers, int32_t my_rank, int64_t n_per_peer,
+                        float rpz, float hpz, float dtlookahead, uint32_t flags, uint32_t *d_nconf_row,
+                        uint32_t *d_nlos_row, float *d_tcpamax, uint8_t *d_inconf, int32_t *d_pairs, int64_t cap,
+                        unsigned long long *d_npairs, void *d_work, int64_t work_bytes, void *stream);
 
 /* ---- roofline denominators measured on the spot (bench.py) ------------------------------------- */
 /* Dense FP32 FMA throughput [FLOP/s] of this device, timed with CUDA events. */

@@ -184,3 +184,46 @@ def test_cull_fraction_and_speed(cuda):
           f"{out[True][1]} conflicts")
     assert out[False][1:3] == out[True][1:3] and torch.equal(out[False][3], out[True][3])
     assert frac < 0.15 and out[True][0] < 0.35 * out[False][0]
+
+
+@pytest.mark.parametrize("cull", [False, True])
+def test_peer_form_equals_gathered_form(cuda, cull):
+    """bsg_cd_detect_peers with the blocks left in separate buffers (here: four buffers on one device standing in for
+    four GPUs' symmetric memory) == bsg_cd_detect on the gathered records, for every 'rank'."""
+    import ctypes as C
+    import torch
+    from bluesky_gym_sasha_b200 import _lib
+    from bluesky_gym_sasha_b200.cd import StateBasedCD
+    W, per = 4, 1024
+    n = W * per
+    s = synth_airspace(n, box_deg=14.0, seed=21)
+    cd = StateBasedCD(device=0)
+    d = [cd._as_dev(x) for x in s]
+    perm = cd.spatial_order(d[0], d[1])
+    d = [x[perm] for x in d]
+    rec_all, _ = cd.pack(*d, 52.0, 4.0)
+    blocks = [rec_all[r * per // 256:(r + 1) * per // 256].clone() for r in range(W)]       # separate allocations
+    ptrs = (C.c_void_p * W)(*[b.data_ptr() for b in blocks])
+    lib = _lib.load()
+    tot = 0
+    for r in range(W):
+        ref = cd.detect_packed(rec_all, n, row0=r * per, n_rows=per, cull=cull)
+        ref = {k: (v.clone() if v is not None else None) for k, v in ref.items()}
+        nconf = torch.zeros(per, dtype=torch.int32, device="cuda")
+        nlos = torch.zeros(per, dtype=torch.int32, device="cuda")
+        tmax = torch.zeros(per, dtype=torch.float32, device="cuda")
+        inconf = torch.zeros(per, dtype=torch.uint8, device="cuda")
+        npairs = torch.zeros(2, dtype=torch.int64, device="cuda")
+        pairs = torch.zeros((1 << 16, 2), dtype=torch.int32, device="cuda")
+        nbytes = int(lib.bsg_cd_cull_workspace(n, per))
+        work = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.bsg_cd_detect_peers(ptrs, W, r, per, RPZ, HPZ, DTL, _lib.CD_CULL if cull else 0, nconf.data_ptr(),
+                                           nlos.data_ptr(), tmax.data_ptr(), inconf.data_ptr(), pairs.data_ptr(), 1 << 16,
+                                           npairs.data_ptr(), work.data_ptr(), nbytes, None))
+        torch.cuda.synchronize()
+        assert torch.equal(nconf, ref["nconf_row"]) and torch.equal(nlos, ref["nlos_row"]) and torch.equal(tmax, ref["tcpamax"])
+        k = int(npairs[0])
+        assert k == int(ref["npairs"][0])
+        assert set(map(tuple, pairs[:k].tolist())) == set(map(tuple, ref["pairs"][:k].tolist()))
+        tot += k
+    assert tot > 100
