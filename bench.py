@@ -267,13 +267,13 @@ def run_b200(args):
         achieved_tf = FLOP_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e12
         traffic, traffic_src = None, None
         try:        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed --set full capture
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["env_kernel<1, 32>"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["env_kernel<1, 32, 0>"]
             traffic, traffic_src = tr["dram_bytes_read"] + tr["dram_bytes_write"], "profiles/ncu_traffic.json <- " + tr["source"]
         except Exception:
             pass
         roof = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32 / 1e12, "unit": "TFLOP/s",
                 "frac": achieved_tf / (fp32 / 1e12), "traffic": traffic, "traffic_unit": "bytes per launch (DRAM)",
-                "traffic_source": traffic_src, "kernel": "env_kernel<HorizontalCR,32>",
+                "traffic_source": traffic_src, "kernel": "env_kernel<HorizontalCR,32,no wind>",
                 "peak_source": "bsg_probe_fp32 (dense FFMA, measured in this run)",
                 "flop_per_env_step": FLOP_PER_ENV_STEP,
                 "hbm": {"achieved": BYTES_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
