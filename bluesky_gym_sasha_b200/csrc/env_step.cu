@@ -189,97 +189,134 @@ __device__ inline bool d_inside_poly(double px, double py, const double* poly, i
 
 constexpr int kSectorMaxV = 32, kSectorMaxAc = 32, kSectorMaxTries = 4096;
 
-// scratch per env for the serial generator: [0..31] lat, [32..63] lon, [64..95] hdg
+// Scenario generator spread over the 32 lanes of the env's warp (a serial version on lane 0 took ~100 us of
+// dependent float64 work and set the duration of the whole launch whenever any env of the batch reset).  Philox draws are
+// addressed by index, so every lane computes the draws it needs; the DRAW ORDER of the reference is unchanged:
+// draw k = polygon point k (k < nv), then the density draw(s), then num_ac perimeter positions, then two draws per
+// rejection-sampling try.  scratch per warp (float64): [0,32) cand x | [32,64) cand y | [64,96) cand angle, later reused
+// as [0,32) lat | [32,64) lon of the accepted aircraft; [96,128) sorted vx | [128,160) sorted vy | [160,192) edge length |
+// [192,225) cumulative edge length | [225,257) sorted perimeter draws | [257,289) wx | [289,321) wy.
+constexpr int kSectorScratch = 324;
+
 template <int G>
 __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot, double* scratch) {
+    // (instantiated for every G by do_reset's dispatch, but only ever run with G == 32: one full warp per env)
     double* poly = P.poly + e * (2 * kSectorMaxV);
+    double* c_x = scratch, *c_y = scratch + 32, *c_a = scratch + 64;
+    double* s_vx = scratch + 96, *s_vy = scratch + 128, *s_el = scratch + 160, *s_cum = scratch + 192;
+    double* s_dl = scratch + 225, *s_wx = scratch + 257, *s_wy = scratch + 289;
+    const Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);
+    const double R = sqrt(3750.0 / 3.141592653589793);
+    const double coslat0 = cos(kSectorLat0 * kDeg2RadD);
+    // ---- A: candidate polygon point `slot` = random_point_on_circle with draw `slot` (functions.py:44-59) ----------
+    {
+        const double al = 6.283185307179586 * rng.u01((uint32_t)slot);
+        const double x = R * cos(al), y = R * sin(al);
+        c_x[slot] = x; c_y[slot] = y; c_a[slot] = atan2(y, x);
+    }
+    __syncwarp();
+    // ---- B (lane 0): insert points in draw order, keep them sorted by angle, until the area is large enough
+    //      (sector_cr_env.py:141-160); then density -> num_ac (:98-103), edge lengths and their running sum (:162-170)
     int num_ac = 0, nv = 0, rflags = 0;
-    double area = 0.0, w0lat = 0.0, w0lon = 0.0;
-    if (slot == 0) {                                                        // sector_cr_env.py:87-115
-        Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);
-        uint32_t d = 0;
+    uint32_t d = 0;
+    double area = 0.0, perim = 0.0, minx = 0.0, maxx = 0.0, miny = 0.0, maxy = 0.0;
+    if (slot == 0) {
         double vx[kSectorMaxV], vy[kSectorMaxV], va[kSectorMaxV];
-        const double R = sqrt(3750.0 / 3.141592653589793);
         auto shoelace = [&](int n) {
             double acc = 0.0;
             for (int i = 0; i < n; ++i) { int j = (i + 1 == n) ? 0 : i + 1; acc += vx[i] * vy[j] - vy[i] * vx[j]; }
             return fabs(acc) / 2.0;
         };
-        auto insert_point = [&]() {         // random_point_on_circle + sort by atan2(y, x) (functions.py:44-75)
-            double al = 6.283185307179586 * rng.u01(d++);
-            double x = R * cos(al), y = R * sin(al), ang = atan2(y, x);
+        auto insert_point = [&]() {         // sort_points_clockwise = ascending atan2(y, x) (functions.py:61-75)
+            const double x = c_x[nv], y = c_y[nv], ang = c_a[nv];
             int k = nv;
             while (k > 0 && va[k - 1] > ang) { vx[k] = vx[k - 1]; vy[k] = vy[k - 1]; va[k] = va[k - 1]; --k; }
             vx[k] = x; vy[k] = y; va[k] = ang; ++nv;
         };
-        insert_point(); insert_point(); insert_point();                     // sector_cr_env.py:141-160
+        insert_point(); insert_point(); insert_point();
         area = shoelace(nv);
         while (area < 2400.0 && nv < kSectorMaxV) { insert_point(); area = shoelace(nv); }
         if (area < 2400.0) rflags |= 1;
-        const double coslat0 = cos(kSectorLat0 * kDeg2RadD);
-        for (int i = 0; i < nv; ++i) {                                      // nm_to_latlong: x north, y east
-            poly[2 * i] = kSectorLat0 + vx[i] / 60.0;
-            poly[2 * i + 1] = kSectorLon0 + vy[i] / (60.0 * coslat0);
-        }
-        double rho;                                                         // sector_cr_env.py:98-103
+        d = (uint32_t)nv;
+        double rho;
         if (P.sector_uniform) { rho = rng.uniform(d, 0.003, 0.007); d += 1; }
         else { rho = rng.normal(d, 0.005, 0.001); d += 2; }
         double nraw = fmax(ceil(rho * area), 5.0);
         if (nraw > (double)kSectorMaxAc) { nraw = (double)kSectorMaxAc; rflags |= 2; }
         num_ac = (int)nraw;
-        // _generate_waypoints: num_ac sorted draws along the perimeter      sector_cr_env.py:162-188
-        double elen[kSectorMaxV], perim = 0.0;
+        minx = maxx = vx[0]; miny = maxy = vy[0];
         for (int i = 0; i < nv; ++i) {
-            int j = (i + 1 == nv) ? 0 : i + 1;
-            double ex = vx[j] - vx[i], ey = vy[j] - vy[i];
-            elen[i] = sqrt(ex * ex + ey * ey);
-            perim += elen[i];
+            const int j = (i + 1 == nv) ? 0 : i + 1;
+            const double ex = vx[j] - vx[i], ey = vy[j] - vy[i];
+            const double el = sqrt(ex * ex + ey * ey);
+            s_vx[i] = vx[i]; s_vy[i] = vy[i]; s_el[i] = el; s_cum[i] = perim;      // cum[i] = el[0] + ... + el[i-1]
+            perim += el;
+            minx = fmin(minx, vx[i]); maxx = fmax(maxx, vx[i]); miny = fmin(miny, vy[i]); maxy = fmax(maxy, vy[i]);
+            poly[2 * i] = kSectorLat0 + vx[i] / 60.0;                              // nm_to_latlong: x north, y east
+            poly[2 * i + 1] = kSectorLon0 + vy[i] / (60.0 * coslat0);
         }
-        double dl[kSectorMaxAc];
-        for (int i = 0; i < num_ac; ++i) {
-            double v = rng.uniform(d++, 0.0, perim);
-            int k = i;
-            while (k > 0 && dl[k - 1] > v) { dl[k] = dl[k - 1]; --k; }
-            dl[k] = v;
-        }
-        double wx[kSectorMaxAc], wy[kSectorMaxAc];
-        {
-            double cur = 0.0; int k = 0;
-            for (int i = 0; i < num_ac; ++i) {
-                while (dl[i] > cur + elen[k] && k < nv - 1) { cur += elen[k]; ++k; }
-                int j = (k + 1 == nv) ? 0 : k + 1;
-                double frac = (dl[i] - cur) / elen[k];
-                wx[i] = vx[k] + frac * (vx[j] - vx[k]);
-                wy[i] = vy[k] + frac * (vy[j] - vy[k]);
-            }
-        }
-        // _generate_ac: rejection sampling in the bounding box              sector_cr_env.py:190-217
-        double minx = vx[0], maxx = vx[0], miny = vy[0], maxy = vy[0];
-        for (int i = 1; i < nv; ++i) { minx = fmin(minx, vx[i]); maxx = fmax(maxx, vx[i]); miny = fmin(miny, vy[i]); maxy = fmax(maxy, vy[i]); }
-        int got = 0, tries = 0;
-        while (got < num_ac && tries < kSectorMaxTries) {
-            ++tries;
-            double x = rng.uniform(d++, minx, maxx), y = rng.uniform(d++, miny, maxy);
-            double la = kSectorLat0 + x / 60.0, lo = kSectorLon0 + y / (60.0 * coslat0);
-            if (d_inside_poly(la, lo, poly, nv)) {
-                double wla = kSectorLat0 + wx[got] / 60.0, wlo = kSectorLon0 + wy[got] / (60.0 * coslat0);
-                // fn.get_hdg: great-circle initial bearing, functions.py:150-178
-                double l1 = la * kDeg2RadD, l2 = wla * kDeg2RadD, dlo = (wlo - lo) * kDeg2RadD;
-                double hx = sin(dlo) * cos(l2), hy = cos(l1) * sin(l2) - sin(l1) * cos(l2) * cos(dlo);
-                double h = fmod(kRad2DegD * atan2(hx, hy) + 360.0, 360.0);
-                scratch[got] = la; scratch[32 + got] = lo; scratch[64 + got] = h;
-                if (got == 0) { w0lat = wla; w0lon = wlo; }
-                ++got;
-            }
-        }
-        if (got < num_ac) { rflags |= 4; num_ac = got > 0 ? got : 1; }
     }
-    __syncwarp(group_mask<G>());
+    __syncwarp();
     num_ac = group_bcast<G>(num_ac, 0); nv = group_bcast<G>(nv, 0); rflags = group_bcast<G>(rflags, 0);
-    area = group_bcast<G>(area, 0); w0lat = group_bcast<G>(w0lat, 0); w0lon = group_bcast<G>(w0lon, 0);
-    if (slot < num_ac) ac_create(a, scratch[slot], scratch[32 + slot], scratch[64 + slot], 350.0, 150.0);
-    else ac_clear(a);
-    __syncwarp(group_mask<G>());
+    d = (uint32_t)group_bcast<G>((int)d, 0);
+    area = group_bcast<G>(area, 0); perim = group_bcast<G>(perim, 0);
+    minx = group_bcast<G>(minx, 0); maxx = group_bcast<G>(maxx, 0); miny = group_bcast<G>(miny, 0); maxy = group_bcast<G>(maxy, 0);
+    // ---- C: _generate_waypoints (:162-188): num_ac draws along the perimeter, sorted, mapped onto the edges ----------
+    {
+        const bool mine = slot < num_ac;
+        const double v = mine ? rng.uniform(d + (uint32_t)slot, 0.0, perim) : 1.0e300;
+        int rank = 0;                                  // position of my draw in ascending order (stable)
+        for (int j = 0; j < G; ++j) {
+            const double vj = group_bcast<G>(v, j);
+            rank += (vj < v || (vj == v && j < slot)) ? 1 : 0;
+        }
+        if (mine) s_dl[rank] = v;
+        __syncwarp();
+        if (mine) {                                    // sorted draw number `slot` -> point on edge k
+            const double dl = s_dl[slot];
+            int k = 0;
+            while (k < nv - 1 && dl > s_cum[k] + s_el[k]) ++k;
+            const int j = (k + 1 == nv) ? 0 : k + 1;
+            const double frac = (dl - s_cum[k]) / s_el[k];
+            s_wx[slot] = s_vx[k] + frac * (s_vx[j] - s_vx[k]);
+            s_wy[slot] = s_vy[k] + frac * (s_vy[j] - s_vy[k]);
+        }
+        d += (uint32_t)num_ac;
+    }
+    __syncwarp();
+    // ---- D: _generate_ac (:190-217): rejection sampling in the bounding box, 32 tries at a time; try t uses draws
+    //         d + 2t and d + 2t + 1 and accepted points keep their try order, exactly as in the serial loop ----------
+    double* a_lat = scratch, *a_lon = scratch + 32;    // (the candidate arrays are no longer needed)
+    int got = 0;
+    for (int base = 0; base < kSectorMaxTries && got < num_ac; base += 32) {
+        const uint32_t t = (uint32_t)(base + slot);
+        const double x = rng.uniform(d + 2u * t, minx, maxx), y = rng.uniform(d + 2u * t + 1u, miny, maxy);
+        const double la = kSectorLat0 + x / 60.0, lo = kSectorLon0 + y / (60.0 * coslat0);
+        const bool in = d_inside_poly(la, lo, poly, nv);
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        const int idx = got + __popc(m & ((1u << slot) - 1u));
+        if (in && idx < num_ac) { a_lat[idx] = la; a_lon[idx] = lo; }
+        got += __popc(m);
+    }
+    __syncwarp();
+    if (got < num_ac) { rflags |= 4; num_ac = got > 0 ? got : 1; }
+    // ---- E: one aircraft per lane: heading towards its waypoint (fn.get_hdg, functions.py:150-178) and Traffic.cre
+    double w0lat = 0.0, w0lon = 0.0;
+    if (slot < num_ac && got > 0) {
+        const double la = a_lat[slot], lo = a_lon[slot];
+        const double wla = kSectorLat0 + s_wx[slot] / 60.0, wlo = kSectorLon0 + s_wy[slot] / (60.0 * coslat0);
+        const double l1 = la * kDeg2RadD, l2 = wla * kDeg2RadD, dlo = (wlo - lo) * kDeg2RadD;
+        const double hx = sin(dlo) * cos(l2), hy = cos(l1) * sin(l2) - sin(l1) * cos(l2) * cos(dlo);
+        const double h = fmod(kRad2DegD * atan2(hx, hy) + 360.0, 360.0);
+        ac_create(a, la, lo, h, 350.0, 150.0);
+        w0lat = wla; w0lon = wlo;
+    } else if (slot < num_ac) {
+        ac_create(a, 0.0, 0.0, 0.0, 350.0, 150.0);      // (no point could be placed: flagged in rflags, as before)
+    } else {
+        ac_clear(a);
+    }
+    w0lat = group_bcast<G>(w0lat, 0); w0lon = group_bcast<G>(w0lon, 0);
+    __syncwarp();
     s.num_ac = num_ac; s.nvert = nv; s.rflags = rflags; s.poly_area = area;
     s.wpt_lat = w0lat; s.wpt_lon = w0lon;
     s.total_reward = 0.0f; s.intrusions = 0; s.drift_sum = 0.0f; s.drift_n = 0; s.wpt_reach = 0;
@@ -604,27 +641,41 @@ __device__ inline int obstacles_hit(double lat, double lon, const double* pe, in
     if (slot < kObsN) inside = d_inside_poly(lat, lon, pe + slot * (2 * kObsMaxV), (int)pe[kObsNv + slot]) ? 1 : 0;
     return group_sum<G>(inside);
 }
+// Scenario generator spread over the group's 16 lanes (serial, it was ~150 us of dependent float64 trigonometry on one
+// lane and, with ~2 % of the envs resetting in any step, set the duration of every launch).  Draw order of the reference
+// kept: [cre heading] | 10 x (distance, bearing) of the obstacle centres | per obstacle: area draw, then one draw per
+// polygon point until the polygon is large enough | (distance, bearing) tries for the waypoint.  Per obstacle the 16
+// candidate points are evaluated by the 16 lanes at once; lane 0 only does the cheap insertion / shoelace loop that
+// decides how many of them are used.  scratch per group (float64): [0,16) cand x | [16,32) cand y | [32,48) cand angle.
+constexpr int kStaticScratch = 48;
+
 template <int G>
-__device__ inline void static_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot) {
+__device__ inline void static_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot, double* scratch) {
     double* pe = P.poly + e * kObsPoly;
-    double hdg = 0.0, wlat = 0.0, wlon = 0.0;
-    int rflags = 0;
+    double* c_x = scratch, *c_y = scratch + 16, *c_a = scratch + 32;
     const double lat0 = 52.0, lon0 = 4.0;
-    if (slot == 0) {                                                        // static_obstacle_env.py:96-131
-        Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);
-        uint32_t d = 0;
-        if (P.hdg_random) (void)rng.randint(d++, 1, 360);                   // cre's heading draw (overwritten below)
-        for (int i = 0; i < kObsN; ++i) {                                   // :221-232
-            int dis = rng.randint(d++, 20, 150), brg = rng.randint(d++, 0, 360);
-            d_point_at_distance(lat0, lon0, (double)dis, (double)brg, pe[kObsCentre + 2 * i], pe[kObsCentre + 2 * i + 1]);
+    const Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);      // static_obstacle_env.py:96-131
+    uint32_t d = P.hdg_random ? 1u : 0u;                                    // cre's heading draw (overwritten below)
+    int rflags = 0;
+    if (slot < kObsN) {                                                     // centres :221-232, one per lane
+        const int dis = rng.randint(d + 2u * slot, 20, 150), brg = rng.randint(d + 2u * slot + 1u, 0, 360);
+        d_point_at_distance(lat0, lon0, (double)dis, (double)brg, pe[kObsCentre + 2 * slot], pe[kObsCentre + 2 * slot + 1]);
+    }
+    d += 2u * kObsN;
+    __syncwarp(group_mask<G>());
+    for (int i = 0; i < kObsN; ++i) {                                       // _generate_polygon :156-169
+        const double R = sqrt((double)rng.randint(d++, 100, 1000) / 3.141592653589793);
+        if (slot < kObsMaxV) {                                              // candidate point `slot` of this obstacle
+            const double al = 6.283185307179586 * rng.u01(d + (uint32_t)slot);
+            const double x = R * cos(al), y = R * sin(al);
+            c_x[slot] = x; c_y[slot] = y; c_a[slot] = atan2(y, x);
         }
-        for (int i = 0; i < kObsN; ++i) {                                   // _generate_polygon :156-169
-            const double R = sqrt((double)rng.randint(d++, 100, 1000) / 3.141592653589793);
+        __syncwarp(group_mask<G>());
+        int nv = 0;
+        if (slot == 0) {
             double vx[kObsMaxV], vy[kObsMaxV], va[kObsMaxV];
-            int nv = 0;
             auto insert_point = [&]() {
-                double al = 6.283185307179586 * rng.u01(d++);
-                double x = R * cos(al), y = R * sin(al), ang = atan2(y, x);
+                const double x = c_x[nv], y = c_y[nv], ang = c_a[nv];
                 int k = nv;
                 while (k > 0 && va[k - 1] > ang) { vx[k] = vx[k - 1]; vy[k] = vy[k - 1]; va[k] = va[k - 1]; --k; }
                 vx[k] = x; vy[k] = y; va[k] = ang; ++nv;
@@ -647,21 +698,21 @@ __device__ inline void static_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
             pe[kObsRadius + i] = R;
             pe[kObsNv + i] = (double)nv;
         }
-        int loops = 0;                                                      // _generate_waypoint :198-219
-        while (true) {
-            ++loops;
-            int dis = rng.randint(d++, 100, 170), brg = rng.randint(d++, 0, 360);
-            d_point_at_distance(lat0, lon0, (double)dis, (double)brg, wlat, wlon);
-            bool in = false;
-            for (int i = 0; i < kObsN; ++i) in |= d_inside_poly(wlat, wlon, pe + i * (2 * kObsMaxV), (int)pe[kObsNv + i]);
-            if (!in) break;
-            if (loops > 1000) { rflags |= 4; break; }
-        }
-        double dnm;
-        d_kwikqdrdist(lat0, lon0, wlat, wlon, hdg, dnm);                    // hdg = ap.trk = initial_wpt_qdr
+        nv = group_bcast<G>(nv, 0);
+        d += (uint32_t)nv;
+        __syncwarp(group_mask<G>());                                        // candidates are rewritten for the next obstacle
     }
-    __syncwarp(group_mask<G>());
-    rflags = group_bcast<G>(rflags, 0); wlat = group_bcast<G>(wlat, 0); wlon = group_bcast<G>(wlon, 0);
+    rflags = group_bcast<G>(rflags, 0);
+    double wlat = 0.0, wlon = 0.0;                                          // _generate_waypoint :198-219
+    for (int loops = 1;; ++loops) {
+        const int dis = rng.randint(d, 100, 170), brg = rng.randint(d + 1u, 0, 360);
+        d += 2u;
+        d_point_at_distance(lat0, lon0, (double)dis, (double)brg, wlat, wlon);      // (every lane: same inputs, same result)
+        if (obstacles_hit<G>(wlat, wlon, pe, slot) == 0) break;             // one obstacle per lane
+        if (loops > 1000) { rflags |= 4; break; }
+    }
+    double hdg = 0.0, dnm;
+    d_kwikqdrdist(lat0, lon0, wlat, wlon, hdg, dnm);                        // hdg = ap.trk = initial_wpt_qdr
     if (slot == 0) ac_create(a, lat0, lon0, hdg, 350.0, 150.0); else ac_clear(a);
     s.wpt_lat = wlat; s.wpt_lon = wlon; s.rflags = rflags;
     s.wpt_reach = 0; s.intrusions = 0; s.total_reward = 0.0f; s.drift_sum = 0.0f; s.drift_n = 0; s.num_ac = 1;
@@ -733,7 +784,7 @@ __device__ __forceinline__ void do_reset(Ac& a, EnvS& s, const EnvParams& P, lon
     if (ENV == BSG_ENV_MERGE) merge_reset<G>(a, s, P, e, slot);
     if (ENV == BSG_ENV_PLAN_WAYPOINT) planwp_reset<G>(a, s, P, e, slot);
     if (ENV == BSG_ENV_VERTICAL_CR) vertical_reset<G>(a, s, P, e, slot);
-    if (ENV == BSG_ENV_STATIC_OBSTACLE) static_reset<G>(a, s, P, e, slot);
+    if (ENV == BSG_ENV_STATIC_OBSTACLE) static_reset<G>(a, s, P, e, slot, scratch);
     s.step = 0; s.needs_reset = 0; s.episode += 1; s.nconf = 0; s.nlos = 0;
 }
 template <int ENV, int G>
@@ -777,12 +828,14 @@ __global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) 
         build_pair_table(s_pairs);
         __syncthreads();
     }
-    __shared__ double s_scratch[(ENV == BSG_ENV_SECTOR_CR) ? (kEnvThreads / 32) * 96 : 1];
+    __shared__ double s_scratch[(ENV == BSG_ENV_SECTOR_CR) ? (kEnvThreads / 32) * kSectorScratch
+                                : (ENV == BSG_ENV_STATIC_OBSTACLE) ? (kEnvThreads / G) * kStaticScratch : 1];
     const long long gt = (long long)blockIdx.x * kEnvThreads + threadIdx.x;
     const long long e = gt / G;
     const int slot = (int)(gt % G);
     if (e >= P.E) return;                       // group-uniform (G divides the block size)
-    double* scratch = (ENV == BSG_ENV_SECTOR_CR) ? &s_scratch[(threadIdx.x / 32) * 96] : s_scratch;
+    double* scratch = (ENV == BSG_ENV_SECTOR_CR) ? &s_scratch[(threadIdx.x / 32) * kSectorScratch]
+                    : (ENV == BSG_ENV_STATIC_OBSTACLE) ? &s_scratch[(threadIdx.x / G) * kStaticScratch] : s_scratch;
 
     EnvS s;
     env_load_pre(s, P, e);
