@@ -108,25 +108,30 @@ __device__ __forceinline__ float rwgs84(float latd) {
 // geo.qdrdist (WGS-84 radius haversine).  The bearing's second atan2 argument is rewritten as
 // sin(dlat) + 2 sin(lat1) cos(lat2) sin^2(dlon/2), algebraically identical and free of the float32
 // cancellation of cos(lat1) sin(lat2) - sin(lat1) cos(lat2) cos(dlon).  qdr in [-180, 180], dist [m].
+// `want_dist` (warp-uniform at the call sites): the distance -- WGS-84 radius, two square roots and an atan2 -- is
+// only looked at when the FMS timer fires; the bearing is needed every substep.
 __device__ __forceinline__ void qdrdist_wgs(double lat1d, double lon1d, double lat2d, double lon2d,
-                                            float& qdr, float& dist_m) {
+                                            float& qdr, float& dist_m, bool want_dist = true) {
     float la1 = (float)lat1d, la2 = (float)lat2d;
-    float r;
-    if (la1 * la2 >= 0.0f) {
-        r = rwgs84(0.5f * (la1 + la2));
-    } else {
-        const float a = 6378137.0f;
-        r = 0.5f * (fabsf(la1) * (rwgs84(la1) + a) + fabsf(la2) * (rwgs84(la2) + a)) /
-            fmaxf(0.000001f, fabsf(la1) + fabsf(la2));
-    }
     float dlat = (float)((lat2d - lat1d) * kDeg2RadD);
     float dlon = (float)((lon2d - lon1d) * kDeg2RadD);
     float s1, c1, s2, c2;
     sincosf(la1 * kDeg2Rad, &s1, &c1);
     sincosf(la2 * kDeg2Rad, &s2, &c2);
     float sh1 = sinf(0.5f * dlat), sh2 = sinf(0.5f * dlon);
-    float root = sh1 * sh1 + c1 * c2 * sh2 * sh2;
-    dist_m = 2.0f * r * atan2f(sqrtf(root), sqrtf(fmaxf(0.0f, 1.0f - root)));
+    dist_m = 0.0f;
+    if (want_dist) {
+        float r;
+        if (la1 * la2 >= 0.0f) {
+            r = rwgs84(0.5f * (la1 + la2));
+        } else {
+            const float a = 6378137.0f;
+            r = 0.5f * (fabsf(la1) * (rwgs84(la1) + a) + fabsf(la2) * (rwgs84(la2) + a)) /
+                fmaxf(0.000001f, fabsf(la1) + fabsf(la2));
+        }
+        float root = sh1 * sh1 + c1 * c2 * sh2 * sh2;
+        dist_m = 2.0f * r * atan2f(sqrtf(root), sqrtf(fmaxf(0.0f, 1.0f - root)));
+    }
     float sdlon = sinf(dlon);
     qdr = kRad2Deg * atan2f(sdlon * c2, sinf(dlat) + 2.0f * s1 * c2 * sh2 * sh2);
 }

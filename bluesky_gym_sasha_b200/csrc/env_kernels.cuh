@@ -295,7 +295,7 @@ __device__ __forceinline__ void ac_autopilot(Ac& a, const EnvParams& P, bool fms
             int iwp = (int)(a.flags >> kFlWpShift);
             if (iwp == 0) { wlat = P.fix_lat; wlon = P.fix_lon; } else { wlat = kRwyLat; wlon = kRwyLon; }
             float qdr, dist;
-            qdrdist_wgs(a.lat, a.lon, wlat, wlon, qdr, dist);
+            qdrdist_wgs(a.lat, a.lon, wlat, wlon, qdr, dist, fms_ready);
             if (fms_ready) {
                 // ActiveWaypoint.reached: next_qdr is -999 for both legs of this route => turndist = 0
                 bool close2wp = dist / fmaxf(0.0001f, fabsf(ac_gs(a, P))) < 4.0f;
