@@ -357,3 +357,37 @@ def test_reset_seed_rekeys_streams(cuda):
     assert not np.array_equal(o2["x_r"], oa["x_r"])
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("env_id,kw", [("DescentEnv-v0", {}), ("PlanWaypointEnv-v0", {}), ("HorizontalCREnv-v0", dict(n_intruders=20, cd_enabled=True)),
+                                       ("VerticalCREnv-v0", dict(cd_enabled=True)), ("SectorCREnv-v0", dict(cd_enabled=True)),
+                                       ("StaticObstacleEnv-v0", {}), ("MergeEnv-v0", dict(cd_enabled=True))])
+def test_soak_many_episodes_stay_finite(cuda, env_id, kw):
+    """Several hundred steps of random actions with same-step autoreset: every output stays finite, every env keeps
+    finishing episodes within the registered cap, and no scenario generator reports a failure."""
+    import torch
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    E, steps = 512, 450
+    v = BlueSkyVectorEnv(env_id, E, seed=5, autoreset_mode="same_step", **kw)
+    cap = v.cfg.max_episode_steps
+    v.reset_torch()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    since = torch.zeros(E, dtype=torch.int32, device="cuda")
+    n_done = 0
+    for i in range(steps):
+        a = torch.rand((E, v.layout.act_dim), device="cuda", generator=g) * 2 - 1
+        obs, rew, term, trunc = v.step_torch(a)
+        since += 1
+        done = (term != 0) | (trunc != 0)
+        assert int(since.max()) <= cap, (env_id, i, "an env ran past its TimeLimit")
+        since = torch.where(done, torch.zeros_like(since), since)
+        n_done += int(done.sum())
+        if i % 50 == 49 or i == steps - 1:
+            assert bool(torch.isfinite(v.t["obs"]).all()) and bool(torch.isfinite(rew).all()), (env_id, i)
+            assert bool(torch.isfinite(v.t["pos"]).all()) and bool(torch.isfinite(v.t["kin"]).all()), (env_id, i)
+            info = v.t["info"][:, :3]
+            assert bool(torch.isfinite(info[~torch.isnan(info)]).all())
+    assert n_done >= E * (steps // cap)                                   # at least the TimeLimit-driven episodes
+    assert int((v.t["env_i32"][:, _lib.I32_RESET_FLAGS] & 4).sum()) == 0        # no generator gave up
+    assert int(v.t["env_i32"][:, _lib.I32_EPISODE].min()) >= 1 + steps // cap
+    v.close()
