@@ -386,6 +386,22 @@ def bench_cd(torch, dev, StateBasedCD, fp32_peak, n=CD_N, reps=5):
     n_tiles = (n + 255) // 256
     off = 16 * ((n_tiles * 12 * 4 + 15) // 16)
     kept = int(cd._buf["cull_work"][off:off + 4 * n_tiles].view(torch.int32).sum())
+    for name, kw in (("symmetric", dict(symmetric=True)), ("culled_symmetric", dict(symmetric=True, cull=True))):
+        for _ in range(2):
+            outs = cd.detect_packed(rec_s, n, **kw)
+        torch.cuda.synchronize(dev)
+        bests = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            outs = cd.detect_packed(rec_s, n, **kw)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            bests = min(bests, e0.elapsed_time(e1) * 1e-3)
+        res[name] = {"ordered_pairs_per_s": pairs / bests, "ms": bests * 1e3, "n_conf": int(outs["npairs"][0]),
+                     "n_los": int(outs["npairs"][1]),
+                     "note": "BSG_CD_SYMMETRIC: every unordered tile pair once, both ordered results emitted (executed fraction ~0.5"
+                             + (" of the culled tile pairs)" if "cull" in kw else ")")}
     res["culled"] = {"ordered_pairs_per_s": pairs / bestc, "ms": bestc * 1e3, "ms_sort_and_pack": prep * 1e3,
                      "executed_fraction": kept / float(n_tiles * n_tiles), "n_conf": int(outc["npairs"][0]),
                      "n_los": int(outc["npairs"][1]),

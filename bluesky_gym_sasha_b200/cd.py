@@ -61,9 +61,11 @@ class StateBasedCD:
         return rec, n
 
     # ---------------------------------------------------------------- detection on packed records
-    def detect_packed(self, rec, n_all, row0=0, n_rows=None, lon_wrap=False, want_pairs=True, cull=False):
+    def detect_packed(self, rec, n_all, row0=0, n_rows=None, lon_wrap=False, want_pairs=True, cull=False, symmetric=False):
         """Rows [row0, row0+n_rows) x all n_all columns.  Asynchronous; returns device tensors.
-        ``cull=True``: bsg_cd_detect_culled (identical outputs; pays off on spatially sorted records)."""
+        ``cull=True``: bsg_cd_detect_culled (identical outputs; pays off on spatially sorted records).
+        ``symmetric=True`` (full N x N only): each unordered tile pair is evaluated once and both ordered results are
+        emitted (BSG_CD_SYMMETRIC; identical outputs, half the pair evaluations); combines with ``cull``."""
         n_rows = n_all - row0 if n_rows is None else n_rows
         m = max(n_rows, 1)
         nconf = self._get("nconf", (m,), torch.int32)
@@ -73,8 +75,10 @@ class StateBasedCD:
         npairs = self._get("npairs", (2,), torch.int64)
         pairs = self._get("pairs", (max(self.pair_capacity, 1), 2), torch.int32) if want_pairs else None
         flags = _lib.CD_LON_WRAP if lon_wrap else 0
+        if symmetric:
+            flags |= _lib.CD_SYMMETRIC | (0 if cull else _lib.CD_ALLTILES)
         with torch.cuda.device(self.device):
-            if cull:
+            if cull or symmetric:
                 nbytes = int(self.lib.bsg_cd_cull_workspace(n_all, n_rows))
                 work = self._get("cull_work", (nbytes,), torch.uint8)
                 _lib.check(self.lib.bsg_cd_detect_culled(_ptr(rec), n_all, row0, n_rows, self.rpz, self.hpz, self.dtlookahead,
@@ -113,7 +117,7 @@ class StateBasedCD:
         return torch.argsort(key)
 
     # ---------------------------------------------------------------- convenience: StateBased.detect
-    def detect(self, lat, lon, trk, gs, alt, vs, lat0=None, lon0=None, cull=False):
+    def detect(self, lat, lon, trk, gs, alt, vs, lat0=None, lon0=None, cull=False, symmetric=False):
         """Full N x N detection.  Returns host results shaped like upstream's ``detect`` outputs.
         ``cull=True`` sorts the aircraft into spatially compact tiles and skips tile pairs that are out of each other's
         reach (bsg_cd_detect_culled); results are identical, indices are mapped back to the caller's order."""
@@ -135,7 +139,7 @@ class StateBasedCD:
             lat_d, lon_d = lat_d[perm], lon_d[perm]
             trk, gs, alt, vs = (self._as_dev(x)[perm] for x in (trk, gs, alt, vs))
         rec, n = self.pack(lat_d, lon_d, trk, gs, alt, vs, lat0, lon0)
-        out = self.detect_packed(rec, n, lon_wrap=span >= 90.0, cull=cull)
+        out = self.detect_packed(rec, n, lon_wrap=span >= 90.0, cull=cull, symmetric=symmetric and span < 90.0)
         torch.cuda.synchronize(self.device)
         n_conf, n_los = (int(v) for v in out["npairs"].cpu())
         k = min(n_conf, self.pair_capacity)

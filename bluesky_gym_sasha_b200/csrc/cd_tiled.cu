@@ -132,8 +132,11 @@ struct RowPack {            // loop-invariant operands of one own-row, duplicate
     u64 nX, nY, CH, nSH, nU, nV, nALT, nVS;
 };
 
-// true when either column of the packed pair is a conflict candidate for this row
-template <bool WRAP>
+// true when either column of the packed pair is a conflict candidate for this row.  SYM: ... or for the column as own
+// aircraft against this row.  The two orders of a pair only differ through upstream's clamp of a near-zero relative
+// vertical speed to +1e-6 in BOTH orders (the crossing time changes sign with the order): for clamped pairs the test
+// is made with dalt := -|dalt|, which is the union of the two orders' windows.
+template <bool WRAP, bool SYM>
 __device__ __forceinline__ bool cd_hot2(const RowPack& r, u64 Xc, u64 Yc, u64 CHc, u64 SHc, u64 Uc, u64 Vc,
                                             u64 ALTc, u64 VSc, u64 R2P, u64 HPZP, u64 NEG1, float dtl) {
     u64 dy = add2(Yc, r.nY);
@@ -169,12 +172,14 @@ __device__ __forceinline__ bool cd_hot2(const RowPack& r, u64 Xc, u64 Yc, u64 CH
     float s0, s1, a0, a1;
     up2(dvs, s0, s1);
     up2(dalt, a0, a1);
-    s0 = fabsf(s0) < 1e-6f ? 1e-6f : s0;
-    s1 = fabsf(s1) < 1e-6f ? 1e-6f : s1;
+    const bool c0 = fabsf(s0) < 1e-6f, c1 = fabsf(s1) < 1e-6f;
+    s0 = c0 ? 1e-6f : s0;
+    s1 = c1 ? 1e-6f : s1;
     float r0 = rcp_approx(fabsf(s0)), r1 = rcp_approx(fabsf(s1));
     // t0 = dalt / -dvs = (-sign(dvs) dalt) / |dvs|
     a0 = __uint_as_float(__float_as_uint(a0) ^ (~__float_as_uint(s0) & 0x80000000u));
     a1 = __uint_as_float(__float_as_uint(a1) ^ (~__float_as_uint(s1) & 0x80000000u));
+    if (SYM) { a0 = c0 ? fabsf(a0) : a0; a1 = c1 ? fabsf(a1) : a1; }
     u64 RV = pk2(r0, r1);
     u64 t0 = mul2(pk2(a0, a1), RV);
     u64 hw = mul2(HPZP, RV);
@@ -194,12 +199,13 @@ __device__ __forceinline__ bool cd_hot2(const RowPack& r, u64 Xc, u64 Yc, u64 CH
 
 // One work item: 256 own rows (2 per thread, in packed registers) against n_t column tiles, which are either
 // consecutive (t_begin ..) or taken from a list (culled form).  Column tiles arrive through the 2-stage TMA ring.
-template <bool WRAP, bool LIST>
+template <bool WRAP, bool LIST, bool SYM>
 __device__ __forceinline__ void cd_process_item(const CdArgs& a, float (*s_tile)[kTileFloats], uint64_t* s_full, uint32_t* parity,
                                                 const int rb, const int t_begin, const int n_t, const int32_t* __restrict__ list,
                                                 const u64 R2P, const u64 HPZP, const u64 NEG1, const float dtlh, const int row_end) {
     const int tid = threadIdx.x;
     auto tile_of = [&](int tt) { return LIST ? (int)list[tt] : t_begin + tt; };
+    const int own_tile = a.row0 / kRowsPerCta + rb;          // (SYM: rows are tile-aligned)
     // own rows -> packed registers.  Rows past the shard end are made inert (alt -3e9: can never be a
     // candidate), so the hot loop needs no validity test.
     RowPack rp[kR];
@@ -251,8 +257,8 @@ __device__ __forceinline__ void cd_process_item(const CdArgs& a, float (*s_tile)
             bool hit[kR];               // per own row: any of the four columns j .. j+3 flagged
 #pragma unroll
             for (int k = 0; k < kR; ++k) {
-                hit[k] = cd_hot2<WRAP>(rp[k], X.x, Y.x, CH.x, SH.x, U.x, V.x, AL.x, VS.x, R2P, HPZP, NEG1, dtlh);
-                hit[k] |= cd_hot2<WRAP>(rp[k], X.y, Y.y, CH.y, SH.y, U.y, V.y, AL.y, VS.y, R2P, HPZP, NEG1, dtlh);
+                hit[k] = cd_hot2<WRAP, SYM>(rp[k], X.x, Y.x, CH.x, SH.x, U.x, V.x, AL.x, VS.x, R2P, HPZP, NEG1, dtlh);
+                hit[k] |= cd_hot2<WRAP, SYM>(rp[k], X.y, Y.y, CH.y, SH.y, U.y, V.y, AL.y, VS.y, R2P, HPZP, NEG1, dtlh);
             }
             bool any = false;
 #pragma unroll
@@ -264,11 +270,28 @@ __device__ __forceinline__ void cd_process_item(const CdArgs& a, float (*s_tile)
                 up2(rp[k].nX, nx, dummy); up2(rp[k].nY, ny, dummy); up2(rp[k].CH, chh, dummy); up2(rp[k].nSH, nsh, dummy);
                 up2(rp[k].nU, nu, dummy); up2(rp[k].nV, nv, dummy); up2(rp[k].nALT, nal, dummy); up2(rp[k].nVS, nvs, dummy);
                 float tc;
-                const uint32_t f = cd_candidate_rec<WRAP>(
-                    make_float4(-nx, -ny, chh, -nsh), make_float4(-nu, -nv, -nal, -nvs),
-                    make_float4(tile[FX * kTJ + jc], tile[FY * kTJ + jc], tile[FCH * kTJ + jc], tile[FSH * kTJ + jc]),
-                    make_float4(tile[FU * kTJ + jc], tile[FV * kTJ + jc], tile[FALT * kTJ + jc], tile[FVS * kTJ + jc]),
-                    a.R2, a.hpz, a.dtlook, ri[k] == cj, tc);
+                const float4 Ai = make_float4(-nx, -ny, chh, -nsh), Bi = make_float4(-nu, -nv, -nal, -nvs);
+                const float4 Aj = make_float4(tile[FX * kTJ + jc], tile[FY * kTJ + jc], tile[FCH * kTJ + jc], tile[FSH * kTJ + jc]);
+                const float4 Bj = make_float4(tile[FU * kTJ + jc], tile[FV * kTJ + jc], tile[FALT * kTJ + jc], tile[FVS * kTJ + jc]);
+                const uint32_t f = cd_candidate_rec<WRAP>(Ai, Bi, Aj, Bj, a.R2, a.hpz, a.dtlook, ri[k] == cj, tc);
+                if (SYM && t > own_tile) {       // the mirrored ordered pair (cj, ri): its row lives in another tile
+                    float tcr;
+                    const uint32_t fr = cd_candidate_rec<WRAP>(Aj, Bj, Ai, Bi, a.R2, a.hpz, a.dtlook, false, tcr);
+                    const int o = cj - a.row0;
+                    if ((fr & 2u) && a.nlos_row) atomicAdd(&a.nlos_row[o], 1u);
+                    if ((fr & 2u) && a.npairs) atomicAdd(a.npairs + 1, 1ULL);
+                    if (fr & 1u) {
+                        atomicAdd(&a.nconf_row[o], 1u);
+                        if (a.tcpamax && tcr > 0.0f) atomicMax((int*)&a.tcpamax[o], __float_as_int(tcr));
+                        if (a.npairs) {
+                            unsigned long long slot = atomicAdd(a.npairs, 1ULL);
+                            if (a.pairs && (long long)slot < a.cap) {
+                                a.pairs[2 * slot] = cj;
+                                a.pairs[2 * slot + 1] = ri[k];
+                            }
+                        }
+                    }
+                }
                 if (f & 2u) {
                     nlos[k]++;
                     if (a.npairs) atomicAdd(a.npairs + 1, 1ULL);
@@ -301,7 +324,7 @@ __device__ __forceinline__ void cd_process_item(const CdArgs& a, float (*s_tile)
     }
 }
 
-template <bool WRAP, bool LIST>
+template <bool WRAP, bool LIST, bool SYM>
 __global__ void __launch_bounds__(kNT, 4) cd_tiled_kernel(const CdArgs a) {
     __shared__ __align__(128) float s_tile[2][kTileFloats];
     __shared__ __align__(8) uint64_t s_full[2];
@@ -328,7 +351,7 @@ __global__ void __launch_bounds__(kNT, 4) cd_tiled_kernel(const CdArgs a) {
             const int rb = (int)(item / a.n_colgroups);
             const int t_begin = (int)(item % a.n_colgroups) * kTilesPerItem;
             const int n_t = min(kTilesPerItem, a.n_tiles - t_begin);
-            cd_process_item<WRAP, false>(a, s_tile, s_full, parity, rb, t_begin, n_t, nullptr, R2P, HPZP, NEG1, dtlh, row_end);
+            cd_process_item<WRAP, false, false>(a, s_tile, s_full, parity, rb, t_begin, n_t, nullptr, R2P, HPZP, NEG1, dtlh, row_end);
         }
     } else {
         // culled form: items (row block, chunk of its tile list) differ in size and are handed out through a global
@@ -352,7 +375,7 @@ __global__ void __launch_bounds__(kNT, 4) cd_tiled_kernel(const CdArgs a) {
             const int rb = s_item[0], k0 = s_item[1] * kTilesPerChunk, item = s_item[2];
             __syncthreads();                       // s_item is rewritten for the next item
             if (item >= n_items) break;
-            cd_process_item<WRAP, true>(a, s_tile, s_full, parity, rb, 0, min(kTilesPerChunk, a.list_cnt[rb] - k0),
+            cd_process_item<WRAP, true, SYM>(a, s_tile, s_full, parity, rb, 0, min(kTilesPerChunk, a.list_cnt[rb] - k0),
                                         a.tile_list + (size_t)rb * a.list_stride + k0, R2P, HPZP, NEG1, dtlh, row_end);
         }
     }
@@ -401,10 +424,13 @@ __global__ void __launch_bounds__(kTJ) cd_tile_bounds_kernel(const CdArgs a, int
 // to touch within the look-ahead T, and so is a vertical gap below hpz + (|vs_a| + |vs_b|) T.  Margins cover
 // float rounding.  Kept tiles are appended to the row block's list in arbitrary order.
 __global__ void cd_cull_kernel(const float* __restrict__ bounds, int n_tiles, int row_tile0, int n_rowblocks, float R,
-                               float hpz, float T, int32_t* __restrict__ list, int32_t* __restrict__ cnt, int stride) {
+                               float hpz, float T, int32_t* __restrict__ list, int32_t* __restrict__ cnt, int stride,
+                               int sym, int alltiles) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (long long)n_rowblocks * n_tiles) return;
     const int rb = (int)(p / n_tiles), ct = (int)(p % n_tiles);
+    if (sym && ct < row_tile0 + rb) return;                     // symmetric form: the mirror tile pair covers it
+    if (alltiles) { list[(size_t)rb * stride + atomicAdd(&cnt[rb], 1)] = ct; return; }
     const float* A = bounds + (size_t)(row_tile0 + rb) * TB_COUNT;
     const float* B = bounds + (size_t)ct * TB_COUNT;
     if (A[TB_XMIN] > A[TB_XMAX] || B[TB_XMIN] > B[TB_XMAX]) return;         // a tile of padding only
@@ -512,7 +538,8 @@ static int cd_fill_args(CdArgs& a, int64_t n_all, int64_t row0, int64_t n_rows, 
     return BSG_OK;
 }
 
-static int cd_launch(CdArgs& a, bool wrap, bool cull, void* d_work, int64_t work_bytes, uint8_t* d_inconf, cudaStream_t st) {
+static int cd_launch(CdArgs& a, bool wrap, bool cull, bool sym, bool alltiles, void* d_work, int64_t work_bytes, uint8_t* d_inconf,
+                     cudaStream_t st) {
     if (a.npairs) BSG_CUDA(cudaMemsetAsync(a.npairs, 0, 2 * sizeof(unsigned long long), st));
     if (a.n_rows == 0) return BSG_OK;
     BSG_CUDA(cudaMemsetAsync(a.nconf_row, 0, sizeof(uint32_t) * a.n_rows, st));
@@ -523,6 +550,7 @@ static int cd_launch(CdArgs& a, bool wrap, bool cull, void* d_work, int64_t work
     BSG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (cull) {
         if (a.row0 % kRowsPerCta) return bsg_fail(BSG_EINVAL, "culled CD: row0 must be a multiple of 256");
+        if (sym && (a.row0 != 0 || a.n_rows != a.n_all)) return bsg_fail(BSG_EINVAL, "BSG_CD_SYMMETRIC needs n_rows == n_all (one GPU holds every row)");
         if (wrap) return bsg_fail(BSG_EINVAL, "culled CD: airspaces across the antimeridian use the plain form");
         if (!d_work || work_bytes < bsg_cd_cull_workspace(a.n_all, a.n_rows))
             return bsg_fail(BSG_EINVAL, "culled CD: workspace missing or too small (bsg_cd_cull_workspace)");
@@ -538,20 +566,23 @@ static int cd_launch(CdArgs& a, bool wrap, bool cull, void* d_work, int64_t work
         cd_tile_bounds_kernel<<<a.n_tiles, kTJ, 0, st>>>(a, a.n_all, bounds);
         const long long n_pairs = (long long)a.n_rowblocks * a.n_tiles;
         cd_cull_kernel<<<(int)((n_pairs + 255) / 256), 256, 0, st>>>(bounds, a.n_tiles, a.row0 / kRowsPerCta, a.n_rowblocks,
-                                                                     sqrtf(a.R2), a.hpz, a.dtlook, list, cnt, a.list_stride);
+                                                                     sqrtf(a.R2), a.hpz, a.dtlook, list, cnt, a.list_stride,
+                                                                     sym ? 1 : 0, alltiles ? 1 : 0);
         cd_chunk_scan_kernel<<<1, 1024, 0, st>>>(cnt, a.n_rowblocks, chunk_off);
         BSG_CUDA(cudaGetLastError());
-        BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, true>, kNT, 0));
+        if (sym) BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, true, true>, kNT, 0));
+        else BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, true, false>, kNT, 0));
         if (occ < 1) occ = 1;
-        cd_tiled_kernel<false, true><<<sms * occ, kNT, 0, st>>>(a);
+        if (sym) cd_tiled_kernel<false, true, true><<<sms * occ, kNT, 0, st>>>(a);
+        else cd_tiled_kernel<false, true, false><<<sms * occ, kNT, 0, st>>>(a);
     } else {
-        if (wrap) BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<true, false>, kNT, 0));
-        else BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, false>, kNT, 0));
+        if (wrap) BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<true, false, false>, kNT, 0));
+        else BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, false, false>, kNT, 0));
         if (occ < 1) occ = 1;
         const long long n_items = (long long)a.n_rowblocks * a.n_colgroups;
         const int grid = (int)((n_items < (long long)sms * occ) ? n_items : (long long)sms * occ);
-        if (wrap) cd_tiled_kernel<true, false><<<grid, kNT, 0, st>>>(a);
-        else cd_tiled_kernel<false, false><<<grid, kNT, 0, st>>>(a);
+        if (wrap) cd_tiled_kernel<true, false, false><<<grid, kNT, 0, st>>>(a);
+        else cd_tiled_kernel<false, false, false><<<grid, kNT, 0, st>>>(a);
     }
     BSG_CUDA(cudaGetLastError());
     if (d_inconf) {
@@ -565,13 +596,13 @@ extern "C" int bsg_cd_detect(const float* d_rec, int64_t n_all, int64_t row0, in
                              float dtlookahead, uint32_t flags, uint32_t* d_nconf_row, uint32_t* d_nlos_row,
                              float* d_tcpamax, uint8_t* d_inconf, int32_t* d_pairs, int64_t cap,
                              unsigned long long* d_npairs, void* stream) {
-    if (flags & BSG_CD_SYMMETRIC) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: BSG_CD_SYMMETRIC not implemented yet");
+    if (flags & BSG_CD_SYMMETRIC) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: BSG_CD_SYMMETRIC is served by bsg_cd_detect_culled (it needs the work-list scratch)");
     CdArgs a;
     int rc = cd_fill_args(a, n_all, row0, n_rows, rpz, hpz, dtlookahead, d_nconf_row, d_nlos_row, d_tcpamax, d_pairs, cap, d_npairs);
     if (rc != BSG_OK) return rc;
     if (n_rows > 0 && !d_rec) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: null d_rec");
     a.rec = d_rec; a.rec_rows = d_rec; a.rows_base = 0;
-    return cd_launch(a, (flags & BSG_CD_LON_WRAP) != 0, false, nullptr, 0, d_inconf, (cudaStream_t)stream);
+    return cd_launch(a, (flags & BSG_CD_LON_WRAP) != 0, false, false, false, nullptr, 0, d_inconf, (cudaStream_t)stream);
 }
 
 extern "C" int64_t bsg_cd_cull_workspace(int64_t n_all, int64_t n_rows) {
@@ -590,7 +621,8 @@ extern "C" int bsg_cd_detect_culled(const float* d_rec, int64_t n_all, int64_t r
     if (rc != BSG_OK) return rc;
     if (n_rows > 0 && !d_rec) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: null d_rec");
     a.rec = d_rec; a.rec_rows = d_rec; a.rows_base = 0;
-    return cd_launch(a, (flags & BSG_CD_LON_WRAP) != 0, true, d_work, work_bytes, d_inconf, (cudaStream_t)stream);
+    return cd_launch(a, (flags & BSG_CD_LON_WRAP) != 0, true, (flags & BSG_CD_SYMMETRIC) != 0, (flags & BSG_CD_ALLTILES) != 0, d_work, work_bytes,
+                     d_inconf, (cudaStream_t)stream);
 }
 
 extern "C" int bsg_cd_detect_peers(const float* const* h_peer_rec, int32_t n_peers, int32_t my_rank, int64_t n_per_peer,
@@ -610,5 +642,6 @@ extern "C" int bsg_cd_detect_peers(const float* const* h_peer_rec, int32_t n_pee
     for (int p = 0; p < n_peers; ++p) a.peer_rec[p] = h_peer_rec[p];
     a.n_peers = n_peers; a.tiles_per_peer = (int)(n_per_peer / kTJ);
     a.rec_rows = h_peer_rec[my_rank]; a.rows_base = (int)(n_per_peer * my_rank);
-    return cd_launch(a, (flags & BSG_CD_LON_WRAP) != 0, (flags & BSG_CD_CULL) != 0, d_work, work_bytes, d_inconf, (cudaStream_t)stream);
+    return cd_launch(a, (flags & BSG_CD_LON_WRAP) != 0, (flags & BSG_CD_CULL) != 0, false, false, d_work, work_bytes, d_inconf,
+                     (cudaStream_t)stream);
 }

@@ -206,8 +206,11 @@ int bsg_cd_pack(const double *d_lat, const double *d_lon, const double *d_trk, c
                 float *d_rec, void *stream);
 
 enum { BSG_CD_LON_WRAP = 1,     /* pairs may straddle the +-180 deg meridian relative to lon0        */
-       BSG_CD_SYMMETRIC = 2,    /* evaluate each unordered pair once (needs n_rows == n_all)         */
-       BSG_CD_CULL = 4 };       /* bsg_cd_detect_peers: use the culled form (needs the workspace)    */
+       BSG_CD_SYMMETRIC = 2,    /* bsg_cd_detect_culled: evaluate each unordered tile pair once and emit both
+                                 * ordered results (needs n_rows == n_all); same outputs, half the work  */
+       BSG_CD_CULL = 4,         /* bsg_cd_detect_peers: use the culled form (needs the workspace)    */
+       BSG_CD_ALLTILES = 8 };   /* bsg_cd_detect_culled: keep every tile pair (no culling; with
+                                 * BSG_CD_SYMMETRIC = brute force over unordered pairs)              */
 
 /* Rows [row0, row0+n_rows) of d_rec against all n_all aircraft (row sharding for multi-GPU).
  * Outputs (caller-owned, device): per-row nconf / nlos counts and tcpamax, inconf flags, and a pair

@@ -143,6 +143,13 @@ def test_culled_form_is_identical_to_plain(cuda, n, box, seed):
     assert np.array_equal(plain["tcpamax"], culled["tcpamax"])
     if n >= 5000:
         assert plain["n_conf"] > 0
+    # BSG_CD_SYMMETRIC: each unordered tile pair once, both ordered results emitted -- with and without culling
+    for kw in (dict(symmetric=True), dict(symmetric=True, cull=True)):
+        sym = cd.detect(*s, **kw)
+        assert plain["n_conf"] == sym["n_conf"] and plain["n_los"] == sym["n_los"], kw
+        assert set(map(tuple, plain["confpairs"].tolist())) == set(map(tuple, sym["confpairs"].tolist())), kw
+        assert np.array_equal(plain["nconf_row"], sym["nconf_row"]) and np.array_equal(plain["nlos_row"], sym["nlos_row"]), kw
+        assert np.array_equal(plain["inconf"], sym["inconf"]) and np.array_equal(plain["tcpamax"], sym["tcpamax"]), kw
 
 
 def test_culled_form_against_oracle(cuda):
