@@ -112,3 +112,21 @@ def test_shipped_policy_on_cuda_env(cuda, env_id, algo, check_len):
         assert abs(length - st["length_mean"]) < 0.12 * st["length_mean"], (length, st["length_mean"])
     learned = st["total_reward_mean"] - st["total_reward_first200_mean"]
     assert ret - ret_rnd > 0.7 * learned, (ret, ret_rnd, learned)
+
+
+@pytest.mark.gpu
+def test_shipped_merge_policy_completes_the_task(cuda):
+    """MergeEnv: the reference ships PPO / SAC models but logs only for DDPG / TD3 runs that never learned (return ~ -9.2,
+    faf_reach 0).  The shipped PPO actor, trained on the real BlueSky, must complete the task here: pass the FAF and reach
+    the runway (faf_reach == 2: merge_env.py:246-284) in nearly every episode, far above a random policy."""
+    from bluesky_gym_sasha_b200.policy import SB3Actor, evaluate
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    venv = BlueSkyVectorEnv("MergeEnv-v0", 2048, seed=123, autoreset_mode="same_step")
+    actor = SB3Actor.from_npz(os.path.join(POL, "MergeEnv-v0_PPO.npz"), venv)
+    res = evaluate(venv, actor, episodes_per_env=1)
+    rnd = evaluate(venv, None, episodes_per_env=1)
+    venv.close()
+    print(f"MergeEnv PPO: return {res['returns'].mean():.3f}, faf_reach {res['info_faf_reach'].mean():.3f}, length "
+          f"{res['lengths'].mean():.1f}; random policy return {rnd['returns'].mean():.3f}, faf_reach {rnd['info_faf_reach'].mean():.3f}")
+    assert res["info_faf_reach"].mean() > 1.9 and res["lengths"].mean() < 35
+    assert res["returns"].mean() > -4.0 and rnd["returns"].mean() < -8.0 and rnd["info_faf_reach"].mean() < 0.5
