@@ -402,6 +402,8 @@ def bench_cd(torch, dev, StateBasedCD, fp32_peak, n=CD_N, reps=5):
                      "n_los": int(outs["npairs"][1]),
                      "note": "BSG_CD_SYMMETRIC: every unordered tile pair once, both ordered results emitted (executed fraction ~0.5"
                              + (" of the culled tile pairs)" if "cull" in kw else ")")}
+    res["forms_agree"] = all(res[k]["n_conf"] == res["n_conf"] and res[k]["n_los"] == res["n_los"] for k in ("symmetric", "culled_symmetric")) \
+        and int(outc["npairs"][0]) == res["n_conf"] and int(outc["npairs"][1]) == res["n_los"]
     res["culled"] = {"ordered_pairs_per_s": pairs / bestc, "ms": bestc * 1e3, "ms_sort_and_pack": prep * 1e3,
                      "executed_fraction": kept / float(n_tiles * n_tiles), "n_conf": int(outc["npairs"][0]),
                      "n_los": int(outc["npairs"][1]),
@@ -481,6 +483,8 @@ def bench_cd_sharded(torch, dist, dev, StateBasedCD, world, rank, max_over_ranks
                          "collective": "none on the data path: TMA loads of peer tiles over NVLink (symmetric memory)"}
     except Exception as ex:                      # symmetric memory unavailable on this box: report, do not fail the bench
         res["p2p"] = {"unavailable": repr(ex)[:200]}
+    # every form must find the same conflicts
+    res["forms_agree"] = all(v.get("n_conf", res["n_conf"]) == res["n_conf"] for v in res.values() if isinstance(v, dict))
     return res
 
 

@@ -24,7 +24,11 @@
 
 namespace bsg {
 
-constexpr int kEnvThreads = 128;
+#ifndef BSG_ENV_THREADS
+#define BSG_ENV_THREADS 128
+#endif
+constexpr int kEnvThreads = BSG_ENV_THREADS;
+constexpr int kEnvBlocksPerSm = 896 / BSG_ENV_THREADS;      // 28 warps per SM: what 72 registers per thread allow
 constexpr uint32_t kFlAlive = 1u, kFlLnav = 2u, kFlLastWp = 4u, kFlWpShift = 8u;
 enum { kModeStep = 0, kModeReset = 1, kModeTraf = 2 };
 

@@ -817,7 +817,7 @@ __device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float
 // K6: the env-step megakernel (also serves reset and the kinematics-only parity entry point)
 // =====================================================================================================
 template <int ENV, int G, bool WIND>
-__global__ void __launch_bounds__(kEnvThreads, 7) env_kernel(const EnvParams P) {
+__global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const EnvParams P) {
     __shared__ __align__(16) float4 s_rec[(G > 1) ? kEnvThreads * 2 : 1];
     __shared__ float s_hot[(G > 8) ? kEnvThreads * 2 * kHotFields : 1];
     __shared__ uint16_t s_queue[(G > 8) ? kEnvThreads * kQueuePerThread : 1];
