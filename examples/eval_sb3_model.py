@@ -3,8 +3,10 @@ scripts/common/results/models_backup/<env>/<env>_<ALGO>/model.zip) on the batche
 
     python examples/eval_sb3_model.py HorizontalCREnv-v0 path/to/model.zip [NUM_ENVS]
 """
+import os
 import sys
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from a checkout
 from bluesky_gym_sasha_b200 import BlueSkyVectorEnv
 from bluesky_gym_sasha_b200.policy import SB3Actor, evaluate
 

@@ -2,11 +2,13 @@
 
     python examples/random_rollout.py [ENV_ID] [NUM_ENVS]
 """
+import os
 import sys
 import time
 
 import numpy as np
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from a checkout
 import bluesky_gym                                   # the alias package: same import as with the reference
 from bluesky_gym_sasha_b200 import BlueSkyVectorEnv
 
