@@ -382,7 +382,8 @@ __device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const T
 //   a division as |d x w|^2 < R^2 |w|^2 (inflated by 2e-4 and by an absolute term that lets co-moving pairs
 //   through, so the filter is a superset of what the exact routine accepts; ~11 % of the pairs of a
 //   HorizontalCR-20 env pass).  (Also dropping pairs that move apart outside the zone was tried: it removes
-//   most candidates late in an episode but costs more in the filter than it saves while traffic converges.)  The group's records are staged as a structure of arrays written twice,
+//   most candidates late in an episode but costs more in the filter than it saves: +4 us/step with converging traffic,
+//   +2 us/step even late in an episode -- scripts/ab_regimes.py.)  The group's records are staged as a structure of arrays written twice,
 //   n apart, so (i + k) mod n is a plain offset and consecutive lanes read consecutive words.
 //   Exact phase: the candidates (i, k) are compacted into a per-group queue in shared memory, spread over
 //   the lanes, and evaluated by cd_pair_sym() -- the same routine as before, so results are bit-identical
