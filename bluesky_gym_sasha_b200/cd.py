@@ -117,9 +117,10 @@ class StateBasedCD:
         return torch.argsort(key)
 
     # ---------------------------------------------------------------- convenience: StateBased.detect
-    def detect(self, lat, lon, trk, gs, alt, vs, lat0=None, lon0=None, cull=False, symmetric=False):
-        """Full N x N detection.  Returns host results shaped like upstream's ``detect`` outputs.
-        ``cull=True`` sorts the aircraft into spatially compact tiles and skips tile pairs that are out of each other's
+    def detect(self, lat, lon, trk, gs, alt, vs, lat0=None, lon0=None, cull=True, symmetric=True):
+        """Full N x N detection.  Returns host results shaped like upstream's ``detect`` outputs.  By default the fastest
+        form with identical outputs is used (culled + symmetric); ``cull=False, symmetric=False`` evaluates every ordered
+        pair.  ``cull=True`` sorts the aircraft into spatially compact tiles and skips tile pairs that are out of each other's
         reach (bsg_cd_detect_culled); results are identical, indices are mapped back to the caller's order."""
         lat_d, lon_d = self._as_dev(lat), self._as_dev(lon)
         n = lat_d.numel()
