@@ -17,6 +17,39 @@ except ImportError:
     HAVE_SB3 = False
 
 
+class _LazyInfos(list):
+    """SB3's per-env info dicts (``infos[i]``), built on first access.  With thousands of envs a Python loop that builds
+    every dict on every step costs more than the simulation; SB3 itself only looks at the envs that finished
+    (``terminal_observation``, ``TimeLimit.truncated``) and callbacks such as the reference's ``CSVLoggerCallback``
+    at ``infos[0]`` (bluesky_gym/utils/logger.py:18,25).  Behaves like the list of dicts it stands for."""
+
+    def __init__(self, infos, term, trunc, dones):
+        super().__init__([None] * len(dones))
+        self._src, self._term, self._trunc, self._dones = infos, term, trunc, dones
+        self._keys = [k for k in infos if not k.startswith("_") and k != "final_obs"]
+
+    def _build(self, i):
+        src = self._src
+        d = {k: (float(src[k][i]) if src[k].dtype.kind == "f" else int(src[k][i])) for k in self._keys}
+        d["TimeLimit.truncated"] = bool(self._trunc[i] and not self._term[i])
+        if self._dones[i] and "final_obs" in src:
+            d["terminal_observation"] = {k: v[i].copy() for k, v in src["final_obs"].items()}
+        return d
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        v = super().__getitem__(i)
+        if v is None:
+            v = self._build(i if i >= 0 else i + len(self))
+            super().__setitem__(i, v)
+        return v
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+
 class BlueSkySB3VecEnv(_Base):
     def __init__(self, venv):
         assert venv.autoreset_mode == "same_step", "SB3 expects same-step autoreset"
@@ -40,15 +73,9 @@ class BlueSkySB3VecEnv(_Base):
     def step_wait(self):
         obs, rew, term, trunc, infos = self.venv.step(self._actions)
         dones = term | trunc
-        keys = [k for k in infos if not k.startswith("_") and k != "final_obs"]
-        out = []
-        for i in range(self.num_envs):
-            d = {k: (float(infos[k][i]) if infos[k].dtype.kind == "f" else int(infos[k][i])) for k in keys}
-            d["TimeLimit.truncated"] = bool(trunc[i] and not term[i])
-            if dones[i] and "final_obs" in infos:
-                d["terminal_observation"] = {k: v[i].copy() for k, v in infos["final_obs"].items()}
-            out.append(d)
-        return {k: v.copy() for k, v in obs.items()}, rew.astype(np.float32), dones, out
+        # copy=True: the arrays are already fresh; copy=False: views of the pinned ring, copied here as SB3 keeps them
+        obs_out = obs if self.venv.copy else {k: v.copy() for k, v in obs.items()}
+        return obs_out, rew.astype(np.float32), dones, _LazyInfos(infos, term, trunc, dones)
 
     def step(self, actions):
         self.step_async(actions)

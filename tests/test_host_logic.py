@@ -113,3 +113,24 @@ def test_row_sharding_world2_gloo():
     full = cbind.detect_rows(*synth_airspace(512, box_deg=3.0, seed=9), 9260.0, 304.8, 300.0, pair_cap=100000)
     assert res[0][1] + res[1][1] == full["nconf_row"].tolist()
     assert res[0][2] + res[1][2] == full["confpairs"].tolist() and len(full["confpairs"]) > 0
+
+
+def test_sb3_lazy_infos_behave_like_a_list_of_dicts():
+    """BlueSkySB3VecEnv's infos: built per env on first access, same content as an eager list of dicts."""
+    import numpy as np
+    from bluesky_gym_sasha_b200.sb3_vec_env import _LazyInfos
+    E = 6
+    infos = {"total_reward": np.linspace(-1, 1, E), "total_intrusions": np.arange(E), "_final_obs": np.ones(E, bool),
+             "final_obs": {"a": np.arange(2 * E, dtype=np.float32).reshape(E, 2)}}
+    term = np.array([1, 0, 0, 0, 0, 1], bool)
+    trunc = np.array([0, 1, 0, 0, 0, 1], bool)
+    lazy = _LazyInfos(infos, term, trunc, term | trunc)
+    assert isinstance(lazy, list) and len(lazy) == E
+    assert lazy[0]["total_reward"] == -1.0 and isinstance(lazy[3]["total_intrusions"], int)
+    assert lazy[1]["TimeLimit.truncated"] is True and lazy[5]["TimeLimit.truncated"] is False      # terminated wins
+    assert "terminal_observation" in lazy[0] and "terminal_observation" not in lazy[2]
+    assert np.array_equal(lazy[1]["terminal_observation"]["a"], [2.0, 3.0])
+    assert [d["total_intrusions"] for d in lazy] == list(range(E)) and lazy[-1]["total_intrusions"] == E - 1
+    assert len(lazy[1:4]) == 3
+    lazy[2] = {"replaced": 1}                    # wrappers may overwrite entries
+    assert lazy[2] == {"replaced": 1}
