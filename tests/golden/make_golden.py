@@ -2,6 +2,7 @@
 """Generates tests/golden/*.npz by importing the REFERENCE in this container (it cannot travel to the GPU box).
 
     python tests/golden/make_golden.py            # needs /root/reference; rewrites the fixtures
+    python tests/golden/make_golden.py --real     # same, on a machine where bluesky-simulator itself is installed
 
 Two kinds of fixture:
 
@@ -165,8 +166,16 @@ def gen_functions():
 def main():
     if not os.path.isdir("/root/reference/bluesky_gym"):
         raise SystemExit("make_golden.py needs the reference at /root/reference (build container only)")
-    from oracle import bs_shim
-    bs = bs_shim.install()
+    if "--real" in sys.argv:
+        # With a real ``bluesky-simulator`` (+ gymnasium, pygame) installed the same script records the vectors of the
+        # UNMODIFIED reference stack: that turns the partial pin into a full one and settles every [UPSTREAM-RECALL]
+        # item of oracle/ (tests/test_golden.py then checks the oracle and the CUDA path against the real thing).
+        import bluesky as bs                        # noqa: F401  (raises here if it is not installed)
+        sys.path.insert(0, "/root/reference")
+        print("recording with the REAL bluesky package:", bs.__file__)
+    else:
+        from oracle import bs_shim
+        bs = bs_shim.install()
     gen_functions()
     for spec in SPEC:
         gen_env(bs, *spec)
