@@ -276,6 +276,10 @@ def run_b200(args):
                 "traffic_source": traffic_src, "kernel": "env_kernel<HorizontalCR,32,no wind>",
                 "peak_source": "bsg_probe_fp32 (dense FFMA, measured in this run)",
                 "flop_per_env_step": FLOP_PER_ENV_STEP,
+                "note": "achieved = algorithmic flops (every ordered pair, every substep) / time; the in-group CD evaluates "
+                        "exactly only the pairs its conservative filters keep (dcpa < R, not past the zone, entry within the "
+                        "look-ahead) and keeps the intruder-intruder candidate list across the substeps of an env step "
+                        "while velocities hold: results bit-identical to cd_enabled=2 (filter redone every substep)",
                 "hbm": {"achieved": BYTES_PER_ENV_STEP * E / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
                         "bytes_per_env_step": BYTES_PER_ENV_STEP}}

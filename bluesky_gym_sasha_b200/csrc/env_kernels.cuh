@@ -38,7 +38,7 @@ enum { PH_NA = 0, PH_TO = 1, PH_IC = 2, PH_CL = 3, PH_CR = 4, PH_DE = 5, PH_AP =
 struct EnvParams {
     int env_type, E, n_int, cd_enabled, autoreset, max_steps, hdg_random, n_sub, fms_rel_freq, mode;
     int obs_dim, act_dim, info_dim;
-    float simdt, R2, hpz, dtlook;
+    float simdt, R2, hpz, dtlook, rpz;
     double fix_lat, fix_lon;      // MergeEnv FIX (merge_env.py:43-46), evaluated on the host in double
     uint64_t seed;
     long long gid0;
@@ -377,18 +377,27 @@ __device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const T
 
 // ====================================================================================================
 // K3: in-group all-pairs CD in two phases.
-//   Hot phase (packed f32x2): lane i tests the n/2 unordered pairs {i, (i + k) mod n}, k = 1 .. n/2, two
-//   offsets per iteration, for the ONLY condition every conflict or LoS needs: dcpa < R, evaluated without
-//   a division as |d x w|^2 < R^2 |w|^2 (inflated by 2e-4 and by an absolute term that lets co-moving pairs
-//   through, so the filter is a superset of what the exact routine accepts; ~11 % of the pairs of a
-//   HorizontalCR-20 env pass).  (Also dropping pairs that move apart outside the zone was tried: it removes
-//   most candidates late in an episode but costs more in the filter than it saves: +4 us/step with converging traffic,
-//   +2 us/step even late in an episode -- scripts/ab_regimes.py.)  The group's records are staged as a structure of arrays written twice,
-//   n apart, so (i + k) mod n is a plain offset and consecutive lanes read consecutive words.
-//   Exact phase: the candidates (i, k) are compacted into a per-group queue in shared memory, spread over
-//   the lanes, and evaluated by cd_pair_sym() -- the same routine as before, so results are bit-identical
-//   to evaluating every pair -- with per-aircraft results scattered through shared-memory atomics that
-//   only fire for conflicting pairs.
+//   Hot phase: the ONLY condition every conflict or LoS needs is dcpa < R, evaluated without a division as
+//   |d x w|^2 < R^2 |w|^2 (inflated by 2e-4 and by an absolute term that lets co-moving pairs through, so the
+//   filter is a superset of what the exact routine accepts; ~11 % of the pairs of a HorizontalCR-20 env pass).
+//   A pair that is moving apart and already more than R past its closest point (d.w > R |w|) can neither be a
+//   conflict (touthor < 0) nor a loss of separation (dist >= d.w / |w| > R): it is dropped as well.  (With the
+//   filter run on every pair in every substep that test cost more than it saved -- scripts/ab_regimes.py; with (B)
+//   below evaluated once per env step it is almost free and removes most candidates late in an episode.)
+//     (A) pairs with slot 0 -- the only aircraft the agent steers, in every env of the reference -- are filtered
+//         every substep, one pair per lane.
+//     (B) pairs among the other aircraft (a ring of m = n - 1 members; lane r tests the offsets 1 .. m/2, two per
+//         iteration in packed f32x2, records staged as a structure of arrays written twice, m apart, so that
+//         (r + k) mod m is a plain offset) are filtered when the env step starts and again only after one of them
+//         changed its ground-speed vector (BSG_CD_REUSE).  While both aircraft of a pair keep (u, v) bit for bit,
+//         d x w is constant up to the flat-earth terms -- cos(mean lat) and the longitude rate drift as the pair
+//         moves in latitude -- which change dcpa by at most  kappa (|dx| + |dy| + 2 vmax T),
+//         kappa = 1.5 T vmax tan(lat_max) / Re,  over the T seconds left in the env step; the (B) filter adds that
+//         to R, so its candidate list stays a superset for every remaining substep and is kept in shared memory.
+//   Exact phase, every substep: the candidates (i, j) sit in a per-group queue in shared memory ((B) entries first,
+//   (A) entries appended), are spread over the lanes and evaluated by cd_pair_sym() -- the same routine as
+//   evaluating every pair, so results are bit-identical -- with per-aircraft results scattered through
+//   shared-memory atomics that only fire for conflicting pairs.
 // ====================================================================================================
 enum { HX = 0, HY = 1, HCH = 2, HSH = 3, HU = 4, HV = 5, kHotFields = 6 };
 constexpr int kQueuePerThread = 16;      // G/2 candidates per lane at most
@@ -396,6 +405,11 @@ constexpr int kQueuePerThread = 16;      // G/2 candidates per lane at most
 #define BSG_HOT_UNROLL 1
 #endif
 constexpr int kHotUnroll = BSG_HOT_UNROLL;
+#ifndef BSG_CD_REUSE
+#define BSG_CD_REUSE 1
+#endif
+constexpr float kCdVelTol = 0.05f;       // [m/s] |du| + |dv| an aircraft may drift from the velocity of the kept (B) pass
+constexpr float kCdAbsEps = 1500.0f;     // [m^2/s] lets co-moving pairs (|w| ~ 0, clamped upstream) through every test
 
 constexpr int kSmallPairs = 8 * 7 / 2;
 // pair p (ordered by j, then i < j) -> (i, j); the first n(n-1)/2 entries cover exactly the aircraft < n
@@ -409,9 +423,13 @@ __device__ __forceinline__ void build_pair_table(uint16_t* s_pairs) {
     }
 }
 
+__device__ __forceinline__ u64 abs2(u64 v) { return v & 0x7fffffff7fffffffULL; }
+__device__ __forceinline__ u64 neg2(u64 v) { return v ^ 0x8000000080000000ULL; }
+
+// `horizon`: simulated seconds between this substep and the last one of the env step (what a kept (B) list must cover)
 template <int G>
-__device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvParams& P, float4* s_rec,
-                                         float* s_hot, uint16_t* s_queue, int* s_tmax, int* s_cnt,
+__device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvParams& P, float horizon, float4* s_rec,
+                                         float* s_hot, uint16_t* s_queue, int* s_tmax, int* s_cnt, int* s_nb,
                                          const uint16_t* s_pairs, int& nconf_env, int& nlos_env) {
     const int lane = threadIdx.x & 31;
     const int lane_g = threadIdx.x & (G - 1);
@@ -427,20 +445,10 @@ __device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvPa
     const float x = (float)(kRearthD * kDeg2RadD * dl), y = (float)(kRearthD * kDeg2RadD * (a.lat - lat0));
     s_rec[2 * threadIdx.x] = make_float4(x, y, ch, sh);
     s_rec[2 * threadIdx.x + 1] = make_float4(a.gse, a.gsn, a.alt, a.vs);
-    float* hot = s_hot + gbase * (2 * kHotFields);    // [field][2G] for this group
-    if (lane_g < nac) {
-        float* w = hot + lane_g;
-        w[HX * 2 * G] = -x; w[HY * 2 * G] = y;  w[HCH * 2 * G] = ch;      // (x is stored negated: see crs below)
-        w[HSH * 2 * G] = sh; w[HU * 2 * G] = a.gse; w[HV * 2 * G] = a.gsn;
-        w += nac;
-        w[HX * 2 * G] = -x; w[HY * 2 * G] = y;  w[HCH * 2 * G] = ch;
-        w[HSH * 2 * G] = sh; w[HU * 2 * G] = a.gse; w[HV * 2 * G] = a.gsn;
-    }
     s_tmax[threadIdx.x] = 0;
-    if (G > 8 && lane_g == 0) s_cnt[grp] = 0;
-    __syncwarp(group_mask<G>());
     unsigned confmask = 0u;       // bit = warp lane of an aircraft that is in conflict (this lane's pairs only)
     int counts = 0;               // ordered conflict pairs (low half) / ordered LoS pairs (high half) found by this lane
+    bool found = true;
     auto exact_pair = [&](int i, int j) {
         CdSym r = cd_pair_sym(s_rec[2 * (gbase + i)], s_rec[2 * (gbase + i) + 1], s_rec[2 * (gbase + j)],
                               s_rec[2 * (gbase + j) + 1], P.R2, P.hpz, P.dtlook);
@@ -452,81 +460,148 @@ __device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvPa
             if (r.conf_ji) atomicMax(&s_tmax[gbase + j], tb);
         }
     };
-    const int kmax = nac >> 1;
     if (G <= 8) {
         // small groups (<= 8 aircraft, <= 28 pairs): the filter + queue cost more than they save; the
         // unordered pairs are dealt to the lanes from a table (pair p -> lane p % G) and evaluated exactly
+        __syncwarp(group_mask<G>());
         const int npairs = nac * (nac - 1) / 2;
         for (int p = lane_g; p < npairs; p += G) {
             const unsigned ij = s_pairs[p];
             exact_pair((int)(ij >> 8), (int)(ij & 0xffu));
         }
     } else {
-    // ---- hot phase ---------------------------------------------------------------------------------
-    unsigned cand = 0u;
-    {
-        const u64 pX = pk2(x, x), nY = pk2(-y, -y), CH = pk2(ch, ch), nSH = pk2(-sh, -sh);
-        const u64 nU = pk2(-a.gse, -a.gse), nV = pk2(-a.gsn, -a.gsn);
-        const float R2h = P.R2 * 1.0002f;
-        const float* q = hot + lane_g + 1;
-#pragma unroll kHotUnroll
-        for (int kk = 0; kk < kmax; kk += 2, q += 2) {        // offsets k = kk + 1 and kk + 2
-            const u64 nX = pk2(q[HX * 2 * G], q[HX * 2 * G + 1]);
-            const u64 Y = pk2(q[HY * 2 * G], q[HY * 2 * G + 1]);
-            const u64 CHc = pk2(q[HCH * 2 * G], q[HCH * 2 * G + 1]);
-            const u64 SHc = pk2(q[HSH * 2 * G], q[HSH * 2 * G + 1]);
-            const u64 U = pk2(q[HU * 2 * G], q[HU * 2 * G + 1]);
-            const u64 V = pk2(q[HV * 2 * G], q[HV * 2 * G + 1]);
-            const u64 dy = add2(Y, nY);
-            const u64 cav = fma2(SHc, nSH, mul2(CHc, CH));
-            const u64 ndx = mul2(add2(nX, pX), cav);              // -(x_j - x_i) cos(mean lat)
-            const u64 du = add2(U, nU), dv = add2(V, nV);
-            const u64 dv2 = fma2(du, du, mul2(dv, dv));
-            const u64 crs = fma2(ndx, dv, mul2(dy, du));          // -(dx dv - dy du): only its square is used
-            const u64 lhs = mul2(crs, crs);
-            float l0, l1, w0, w1;
-            up2(lhs, l0, l1);
-            up2(dv2, w0, w1);
-            cand |= ((l0 < fmaf(w0, R2h, 2.0e6f) ? 1u : 0u) | (l1 < fmaf(w1, R2h, 2.0e6f) ? 2u : 0u)) << kk;
-        }
-        // offsets 1 .. n/2 only; for even n the offset n/2 names each pair twice: the lower half keeps it
-        unsigned valid = (1u << kmax) - 1u;
-        if (!(nac & 1) && lane_g >= kmax) valid >>= 1;
-        cand = (lane_g < nac) ? (cand & valid) : 0u;
-    }
-
-    // ---- compaction: (i, k) entries into the group's queue (skipped when the whole group found nothing) --------
+    const unsigned gm = group_mask<G>();
+    const int m = nac - 1, r = lane_g - 1;            // ring of the aircraft the agent does not steer
+    const bool ring = lane_g >= 1 && lane_g < nac;
+    const int kmax = m >> 1;
+    float* hot = s_hot + gbase * (2 * kHotFields);    // [field][2G] for this group
     uint16_t* queue = s_queue + gbase * kQueuePerThread;
-    int ncand = 0;
-    if (__any_sync(group_mask<G>(), cand != 0u)) {
-        const int cnt = __popc(cand);
-        int pos = 0;
-        if (cnt) pos = atomicAdd(&s_cnt[grp], cnt);
-        uint16_t* qp = queue + pos;
-        unsigned val = ((unsigned)lane_g << 8) | 1u, c = cand;
-#pragma unroll 1
-        for (int b = 0; b < kmax; b += 4, c >>= 4, val += 4u) {
-            if (c & 1u) *qp++ = (uint16_t)val;
-            if (c & 2u) *qp++ = (uint16_t)(val + 1u);
-            if (c & 4u) *qp++ = (uint16_t)(val + 2u);
-            if (c & 8u) *qp++ = (uint16_t)(val + 3u);
+    const float Rh = P.rpz * 1.0002f, Lh = P.dtlook * 1.0002f;
+    // ---- is the kept (B) list still good?  (hot[HU], hot[HV] hold the velocities it was computed from)
+    int nb = s_nb[grp];
+    const bool moved = ring && (fabsf(a.gse - hot[HU * 2 * G + (lane_g - 1)]) + fabsf(a.gsn - hot[HV * 2 * G + (lane_g - 1)]) > kCdVelTol);
+    const bool eval_b = !BSG_CD_REUSE || P.cd_enabled == 2 || nb < 0 || __any_sync(gm, moved);
+    u64 KAP = 0, RR = 0, D0 = 0, DW = 0, LH = 0;
+    if (eval_b) {
+        if (ring) {
+            float* w = hot + r;
+            w[HX * 2 * G] = -x; w[HY * 2 * G] = y;  w[HCH * 2 * G] = ch;      // (x is stored negated: see crs below)
+            w[HSH * 2 * G] = sh; w[HU * 2 * G] = a.gse; w[HV * 2 * G] = a.gsn;
+            w += m;
+            w[HX * 2 * G] = -x; w[HY * 2 * G] = y;  w[HCH * 2 * G] = ch;
+            w[HSH * 2 * G] = sh; w[HU * 2 * G] = a.gse; w[HV * 2 * G] = a.gsn;
         }
-        __syncwarp(group_mask<G>());
-        ncand = s_cnt[grp];
+        if (lane_g == 0) s_cnt[grp] = 0;
+        // allowances for keeping the list over `horizon` seconds (see the header comment)
+        float kap = 0.0f, d0 = 0.0f, dw = 0.0f;
+        if (BSG_CD_REUSE && P.cd_enabled != 2 && horizon > 0.0f) {
+            const bool in = lane_g < nac;
+            const float spd = in ? sqrtf(fmaf(a.gse, a.gse, a.gsn * a.gsn)) : 0.0f;
+            const float tl = in ? tanf(fminf(fabsf((float)a.lat), 89.0f) * kDeg2Rad) : 0.0f;
+            const float vmax = __uint_as_float(__reduce_max_sync(gm, __float_as_uint(spd))) + kCdVelTol;
+            const float tmax = __uint_as_float(__reduce_max_sync(gm, __float_as_uint(tl)));
+            kap = 1.5f * horizon * vmax * tmax * (1.0f / kRearth);
+            d0 = (4.0f * vmax + 1.0f) * horizon;
+            dw = 2.0f * kCdVelTol;
+        }
+        KAP = pk2(kap, kap); RR = pk2(fmaf(kap, d0, Rh), fmaf(kap, d0, Rh)); D0 = pk2(d0, d0); DW = pk2(dw, dw);
+        const float lh = P.cd_enabled != 2 ? Lh + horizon * 1.0002f : Lh;
+        LH = pk2(lh, lh);
     }
-
+    __syncwarp(gm);
+    if (eval_b) {
+        // ---- (B) hot phase ---------------------------------------------------------------------------
+        unsigned cand = 0u;
+        {
+            const u64 pX = pk2(x, x), nY = pk2(-y, -y), CH = pk2(ch, ch), nSH = pk2(-sh, -sh);
+            const u64 nU = pk2(-a.gse, -a.gse), nV = pk2(-a.gsn, -a.gsn);
+            const u64 EPS = pk2(kCdAbsEps, kCdAbsEps);
+            const float* q = hot + r + 1;
+#pragma unroll kHotUnroll
+            for (int kk = 0; kk < kmax; kk += 2, q += 2) {        // offsets k = kk + 1 and kk + 2
+                const u64 nX = pk2(q[HX * 2 * G], q[HX * 2 * G + 1]);
+                const u64 Y = pk2(q[HY * 2 * G], q[HY * 2 * G + 1]);
+                const u64 CHc = pk2(q[HCH * 2 * G], q[HCH * 2 * G + 1]);
+                const u64 SHc = pk2(q[HSH * 2 * G], q[HSH * 2 * G + 1]);
+                const u64 U = pk2(q[HU * 2 * G], q[HU * 2 * G + 1]);
+                const u64 V = pk2(q[HV * 2 * G], q[HV * 2 * G + 1]);
+                const u64 dy = add2(Y, nY);
+                const u64 cav = fma2(SHc, nSH, mul2(CHc, CH));
+                const u64 ndxl = add2(nX, pX);
+                const u64 ndx = mul2(ndxl, cav);                      // -(x_j - x_i) cos(mean lat)
+                const u64 du = add2(U, nU), dv = add2(V, nV);
+                const u64 dv2 = fma2(du, du, mul2(dv, dv));
+                const u64 crs = fma2(ndx, dv, mul2(dy, du));          // -(dx dv - dy du): only its magnitude is used
+                const u64 dot = fma2(neg2(du), ndx, mul2(dv, dy));    // d . w (same rounding as cd_pair_sym's)
+                float w0, w1;
+                up2(dv2, w0, w1);
+                const u64 W = add2(pk2(sqrt_approx(w0), sqrt_approx(w1)), DW);        // |w| + what it may still change by
+                const u64 l1 = add2(abs2(ndxl), abs2(dy));                            // |dx| + |dy| >= separation
+                const u64 rm = fma2(KAP, l1, RR);                                     // R + flat-earth allowance
+                const u64 t0 = fma2(W, rm, fma2(add2(l1, D0), DW, EPS));              // bound on |d x w| and on d . w
+                const u64 tf = fma2(mul2(W, W), LH, t0);                              // bound on -(d . w): zone entry in time
+                float c0, c1, d0, d1, a0, a1, f0, f1;
+                up2(abs2(crs), c0, c1);
+                up2(dot, d0, d1);
+                up2(t0, a0, a1);
+                up2(tf, f0, f1);
+                // kept: dcpa < R, not yet out of the zone for good (d . w < R |w|), zone entry before the look-ahead
+                // runs out (-(d . w) < R |w| + |w|^2 (dtlook + horizon)) -- each with its allowance
+                cand |= (((c0 < a0 && d0 < a0 && -d0 < f0) ? 1u : 0u) | ((c1 < a1 && d1 < a1 && -d1 < f1) ? 2u : 0u)) << kk;
+            }
+            // offsets 1 .. m/2 only; for even m the offset m/2 names each pair twice: the lower half keeps it
+            unsigned valid = (1u << kmax) - 1u;
+            if (!(m & 1) && r >= kmax) valid >>= 1;
+            cand = ring ? (cand & valid) : 0u;
+        }
+        // ---- (B) compaction: (i, j) slot pairs into the group's queue (rare path: kept simple) ----------
+        if (__any_sync(gm, cand != 0u)) {
+            const int cnt = __popc(cand);
+            int pos = 0;
+            if (cnt) pos = atomicAdd(&s_cnt[grp], cnt);
+            uint16_t* qp = queue + pos;
+#pragma unroll 1
+            for (unsigned c = cand; c; c &= c - 1u) {
+                int rj = r + __ffs(c);                            // offset k = (bit index) + 1
+                rj = rj >= m ? rj - m : rj;
+                *qp++ = (uint16_t)((lane_g << 8) | (rj + 1));
+            }
+            __syncwarp(gm);
+            nb = s_cnt[grp];
+        } else {
+            nb = 0;
+        }
+        if (lane_g == 0) s_nb[grp] = nb;
+    }
+    // ---- (A) pairs with slot 0 (x = y = 0 by construction), every substep ------------------------------------
+    int ncand;
+    {
+        const float4 A0 = s_rec[2 * gbase], B0 = s_rec[2 * gbase + 1];
+        const float cav = fmaf(-A0.w, sh, A0.z * ch);
+        const float dx = x * cav;
+        const float du = a.gse - B0.x, dv = a.gsn - B0.y;
+        const float dv2 = fmaf(du, du, dv * dv);
+        const float crs = fmaf(dx, dv, -y * du);
+        const float dot = fmaf(du, dx, dv * y);
+        const float t0 = fmaf(sqrt_approx(dv2), Rh, kCdAbsEps);
+        const bool pass = ring && fabsf(crs) < t0 && dot < t0 && -dot < fmaf(dv2, Lh, t0);
+        const unsigned bm = (G >= 32) ? __ballot_sync(gm, pass) : ((__ballot_sync(gm, pass) >> wbase) & ((1u << (G & 31)) - 1u));
+        if (pass) queue[nb + __popc(bm & ((1u << lane_g) - 1u))] = (uint16_t)lane_g;      // (i, j) = (0, lane_g)
+        ncand = nb + __popc(bm);
+        __syncwarp(gm);
+    }
     // ---- exact phase -------------------------------------------------------------------------------
     for (int p = lane_g; p < ncand; p += G) {
         const unsigned e = queue[p];
-        const int i = (int)(e >> 8);
-        int j = i + (int)(e & 0xffu);
-        j = j >= nac ? j - nac : j;
-        exact_pair(i, j);
+        exact_pair((int)(e >> 8), (int)(e & 0xffu));
     }
+    found = ncand > 0;
     }
     // one REDUX.OR over the group merges every lane's findings; each aircraft then reads its own bit
-    confmask = __reduce_or_sync(group_mask<G>(), confmask);
-    counts = (int)__reduce_add_sync(group_mask<G>(), (unsigned)counts);
+    if (found) {                                      // (group-uniform)
+        confmask = __reduce_or_sync(group_mask<G>(), confmask);
+        counts = (int)__reduce_add_sync(group_mask<G>(), (unsigned)counts);
+    }
     a.inconf = alive && ((confmask >> lane) & 1u);
     a.tcpamax = __int_as_float(s_tmax[threadIdx.x]);
     nconf_env = counts & 0xffff;

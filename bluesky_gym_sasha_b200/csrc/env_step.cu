@@ -823,6 +823,7 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
     __shared__ uint16_t s_queue[(G > 8) ? kEnvThreads * kQueuePerThread : 1];
     __shared__ int s_tmax[(G > 1) ? kEnvThreads : 1];
     __shared__ int s_cnt[(G > 8) ? kEnvThreads / G : 1];
+    __shared__ int s_nb[(G > 8) ? kEnvThreads / G : 1];       // candidates kept from the last (B) filter pass, -1 = none
     __shared__ uint16_t s_pairs[(G > 1 && G <= 8) ? kSmallPairs : 1];
     if (G > 1 && G <= 8 && P.cd_enabled && P.mode != kModeReset) {
         build_pair_table(s_pairs);
@@ -873,6 +874,10 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
             }
         }
         int nconf = s.nconf, nlos = s.nlos;
+        if (G > 8 && P.cd_enabled) {
+            if (slot == 0) s_nb[threadIdx.x / G] = -1;
+            __syncwarp(group_mask<G>());
+        }
         Targets T;
         compute_targets(a, P, T);
 #pragma unroll 1
@@ -883,7 +888,7 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
                 if (a.alt != T.k_alt || a.vs != T.k_vs) compute_targets(a, P, T);
                 ac_autopilot<ENV>(a, P, fms_ready);
             }
-            if (G > 1 && P.cd_enabled) group_cd<G>(a, alive, s.num_ac, P, s_rec, s_hot, s_queue, s_tmax, s_cnt, s_pairs, nconf, nlos);
+            if (G > 1 && P.cd_enabled) group_cd<G>(a, alive, s.num_ac, P, (float)(P.n_sub - 1 - k) * P.simdt, s_rec, s_hot, s_queue, s_tmax, s_cnt, s_nb, s_pairs, nconf, nlos);
             if (alive) ac_kinematics<WIND>(a, P, T);
             if (ENV == BSG_ENV_STATIC_OBSTACLE && P.mode == kModeStep) {   // per-substep reward / termination
                 if (k == 0) env_load_post(s, P, e);

@@ -61,7 +61,7 @@ class BlueSkyVectorEnv(VectorEnv):
         pf = _lib.Perf(**{**A320_PERF, **(perf or {})})
         self.cfg = _lib.Config(
             env_type=self.spec_b200.env_type, num_envs=self.num_envs, n_intruders=n_int,
-            cd_enabled=int(bool(cd_enabled)), autoreset_mode=AUTORESET[autoreset_mode],
+            cd_enabled=(2 if cd_enabled == 2 else int(bool(cd_enabled))), autoreset_mode=AUTORESET[autoreset_mode],
             max_episode_steps=self.spec_b200.max_episode_steps if max_episode_steps is None else int(max_episode_steps),
             default_hdg_random=1 if default_hdg == "random" else 0, device=self.device.index,
             seed=int(seed) & (2 ** 64 - 1), env_id_offset=int(env_id_offset), rpz=rpz, hpz=hpz,

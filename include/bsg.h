@@ -56,7 +56,8 @@ typedef struct bsg_config {
     int32_t env_type;           /* BSG_ENV_*                                                        */
     int32_t num_envs;           /* E: env instances on this device                                   */
     int32_t n_intruders;        /* HorizontalCR only: reference 5 (horizontal_cr_env.py:17)          */
-    int32_t cd_enabled;         /* run StateBased.detect every substep (off in the reference)        */
+    int32_t cd_enabled;         /* run StateBased.detect every substep (off in the reference);        */
+                                /* 2 = same results, candidate filter redone every substep (test knob) */
     int32_t autoreset_mode;     /* BSG_AUTORESET_*                                                   */
     int32_t max_episode_steps;  /* TimeLimit of the registration, bluesky_gym/__init__.py:9-45       */
     int32_t default_hdg_random; /* Traffic.cre(achdg=None) draws randint(1,360) when 1, else 0 deg   */

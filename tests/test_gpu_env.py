@@ -391,3 +391,44 @@ def test_soak_many_episodes_stay_finite(cuda, env_id, kw):
     assert int((v.t["env_i32"][:, _lib.I32_RESET_FLAGS] & 4).sum()) == 0        # no generator gave up
     assert int(v.t["env_i32"][:, _lib.I32_EPISODE].min()) >= 1 + steps // cap
     v.close()
+
+
+@pytest.mark.parametrize("env_id,kw,nsub", [("HorizontalCREnv-v0", dict(n_intruders=20), 10), ("HorizontalCREnv-v0", dict(n_intruders=12), 10),
+                                            ("SectorCREnv-v0", {}, 5), ("MergeEnv-v0", {}, 10)])
+def test_in_group_cd_kept_candidates_are_a_superset(cuda, env_id, kw, nsub):
+    """K3 keeps the candidate list of the pairs among the un-steered aircraft across the substeps of an env step while
+    they hold their velocity (env_kernels.cuh, BSG_CD_REUSE).  cd_enabled=2 redoes the filter in every substep with no
+    allowance; both must give bit-identical results -- after every substep count (bsg_traf_update with n = 1 .. n_sub
+    from saved states, so a list kept for 1 .. n_sub - 1 substeps is compared), and along whole rollouts."""
+    import torch
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    E = 512
+    va = BlueSkyVectorEnv(env_id, E, seed=11, cd_enabled=True, autoreset_mode="same_step", **kw)
+    vb = BlueSkyVectorEnv(env_id, E, seed=11, cd_enabled=2, autoreset_mode="same_step", **kw)
+    va.reset_torch()
+    vb.reset_torch()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    keys = ("tcpamax", "inconf", "env_i32", "pos", "kin")
+    n_conf = 0
+    for step in range(60):
+        if step % 4 == 0:
+            sa, sb = va.state_dict(), vb.state_dict()
+            for n in range(1, nsub + 1):
+                va.load_state_dict(sa)
+                vb.load_state_dict(sb)
+                va.traf_update(n)
+                vb.traf_update(n)
+                for k in keys:
+                    assert torch.equal(va.t[k], vb.t[k]), (env_id, step, n, k)
+                n_conf += int(va.t["env_i32"][:, _lib.I32_NCONF].sum())
+            va.load_state_dict(sa)
+            vb.load_state_dict(sb)
+        a = torch.rand((E, va.layout.act_dim), device="cuda", generator=g) * 2 - 1
+        va.step_torch(a)
+        vb.step_torch(a)
+        for k in keys + ("obs", "reward", "terminated", "truncated"):
+            assert torch.equal(va.t[k], vb.t[k]), (env_id, step, k)
+        assert torch.equal(torch.nan_to_num(va.t["info"]), torch.nan_to_num(vb.t["info"])), (env_id, step)
+    assert n_conf > 0                                  # the comparison saw conflicts
+    va.close()
+    vb.close()
