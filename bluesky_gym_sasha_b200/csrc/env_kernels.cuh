@@ -377,23 +377,29 @@ __device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const T
 
 // ====================================================================================================
 // K3: in-group all-pairs CD in two phases.
-//   Hot phase: the ONLY condition every conflict or LoS needs is dcpa < R, evaluated without a division as
-//   |d x w|^2 < R^2 |w|^2 (inflated by 2e-4 and by an absolute term that lets co-moving pairs through, so the
-//   filter is a superset of what the exact routine accepts; ~11 % of the pairs of a HorizontalCR-20 env pass).
-//   A pair that is moving apart and already more than R past its closest point (d.w > R |w|) can neither be a
-//   conflict (touthor < 0) nor a loss of separation (dist >= d.w / |w| > R): it is dropped as well.  (With the
-//   filter run on every pair in every substep that test cost more than it saved -- scripts/ab_regimes.py; with (B)
-//   below evaluated once per env step it is almost free and removes most candidates late in an episode.)
+//   Hot phase: three conditions every conflict or LoS needs, none of which takes a division:
+//     dcpa < R                 |d x w| < R |w|
+//     not past the zone        d . w < R |w|       (moving apart and more than R beyond the closest point: touthor < 0,
+//                                                   and dist >= d . w / |w| > R)
+//     zone within reach        dist < R + |w| dtlook   (the distance shrinks by at most |w| per second, so tinhor >= dtlook
+//                                                   otherwise; this also settles the co-moving pairs whose |w|^2 upstream
+//                                                   clamps to 1e-6: they can only be flagged when dist < R + 0.3 m)
+//   each inflated by 2e-4, so the filter is a superset of what the exact routine accepts (a few % of the pairs of a
+//   HorizontalCR-20 env pass early in an episode, almost none later).
 //     (A) pairs with slot 0 -- the only aircraft the agent steers, in every env of the reference -- are filtered
 //         every substep, one pair per lane.
 //     (B) pairs among the other aircraft (a ring of m = n - 1 members; lane r tests the offsets 1 .. m/2, two per
 //         iteration in packed f32x2, records staged as a structure of arrays written twice, m apart, so that
 //         (r + k) mod m is a plain offset) are filtered when the env step starts and again only after one of them
-//         changed its ground-speed vector (BSG_CD_REUSE).  While both aircraft of a pair keep (u, v) bit for bit,
-//         d x w is constant up to the flat-earth terms -- cos(mean lat) and the longitude rate drift as the pair
-//         moves in latitude -- which change dcpa by at most  kappa (|dx| + |dy| + 2 vmax T),
-//         kappa = 1.5 T vmax tan(lat_max) / Re,  over the T seconds left in the env step; the (B) filter adds that
-//         to R, so its candidate list stays a superset for every remaining substep and is kept in shared memory.
+//         moved its ground-speed vector by more than kCdVelTol (BSG_CD_REUSE).  With w(t) = w0 + eps(t), |eps| <= dw,
+//         d x w and d . w - t |w0|^2 stay within dw (|d0| + 2 t |w0| + t dw) of their values at the filter pass, plus
+//         the flat-earth terms -- cos(mean lat) and the longitude rate drift as the pair moves in latitude -- which
+//         change dcpa by at most  kappa (|dx| + |dy| + d0),  kappa = 1.5 T vmax tan(lat_max) / Re,  d0 = (4 vmax + 1) T,
+//         over the T seconds left in the env step.  The (B) pass tests with |w0| + dw for |w|, R + kappa (...) for R,
+//         dtlook + T for dtlook and adds dw (|dx| + |dy| + d0): its candidate list stays a superset for every remaining
+//         substep and is kept in shared memory.  (HorizontalCR / SectorCR intruders fly straight: one pass per env step;
+//         MergeEnv's follow a great-circle bearing that creeps by ~0.01 m/s per substep -- scripts/merge_vel_probe.py --
+//         which kCdVelTol = 0.15 m/s covers for a whole env step; an aircraft turning at a waypoint forces a new pass.)
 //   Exact phase, every substep: the candidates (i, j) sit in a per-group queue in shared memory ((B) entries first,
 //   (A) entries appended), are spread over the lanes and evaluated by cd_pair_sym() -- the same routine as
 //   evaluating every pair, so results are bit-identical -- with per-aircraft results scattered through
@@ -408,8 +414,8 @@ constexpr int kHotUnroll = BSG_HOT_UNROLL;
 #ifndef BSG_CD_REUSE
 #define BSG_CD_REUSE 1
 #endif
-constexpr float kCdVelTol = 0.05f;       // [m/s] |du| + |dv| an aircraft may drift from the velocity of the kept (B) pass
-constexpr float kCdAbsEps = 1500.0f;     // [m^2/s] lets co-moving pairs (|w| ~ 0, clamped upstream) through every test
+constexpr float kCdVelTol = 0.15f;       // [m/s] |du| + |dv| an aircraft may drift from the velocity of the kept (B) pass
+constexpr float kCdAbsEps = 1.0f;        // [m^2/s] rounding slack of the |d x w|, d . w tests at |w| ~ 0
 
 constexpr int kSmallPairs = 8 * 7 / 2;
 // pair p (ordered by j, then i < j) -> (i, j); the first n(n-1)/2 entries cover exactly the aircraft < n
@@ -539,15 +545,16 @@ __device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvPa
                 const u64 l1 = add2(abs2(ndxl), abs2(dy));                            // |dx| + |dy| >= separation
                 const u64 rm = fma2(KAP, l1, RR);                                     // R + flat-earth allowance
                 const u64 t0 = fma2(W, rm, fma2(add2(l1, D0), DW, EPS));              // bound on |d x w| and on d . w
-                const u64 tf = fma2(mul2(W, W), LH, t0);                              // bound on -(d . w): zone entry in time
-                float c0, c1, d0, d1, a0, a1, f0, f1;
+                const u64 reach = fma2(W, LH, rm);                                    // zone entry before the look-ahead ends
+                float c0, c1, d0, d1, a0, a1, s0, s1, f0, f1;
                 up2(abs2(crs), c0, c1);
                 up2(dot, d0, d1);
                 up2(t0, a0, a1);
-                up2(tf, f0, f1);
-                // kept: dcpa < R, not yet out of the zone for good (d . w < R |w|), zone entry before the look-ahead
-                // runs out (-(d . w) < R |w| + |w|^2 (dtlook + horizon)) -- each with its allowance
-                cand |= (((c0 < a0 && d0 < a0 && -d0 < f0) ? 1u : 0u) | ((c1 < a1 && d1 < a1 && -d1 < f1) ? 2u : 0u)) << kk;
+                up2(fma2(ndx, ndx, mul2(dy, dy)), s0, s1);
+                up2(mul2(reach, reach), f0, f1);
+                // kept: dcpa < R, not yet out of the zone for good (d . w < R |w|), and close enough to enter the zone
+                // before the look-ahead runs out (dist < R + |w| (dtlook + horizon)) -- each with its allowance
+                cand |= (((c0 < a0 && d0 < a0 && s0 < f0) ? 1u : 0u) | ((c1 < a1 && d1 < a1 && s1 < f1) ? 2u : 0u)) << kk;
             }
             // offsets 1 .. m/2 only; for even m the offset m/2 names each pair twice: the lower half keeps it
             unsigned valid = (1u << kmax) - 1u;
@@ -583,8 +590,9 @@ __device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvPa
         const float dv2 = fmaf(du, du, dv * dv);
         const float crs = fmaf(dx, dv, -y * du);
         const float dot = fmaf(du, dx, dv * y);
-        const float t0 = fmaf(sqrt_approx(dv2), Rh, kCdAbsEps);
-        const bool pass = ring && fabsf(crs) < t0 && dot < t0 && -dot < fmaf(dv2, Lh, t0);
+        const float w = sqrt_approx(dv2);
+        const float t0 = fmaf(w, Rh, kCdAbsEps), reach = fmaf(w, Lh, Rh);
+        const bool pass = ring && fabsf(crs) < t0 && dot < t0 && fmaf(dx, dx, y * y) < reach * reach;
         const unsigned bm = (G >= 32) ? __ballot_sync(gm, pass) : ((__ballot_sync(gm, pass) >> wbase) & ((1u << (G & 31)) - 1u));
         if (pass) queue[nb + __popc(bm & ((1u << lane_g) - 1u))] = (uint16_t)lane_g;      // (i, j) = (0, lane_g)
         ncand = nb + __popc(bm);
