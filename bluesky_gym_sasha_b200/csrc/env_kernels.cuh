@@ -263,7 +263,6 @@ __device__ __forceinline__ void compute_targets(const Ac& a, const EnvParams& P,
     const bsg_perf& pf = P.perf;
     T.k_alt = a.alt; T.k_vs = a.vs;
     T.at = vatmos(a.alt);
-    float ap_tas = casormach2tas(a.selspd, T.at);          // Autopilot.update: ap.tas = vcasormach2tas(selspd, alt)
     // ---- perfoap.update: phase.get (later assignments overwrite earlier ones)
     float alt_ft = a.alt * (1.0f / kFt), roc = a.vs * (1.0f / kFpm);
     int ph = PH_NA;
@@ -281,11 +280,24 @@ __device__ __forceinline__ void compute_targets(const Ac& a, const EnvParams& P,
     T.inv_amax = 1.0f / T.amax;
     // ---- perfoap.limits (CAS round trip evaluated at the allowed commanded altitude)
     T.allow_h = a.selalt > pf.hmax ? pf.hmax : a.selalt;
-    Atmos ah = (T.allow_h == a.alt) ? T.at : vatmos(T.allow_h);
-    float intent_cas = tas2cas(ap_tas, ah);
-    float allow_tas = ap_tas;                           // vcas2tas(vtas2cas(x)) == x when not clamped
-    if (intent_cas < vmin) allow_tas = cas2tas(vmin, ah);
-    if (intent_cas > vmax) allow_tas = cas2tas(vmax, ah);
+    const bool level = T.allow_h == a.alt;
+    Atmos ah = level ? T.at : vatmos(T.allow_h);
+    float allow_tas = 0.0f, cas_c = a.selspd;
+    bool convert = true;
+    if (level && fabsf(a.selspd) >= 1.0f) {
+        // a CAS command held at the commanded altitude: vtas2cas(vcas2tas(selspd)) is selspd itself, so the clamp applies
+        // to the command and ONE CAS -> TAS conversion is left (same bits as the general path, minus 4 pow's)
+        if (cas_c < vmin) cas_c = vmin;
+        if (cas_c > vmax) cas_c = vmax;
+    } else {
+        float ap_tas = casormach2tas(a.selspd, T.at);      // Autopilot.update: ap.tas = vcasormach2tas(selspd, alt)
+        float intent_cas = tas2cas(ap_tas, ah);
+        allow_tas = ap_tas;                             // vcas2tas(vtas2cas(x)) == x when not clamped
+        convert = false;
+        if (intent_cas < vmin) { cas_c = vmin; convert = true; }
+        if (intent_cas > vmax) { cas_c = vmax; convert = true; }
+    }
+    if (convert) allow_tas = cas2tas(cas_c, ah);
     float snd = vsound(ah);
     if (allow_tas > pf.mmo * snd) allow_tas = pf.mmo * snd;
     T.allow_tas = allow_tas;
