@@ -310,6 +310,8 @@ def bench_other_envs(torch, dev, BlueSkyVectorEnv, steps=60):
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
     for name, env_id, E, kw in (("SectorCREnv-v0 (configs[2] per-GPU share)", "SectorCREnv-v0", 8192, dict(cd_enabled=True)),
                                 ("MergeEnv-v0 (configs[3])", "MergeEnv-v0", 4096, dict(cd_enabled=True)),
+                                ("HorizontalCREnv-v0 configs[1] at 3000 m instead of the reference's 0 m (SURVEY 8d variant)", "HorizontalCREnv-v0", 4096,
+                                 dict(cd_enabled=True, n_intruders=20, init_alt=3000.0)),
                                 ("DescentEnv-v0 (configs[0], batched)", "DescentEnv-v0", 65536, {}),
                                 ("HorizontalCREnv-v0 reference default (5 intruders, no CD)", "HorizontalCREnv-v0", 65536, {})):
         v = BlueSkyVectorEnv(env_id, E, device=dev.index, seed=0, autoreset_mode="same_step", **kw)

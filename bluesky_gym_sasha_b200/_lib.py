@@ -34,7 +34,7 @@ class Config(C.Structure):
                 ("default_hdg_random", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64),
                 ("env_id_offset", C.c_int64), ("rpz", C.c_float), ("hpz", C.c_float),
                 ("dtlookahead", C.c_float), ("perf", Perf), ("wind_obs", C.c_int32),
-                ("sector_density_uniform", C.c_int32)]
+                ("sector_density_uniform", C.c_int32), ("init_alt", C.c_float)]
 
 
 class Wind(C.Structure):

@@ -118,6 +118,7 @@ extern "C" int bsg_create(const bsg_config* cfg, bsg_handle** out) {
     float rpz = cfg->rpz > 0.0f ? cfg->rpz : 5.0f * 1852.0f;
     P.R2 = rpz * rpz;
     P.rpz = rpz;
+    P.init_alt = cfg->init_alt;
     P.hpz = cfg->hpz > 0.0f ? cfg->hpz : 1000.0f * 0.3048f;
     P.dtlook = cfg->dtlookahead > 0.0f ? cfg->dtlookahead : 300.0f;
     P.seed = cfg->seed; P.gid0 = cfg->env_id_offset; P.perf = cfg->perf;

@@ -38,7 +38,7 @@ enum { PH_NA = 0, PH_TO = 1, PH_IC = 2, PH_CL = 3, PH_CR = 4, PH_DE = 5, PH_AP =
 struct EnvParams {
     int env_type, E, n_int, cd_enabled, autoreset, max_steps, hdg_random, n_sub, fms_rel_freq, mode;
     int obs_dim, act_dim, info_dim;
-    float simdt, R2, hpz, dtlook, rpz;
+    float simdt, R2, hpz, dtlook, rpz, init_alt;
     double fix_lat, fix_lon;      // MergeEnv FIX (merge_env.py:43-46), evaluated on the host in double
     uint64_t seed;
     long long gid0;

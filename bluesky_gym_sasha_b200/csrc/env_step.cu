@@ -75,7 +75,7 @@ __device__ inline void horizontal_reset(Ac& a, EnvS& s, const EnvParams& P, long
     Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);      // horizontal_cr_env.py:82-101
     const int n = P.n_int;
     const double hdg0 = P.hdg_random ? (double)rng.randint(0, 1, 360) : 0.0;
-    const double lat0 = 52.0, lon0 = 4.0, alt0 = 0.0;
+    const double lat0 = 52.0, lon0 = 4.0, alt0 = (double)P.init_alt;     // reference: cre without acalt => 0
     const double tas0 = d_cas2tas(150.0, alt0);
     if (slot == 0) {
         ac_create(a, lat0, lon0, hdg0, alt0, 150.0);

@@ -34,7 +34,7 @@ class BlueSkyVectorEnv(VectorEnv):
                  autoreset_mode="next_step", env_id_offset=0, max_episode_steps=None, perf=None,
                  default_hdg="random", rpz=0.0, hpz=0.0, dtlookahead=0.0, render_mode=None,
                  obs_dtype=np.float32, copy=True, obs_noise=0.0, wind=None, wind_obs=False,
-                 ac_density_mode="normal"):
+                 ac_density_mode="normal", init_alt=0.0):
         if env_id in NOT_ACCELERATED:
             raise NotImplementedError(f"{env_id} is registered by the reference but is not on the accelerated "
                                       "path yet (SURVEY.md section 8f)")
@@ -66,7 +66,8 @@ class BlueSkyVectorEnv(VectorEnv):
             default_hdg_random=1 if default_hdg == "random" else 0, device=self.device.index,
             seed=int(seed) & (2 ** 64 - 1), env_id_offset=int(env_id_offset), rpz=rpz, hpz=hpz,
             dtlookahead=dtlookahead, perf=pf, wind_obs=int(bool(wind_obs)),
-            sector_density_uniform=0 if ac_density_mode == "normal" else 1)     # sector_cr_env.py:98-103: anything else = uniform
+            sector_density_uniform=0 if ac_density_mode == "normal" else 1,     # sector_cr_env.py:98-103: anything else = uniform
+            init_alt=float(init_alt))                   # HorizontalCR only: 0 = the reference; 3000 = SURVEY 8d's airborne variant
         self.layout = _lib.query_layout(self.cfg)
         L, E, G = self.layout, self.num_envs, self.layout.slots
         self.slots = G

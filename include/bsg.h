@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BSG_ABI_VERSION 2
+#define BSG_ABI_VERSION 3
 
 enum { BSG_OK = 0, BSG_EINVAL = -1, BSG_ECUDA = -2, BSG_ESTATE = -3, BSG_ENOMEM = -4 };
 
@@ -69,6 +69,9 @@ typedef struct bsg_config {
     int32_t wind_obs;           /* WindFieldWrapper(augment_obs=True): append wind_u, wind_v to obs  */
     int32_t sector_density_uniform; /* SectorCREnv(ac_density_mode != "normal"): uniform(0.003, 0.007) traffic
                                      * density instead of normal(0.005, 0.001), sector_cr_env.py:98-103  */
+    float init_alt;             /* HorizontalCR: altitude [m] every aircraft is created at.  Reference: 0
+                                 * (horizontal_cr_env.py:91, cre without acalt => ground phase, CAS capped near
+                                 * 88 m/s); SURVEY 8d also measures a 3000 m variant (aircraft keep 150 m/s CAS) */
 } bsg_config;
 
 /* What the caller must allocate (all device memory, zero-initialised) for a given config. */

@@ -103,9 +103,10 @@ class HorizontalCREnv(_Base):
     SIMDT = 5.0
     N_SUB = 10
 
-    def __init__(self, n_intruders=5, **kw):
+    def __init__(self, n_intruders=5, init_alt=0.0, **kw):
         super().__init__(**kw)
         self.n_int = n_intruders
+        self.init_alt = float(init_alt)    # reference: 0 (cre without acalt); SURVEY 8d's airborne variant: 3000 m
 
     def reset(self):                                   # horizontal_cr_env.py:82-101
         t = self.traf
@@ -113,7 +114,7 @@ class HorizontalCREnv(_Base):
         self.total_reward = 0.0
         self.total_intrusions = 0
         self.drift_hist = []
-        t.cre("KL001", actype="A320", acspd=150.0)
+        t.cre("KL001", actype="A320", acspd=150.0, acalt=self.init_alt)
         for i in range(self.n_int):                    # :127-133
             dpsi = self.draws.randint(45, 315)
             cpa = self.draws.randint(0, 5)

@@ -23,7 +23,7 @@ def test_header_symbols_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/bsg.h but not exported"
     assert set(_lib.SYMBOLS) == set(names)
-    assert lib.bsg_abi_version() == 2
+    assert lib.bsg_abi_version() == 3
 
 
 def test_layout_queries(lib):

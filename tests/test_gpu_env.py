@@ -26,9 +26,9 @@ pytestmark = pytest.mark.gpu
 TOL = dict(pos=2e-5, alt=0.5, tas=2e-2, vs=2e-2, hdg=5e-3)
 
 
-def _make_oracle(env_id, draws=None, cd=False, n_int=5, density="normal"):
+def _make_oracle(env_id, draws=None, cd=False, n_int=5, density="normal", init_alt=0.0):
     if env_id == "HorizontalCREnv-v0":
-        return oenvs.HorizontalCREnv(n_intruders=n_int, draws=draws, cd_enabled=cd)
+        return oenvs.HorizontalCREnv(n_intruders=n_int, draws=draws, cd_enabled=cd, init_alt=init_alt)
     if env_id == "DescentEnv-v0":
         return oenvs.DescentEnv(draws=draws)
     if env_id == "SectorCREnv-v0":
@@ -432,3 +432,36 @@ def test_in_group_cd_kept_candidates_are_a_superset(cuda, env_id, kw, nsub):
     assert n_conf > 0                                  # the comparison saw conflicts
     va.close()
     vb.close()
+
+
+def test_horizontal_airborne_variant_matches_oracle(cuda):
+    """SURVEY 8d's second C2 input: every aircraft created at 3000 m instead of the reference's 0 (no ground-phase CAS
+    cap, aircraft keep 150 m/s CAS).  Device reset against the Philox-driven oracle, then 12 steps with CD on."""
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    E, seed, n_int = 8, 31, 20
+    venv = BlueSkyVectorEnv("HorizontalCREnv-v0", E, seed=seed, autoreset_mode="disabled", n_intruders=n_int,
+                            cd_enabled=True, init_alt=3000.0)
+    gobs, _ = venv.reset()
+    d = device_traffic(venv)
+    orc = []
+    for e in range(E):
+        o = _make_oracle("HorizontalCREnv-v0", draws=PhiloxDraws(seed, e, 0), n_int=n_int, cd=True, init_alt=3000.0)
+        oobs, _ = o.reset()
+        assert np.max(np.abs(d["alt"][e, :n_int + 1] - 3000.0)) < 1e-3 and np.max(np.abs(d["tas"][e, :n_int + 1] - o.traf.tas)) < 1e-3
+        assert np.max(np.abs(d["lat"][e, :n_int + 1] - o.traf.lat)) < 1e-9
+        _compare_obs(gobs, oobs, e, -1)
+        orc.append(o)
+    rng = np.random.default_rng(2)
+    for step in range(12):
+        a = rng.uniform(-1, 1, (E, 1))
+        gobs, grew, gterm, gtrunc, ginfo = venv.step(a)
+        d = device_traffic(venv)
+        for e, o in enumerate(orc):
+            oobs, orew, oterm, _, _ = o.step(a[e])
+            assert np.max(np.abs(d["tas"][e, :n_int + 1] - o.traf.tas)) < TOL["tas"]          # ~172 m/s: not capped at 88
+            assert np.max(np.abs(d["lat"][e, :n_int + 1] - o.traf.lat)) < TOL["pos"]
+            _compare_obs(gobs, oobs, e, step)
+            assert abs(grew[e] - orew) < 1e-3 and bool(gterm[e]) == bool(oterm)
+            assert ginfo["asas_nconf"][e] == len(o.traf.confpairs), (step, e)
+    assert float(d["tas"][0, 0]) > 160.0
+    venv.close()
