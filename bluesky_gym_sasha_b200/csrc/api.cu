@@ -119,6 +119,12 @@ extern "C" int bsg_create(const bsg_config* cfg, bsg_handle** out) {
     P.R2 = rpz * rpz;
     P.rpz = rpz;
     P.init_alt = cfg->init_alt;
+    {   // ISA at init_alt (bluesky/tools/aero.py::vatmos as restated in oracle/aero.py), evaluated once here
+        const double hh = (double)cfg->init_alt, T = fmax(288.15 - 0.0065 * hh, 216.65);
+        const double rhotrop = 1.225 * pow(T / 288.15, 4.256848030018761);
+        P.init_rho = rhotrop * exp(-fmax(0.0, hh - 11000.0) / 6341.552161);
+        P.init_p = P.init_rho * 287.05287 * T;
+    }
     P.hpz = cfg->hpz > 0.0f ? cfg->hpz : 1000.0f * 0.3048f;
     P.dtlook = cfg->dtlookahead > 0.0f ? cfg->dtlookahead : 300.0f;
     P.seed = cfg->seed; P.gid0 = cfg->env_id_offset; P.perf = cfg->perf;

@@ -39,6 +39,7 @@ struct EnvParams {
     int env_type, E, n_int, cd_enabled, autoreset, max_steps, hdg_random, n_sub, fms_rel_freq, mode;
     int obs_dim, act_dim, info_dim;
     float simdt, R2, hpz, dtlook, rpz, init_alt;
+    double init_p, init_rho;      // ISA pressure / density at init_alt (host-evaluated, HorizontalCR scenario generator)
     double fix_lat, fix_lon;      // MergeEnv FIX (merge_env.py:43-46), evaluated on the host in double
     uint64_t seed;
     long long gid0;
@@ -84,19 +85,27 @@ __device__ inline void d_atmos(double h, double& p, double& rho, double& T) {
     rho = rhotrop * exp(-fmax(0.0, h - 11000.0) / 6341.552161);
     p = rho * 287.05287 * T;
 }
-__device__ inline double d_cas2tas(double cas, double h) {
-    double p, rho, T;
-    d_atmos(h, p, rho, T);
+// (the _at forms take the pressure and density at the altitude: the host evaluates them once when the altitude is a
+// configuration constant, which keeps the double-precision pow / exp of d_atmos out of that env's kernel)
+__device__ inline double d_cas2tas_at(double cas, double p, double rho) {
     double q = 101325.0 * (pow(1.0 + 1.225 * cas * cas / (7.0 * 101325.0), 3.5) - 1.0);
     double t = sqrt(7.0 * p / rho * (pow(q / p + 1.0, 2.0 / 7.0) - 1.0));
     return cas < 0 ? -t : t;
 }
-__device__ inline double d_tas2cas(double tas, double h) {
-    double p, rho, T;
-    d_atmos(h, p, rho, T);
+__device__ inline double d_tas2cas_at(double tas, double p, double rho) {
     double q = p * (pow(1.0 + rho * tas * tas / (7.0 * p), 3.5) - 1.0);
     double c = sqrt(7.0 * 101325.0 / 1.225 * (pow(q / 101325.0 + 1.0, 2.0 / 7.0) - 1.0));
     return tas < 0 ? -c : c;
+}
+__device__ inline double d_cas2tas(double cas, double h) {
+    double p, rho, T;
+    d_atmos(h, p, rho, T);
+    return d_cas2tas_at(cas, p, rho);
+}
+__device__ inline double d_tas2cas(double tas, double h) {
+    double p, rho, T;
+    d_atmos(h, p, rho, T);
+    return d_tas2cas_at(tas, p, rho);
 }
 // functions.py:24-42
 __device__ inline void d_point_at_distance(double lat1, double lon1, double d_km, double brg, double& lat2, double& lon2) {
@@ -107,9 +116,8 @@ __device__ inline void d_point_at_distance(double lat1, double lon1, double d_km
 }
 
 // Traffic.cre with SI arguments (oracle/traffic.py::Traffic.cre)
-__device__ inline void ac_create(Ac& a, double lat, double lon, double hdg, double alt, double cas_cmd) {
+__device__ inline void ac_create_tas(Ac& a, double lat, double lon, double hdg, double alt, double cas_cmd, double tas) {
     a.lat = lat; a.lon = lon > 180.0 ? lon - 360.0 : (lon < -180.0 ? lon + 360.0 : lon);
-    double tas = d_cas2tas(cas_cmd, alt);        // the reference never passes a Mach number to cre
     a.alt = (float)alt; a.tas = (float)tas; a.hdg = (float)hdg; a.vs = 0.0f;
     a.selspd = (float)cas_cmd; a.selalt = (float)alt; a.selvs = 0.0f; a.aptrk = (float)hdg;
     a.ax = 0.0f; a.curlegdir = -999.0f; a.cas = (float)cas_cmd;
@@ -118,6 +126,9 @@ __device__ inline void ac_create(Ac& a, double lat, double lon, double hdg, doub
     a.gsn = (float)(tas * cos(hr)); a.gse = (float)(tas * sin(hr));
     a.coslat = (float)cos(a.lat * kDeg2RadD);
     a.tcpamax = 0.0f; a.inconf = false;
+}
+__device__ inline void ac_create(Ac& a, double lat, double lon, double hdg, double alt, double cas_cmd) {
+    ac_create_tas(a, lat, lon, hdg, alt, cas_cmd, d_cas2tas(cas_cmd, alt));     // the reference never passes a Mach number to cre
 }
 __device__ inline void ac_clear(Ac& a) {
     a.lat = 0.0; a.lon = 0.0; a.alt = 0.0f; a.tas = 0.0f; a.hdg = 0.0f; a.vs = 0.0f;

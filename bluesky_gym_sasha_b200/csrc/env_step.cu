@@ -76,9 +76,9 @@ __device__ inline void horizontal_reset(Ac& a, EnvS& s, const EnvParams& P, long
     const int n = P.n_int;
     const double hdg0 = P.hdg_random ? (double)rng.randint(0, 1, 360) : 0.0;
     const double lat0 = 52.0, lon0 = 4.0, alt0 = (double)P.init_alt;     // reference: cre without acalt => 0
-    const double tas0 = d_cas2tas(150.0, alt0);
+    const double tas0 = d_cas2tas_at(150.0, P.init_p, P.init_rho);
     if (slot == 0) {
-        ac_create(a, lat0, lon0, hdg0, alt0, 150.0);
+        ac_create_tas(a, lat0, lon0, hdg0, alt0, 150.0, tas0);
     } else if (slot <= n) {
         // Traffic.creconfs (oracle/traffic.py::creconfs), horizontal_cr_env.py:127-133
         const uint32_t d = 1u + 3u * (uint32_t)(slot - 1);
@@ -100,9 +100,9 @@ __device__ inline void horizontal_reset(Ac& a, EnvS& s, const EnvParams& P, long
         double lat = lat0 + dnm * cos(brn * kDeg2RadD) / 60.0;
         double lon = lon0 + dnm * sin(brn * kDeg2RadD) / fmax(0.01, 60.0 * cos(lat0 * kDeg2RadD));
         lon = fmod(lon + 180.0, 360.0); if (lon < 0.0) lon += 360.0; lon -= 180.0;
-        double acspd = d_tas2cas(sqrt(gsn * gsn + gse * gse), alt0);
+        double acspd = d_tas2cas_at(sqrt(gsn * gsn + gse * gse), P.init_p, P.init_rho);
         double achdg = kRad2DegD * atan2(gse, gsn);
-        ac_create(a, lat, lon, achdg, alt0, acspd);
+        ac_create_tas(a, lat, lon, achdg, alt0, acspd, d_cas2tas_at(acspd, P.init_p, P.init_rho));
     } else {
         ac_clear(a);
     }
