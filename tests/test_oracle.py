@@ -154,6 +154,17 @@ def test_ground_phase_speed_cap_pin():
     assert abs(t.hdg[0]) < 1e-9 and t.alt[0] == 0.0
 
 
+def test_horizontal_airborne_variant_keeps_commanded_speed():
+    """SURVEY 8d's second C2 input (aircraft created at 3000 m): no ground-phase cap, TAS = vcas2tas(150, 3000 m) = 172.4 m/s
+    (the ISA table of SURVEY 8c), and the creconfs geometry still produces conflicts with the ownship."""
+    o = envs.HorizontalCREnv(n_intruders=20, cd_enabled=True, draws=philox.PhiloxDraws(31, 0, 0), init_alt=3000.0)
+    o.reset()
+    for _ in range(4):
+        o.step(np.array([0.0]))
+    assert np.allclose(o.traf.alt, 3000.0) and np.all(np.abs(o.traf.tas - 172.39) < 0.05)
+    assert any(i == 0 for i, _ in o.traf.confpairs)
+
+
 def test_turn_and_climb_response():
     t = Traffic(simdt=1.0, default_hdg=0.0)
     t.cre("A", "A320", achdg=0.0, acalt=3000.0, acspd=150.0)
