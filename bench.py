@@ -62,6 +62,9 @@ def _cpu_worker(args):
     return n, time.perf_counter() - t0
 
 
+_OUT = sys.stdout
+
+
 def cpu_baseline(budget_s=12.0, cores=None):
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
@@ -86,7 +89,7 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.gpus), "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 def workload_config(n_gpus):
@@ -301,7 +304,7 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
 
 
 def bench_other_envs(torch, dev, BlueSkyVectorEnv, steps=60):
@@ -502,10 +505,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs under ncu)")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write banners to fd 1 from native code (NCCL prints its version
+    # there when NCCL_DEBUG asks for it), so fd 1 points at stderr while the bench runs and the line goes to the saved fd.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    _OUT.flush()
 
 
 if __name__ == "__main__":

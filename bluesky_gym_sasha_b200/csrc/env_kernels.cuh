@@ -182,11 +182,13 @@ __device__ __forceinline__ void ac_load(Ac& a, const EnvParams& P, long long idx
     a.selspd = c.x; a.selalt = c.y; a.selvs = c.z; a.aptrk = c.w;
     a.ax = x.x; a.curlegdir = x.y; a.cas = x.z;
     a.flags = P.flags[idx];
+    // the cached ground-speed components and cos(lat) are rebuilt with the very expressions of ac_kinematics, so a launch
+    // continues bit for bit where the previous one stopped (n substeps in one launch == the same n split over launches)
     float s, co;
-    sincosf(a.hdg * kDeg2Rad, &s, &co);
-    a.gsn = a.tas * co; a.gse = a.tas * s;
+    __sincosf((a.hdg - 180.0f) * kDeg2Rad, &s, &co);
+    a.gsn = -a.tas * co; a.gse = -a.tas * s;
     if (P.gsv) { float2 g = P.gsv[idx]; a.gsn = g.x; a.gse = g.y; }      // with wind the ground speed is state
-    a.coslat = cosf((float)a.lat * kDeg2Rad);
+    a.coslat = __cosf((float)a.lat * kDeg2Rad);
     a.tcpamax = 0.0f; a.inconf = false;
 }
 __device__ __forceinline__ void ac_store(const Ac& a, const EnvParams& P, long long idx) {

@@ -465,3 +465,33 @@ def test_horizontal_airborne_variant_matches_oracle(cuda):
             assert ginfo["asas_nconf"][e] == len(o.traf.confpairs), (step, e)
     assert float(d["tas"][0, 0]) > 160.0
     venv.close()
+
+
+@pytest.mark.parametrize("env_id,kw", [("HorizontalCREnv-v0", dict(n_intruders=20, cd_enabled=True)), ("MergeEnv-v0", dict(cd_enabled=True)),
+                                       ("SectorCREnv-v0", dict(cd_enabled=True)), ("VerticalCREnv-v0", dict(cd_enabled=True)),
+                                       ("DescentEnv-v0", {})])
+def test_substeps_split_over_launches_are_bit_identical(cuda, env_id, kw):
+    """bsg_traf_update(n) == bsg_traf_update(k) followed by bsg_traf_update(n - k), bit for bit: everything a launch
+    caches in registers (ground-speed components, cos(lat), ISA / CAS targets, the kept CD candidate list) is rebuilt
+    from the stored state exactly as the substep loop would have carried it."""
+    import torch
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    E = 256
+    v = BlueSkyVectorEnv(env_id, E, seed=17, autoreset_mode="same_step", **kw)
+    v.reset_torch()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    keys = ("pos", "kin", "cmd", "aux", "flags", "env_i32") + (("tcpamax", "inconf") if kw.get("cd_enabled") else ())
+    for step in range(12):
+        v.step_torch(torch.rand((E, v.layout.act_dim), device="cuda", generator=g) * 2 - 1)
+        if step % 3 == 2:
+            sd = v.state_dict()
+            v.traf_update(7)
+            one = {k: v.t[k].clone() for k in keys}
+            for k in (1, 3, 6):
+                v.load_state_dict(sd)
+                v.traf_update(k)
+                v.traf_update(7 - k)
+                for name in keys:
+                    assert torch.equal(v.t[name], one[name]), (env_id, step, k, name)
+            v.load_state_dict(sd)
+    v.close()
