@@ -90,7 +90,7 @@ __device__ __forceinline__ void kwikqdrdist(double lata, double lona, double lat
                                             float& qdr, float& dist_nm) {
     float dlat = (float)((latb - lata) * kDeg2RadD);
     float dlon = (float)((dmod360((lonb - lona) + 180.0) - 180.0) * kDeg2RadD);
-    float cavelat = cosf((float)((lata + latb) * (0.5 * kDeg2RadD)));
+    float cavelat = __cosf((float)((lata + latb) * (0.5 * kDeg2RadD)));      // |mean lat| <= pi/2: ~4e-7 absolute
     float dx = dlon * cavelat;
     dist_nm = (kRearth / kNm) * sqrtf(dlat * dlat + dx * dx);
     qdr = mod360(kRad2Deg * atan2f(dx, dlat));
@@ -98,6 +98,12 @@ __device__ __forceinline__ void kwikqdrdist(double lata, double lona, double lat
 
 // sin / cos of a latitude in degrees (|lat| <= 90): MUFU.SIN / MUFU.COS, absolute error ~4e-7 on factors of order one
 __device__ __forceinline__ void sincos_lat(float latd, float& s, float& c) { __sincosf(latd * kDeg2Rad, &s, &c); }
+// sin / cos of an angle in degrees anywhere in (-540, 540) -- a difference of two headings / bearings: folded into
+// [-180, 180], where MUFU.SIN / MUFU.COS are good to ~4e-7 absolute (the observations they feed are compared at 5e-4)
+__device__ __forceinline__ void sincos_deg(float deg, float& s, float& c) {
+    deg = deg > 180.0f ? deg - 360.0f : (deg < -180.0f ? deg + 360.0f : deg);
+    __sincosf(deg * kDeg2Rad, &s, &c);
+}
 // sin of a small angle (differences of nearby positions, a few hundredths of a radian): odd polynomial to x^9, relative
 // error < 1e-7 up to |x| = 0.5 -- the MUFU's ABSOLUTE error would be a relative one of 1e-3 at 2 km from a waypoint
 __device__ __forceinline__ float sin_small(float x) {

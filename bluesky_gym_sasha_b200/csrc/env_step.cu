@@ -130,8 +130,8 @@ __device__ inline StepOut horizontal_obs_reward(const Ac& a, EnvS& s, const EnvP
     if (intr) {
         kwikqdrdist(lat0, lon0, a.lat, a.lon, qdr, dis);
         float sb, cb, sd, cd;
-        sincosf(wrap180_fold(hdg0 - qdr) * kDeg2Rad, &sb, &cb);
-        sincosf((hdg0 - a.hdg) * kDeg2Rad, &sd, &cd);
+        sincos_deg(wrap180_fold(hdg0 - qdr), sb, cb);
+        sincos_deg((hdg0 - a.hdg), sd, cd);
         const int k = slot - 1;
         obs[k] = dis * (1.852f / 150.0f);
         obs[n + k] = cb;
@@ -145,7 +145,7 @@ __device__ inline StepOut horizontal_obs_reward(const Ac& a, EnvS& s, const EnvP
     const float drift = wrap180_fold(hdg0 - wq);
     if (slot == 0) {
         float sd, cd;
-        sincosf(drift * kDeg2Rad, &sd, &cd);
+        sincos_deg(drift, sd, cd);
         obs[5 * n] = wkm * (1.0f / 150.0f);
         obs[5 * n + 1] = cd;
         obs[5 * n + 2] = sd;
@@ -345,7 +345,7 @@ __device__ inline StepOut sector_obs_reward(const Ac& a, EnvS& s, const EnvParam
     const float drift = wrap180_fold(hdg0 - wq);
     if (slot == 0) {
         float sd, cd;
-        sincosf(drift * kDeg2Rad, &sd, &cd);
+        sincos_deg(drift, sd, cd);
         obs[0] = cd; obs[1] = sd; obs[2] = (tas0 - 150.0f) * (1.0f / 6.0f);
     }
     const bool other = slot >= 1 && slot < s.num_ac;
@@ -438,7 +438,7 @@ __device__ inline StepOut merge_obs_reward(const Ac& a, EnvS& s, const EnvParams
     const float drift = wrap180_fold(hdg0 - wq);
     if (slot == 0) {
         float sd, cd;
-        sincosf(drift * kDeg2Rad, &sd, &cd);
+        sincos_deg(drift, sd, cd);
         obs[0] = cd; obs[1] = sd; obs[2] = tas0; obs[3] = wd * (1.0f / 250.0f); obs[4] = (float)s.wpt_reach;
     }
     const bool other = slot >= 1 && slot < s.num_ac;
@@ -447,7 +447,7 @@ __device__ inline StepOut merge_obs_reward(const Ac& a, EnvS& s, const EnvParams
     int rank = nearest_rank<G>(dnm, other, 5);
     if (rank >= 0) {
         float sb, cb;
-        sincosf(brg * kDeg2Rad, &sb, &cb);
+        sincos_deg(brg, sb, cb);
         float dm = dnm * 1852.0f;
         float dvx = avx - vx0, dvy = avy - vy0;
         float hyp = sqrtf(dvx * dvx + dvy * dvy);
@@ -504,7 +504,7 @@ __device__ inline StepOut planwp_obs_reward(const Ac& a, EnvS& s, const EnvParam
         float q, dnm;
         kwikqdrdist(a.lat, a.lon, w[2 * k], w[2 * k + 1], q, dnm);
         float dkm = dnm * 1.852f, sd, cd;
-        sincosf(wrap180_fold(a.hdg - q) * kDeg2Rad, &sd, &cd);
+        sincos_deg(wrap180_fold(a.hdg - q), sd, cd);
         const float live = (s.wpt_reach >> k) & 1 ? 0.0f : 1.0f;           // flags from BEFORE this step's check
         obs[k] = live * dkm * (1.0f / 75.0f);
         obs[5 + k] = live * cd;
@@ -593,8 +593,8 @@ __device__ inline StepOut vertical_obs_reward(const Ac& a, EnvS& s, const EnvPar
         float qdr;
         kwikqdrdist(lat0, lon0, a.lat, a.lon, qdr, dis);
         float sb, cb, sd, cd;
-        sincosf(wrap180_fold(hdg0 - qdr) * kDeg2Rad, &sb, &cb);
-        sincosf((hdg0 - a.hdg) * kDeg2Rad, &sd, &cd);
+        sincos_deg(wrap180_fold(hdg0 - qdr), sb, cb);
+        sincos_deg((hdg0 - a.hdg), sd, cd);
         const int k = slot - 1;
         obs[4 + k] = dis * (1.852f / 200.0f);
         obs[9 + k] = cb;
@@ -753,13 +753,13 @@ __device__ inline StepOut static_obs_reward(const Ac& a, EnvS& s, const EnvParam
     s.last_drift = wrap180_fold(hdg0 - wq);
     if (slot == 0) {
         float sd, cd;
-        sincosf(s.last_drift * kDeg2Rad, &sd, &cd);
+        sincos_deg(s.last_drift, sd, cd);
         obs[0] = s.last_wdist * (1.0f / 170.0f); obs[1] = cd; obs[2] = sd;
     }
     if (slot < kObsN) {
         float q, dnm, sb, cb;
         kwikqdrdist(lat0, lon0, pe[kObsCentre + 2 * slot], pe[kObsCentre + 2 * slot + 1], q, dnm);
-        sincosf(wrap180_fold(hdg0 - q) * kDeg2Rad, &sb, &cb);
+        sincos_deg(wrap180_fold(hdg0 - q), sb, cb);
         obs[3 + slot] = (float)pe[kObsRadius + slot] * (1.0f / 50.0f);
         obs[13 + slot] = dnm * (1.852f / 170.0f);
         obs[23 + slot] = cb;
