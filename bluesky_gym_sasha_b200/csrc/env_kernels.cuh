@@ -459,14 +459,14 @@ __device__ __forceinline__ u64 neg2(u64 v) { return v ^ 0x8000000080000000ULL; }
 
 // `horizon`: simulated seconds between this substep and the last one of the env step (what a kept (B) list must cover)
 template <int G>
-__device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvParams& P, float horizon, float4* s_rec,
+__device__ __forceinline__ void group_cd(const int tid, Ac& a, bool alive, int nac, const EnvParams& P, float horizon, float4* s_rec,
                                          float* s_hot, uint16_t* s_queue, int* s_tmax, int* s_cnt, int* s_nb,
                                          const uint16_t* s_pairs, int& nconf_env, int& nlos_env) {
-    const int lane = threadIdx.x & 31;
-    const int lane_g = threadIdx.x & (G - 1);
-    const int gbase = threadIdx.x - lane_g;           // first thread of this group in the block
+    const int lane = tid & 31;
+    const int lane_g = tid & (G - 1);
+    const int gbase = tid - lane_g;           // first thread of this group in the block
     const int wbase = lane - lane_g;                  // first lane of this group in the warp
-    const int grp = threadIdx.x / G;
+    const int grp = tid / G;
     double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);
     // cos / sin of lat/2 from the cached cos(lat): half-angle identities (absolute error ~1e-7)
     const float ch = sqrt_approx(fmaf(0.5f, a.coslat, 0.5f));
@@ -474,9 +474,9 @@ __device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvPa
     double dl = a.lon - lon0;
     dl = dl > 180.0 ? dl - 360.0 : (dl < -180.0 ? dl + 360.0 : dl);
     const float x = (float)(kRearthD * kDeg2RadD * dl), y = (float)(kRearthD * kDeg2RadD * (a.lat - lat0));
-    s_rec[2 * threadIdx.x] = make_float4(x, y, ch, sh);
-    s_rec[2 * threadIdx.x + 1] = make_float4(a.gse, a.gsn, a.alt, a.vs);
-    s_tmax[threadIdx.x] = 0;
+    s_rec[2 * tid] = make_float4(x, y, ch, sh);
+    s_rec[2 * tid + 1] = make_float4(a.gse, a.gsn, a.alt, a.vs);
+    s_tmax[tid] = 0;
     unsigned confmask = 0u;       // bit = warp lane of an aircraft that is in conflict (this lane's pairs only)
     int counts = 0;               // ordered conflict pairs (low half) / ordered LoS pairs (high half) found by this lane
     bool found = true;
@@ -636,7 +636,7 @@ __device__ __forceinline__ void group_cd(Ac& a, bool alive, int nac, const EnvPa
         counts = (int)__reduce_add_sync(group_mask<G>(), (unsigned)counts);
     }
     a.inconf = alive && ((confmask >> lane) & 1u);
-    a.tcpamax = __int_as_float(s_tmax[threadIdx.x]);
+    a.tcpamax = __int_as_float(s_tmax[tid]);
     nconf_env = counts & 0xffff;
     nlos_env = counts >> 16;
     __syncwarp(group_mask<G>());

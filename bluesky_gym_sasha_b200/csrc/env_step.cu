@@ -831,7 +831,8 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
     }
     __shared__ double s_scratch[(ENV == BSG_ENV_SECTOR_CR) ? (kEnvThreads / 32) * kSectorScratch
                                 : (ENV == BSG_ENV_STATIC_OBSTACLE) ? (kEnvThreads / G) * kStaticScratch : 1];
-    const long long gt = (long long)blockIdx.x * kEnvThreads + threadIdx.x;
+    const int tid = threadIdx.x;
+    const long long gt = (long long)blockIdx.x * kEnvThreads + tid;
     const long long e = gt / G;
     const int slot = (int)(gt % G);
     if (e >= P.E) return;                       // group-uniform (G divides the block size)
@@ -888,7 +889,7 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
                 if (a.alt != T.k_alt || a.vs != T.k_vs) compute_targets(a, P, T);
                 ac_autopilot<ENV>(a, P, fms_ready);
             }
-            if (G > 1 && P.cd_enabled) group_cd<G>(a, alive, s.num_ac, P, (float)(P.n_sub - 1 - k) * P.simdt, s_rec, s_hot, s_queue, s_tmax, s_cnt, s_nb, s_pairs, nconf, nlos);
+            if (G > 1 && P.cd_enabled) group_cd<G>(tid, a, alive, s.num_ac, P, (float)(P.n_sub - 1 - k) * P.simdt, s_rec, s_hot, s_queue, s_tmax, s_cnt, s_nb, s_pairs, nconf, nlos);
             if (alive) ac_kinematics<WIND>(a, P, T);
             if (ENV == BSG_ENV_STATIC_OBSTACLE && P.mode == kModeStep) {   // per-substep reward / termination
                 if (k == 0) env_load_post(s, P, e);
