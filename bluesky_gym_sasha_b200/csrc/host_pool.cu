@@ -111,7 +111,12 @@ void init_pool() {
     int w = 3;                                   // + the calling thread = 4 copiers
     if (const char* e = getenv("BSG_HOST_THREADS")) w = atoi(e) - 1;
     unsigned hc = std::thread::hardware_concurrency();
-    if (hc && w > (int)hc - 1) w = (int)hc - 1;
+    // one process per GPU (torchrun): the ranks of a node share its cores, and the workers poll while they wait, so
+    // each rank takes its share of the cores at most (8 ranks on a 16-core host: 1 worker + the caller each)
+    int ranks = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e);
+    if (ranks < 1) ranks = 1;
+    if (hc && w > (int)(hc / (unsigned)ranks) - 1) w = (int)(hc / (unsigned)ranks) - 1;
     if (w < 0) w = 0;
     if (w > 15) w = 15;
     if (w > 0) g_pool = new Pool(w);             // lives for the process; idle workers sleep on a condition variable
