@@ -57,7 +57,7 @@ class TensorTable(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in TENSOR_FIELDS]
 
 
-SYMBOLS = ("bsg_abi_version", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
+SYMBOLS = ("bsg_abi_version", "bsg_abi_struct_size", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
            "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_host_copy", "bsg_set_obs_noise", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
            "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_cd_cull_workspace", "bsg_cd_detect_culled", "bsg_cd_detect_peers", "bsg_probe_fp32")
 
@@ -118,6 +118,13 @@ def load():
     for name in ("bsg_query_layout", "bsg_create", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy",
                  "bsg_traf_update", "bsg_cd_pack", "bsg_cd_detect", "bsg_probe_fp32"):
         getattr(lib, name).restype = C.c_int
+    if hasattr(lib, "bsg_abi_struct_size"):     # (absent only in older A/B builds loaded through BSG_B200_LIB)
+        lib.bsg_abi_struct_size.argtypes = [C.c_int]
+        lib.bsg_abi_struct_size.restype = C.c_int
+        for which, st in enumerate((Config, Layout, TensorTable, Wind, Perf)):
+            if lib.bsg_abi_struct_size(which) != C.sizeof(st):
+                raise BsgError(f"{LIB_PATH}: sizeof({st.__name__}) is {lib.bsg_abi_struct_size(which)} in the library, "
+                               f"{C.sizeof(st)} in bluesky_gym_sasha_b200/_lib.py (include/bsg.h changed: rebuild / update the binding)")
     _lib = lib
     return lib
 

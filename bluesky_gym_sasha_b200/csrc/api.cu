@@ -51,6 +51,16 @@ struct bsg_handle {
 };
 
 extern "C" int bsg_abi_version(void) { return BSG_ABI_VERSION; }
+extern "C" int bsg_abi_struct_size(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(bsg_config);
+        case 1: return (int)sizeof(bsg_layout);
+        case 2: return (int)sizeof(bsg_tensor_table);
+        case 3: return (int)sizeof(bsg_wind);
+        case 4: return (int)sizeof(bsg_perf);
+    }
+    return -1;
+}
 extern "C" const char* bsg_last_error(void) { return g_err; }
 extern "C" int bsg_device_count(void) {
     int n = 0;

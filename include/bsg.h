@@ -125,6 +125,9 @@ enum {
 typedef struct bsg_handle bsg_handle;
 
 int bsg_abi_version(void);
+/* sizeof of the library's view of an interface structure (which: 0 bsg_config, 1 bsg_layout, 2 bsg_tensor_table,
+ * 3 bsg_wind, 4 bsg_perf; anything else -1): a binding in another language checks its own declarations against it */
+int bsg_abi_struct_size(int which);
 const char *bsg_last_error(void);
 int bsg_device_count(void);
 
