@@ -431,7 +431,7 @@ __device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const T
 //   shared-memory atomics that only fire for conflicting pairs.
 // ====================================================================================================
 enum { HX = 0, HY = 1, HCH = 2, HSH = 3, HU = 4, HV = 5, kHotFields = 6 };
-constexpr int kQueuePerThread = 16;      // G/2 candidates per lane at most
+constexpr int kQueuePerThread = 16;      // queue entries per lane: (B) <= (G-1)(G-2)/2 plus (A) <= G-1 < 16 G for G <= 32
 #ifndef BSG_HOT_UNROLL
 #define BSG_HOT_UNROLL 1
 #endif
