@@ -108,15 +108,22 @@ std::once_flag g_once;
 std::atomic<bool> g_busy{false};
 
 void init_pool() {
-    int w = 3;                                   // + the calling thread = 4 copiers
-    if (const char* e = getenv("BSG_HOST_THREADS")) w = atoi(e) - 1;
+    // Copiers (workers + the calling thread).  Measured at E = 4096 on a 16-core host (scripts/e2e_variants.py): 4 copiers
+    // 160 us per step, 8: 151 us, 12: 147 us -- the tail of the copy that cannot overlap the transfer shrinks with the
+    // number of copiers.  Default: three quarters of this rank's share of the cores, between 2 and 12.  One process per
+    // GPU (torchrun): the ranks of a node share its cores and the workers poll while they wait, so the share is
+    // cores / LOCAL_WORLD_SIZE (8 ranks on a 32-core host: 3 copiers each; 2 measured 5 % better than 4 there,
+    // scripts/e2e_ranks.py).  BSG_HOST_THREADS overrides.
     unsigned hc = std::thread::hardware_concurrency();
-    // one process per GPU (torchrun): the ranks of a node share its cores, and the workers poll while they wait, so
-    // each rank takes its share of the cores at most (8 ranks on a 16-core host: 1 worker + the caller each)
     int ranks = 1;
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e);
     if (ranks < 1) ranks = 1;
-    if (hc && w > (int)(hc / (unsigned)ranks) - 1) w = (int)(hc / (unsigned)ranks) - 1;
+    int copiers = hc ? (int)(hc * 3u / 4u) / ranks : 4;
+    if (copiers < 2) copiers = 2;
+    if (copiers > 12) copiers = 12;
+    if (const char* e = getenv("BSG_HOST_THREADS")) copiers = atoi(e);
+    if (hc && copiers > (int)hc) copiers = (int)hc;
+    int w = copiers - 1;
     if (w < 0) w = 0;
     if (w > 15) w = 15;
     if (w > 0) g_pool = new Pool(w);             // lives for the process; idle workers sleep on a condition variable
