@@ -58,7 +58,7 @@ class TensorTable(C.Structure):
 
 
 SYMBOLS = ("bsg_abi_version", "bsg_abi_struct_size", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
-           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_host_copy", "bsg_set_obs_noise", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
+           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_step_host_begin", "bsg_step_host_wait", "bsg_host_copy", "bsg_set_obs_noise", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
            "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_cd_cull_workspace", "bsg_cd_detect_culled", "bsg_cd_detect_peers", "bsg_probe_fp32")
 
 _lib = None
@@ -90,6 +90,11 @@ def load():
     lib.bsg_step.argtypes = [vp, vp, vp]
     lib.bsg_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.bsg_step_host_block.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    if hasattr(lib, "bsg_step_host_begin"):     # (absent only in older A/B builds loaded through BSG_B200_LIB)
+        lib.bsg_step_host_begin.argtypes = [vp, vp, vp, C.c_size_t, vp]
+        lib.bsg_step_host_begin.restype = C.c_int
+        lib.bsg_step_host_wait.argtypes = [vp, vp, vp, C.c_size_t]
+        lib.bsg_step_host_wait.restype = C.c_int
     lib.bsg_set_obs_noise.argtypes = [vp, f32]
     lib.bsg_set_obs_noise.restype = C.c_int
     if hasattr(lib, "bsg_set_seed"):

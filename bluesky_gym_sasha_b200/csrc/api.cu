@@ -46,6 +46,7 @@ struct bsg_handle {
     bsg::EnvParams P;
     cudaEvent_t ev[4];      // chunk-arrival events of bsg_step_host_copy (created on first use)
     bool have_ev;
+    bool pending;           // a bsg_step_host_begin without its bsg_step_host_wait
     float obs_noise;        // NoisyObservationWrapper sigma (0 = off)
     uint32_t noise_calls;   // reset / step calls so far: the noise stream's call index
 };
@@ -336,6 +337,39 @@ extern "C" int bsg_step_host_copy(bsg_handle* h, const float* h_actions, void* h
             if (hi > lo) bsg::host_copy_mt((char*)dst + lo, h0 + lo, hi - lo);
         }
     }
+    return BSG_OK;
+}
+
+extern "C" int bsg_step_host_begin(bsg_handle* h, const float* h_actions, void* h_block, size_t nbytes, void* stream) {
+    if (!h || !h_actions || !h_block) return bsg_fail(BSG_EINVAL, "bsg_step_host_begin: null argument");
+    if (!h->bound) return bsg_fail(BSG_ESTATE, "bsg_bind_state has not been called");
+    if (!h->t.actions_staging) return bsg_fail(BSG_ESTATE, "bsg_step_host_begin needs tensor_table.actions_staging");
+    if (h->pending) return bsg_fail(BSG_ESTATE, "bsg_step_host_begin: the previous step has not been waited for");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t E = (size_t)h->cfg.num_envs;
+    DeviceGuard guard(h->cfg.device);
+    if (!h->have_ev) {
+        for (int k = 0; k < 4; ++k) BSG_CUDA(cudaEventCreateWithFlags(&h->ev[k], cudaEventDisableTiming));
+        h->have_ev = true;
+    }
+    BSG_CUDA(cudaMemcpyAsync(h->t.actions_staging, h_actions, E * h->lay.act_dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = run_mode(h, bsg::kModeStep, h->t.actions_staging, nullptr, 0, stream);
+    if (rc != BSG_OK) return rc;
+    BSG_CUDA(cudaMemcpyAsync(h_block, h->t.obs, nbytes, cudaMemcpyDeviceToHost, st));
+    BSG_CUDA(cudaEventRecord(h->ev[0], st));
+    h->pending = true;
+    return BSG_OK;
+}
+
+extern "C" int bsg_step_host_wait(bsg_handle* h, const void* h_block, void* dst, size_t dst_bytes) {
+    if (!h) return bsg_fail(BSG_EINVAL, "bsg_step_host_wait: null handle");
+    if (!h->pending) return bsg_fail(BSG_ESTATE, "bsg_step_host_wait without bsg_step_host_begin");
+    if (dst && !h_block) return bsg_fail(BSG_EINVAL, "bsg_step_host_wait: null block");
+    DeviceGuard guard(h->cfg.device);
+    if (dst) bsg::host_pool_prewake();
+    h->pending = false;
+    BSG_CUDA(cudaEventSynchronize(h->ev[0]));
+    if (dst && dst_bytes) bsg::host_copy_mt((char*)dst, (const char*)h_block, dst_bytes);
     return BSG_OK;
 }
 

@@ -68,10 +68,10 @@ class BlueSkySB3VecEnv(_Base):
         return {k: v.copy() for k, v in obs.items()}
 
     def step_async(self, actions):
-        self._actions = np.asarray(actions)
+        self.venv.step_async(np.asarray(actions))        # enqueued on the device; returns without waiting
 
     def step_wait(self):
-        obs, rew, term, trunc, infos = self.venv.step(self._actions)
+        obs, rew, term, trunc, infos = self.venv.step_wait()
         dones = term | trunc
         # copy=True: the arrays are already fresh; copy=False: views of the pinned ring, copied here as SB3 keeps them
         obs_out = obs if self.venv.copy else {k: v.copy() for k, v in obs.items()}

@@ -134,6 +134,7 @@ class BlueSkyVectorEnv(VectorEnv):
             hb["block"], hb["ptr"] = blk, _ptr(blk)
             self._hbuf.append(hb)
         self._hsel = 0
+        self._pending = None        # mirrored block of a step_async() whose step_wait() has not run yet
         self.h = dict(actions=ph((E, L.act_dim), torch.float32))
         self._act_np, self._act_ptr = self.h["actions"].numpy(), _ptr(self.h["actions"])
         self._final_np = np.zeros((E, L.obs_dim), dtype=np.float32)
@@ -260,6 +261,8 @@ class BlueSkyVectorEnv(VectorEnv):
         return self._obs_dict_np(obs), self._infos_np(info)
 
     def step(self, actions):
+        if self._pending is not None:
+            raise _lib.BsgError("step(): a step_async() is in flight; call step_wait() first")
         E = self.num_envs
         self._act_np[...] = np.asarray(actions, dtype=np.float32).reshape(E, self.layout.act_dim)
         self._hsel ^= 1
@@ -276,7 +279,42 @@ class BlueSkyVectorEnv(VectorEnv):
         if rc:
             _lib.check(rc)
         self.gpu_launches += 1
-        if fresh:
+        return self._step_results(h, flat if fresh else None)
+
+    def step_async(self, actions):
+        """First half of ``step`` (the SB3 / older-gymnasium ``step_async`` / ``step_wait`` pair): copies the actions in,
+        enqueues the step and the transfer of its results, and returns at once -- the caller's own work (policy
+        bookkeeping, logging, the optimiser) overlaps the ~0.1 ms the device and the bus are busy."""
+        if self._pending is not None:
+            raise _lib.BsgError("step_async(): the previous step has not been waited for (one step in flight per env batch)")
+        E = self.num_envs
+        self._act_np[...] = np.asarray(actions, dtype=np.float32).reshape(E, self.layout.act_dim)
+        self._hsel ^= 1
+        h = self._hbuf[self._hsel]
+        rc = self._lib.bsg_step_host_begin(self._h, self._act_ptr, h["ptr"], self._out_bytes,
+                                           torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _lib.check(rc)
+        self.gpu_launches += 1
+        self._pending = h
+
+    def step_wait(self):
+        """Second half: waits for the step enqueued by ``step_async`` and returns what ``step`` returns."""
+        h = getattr(self, "_pending", None)
+        if h is None:
+            raise RuntimeError("step_wait() without step_async()")
+        self._pending = None
+        fresh = self.copy and self.obs_dtype == np.float32
+        flat = np.empty((self.num_envs, self.layout.obs_dim), dtype=np.float32) if fresh else None
+        rc = self._lib.bsg_step_host_wait(self._h, h["ptr"], flat.ctypes.data if fresh else None, flat.nbytes if fresh else 0)
+        if rc:
+            _lib.check(rc)
+        return self._step_results(h, flat)
+
+    def _step_results(self, h, flat):
+        """The (obs, reward, terminated, truncated, infos) tuple from mirrored block ``h`` (and, when the observations
+        were copied out by the library, the fresh array ``flat``)."""
+        if flat is not None:
             obs = OrderedDict((k, flat[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
         else:
             obs = self._obs_dict_np(h["obs"])

@@ -162,10 +162,19 @@ int bsg_step_host_block(bsg_handle *h, const float *h_actions, void *h_block, si
 
 /* bsg_step_host_block that additionally copies the first `dst_bytes` bytes of the mirrored block (the
  * observations) from the pinned mirror into `dst`, the caller's own (pageable) result array, using the
- * library's host threads (BSG_HOST_THREADS, default 4) and overlapping that copy with the device->host
+ * library's host threads (BSG_HOST_THREADS; default 3/4 of the rank's share of the cores) and overlapping that copy with the device->host
  * transfer chunk by chunk.  dst may be NULL (then identical to bsg_step_host_block). */
 int bsg_step_host_copy(bsg_handle *h, const float *h_actions, void *h_block, size_t nbytes,
                        void *dst, size_t dst_bytes, void *stream);
+
+/* bsg_step_host_block in two halves, for callers that have work of their own to overlap with the step (SB3's
+ * VecEnv.step_async / step_wait, stable_baselines3 as driven by the reference's main.py:36-55): _begin enqueues the
+ * copy of h_actions, the step and the copy of the first `nbytes` bytes of the output block to h_block on `stream` and
+ * returns without waiting; _wait blocks until that transfer has landed and, when dst is not NULL, copies the first
+ * dst_bytes bytes of h_block into dst with the library's host threads.  One step may be in flight per handle
+ * (BSG_ESTATE otherwise); h_actions and h_block must stay valid until _wait returns. */
+int bsg_step_host_begin(bsg_handle *h, const float *h_actions, void *h_block, size_t nbytes, void *stream);
+int bsg_step_host_wait(bsg_handle *h, const void *h_block, void *dst, size_t dst_bytes);
 
 /* The host-thread copy bsg_step_host_copy uses, on its own (pure host code; works without a GPU). */
 int bsg_host_copy(void *dst, const void *src, size_t nbytes);

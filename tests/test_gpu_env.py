@@ -495,3 +495,42 @@ def test_substeps_split_over_launches_are_bit_identical(cuda, env_id, kw):
                     assert torch.equal(v.t[name], one[name]), (env_id, step, k, name)
             v.load_state_dict(sd)
     v.close()
+
+
+def test_step_async_wait_equals_step(cuda):
+    """step_async() + step_wait() (bsg_step_host_begin / bsg_step_host_wait) return what step() returns, for fresh and
+    for mirrored (copy=False) observation arrays, across same-step autoresets; a second step_async before step_wait and
+    a step_wait without step_async are errors."""
+    from bluesky_gym_sasha_b200 import _lib as L
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    E = 64
+    for copy in (True, False):
+        kw = dict(seed=13, n_intruders=20, cd_enabled=True, autoreset_mode="same_step", max_episode_steps=5, copy=copy)
+        a, b = BlueSkyVectorEnv("HorizontalCREnv-v0", E, **kw), BlueSkyVectorEnv("HorizontalCREnv-v0", E, **kw)
+        a.reset()
+        b.reset()
+        rng = np.random.default_rng(4)
+        saw_final = False
+        for step in range(12):
+            act = rng.uniform(-1, 1, (E, 1))
+            ra = a.step(act)
+            b.step_async(act)
+            if step == 3:
+                with pytest.raises(L.BsgError):
+                    b.step_async(act)                      # one step in flight per handle
+            rb = b.step_wait()
+            for k in ra[0]:
+                assert np.array_equal(ra[0][k], rb[0][k]), (copy, step, k)
+            for x, y in zip(ra[1:4], rb[1:4]):
+                assert np.array_equal(x, y)
+            assert set(ra[4]) == set(rb[4])
+            if "final_obs" in ra[4]:
+                saw_final = True
+                for k in ra[4]["final_obs"]:
+                    m = ra[4]["_final_obs"]
+                    assert np.array_equal(ra[4]["final_obs"][k][m], rb[4]["final_obs"][k][m])
+        assert saw_final
+        with pytest.raises(RuntimeError):
+            b.step_wait()
+        a.close()
+        b.close()
