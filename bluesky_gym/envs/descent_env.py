@@ -1,0 +1,3 @@
+"""Drop-in alias of the reference module path ``bluesky_gym.envs.descent_env`` (the registration's entry point,
+bluesky_gym/__init__.py:6-46) -> the accelerated env class."""
+from bluesky_gym_sasha_b200.envs import DescentEnv  # noqa: F401

@@ -43,6 +43,12 @@ class Wind(C.Structure):
                 ("d_gs", C.c_void_p)]
 
 
+class AcState(C.Structure):
+    _fields_ = [("n", C.c_int32)] + [(k, C.c_void_p) for k in (
+        "lat", "lon", "alt", "tas", "hdg", "vs", "selspd", "selalt", "selvs", "ap_trk", "cas", "ax", "curlegdir",
+        "swlnav", "iactwp", "env_f64", "env_f32", "env_i32", "poly")]
+
+
 class Layout(C.Structure):
     _fields_ = [("slots", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("info_dim", C.c_int32),
                 ("n_sub", C.c_int32), ("env_f64", C.c_int32), ("env_f32", C.c_int32), ("env_i32", C.c_int32),
@@ -58,7 +64,7 @@ class TensorTable(C.Structure):
 
 
 SYMBOLS = ("bsg_abi_version", "bsg_abi_struct_size", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
-           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_step_host_begin", "bsg_step_host_wait", "bsg_host_copy", "bsg_set_obs_noise", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
+           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_step_host_begin", "bsg_step_host_wait", "bsg_host_copy", "bsg_set_obs_noise", "bsg_get_noise_calls", "bsg_set_noise_calls", "bsg_load_state", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
            "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_cd_cull_workspace", "bsg_cd_detect_culled", "bsg_cd_detect_peers", "bsg_probe_fp32")
 
 _lib = None
@@ -103,6 +109,13 @@ def load():
     if hasattr(lib, "bsg_set_wind"):            # (absent only in older A/B builds loaded through BSG_B200_LIB)
         lib.bsg_set_wind.argtypes = [vp, C.POINTER(Wind)]
         lib.bsg_set_wind.restype = C.c_int
+    if hasattr(lib, "bsg_load_state"):          # (absent only in older A/B builds loaded through BSG_B200_LIB)
+        lib.bsg_load_state.argtypes = [vp, i32, C.POINTER(AcState), vp]
+        lib.bsg_load_state.restype = C.c_int
+        lib.bsg_get_noise_calls.argtypes = [vp, C.POINTER(u32)]
+        lib.bsg_get_noise_calls.restype = C.c_int
+        lib.bsg_set_noise_calls.argtypes = [vp, u32]
+        lib.bsg_set_noise_calls.restype = C.c_int
     lib.bsg_host_copy.argtypes = [vp, vp, C.c_size_t]
     lib.bsg_host_copy.restype = C.c_int
     lib.bsg_step_host_copy.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp]
@@ -126,7 +139,7 @@ def load():
     if hasattr(lib, "bsg_abi_struct_size"):     # (absent only in older A/B builds loaded through BSG_B200_LIB)
         lib.bsg_abi_struct_size.argtypes = [C.c_int]
         lib.bsg_abi_struct_size.restype = C.c_int
-        for which, st in enumerate((Config, Layout, TensorTable, Wind, Perf)):
+        for which, st in enumerate((Config, Layout, TensorTable, Wind, Perf, AcState)):
             if lib.bsg_abi_struct_size(which) != C.sizeof(st):
                 raise BsgError(f"{LIB_PATH}: sizeof({st.__name__}) is {lib.bsg_abi_struct_size(which)} in the library, "
                                f"{C.sizeof(st)} in bluesky_gym_sasha_b200/_lib.py (include/bsg.h changed: rebuild / update the binding)")

@@ -59,6 +59,7 @@ extern "C" int bsg_abi_struct_size(int which) {
         case 2: return (int)sizeof(bsg_tensor_table);
         case 3: return (int)sizeof(bsg_wind);
         case 4: return (int)sizeof(bsg_perf);
+        case 5: return (int)sizeof(bsg_ac_state);
     }
     return -1;
 }
@@ -219,6 +220,65 @@ extern "C" int bsg_set_obs_noise(bsg_handle* h, float sigma) {
     if (!h) return bsg_fail(BSG_EINVAL, "null handle");
     if (!(sigma >= 0.0f)) return bsg_fail(BSG_EINVAL, "bsg_set_obs_noise: noise level must be >= 0");
     h->obs_noise = sigma;
+    return BSG_OK;
+}
+
+extern "C" int bsg_get_noise_calls(bsg_handle* h, uint32_t* out) {
+    if (!h || !out) return bsg_fail(BSG_EINVAL, "bsg_get_noise_calls: null argument");
+    *out = h->noise_calls;
+    return BSG_OK;
+}
+extern "C" int bsg_set_noise_calls(bsg_handle* h, uint32_t calls) {
+    if (!h) return bsg_fail(BSG_EINVAL, "null handle");
+    h->noise_calls = calls;
+    return BSG_OK;
+}
+
+extern "C" int bsg_load_state(bsg_handle* h, int32_t env, const bsg_ac_state* s, void* stream) {
+    if (!h || !s) return bsg_fail(BSG_EINVAL, "bsg_load_state: null argument");
+    if (!h->bound) return bsg_fail(BSG_ESTATE, "bsg_bind_state has not been called");
+    const int G = h->lay.slots, n = s->n;
+    if (env < 0 || env >= h->cfg.num_envs) return bsg_fail(BSG_EINVAL, "bsg_load_state: env index out of range");
+    if (n < 0 || n > G) return bsg_fail(BSG_EINVAL, "bsg_load_state: more aircraft than slots");
+    if (n > 0 && (!s->lat || !s->lon || !s->alt || !s->tas || !s->hdg || !s->vs || !s->selspd || !s->selalt || !s->selvs ||
+                  !s->ap_trk || !s->cas))
+        return bsg_fail(BSG_EINVAL, "bsg_load_state: a required aircraft array is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceGuard guard(h->cfg.device);
+    double pos[32 * 2];
+    float kin[32 * 4], cmd[32 * 4], aux[32 * 4];
+    uint32_t fl[32];
+    memset(pos, 0, sizeof(pos)); memset(kin, 0, sizeof(kin)); memset(cmd, 0, sizeof(cmd)); memset(aux, 0, sizeof(aux));
+    memset(fl, 0, sizeof(fl));
+    for (int i = 0; i < n; ++i) {
+        pos[2 * i] = s->lat[i]; pos[2 * i + 1] = s->lon[i];
+        kin[4 * i] = (float)s->alt[i]; kin[4 * i + 1] = (float)s->tas[i]; kin[4 * i + 2] = (float)s->hdg[i]; kin[4 * i + 3] = (float)s->vs[i];
+        cmd[4 * i] = (float)s->selspd[i]; cmd[4 * i + 1] = (float)s->selalt[i]; cmd[4 * i + 2] = (float)s->selvs[i]; cmd[4 * i + 3] = (float)s->ap_trk[i];
+        aux[4 * i] = s->ax ? (float)s->ax[i] : 0.0f;
+        aux[4 * i + 1] = s->curlegdir ? (float)s->curlegdir[i] : -999.0f;
+        aux[4 * i + 2] = (float)s->cas[i];
+        uint32_t f = bsg::kFlAlive;
+        if (s->swlnav && s->swlnav[i]) f |= bsg::kFlLnav;
+        if (s->iactwp) {
+            const int ia = s->iactwp[i] > 0 ? s->iactwp[i] : 0;
+            f |= ((uint32_t)ia << bsg::kFlWpShift) | (ia >= 1 ? bsg::kFlLastWp : 0u);
+        }
+        fl[i] = f;
+    }
+    const size_t o = (size_t)env * G;
+    BSG_CUDA(cudaMemcpyAsync(h->t.pos + 2 * o, pos, sizeof(double) * 2 * G, cudaMemcpyHostToDevice, st));
+    BSG_CUDA(cudaMemcpyAsync(h->t.kin + 4 * o, kin, sizeof(float) * 4 * G, cudaMemcpyHostToDevice, st));
+    BSG_CUDA(cudaMemcpyAsync(h->t.cmd + 4 * o, cmd, sizeof(float) * 4 * G, cudaMemcpyHostToDevice, st));
+    BSG_CUDA(cudaMemcpyAsync(h->t.aux + 4 * o, aux, sizeof(float) * 4 * G, cudaMemcpyHostToDevice, st));
+    BSG_CUDA(cudaMemcpyAsync(h->t.flags + o, fl, sizeof(uint32_t) * G, cudaMemcpyHostToDevice, st));
+    if (s->env_f64) BSG_CUDA(cudaMemcpyAsync(h->t.env_f64 + (size_t)env * h->lay.env_f64, s->env_f64, sizeof(double) * h->lay.env_f64, cudaMemcpyHostToDevice, st));
+    if (s->env_f32) BSG_CUDA(cudaMemcpyAsync(h->t.env_f32 + (size_t)env * h->lay.env_f32, s->env_f32, sizeof(float) * h->lay.env_f32, cudaMemcpyHostToDevice, st));
+    if (s->env_i32) BSG_CUDA(cudaMemcpyAsync(h->t.env_i32 + (size_t)env * h->lay.env_i32, s->env_i32, sizeof(int32_t) * h->lay.env_i32, cudaMemcpyHostToDevice, st));
+    if (s->poly) {
+        if (!h->lay.poly_f64 || !h->t.poly) return bsg_fail(BSG_EINVAL, "bsg_load_state: this env type has no polygon record");
+        BSG_CUDA(cudaMemcpyAsync(h->t.poly + (size_t)env * h->lay.poly_f64, s->poly, sizeof(double) * h->lay.poly_f64, cudaMemcpyHostToDevice, st));
+    }
+    BSG_CUDA(cudaStreamSynchronize(st));         // the staging arrays above live on this stack frame
     return BSG_OK;
 }
 

@@ -1,7 +1,7 @@
 """Scalar ``gymnasium.Env`` views of the batched simulator: the classes ``gym.make(id)`` returns.
 
 Same constructor keywords, spaces, return types and info keys as the reference classes
-(bluesky_gym/envs/{descent,horizontal_cr,sector_cr,merge}_env.py); each is a ``num_envs=1``
+(bluesky_gym/envs/{descent,horizontal_cr,sector_cr,merge,plan_waypoint,vertical_cr,static_obstacle}_env.py); each is a ``num_envs=1``
 BlueSkyVectorEnv with autoreset disabled, so ``reset`` / ``step`` follow the single-env contract
 (float64 numpy observations, python scalars for reward / terminated / truncated).
 """
@@ -87,4 +87,13 @@ class StaticObstacleEnv(_ScalarEnv):
     ENV_ID = "StaticObstacleEnv-v0"
 
 
+class PlanWaypointEnv(_ScalarEnv):                  # plan_waypoint_env.py:36-76
+    ENV_ID = "PlanWaypointEnv-v0"
+
+
+class VerticalCREnv(_ScalarEnv):                    # vertical_cr_env.py:49-102
+    ENV_ID = "VerticalCREnv-v0"
+
+
 __all__ = [s.entry_point.split(":")[1] for s in SPECS.values()]
+assert all(name in globals() for name in __all__), "a registered entry point has no class in this module"

@@ -2,13 +2,8 @@
 from .gym_compat import register, registry
 from .spec import SPECS
 
-_OTHER = {}
-
 
 def register_envs():
     for env_id, spec in SPECS.items():
         if env_id not in registry:
             register(id=env_id, entry_point=spec.entry_point, max_episode_steps=spec.max_episode_steps)
-    for env_id, (cls, cap) in _OTHER.items():
-        if env_id not in registry:
-            register(id=env_id, entry_point=f"bluesky_gym_sasha_b200.envs:{cls}", max_episode_steps=cap)

@@ -75,6 +75,8 @@ class BlueSkySB3VecEnv(_Base):
         dones = term | trunc
         # copy=True: the arrays are already fresh; copy=False: views of the pinned ring, copied here as SB3 keeps them
         obs_out = obs if self.venv.copy else {k: v.copy() for k, v in obs.items()}
+        if not self.venv.copy and "final_obs" in infos:      # views of a persistent buffer: captured now
+            infos["final_obs"] = {k: v.copy() for k, v in infos["final_obs"].items()}
         return obs_out, rew.astype(np.float32), dones, _LazyInfos(infos, term, trunc, dones)
 
     def step(self, actions):

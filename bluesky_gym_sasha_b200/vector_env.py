@@ -197,10 +197,14 @@ class BlueSkyVectorEnv(VectorEnv):
             t["gs"] = torch.stack([kin[..., 1] * torch.cos(h), kin[..., 1] * torch.sin(h)], dim=-1).contiguous()
         else:
             t["gs"] = self._wind_t["gs"]
+        self._install_wind(t, n, n_alt)
+
+    def _install_wind(self, t, n, n_alt):
         w = _lib.Wind(n_points=n, n_alt=n_alt, alt_step=self.ALT_STEP, d_lat=t["lat"].data_ptr(), d_lon=t["lon"].data_ptr(),
                       d_vn=t["vn"].data_ptr(), d_ve=t["ve"].data_ptr(), d_gs=t["gs"].data_ptr())
         _lib.check(self._lib.bsg_set_wind(self._h, C.byref(w)))
         self._wind_t = t                         # keeps the device arrays alive while the library points at them
+        self._wind_meta = dict(n_points=int(n), n_alt=int(n_alt))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -251,9 +255,16 @@ class BlueSkyVectorEnv(VectorEnv):
 
     # ------------------------------------------------------------------ gymnasium VectorEnv API (numpy)
     def reset(self, *, seed=None, options=None):
-        if seed is not None:        # gymnasium: reset(seed=s) re-seeds; here it re-keys every env's Philox stream
+        if self._pending is not None:
+            raise _lib.BsgError("reset(): a step_async() is in flight; call step_wait() first")
+        if seed is not None:
+            # gymnasium: reset(seed=s) re-seeds -- the same s always gives the same scenarios.  The streams are keyed by
+            # (seed, global env id, episode) and the noise stream by (seed, global env id, call index), so the episode
+            # counters and the call index restart with the new key.
             _lib.check(self._lib.bsg_set_seed(self._h, int(seed) & (2 ** 64 - 1)))
             self.cfg.seed = int(seed) & (2 ** 64 - 1)
+            self.t["env_i32"][:, _lib.I32_EPISODE] = 0
+            _lib.check(self._lib.bsg_set_noise_calls(self._h, 0))
         self.reset_torch()
         torch.cuda.synchronize(self.device)
         obs = self.t["obs"].cpu().numpy()
@@ -327,12 +338,16 @@ class BlueSkyVectorEnv(VectorEnv):
             if n_fin:                   # compacted terminal observations of the envs that finished in this step
                 ids = h["final_ids"][:n_fin]
                 cap = self._final_cap
-                self._final_np[ids[:cap]] = h["final_obs"][:min(n_fin, cap)]
+                # copy=True: a fresh array per step (callers such as SB3 read terminal observations later; np.zeros of
+                # this size is lazily mapped, so only the finished envs' rows are ever touched); copy=False: one
+                # persistent buffer, valid until the next step with a finished env
+                dst = np.zeros((self.num_envs, self.layout.obs_dim), dtype=np.float32) if self.copy else self._final_np
+                dst[ids[:cap]] = h["final_obs"][:min(n_fin, cap)]
                 if n_fin > cap:         # more finished than the mirrored window holds: fetch the rest
                     self._h_final[cap:n_fin].copy_(self.t["final_obs"][cap:n_fin], non_blocking=True)
                     torch.cuda.current_stream(self.device).synchronize()
-                    self._final_np[ids[cap:]] = self._h_final.numpy()[cap:n_fin]
-                fo = self._final_np.astype(self.obs_dtype) if self.obs_dtype != np.float32 else self._final_np
+                    dst[ids[cap:]] = self._h_final.numpy()[cap:n_fin]
+                fo = dst.astype(self.obs_dtype) if self.obs_dtype != np.float32 else dst
                 infos["final_obs"] = OrderedDict((k, fo[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
                 infos["_final_obs"] = term | trunc
         return obs, rew, term, trunc, infos
@@ -344,57 +359,90 @@ class BlueSkyVectorEnv(VectorEnv):
         return self.t["env_i32"][:, _lib.I32_RESET_FLAGS].cpu().numpy()
 
     # ------------------------------------------------------------------ state access (parity tests, checkpoints)
+    def _config_key(self):
+        c = self.cfg
+        return dict(env_id=self.env_id, num_envs=self.num_envs, n_intruders=self.n_intruders, seed=int(c.seed),
+                    env_id_offset=int(c.env_id_offset), cd_enabled=int(c.cd_enabled), autoreset_mode=self.autoreset_mode,
+                    max_episode_steps=int(c.max_episode_steps), wind_obs=int(c.wind_obs), init_alt=float(c.init_alt),
+                    sector_density_uniform=int(c.sector_density_uniform), default_hdg_random=int(c.default_hdg_random))
+
     def state_dict(self):
         """Checkpoint: clones of every device tensor that carries simulator state (aircraft SoA, per-env records,
-        polygons, last outputs, the wind ground-speed state and the noise call counter's host mirror)."""
+        polygons, last outputs), the wind field with its ground-speed state, the observation-noise level and the noise
+        stream's call index, and the configuration the streams are keyed by (seed, env id offset, ...)."""
         sd = {k: v.clone() for k, v in self.t.items() if v is not None and k != "actions_staging"}
         if self._wind_t is not None:
-            sd["wind_gs"] = self._wind_t["gs"].clone()
+            sd["wind"] = {k: v.clone() for k, v in self._wind_t.items()}
+            sd["wind_meta"] = dict(self._wind_meta)
+        calls = C.c_uint32(0)
+        _lib.check(self._lib.bsg_get_noise_calls(self._h, C.byref(calls)))
+        sd["obs_noise"] = dict(sigma=float(self.obs_noise), calls=int(calls.value))
+        sd["config"] = self._config_key()
         return sd
 
     def load_state_dict(self, sd):
-        """Resume from ``state_dict()`` of an env built with the same configuration (same seed => same future draws)."""
+        """Resume from ``state_dict()``: the env continues bit for bit (same future scenario draws and noise stream),
+        also when loaded into a freshly built env.  The seed is taken from the checkpoint; any other difference between
+        the checkpoint's configuration and this env's raises."""
+        cfg = sd.get("config")
+        if cfg is not None:
+            mine = self._config_key()
+            diff = {k: (v, mine[k]) for k, v in cfg.items() if k != "seed" and mine[k] != v}
+            if diff:
+                raise ValueError(f"load_state_dict: checkpoint was taken from a different configuration {diff}")
+            if cfg["seed"] != mine["seed"]:
+                _lib.check(self._lib.bsg_set_seed(self._h, cfg["seed"]))
+                self.cfg.seed = cfg["seed"]
+        if "wind" in sd:
+            w, m = sd["wind"], sd["wind_meta"]
+            t = {k: v.clone() for k, v in w.items()}
+            self._install_wind(t, m["n_points"], m["n_alt"])
+        elif cfg is not None and self._wind_t is not None:
+            self.set_wind()
         for k, v in sd.items():
-            dst = self._wind_t["gs"] if k == "wind_gs" else self.t[k]
-            dst.copy_(v)
+            if k in self.t and self.t[k] is not None:
+                self.t[k].copy_(v)
+        if "obs_noise" in sd:
+            self.set_obs_noise(sd["obs_noise"]["sigma"])
+            _lib.check(self._lib.bsg_set_noise_calls(self._h, sd["obs_noise"]["calls"]))
 
     def load_state(self, e, lat, lon, alt, tas, hdg, vs, selspd, selalt, selvs, ap_trk, cas, ax=None,
                    lnav=None, iactwp=None, curlegdir=None, env_f64=None, env_i32=None, env_f32=None, poly=None):
-        """Injects a (reference / oracle) post-reset traffic state into env ``e`` (bsg_load_state of SURVEY 8b)."""
-        n, G = len(lat), self.slots
-        assert n <= G
-        dev = self.device
-        f32 = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float32), device=dev)
-        pos = torch.zeros((G, 2), dtype=torch.float64, device=dev)
-        pos[:n, 0] = torch.as_tensor(np.asarray(lat, dtype=np.float64), device=dev)
-        pos[:n, 1] = torch.as_tensor(np.asarray(lon, dtype=np.float64), device=dev)
-        kin = torch.zeros((G, 4), dtype=torch.float32, device=dev)
-        cmd = torch.zeros((G, 4), dtype=torch.float32, device=dev)
-        aux = torch.zeros((G, 4), dtype=torch.float32, device=dev)
-        for c, v in enumerate((alt, tas, hdg, vs)):
-            kin[:n, c] = f32(v)
-        for c, v in enumerate((selspd, selalt, selvs, ap_trk)):
-            cmd[:n, c] = f32(v)
-        aux[:n, 0] = f32(np.zeros(n) if ax is None else ax)
-        aux[:n, 1] = f32(np.full(n, -999.0) if curlegdir is None else curlegdir)
-        aux[:n, 2] = f32(cas)
-        fl = np.zeros(G, dtype=np.int32)
-        fl[:n] = _lib.FL_ALIVE
-        if lnav is not None:
-            fl[:n] |= np.where(np.asarray(lnav, dtype=bool), _lib.FL_LNAV, 0).astype(np.int32)
-        if iactwp is not None:
-            ia = np.maximum(np.asarray(iactwp, dtype=np.int32), 0)
-            fl[:n] |= (ia << _lib.FL_WPSHIFT) | np.where(ia >= 1, _lib.FL_LASTWP, 0).astype(np.int32)
-        self.t["pos"][e], self.t["kin"][e], self.t["cmd"][e], self.t["aux"][e] = pos, kin, cmd, aux
-        self.t["flags"][e] = torch.as_tensor(fl, device=dev)
-        for name, vals in (("env_f64", env_f64), ("env_i32", env_i32), ("env_f32", env_f32)):
-            if vals:
-                for idx, v in vals.items():
-                    self.t[name][e, idx] = v
+        """Injects a (reference / oracle) post-reset traffic state into env ``e`` through ``bsg_load_state``
+        (include/bsg.h).  ``env_f64`` / ``env_i32`` / ``env_f32`` are {index: value} patches of the env's
+        current records; ``poly`` replaces the polygon record (zero-padded)."""
+        n = len(lat)
+        assert n <= self.slots
+        keep = []
+
+        def arr(x, dt=np.float64):
+            if x is None:
+                return None
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=dt), (n,)))
+            keep.append(a)
+            return a.ctypes.data
+
+        def record(name, patch, dt):
+            if not patch:
+                return None
+            r = self.t[name][e].cpu().numpy().astype(dt)
+            for idx, v in patch.items():
+                r[idx] = v
+            r = np.ascontiguousarray(r)
+            keep.append(r)
+            return r.ctypes.data
+        st = _lib.AcState(
+            n=n, lat=arr(lat), lon=arr(lon), alt=arr(alt), tas=arr(tas), hdg=arr(hdg), vs=arr(vs), selspd=arr(selspd),
+            selalt=arr(selalt), selvs=arr(selvs), ap_trk=arr(ap_trk), cas=arr(cas), ax=arr(ax), curlegdir=arr(curlegdir),
+            swlnav=arr(None if lnav is None else np.asarray(lnav, dtype=bool), np.uint8),
+            iactwp=arr(iactwp, np.int32), env_f64=record("env_f64", env_f64, np.float64),
+            env_f32=record("env_f32", env_f32, np.float32), env_i32=record("env_i32", env_i32, np.int32))
         if poly is not None:
-            p = np.zeros(self.layout.poly_f64)
-            p[:len(poly)] = poly
-            self.t["poly"][e] = torch.as_tensor(p, device=dev)
+            pl = np.zeros(self.layout.poly_f64)
+            pl[:len(poly)] = poly
+            keep.append(pl)
+            st.poly = pl.ctypes.data
+        _lib.check(self._lib.bsg_load_state(self._h, int(e), C.byref(st), self._stream()))
 
     def close(self, **kwargs):
         if not self.closed and self._h:

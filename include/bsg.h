@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BSG_ABI_VERSION 3
+#define BSG_ABI_VERSION 4
 
 enum { BSG_OK = 0, BSG_EINVAL = -1, BSG_ECUDA = -2, BSG_ESTATE = -3, BSG_ENOMEM = -4 };
 
@@ -126,7 +126,7 @@ typedef struct bsg_handle bsg_handle;
 
 int bsg_abi_version(void);
 /* sizeof of the library's view of an interface structure (which: 0 bsg_config, 1 bsg_layout, 2 bsg_tensor_table,
- * 3 bsg_wind, 4 bsg_perf; anything else -1): a binding in another language checks its own declarations against it */
+ * 3 bsg_wind, 4 bsg_perf, 5 bsg_ac_state; anything else -1): a binding in another language checks its own declarations against it */
 int bsg_abi_struct_size(int which);
 const char *bsg_last_error(void);
 int bsg_device_count(void);
@@ -205,6 +205,31 @@ int bsg_set_wind(bsg_handle *h, const bsg_wind *w);
  * Gaussian noise N(0, sigma) per element, drawn from a Philox stream keyed by (seed, global env id, call index).
  * sigma = 0 switches it off.  One extra elementwise kernel per call while it is on. */
 int bsg_set_obs_noise(bsg_handle *h, float sigma);
+
+/* The observation-noise stream's call index (number of reset / step calls made with noise on): part of a checkpoint,
+ * because the stream is keyed by (seed, global env id, call index).  bsg_set_noise_calls restores it. */
+int bsg_get_noise_calls(bsg_handle *h, uint32_t *out);
+int bsg_set_noise_calls(bsg_handle *h, uint32_t calls);
+
+/* replaces: the state a reference env holds after Env.reset() -- bs.traf.* arrays after bs.traf.cre / creconfs
+ * (e.g. horizontal_cr_env.py:85-101) plus the env's own members (waypoint, polygon, counters) -- injected from HOST
+ * arrays into env `env` of the batch, so a parity test can start the device simulator from a reference / oracle
+ * post-reset state.  Arrays hold s->n aircraft (n <= layout.slots; the remaining slots are cleared).  NULL optional
+ * arrays take the stated default; env_f64 / env_f32 / env_i32 / poly are WHOLE per-env records (layout.env_f64 ...
+ * layout.poly_f64 elements) or NULL = left as they are.  Synchronises `stream` before returning. */
+typedef struct bsg_ac_state {
+    int32_t n;
+    const double *lat, *lon;                        /* bs.traf.lat / lon [deg]                       */
+    const double *alt, *tas, *hdg, *vs;             /* bs.traf.alt / tas / hdg / vs                  */
+    const double *selspd, *selalt, *selvs, *ap_trk; /* bs.traf.selspd / selalt / selvs, ap.trk       */
+    const double *cas;                              /* bs.traf.cas                                   */
+    const double *ax;                               /* bs.traf.ax                    (NULL: 0)       */
+    const double *curlegdir;                        /* actwp.curlegdir               (NULL: -999)    */
+    const uint8_t *swlnav;                          /* bs.traf.swlnav                (NULL: off)     */
+    const int32_t *iactwp;                          /* route.iactwp, >= 1 = last wp  (NULL: 0)       */
+    const double *env_f64; const float *env_f32; const int32_t *env_i32; const double *poly;
+} bsg_ac_state;
+int bsg_load_state(bsg_handle *h, int32_t env, const bsg_ac_state *s, void *stream);
 
 /* replaces: n_sub x bs.sim.step() alone (Traffic.update kinematics + autopilot, no obs/reward);
  * used by the trajectory parity tests. */

@@ -288,6 +288,36 @@ def test_scalar_env_api(cuda):
     env.close()
 
 
+@pytest.mark.parametrize("env_id", ["DescentEnv-v0", "PlanWaypointEnv-v0", "HorizontalCREnv-v0", "VerticalCREnv-v0",
+                                    "SectorCREnv-v0", "StaticObstacleEnv-v0", "MergeEnv-v0"])
+def test_gym_make_every_registered_id(cuda, env_id):
+    """bluesky_gym/__init__.py:6-46: every registered id is constructible through ``gym.make``, resets, and steps to the
+    end of an episode (termination or the registration's TimeLimit) with observations inside the declared space."""
+    import bluesky_gym
+    import bluesky_gym.envs  # noqa: F401  (scripts/multi_processing_example.py:17)
+    from bluesky_gym_sasha_b200.spec import SPECS
+    bluesky_gym.register_envs()
+    env = bluesky_gym.make(env_id, render_mode=None)
+    obs, info = env.reset()
+    space = env.observation_space
+    assert list(obs.keys()) == list(space.keys())
+    for k, v in obs.items():
+        assert v.dtype == np.float64 and v.shape == space[k].shape, (env_id, k)
+    assert set(info) >= set(SPECS[env_id].info_keys)
+    rng = np.random.default_rng(0)
+    cap = SPECS[env_id].max_episode_steps
+    for t in range(cap + 1):
+        obs, r, term, trunc, info = env.step(rng.uniform(-1, 1, env.action_space.shape))
+        assert isinstance(r, float) and isinstance(term, bool) and isinstance(trunc, bool)
+        assert all(np.all(np.isfinite(v)) for v in obs.values())
+        if term or trunc:
+            break
+    assert (term or trunc) and t < cap
+    obs2, _ = env.reset()                       # a second episode starts from a new scenario
+    assert list(obs2.keys()) == list(space.keys())
+    env.close()
+
+
 def test_sb3_adapter_contract(cuda):
     """terminal_observation / TimeLimit.truncated / per-env info dicts (bluesky_gym/utils/logger.py:18-33)."""
     from bluesky_gym_sasha_b200.sb3_vec_env import BlueSkySB3VecEnv
@@ -331,6 +361,42 @@ def test_checkpoint_resume_is_bit_exact(cuda):
     v.close()
 
 
+def test_checkpoint_resumes_in_a_fresh_env_with_noise_and_wind(cuda):
+    """state_dict() carries what the streams are keyed by: seed, the noise call index, the wind tables and the wind
+    ground-speed state.  Loaded into a FRESHLY BUILT env (another seed, no noise, no wind yet) the rollout continues
+    bit for bit; a checkpoint from another configuration is refused."""
+    import torch
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    E = 32
+    wind = dict(lat=np.array([51.9, 52.1]), lon=np.array([3.9, 4.1]), vnorth=np.array([[12.0, -6.0]]), veast=np.array([[4.0, 9.0]]))
+    kw = dict(n_intruders=12, cd_enabled=True, autoreset_mode="same_step", max_episode_steps=6, init_alt=3000.0)
+    v = BlueSkyVectorEnv("HorizontalCREnv-v0", E, seed=21, obs_noise=0.05, wind=wind, **kw)
+    v.reset_torch()
+    g = torch.Generator(device="cpu").manual_seed(1)
+    acts = (torch.rand((20, E, 1), generator=g) * 2 - 1).cuda()
+    for i in range(5):
+        v.step_torch(acts[i])
+    sd = v.state_dict()
+    assert sd["obs_noise"] == dict(sigma=pytest.approx(0.05), calls=6) and sd["config"]["seed"] == 21
+    ref = []
+    for i in range(5, 20):
+        o, r, te, tr = v.step_torch(acts[i])
+        ref.append((v.t["obs"].clone(), r.clone(), te.clone(), tr.clone()))
+    w = BlueSkyVectorEnv("HorizontalCREnv-v0", E, seed=99, **kw)          # fresh handle: other seed, no noise, no wind
+    w.reset_torch()
+    w.load_state_dict(sd)
+    for i in range(5, 20):
+        o, r, te, tr = w.step_torch(acts[i])
+        assert torch.equal(w.t["obs"], ref[i - 5][0]) and torch.equal(r, ref[i - 5][1]), i
+        assert torch.equal(te, ref[i - 5][2]) and torch.equal(tr, ref[i - 5][3])
+    assert any(bool(x[3].any()) for x in ref)
+    other = BlueSkyVectorEnv("HorizontalCREnv-v0", E, seed=21, n_intruders=5)
+    with pytest.raises(ValueError, match="different configuration"):
+        other.load_state_dict(sd)
+    for x in (v, w, other):
+        x.close()
+
+
 def test_static_obstacle_scalar_env_reset_flags(cuda):
     """reset_flags() is surfaced (0 for a normal scenario); the scalar env turns flag 4 into the reference's Exception."""
     import bluesky_gym
@@ -355,8 +421,29 @@ def test_reset_seed_rekeys_streams(cuda):
         assert np.array_equal(oa[k], ob[k]), k
     o2, _ = a.reset()                                        # next episode of the same stream differs
     assert not np.array_equal(o2["x_r"], oa["x_r"])
+    # the contract holds on a used env too: after several episodes, and twice in a row (the episode counter and the
+    # noise call index are part of the stream key and restart with the seed)
+    for _ in range(3):
+        a.reset()
+    for _ in range(2):
+        o3, _ = a.reset(seed=77)
+        for k in oa:
+            assert np.array_equal(o3[k], ob[k]), k
     a.close()
     b.close()
+    n1 = BlueSkyVectorEnv("DescentEnv-v0", 8, seed=1, obs_noise=0.1)
+    n1.reset()
+    n1.step(np.zeros((8, 1)))
+    first, _ = n1.reset(seed=5)
+    n1.step(np.zeros((8, 1)))
+    again, _ = n1.reset(seed=5)
+    for k in first:
+        assert np.array_equal(first[k], again[k]), k          # same noise draws as well
+    n1.step_async(np.zeros((8, 1)))
+    with pytest.raises(_lib.BsgError):
+        n1.reset()                                            # a step is in flight
+    n1.step_wait()
+    n1.close()
 
 
 @pytest.mark.parametrize("env_id,kw", [("DescentEnv-v0", {}), ("PlanWaypointEnv-v0", {}), ("HorizontalCREnv-v0", dict(n_intruders=20, cd_enabled=True)),

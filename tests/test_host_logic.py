@@ -25,6 +25,55 @@ def test_all_reference_ids_are_accelerated():
     assert NOT_ACCELERATED == () and len(SPECS) == 7
 
 
+def test_every_registered_entry_point_resolves():
+    """Every id of bluesky_gym/__init__.py:6-46 resolves to a class: through the registered entry point, through
+    ``import bluesky_gym.envs`` (scripts/multi_processing_example.py:17) and through the reference's own module paths
+    (``bluesky_gym.envs.<name>_env:<Class>``)."""
+    import importlib
+
+    import bluesky_gym
+    import bluesky_gym.envs
+    from bluesky_gym_sasha_b200 import envs as penvs
+    from bluesky_gym_sasha_b200.gym_compat import Env, registry
+    from bluesky_gym_sasha_b200.spec import SPECS
+    bluesky_gym.register_envs()
+    ref_paths = {"DescentEnv-v0": "bluesky_gym.envs.descent_env:DescentEnv",
+                 "PlanWaypointEnv-v0": "bluesky_gym.envs.plan_waypoint_env:PlanWaypointEnv",
+                 "HorizontalCREnv-v0": "bluesky_gym.envs.horizontal_cr_env:HorizontalCREnv",
+                 "VerticalCREnv-v0": "bluesky_gym.envs.vertical_cr_env:VerticalCREnv",
+                 "SectorCREnv-v0": "bluesky_gym.envs.sector_cr_env:SectorCREnv",
+                 "StaticObstacleEnv-v0": "bluesky_gym.envs.static_obstacle_env:StaticObstacleEnv",
+                 "MergeEnv-v0": "bluesky_gym.envs.merge_env:MergeEnv"}
+    assert set(ref_paths) == set(SPECS)
+    for env_id, spec in SPECS.items():
+        ep = registry[env_id].entry_point
+        for path in (ep, ref_paths[env_id]):
+            mod, cls = path.split(":")
+            k = getattr(importlib.import_module(mod), cls)
+            assert issubclass(k, Env) and k.ENV_ID == env_id, (env_id, path)
+        assert getattr(bluesky_gym.envs, spec.entry_point.split(":")[1]).ENV_ID == env_id
+    for name in penvs.__all__:
+        assert hasattr(penvs, name), name
+    from bluesky_gym.utils import logger          # scripts/multi_processing_example.py:19
+    assert hasattr(logger, "CSVLoggerCallback")
+
+
+def test_csv_logger_callback_rows(tmp_path):
+    """bluesky_gym/utils/logger.py:15-35: header from infos[0]'s keys, one row per finished episode of env 0."""
+    import csv
+
+    from bluesky_gym.utils.logger import CSVLoggerCallback
+    cb = CSVLoggerCallback(str(tmp_path), "log.csv")
+    for t in range(1, 7):
+        cb.num_timesteps = t
+        cb.locals = {"infos": [{"total_reward": -float(t), "total_intrusions": t % 2}, {"total_reward": 9.0}],
+                     "dones": [t % 3 == 0, True]}
+        assert cb._on_step() is True
+    rows = list(csv.reader(open(tmp_path / "log.csv")))
+    assert rows[0] == ["timesteps", "episodes", "total_reward", "total_intrusions"]
+    assert rows[1:] == [["3", "1", "-3.0", "1"], ["6", "2", "-6.0", "0"]]
+
+
 def test_obs_layout_matches_reference_declarations():
     from bluesky_gym_sasha_b200.spec import SPECS
     lay, dim = SPECS["HorizontalCREnv-v0"].obs_layout(5)

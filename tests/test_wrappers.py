@@ -67,6 +67,10 @@ def test_noisy_observation_scalar_env_follows_reference_draws(cuda):
         np.testing.assert_allclose(o[k], oc[k] + np.random.normal(0, 0.3, size=oc[k].shape))
     o, r, te, tr, info = env.step(np.array([0.1]))
     assert set(o) == set(oc) and isinstance(r, float)
+    from bluesky_gym_sasha_b200 import gym_compat
+    assert isinstance(env, gym_compat.Wrapper) and isinstance(env, gym_compat.Env)      # what Monitor / check_env need
+    assert env.observation_space is ref.observation_space or list(env.observation_space.keys()) == list(ref.observation_space.keys())
+    assert env.unwrapped.ENV_ID == "DescentEnv-v0"
     env.close()
     ref.close()
 
@@ -85,6 +89,8 @@ def test_wind_field_wrapper_api(cuda):
     env = bluesky_gym.make("MergeEnv-v0")
     windy = WindFieldWrapper(env, augment_obs=True, **WIND4)
     assert "wind_u" in windy.observation_space.spaces and windy.observation_space["wind_v"].shape == (1,)
+    from bluesky_gym_sasha_b200 import gym_compat
+    assert isinstance(windy, gym_compat.Wrapper) and list(windy.observation_space.keys())[-2:] == ["wind_u", "wind_v"]
     obs, info = windy.reset()
     assert list(obs)[-2:] == ["wind_u", "wind_v"] and obs["wind_u"].dtype == np.float64
     tas0 = obs["airspeed"][0]
