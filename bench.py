@@ -77,16 +77,98 @@ def cpu_baseline(budget_s=12.0, cores=None):
                        f"one oracle env per process, {cores} processes")
 
 
+def _real_reference_env(seed):
+    """The UNMODIFIED reference env (real bluesky-simulator + gymnasium from baseline/_ref) in the bench's configuration:
+    20 intruders (module constant, horizontal_cr_env.py:17) and ASAS switched on."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    import bluesky as bs
+    import gymnasium as gym
+    import bluesky_gym
+    import bluesky_gym.envs.horizontal_cr_env as ref_env
+    ref_env.NUM_INTRUDERS = N_INTRUDERS
+    bluesky_gym.register_envs()
+    env = gym.make("HorizontalCREnv-v0", render_mode=None)
+
+    class Shim:
+        def reset(self):
+            out = env.reset(seed=seed)
+            bs.stack.stack("ASAS ON")
+            return out
+
+        def step(self, a):
+            o, r, term, trunc, i = env.step(a)
+            return o, r, term or trunc, False, i
+    return Shim()
+
+
+def _ref_arm_worker(args):
+    """One host core of the reference arm: `n_warm` untimed + `n_timed` timed env steps of one env (the oracle port, or the
+    real reference stack when `real`)."""
+    seed, n_warm, n_timed, real = args
+    sys.path.insert(0, ROOT)
+    if real:
+        env = _real_reference_env(seed)
+    else:
+        from oracle import envs as oenvs
+        np.random.seed(seed)
+        env = oenvs.HorizontalCREnv(n_intruders=N_INTRUDERS, cd_enabled=True)
+    env.reset()
+    rng = np.random.default_rng(seed)
+    ep, t0 = 0, 0.0
+    for k in range(n_warm + n_timed):
+        if k == n_warm:
+            t0 = time.perf_counter()
+        _, _, term, _, _ = env.step(rng.uniform(-1, 1, 1))
+        ep += 1
+        if term or ep >= 300:
+            env.reset()
+            ep = 0
+    return n_timed, time.perf_counter() - t0
+
+
+def probe_real_reference():
+    """Is the reference's own stack importable from baseline/_ref (driver-provided on some pods)?  Returns None or a
+    one-line reason why not."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(ref):
+        return "baseline/_ref absent"
+    code = ("import sys; sys.path.insert(0, %r); import bluesky, gymnasium, bluesky_gym, bluesky_gym.envs.horizontal_cr_env" % ref)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    return None if p.returncode == 0 else (p.stderr.strip().splitlines() or ["import failed"])[-1][:200]
+
+
 def run_reference(args):
+    """Reference arm of the bench contract: the reference's CPU step loop on every host core.  One "step" of this arm = every
+    core advances its own env by `per_step` env steps; W warm-up steps, then exactly K timed ones; value = env steps of all
+    cores / the slowest core's wall time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    budget = max(2.0, min(20.0, 2.0 * args.steps))
-    cb = cpu_baseline(budget_s=budget)
+    cores = os.cpu_count() or 1
+    why_not = probe_real_reference()
+    real = why_not is None
+    K, W = max(1, args.steps), max(0, args.warmup)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        try:
+            cal = pool.map(_ref_arm_worker, [(7, 1, 4, real)])[0]           # calibration: seconds per env step on one core
+        except Exception as ex:
+            real, why_not = False, repr(ex)[:200]
+            cal = pool.map(_ref_arm_worker, [(7, 1, 4, False)])[0]
+        t_step = cal[1] / cal[0]
+        per_step = int(min(64, max(1, round(12.0 / (K * t_step)))))         # ~12 s of timed work per core
+        res = pool.map(_ref_arm_worker, [(1000 + i, W * per_step, K * per_step, real) for i in range(cores)])
+    steps, wall = sum(r[0] for r in res), max(r[1] for r in res)
+    cb = dict(value=steps / wall, unit="env-steps/s", cores=cores, kind="reference" if real else "port",
+              sample=f"{steps} env steps of HorizontalCREnv-v0 (20 intruders, CD on) in {wall:.1f} s: {cores} processes x {K} steps x "
+                     f"{per_step} env steps, " + ("the reference's own env on real BlueSky (baseline/_ref)" if real else
+                                                  "one oracle env per process"))
+    if not real:
+        cb["real_reference"] = f"not used: {why_not}"
     line = {"impl": "reference", "metric": "env_steps_per_sec", "value": cb["value"], "unit": "env-steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * ENVS_PER_GPU * args.gpus / cb["value"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * wall / K,
+            "step_definition": f"every host core advances its env by {per_step} env steps ({cores * per_step} env steps per step)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.gpus), "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_OUT, flush=True)
@@ -244,7 +326,8 @@ def run_b200(args):
     h2d = E * L.act_dim * 4
     d2h = venv._out_bytes          # the mirrored head of the output block: obs, reward, info, flags, terminal-obs window
     e2e = {"value": E * world * K / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "api": "BlueSkyVectorEnv.step, default arguments (numpy in; fresh float32 numpy arrays out; bsg_step_host_block)"}
+           "api": "BlueSkyVectorEnv.step, default arguments (numpy in; fresh float32 numpy arrays out; bsg_step_host_copy: one H2D, "
+                  "one launch, one D2H of the output block, pooled host copy into the fresh array)"}
     # same call with copy=False (views of two rotating pinned buffers instead of fresh copies), for context
     venv.copy = False
     barrier()
@@ -254,9 +337,28 @@ def run_b200(args):
     barrier()
     e2e["value_copy_false"] = E * world * K / max_over_ranks(time.perf_counter() - t0)
     venv.copy = True
+    # same call returning float64 observations (the dtype the reference's spaces declare; what the scalar gym.make envs return)
+    venv.obs_dtype = np.dtype(np.float64)
+    for i in range(3):
+        venv.step(host_actions[i % K])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        venv.step(host_actions[i])
+    barrier()
+    e2e["value_f64"] = E * world * K / max_over_ranks(time.perf_counter() - t0)
+    venv.obs_dtype = np.dtype(np.float32)
 
     # single airspace, rows sharded over the ranks after one NCCL all-gather (BASELINE configs[4])
     cd_sharded = bench_cd_sharded(torch, dist, dev, StateBasedCD, world, rank, max_over_ranks, barrier) if world > 1 else None
+
+    # the other BASELINE configs: every rank steps its shard (env-sharded like the headline; max over ranks)
+    legs = {name: bench_env_leg(torch, dev, BlueSkyVectorEnv, env_id, E_, kw, world, rank, max_over_ranks, barrier)
+            for name, env_id, E_, kw in CONFIG_LEGS}
+    other = None
+    if world == 1:
+        other = {name: bench_env_leg(torch, dev, BlueSkyVectorEnv, env_id, E_, kw, 1, 0, max_over_ranks, barrier)
+                 for name, env_id, E_, kw in CONTEXT_LEGS}
 
     peaks = {}
     try:
@@ -288,17 +390,24 @@ def run_b200(args):
                         "bytes_per_env_step": BYTES_PER_ENV_STEP}}
         # CD at N = 100k on this GPU (BASELINE configs[4], single-GPU share)
         cd = bench_cd(torch, dev, StateBasedCD, fp32)
-        other = bench_other_envs(torch, dev, BlueSkyVectorEnv) if world == 1 else None
         cb = None if (args.skip_cpu or world > 1) else cpu_baseline(budget_s=10.0)
+        # compact headline of the second BASELINE metric, early in the line (the full records follow at the end)
+        cd_head = {"n_aircraft": cd["n_aircraft"], "ordered_pairs_per_s": cd["ordered_pairs_per_s"], "ms": cd["ms"],
+                   "frac_of_fp32_peak": cd["roofline"]["frac"], "form": "every ordered pair, 1 GPU"}
+        if cd_sharded is not None:
+            cd_sharded["roofline_frac_per_gpu"] = cd_sharded["ordered_pairs_per_s"] * F_PAIR / world / fp32
+            cd_head.update({"sharded_ordered_pairs_per_s": cd_sharded["ordered_pairs_per_s"], "sharded_ms": cd_sharded["ms"],
+                            "sharded_frac_of_fp32_peak_per_gpu": cd_sharded["roofline_frac_per_gpu"],
+                            "sharded_form": f"rows over {world} GPUs after one NCCL all-gather, every ordered pair"})
         line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (lat/lon f64)", "data": "synthetic", "config": workload_config(world),
-                "value_l2_warm": warm_value, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+                "value_l2_warm": warm_value, "e2e": e2e, "gpu_launches": launches, "cd_pairs_headline": cd_head,
+                "baseline_configs": legs, "roofline": roof,
                 "cpu_baseline": cb, "clocks": clk.summary(), "cd_pairs": cd}
         if other is not None:
             line["other_envs"] = other
         if cd_sharded is not None:
-            cd_sharded["roofline_frac_per_gpu"] = cd_sharded["ordered_pairs_per_s"] * F_PAIR / world / fp32
             line["cd_pairs_sharded"] = cd_sharded
     if world > 1:
         dist.barrier()
@@ -307,32 +416,36 @@ def run_b200(args):
         print(json.dumps(line), file=_OUT, flush=True)
 
 
-def bench_other_envs(torch, dev, BlueSkyVectorEnv, steps=60):
-    """Device time per batched step of the other BASELINE configs on this GPU (context only; not the headline)."""
-    out = {}
+def bench_env_leg(torch, dev, BlueSkyVectorEnv, env_id, E, kw, world, rank, max_over_ranks, barrier, steps=60):
+    """Device time per batched step of one env configuration, E envs on EVERY rank (weak scaling, global env ids), L2
+    flushed between steps, max over ranks; returns whole-job env-steps/s."""
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
-    for name, env_id, E, kw in (("SectorCREnv-v0 (configs[2] per-GPU share)", "SectorCREnv-v0", 8192, dict(cd_enabled=True)),
-                                ("MergeEnv-v0 (configs[3])", "MergeEnv-v0", 4096, dict(cd_enabled=True)),
-                                ("HorizontalCREnv-v0 configs[1] at 3000 m instead of the reference's 0 m (SURVEY 8d variant)", "HorizontalCREnv-v0", 4096,
-                                 dict(cd_enabled=True, n_intruders=20, init_alt=3000.0)),
-                                ("DescentEnv-v0 (configs[0], batched)", "DescentEnv-v0", 65536, {}),
-                                ("HorizontalCREnv-v0 reference default (5 intruders, no CD)", "HorizontalCREnv-v0", 65536, {})):
-        v = BlueSkyVectorEnv(env_id, E, device=dev.index, seed=0, autoreset_mode="same_step", **kw)
-        v.reset_torch()
-        a = torch.rand((steps + 5, E, v.layout.act_dim), device=dev) * 2.0 - 1.0
-        for i in range(5):
-            v.step_torch(a[i])
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for i in range(steps):
-            flush.fill_(float(i))
-            ev[i][0].record()
-            v.step_torch(a[5 + i])
-            ev[i][1].record()
-        torch.cuda.synchronize(dev)
-        ms = sum(x.elapsed_time(y) for x, y in ev) / steps
-        out[name] = {"envs": E, "ms_per_step": ms, "env_steps_per_s": E / ms * 1e3}
-        v.close()
-    return out
+    v = BlueSkyVectorEnv(env_id, E, device=dev.index, seed=0, autoreset_mode="same_step", env_id_offset=rank * E, **kw)
+    v.reset_torch()
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    a = torch.rand((steps + 5, E, v.layout.act_dim), device=dev, generator=g) * 2.0 - 1.0
+    for i in range(5):
+        v.step_torch(a[i])
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        flush.fill_(float(i))
+        ev[i][0].record()
+        v.step_torch(a[5 + i])
+        ev[i][1].record()
+    barrier()
+    t = max_over_ranks(sum(x.elapsed_time(y) for x, y in ev) * 1e-3)
+    v.close()
+    return {"envs_per_gpu": E, "envs_total": E * world, "ms_per_step": 1e3 * t / steps, "env_steps_per_s": E * world * steps / t}
+
+
+# BASELINE configs[2] and [3] (run at every N), then context-only variants (single GPU)
+CONFIG_LEGS = (("configs[2] SectorCREnv-v0, 8192 envs per GPU (65 536 over 8), CD on", "SectorCREnv-v0", 8192, dict(cd_enabled=True)),
+               ("configs[3] MergeEnv-v0, 4096 envs per GPU, FMS-guided intruders, CD on", "MergeEnv-v0", 4096, dict(cd_enabled=True)))
+CONTEXT_LEGS = (("HorizontalCREnv-v0 configs[1] at 3000 m instead of the reference's 0 m (SURVEY 8d variant)", "HorizontalCREnv-v0", 4096,
+                 dict(cd_enabled=True, n_intruders=20, init_alt=3000.0)),
+                ("DescentEnv-v0 (configs[0], batched)", "DescentEnv-v0", 65536, {}),
+                ("HorizontalCREnv-v0 reference default (5 intruders, no CD)", "HorizontalCREnv-v0", 65536, {}))
 
 
 def C_double_probe(lib, device):
@@ -414,6 +527,8 @@ def bench_cd(torch, dev, StateBasedCD, fp32_peak, n=CD_N, reps=5):
     res["forms_agree"] = all(res[k]["n_conf"] == res["n_conf"] and res[k]["n_los"] == res["n_los"] for k in ("symmetric", "culled_symmetric")) \
         and int(outc["npairs"][0]) == res["n_conf"] and int(outc["npairs"][1]) == res["n_los"]
     res["culled"] = {"ordered_pairs_per_s": pairs / bestc, "ms": bestc * 1e3, "ms_sort_and_pack": prep * 1e3,
+                     "ms_incl_sort_and_pack": bestc * 1e3 + prep * 1e3,
+                     "ordered_pairs_per_s_incl_sort_and_pack": pairs / (bestc + prep),
                      "executed_fraction": kept / float(n_tiles * n_tiles), "n_conf": int(outc["npairs"][0]),
                      "n_los": int(outc["npairs"][1]),
                      "note": "bsg_cd_detect_culled on strip-sorted records: tile pairs out of reach (rpz + (v_a+v_b)*300 s) skipped"}

@@ -18,7 +18,8 @@ CD_LON_WRAP, CD_SYMMETRIC, CD_CULL, CD_ALLTILES = 1, 2, 4, 8
 F64_WPT_LAT, F64_WPT_LON, F64_TARGET_ALT, F64_POLY_AREA, F64_WPTS, F64_COUNT = 0, 1, 2, 3, 4, 16
 F32_TOTAL_REWARD, F32_DRIFT_SUM, F32_FINAL_ALT, F32_LAST_HDG, F32_LAST_WDIST, F32_LAST_DRIFT, F32_COUNT = 0, 1, 2, 3, 4, 5, 8
 (I32_STEP, I32_EPISODE, I32_SIMK, I32_WPT_REACH, I32_DRIFT_N, I32_INTRUSIONS, I32_NUM_AC, I32_NVERT,
- I32_NEEDS_RESET, I32_FAF, I32_NCONF, I32_NLOS, I32_RESET_FLAGS) = range(13)
+ I32_NEEDS_RESET, I32_FAF, I32_NCONF, I32_NLOS, I32_RESET_FLAGS, I32_NPAIRS) = range(14)
+PAIR_CONF_IJ, PAIR_CONF_JI, PAIR_LOS, PAIR_ATTR_COUNT = 1 << 16, 1 << 17, 1 << 18, 6
 I32_COUNT = 16
 FL_ALIVE, FL_LNAV, FL_LASTWP, FL_WPSHIFT = 1, 2, 4, 8
 
@@ -34,7 +35,7 @@ class Config(C.Structure):
                 ("default_hdg_random", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64),
                 ("env_id_offset", C.c_int64), ("rpz", C.c_float), ("hpz", C.c_float),
                 ("dtlookahead", C.c_float), ("perf", Perf), ("wind_obs", C.c_int32),
-                ("sector_density_uniform", C.c_int32), ("init_alt", C.c_float)]
+                ("sector_density_uniform", C.c_int32), ("init_alt", C.c_float), ("cd_pair_cap", C.c_int32)]
 
 
 class Wind(C.Structure):
@@ -49,6 +50,14 @@ class AcState(C.Structure):
         "swlnav", "iactwp", "env_f64", "env_f32", "env_i32", "poly")]
 
 
+class CdLists(C.Structure):
+    _fields_ = [("d_conf_pairs", C.c_void_p), ("d_conf_attr", C.c_void_p), ("conf_cap", C.c_int64),
+                ("d_los_pairs", C.c_void_p), ("los_cap", C.c_int64), ("d_npairs", C.c_void_p)]
+
+
+CD_ATTR = ("qdr", "dist", "dcpa", "tcpa", "tinconf")          # BSG_CD_ATTR_* columns of d_conf_attr
+
+
 class Layout(C.Structure):
     _fields_ = [("slots", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("info_dim", C.c_int32),
                 ("n_sub", C.c_int32), ("env_f64", C.c_int32), ("env_f32", C.c_int32), ("env_i32", C.c_int32),
@@ -56,7 +65,8 @@ class Layout(C.Structure):
 
 
 TENSOR_FIELDS = ("pos", "kin", "cmd", "aux", "flags", "tcpamax", "inconf", "env_f64", "env_f32", "env_i32",
-                 "poly", "obs", "final_obs", "final_ids", "final_count", "reward", "terminated", "truncated", "info", "actions_staging")
+                 "poly", "obs", "final_obs", "final_ids", "final_count", "reward", "terminated", "truncated", "info", "actions_staging",
+                 "cd_pairs", "cd_attr")
 
 
 class TensorTable(C.Structure):
@@ -123,14 +133,14 @@ def load():
     lib.bsg_cd_padded.argtypes = [i64]
     lib.bsg_cd_padded.restype = i64
     lib.bsg_cd_pack.argtypes = [vp, vp, vp, vp, vp, vp, i64, f64, f64, vp, vp]
-    lib.bsg_cd_detect.argtypes = [vp, i64, i64, i64, f32, f32, f32, u32, vp, vp, vp, vp, vp, i64, vp, vp]
+    lib.bsg_cd_detect.argtypes = [vp, i64, i64, i64, f32, f32, f32, u32, vp, vp, vp, vp, C.POINTER(CdLists), vp]
     if hasattr(lib, "bsg_cd_detect_culled"):
         lib.bsg_cd_cull_workspace.argtypes = [i64, i64]
         lib.bsg_cd_cull_workspace.restype = i64
-        lib.bsg_cd_detect_culled.argtypes = [vp, i64, i64, i64, f32, f32, f32, u32, vp, vp, vp, vp, vp, i64, vp, vp, i64, vp]
+        lib.bsg_cd_detect_culled.argtypes = [vp, i64, i64, i64, f32, f32, f32, u32, vp, vp, vp, vp, C.POINTER(CdLists), vp, i64, vp]
         lib.bsg_cd_detect_culled.restype = C.c_int
     if hasattr(lib, "bsg_cd_detect_peers"):
-        lib.bsg_cd_detect_peers.argtypes = [C.POINTER(vp), i32, i32, i64, f32, f32, f32, u32, vp, vp, vp, vp, vp, i64, vp, vp, i64, vp]
+        lib.bsg_cd_detect_peers.argtypes = [C.POINTER(vp), i32, i32, i64, f32, f32, f32, u32, vp, vp, vp, vp, C.POINTER(CdLists), vp, i64, vp]
         lib.bsg_cd_detect_peers.restype = C.c_int
     lib.bsg_probe_fp32.argtypes = [i32, C.POINTER(f64)]
     for name in ("bsg_query_layout", "bsg_create", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy",
@@ -139,7 +149,7 @@ def load():
     if hasattr(lib, "bsg_abi_struct_size"):     # (absent only in older A/B builds loaded through BSG_B200_LIB)
         lib.bsg_abi_struct_size.argtypes = [C.c_int]
         lib.bsg_abi_struct_size.restype = C.c_int
-        for which, st in enumerate((Config, Layout, TensorTable, Wind, Perf, AcState)):
+        for which, st in enumerate((Config, Layout, TensorTable, Wind, Perf, AcState, CdLists)):
             if lib.bsg_abi_struct_size(which) != C.sizeof(st):
                 raise BsgError(f"{LIB_PATH}: sizeof({st.__name__}) is {lib.bsg_abi_struct_size(which)} in the library, "
                                f"{C.sizeof(st)} in bluesky_gym_sasha_b200/_lib.py (include/bsg.h changed: rebuild / update the binding)")

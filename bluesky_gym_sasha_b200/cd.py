@@ -1,7 +1,7 @@
 """StateBasedCD -- single-airspace state-based conflict detection on the GPU (kernel K2).
 
 Interface mirrored: ``StateBased.detect(ownship, intruder, rpz, hpz, dtlookahead)`` of upstream BlueSky
-(restated in oracle/statebased.py) -> ``confpairs, lospairs, inconf, tcpamax, ...``.  The reference
+(restated in oracle/statebased.py) -> ``confpairs, lospairs, inconf, tcpamax, qdr, dist, dcpa, tcpa, tinconf``.  The reference
 never switches ASAS on (merge_env.py:157 issues only ``reso off``); BASELINE.json's north_star adds it.
 Inputs are float64 aircraft state (degrees, m/s, m) as numpy arrays or CUDA tensors; the work is done by
 ``bsg_cd_pack`` + ``bsg_cd_detect`` (include/bsg.h).  Multi-GPU: rows are block-sharded over ranks after
@@ -22,13 +22,15 @@ def _ptr(t):
 
 
 class StateBasedCD:
-    def __init__(self, device=0, rpz=5.0 * NM, hpz=1000.0 * FT, dtlookahead=300.0, pair_capacity=1 << 22):
+    def __init__(self, device=0, rpz=5.0 * NM, hpz=1000.0 * FT, dtlookahead=300.0, pair_capacity=1 << 22,
+                 los_capacity=None):
         if not torch.cuda.is_available():
             raise _lib.BsgError("StateBasedCD needs a CUDA device: there is no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device("cuda", device)
         self.rpz, self.hpz, self.dtlookahead = float(rpz), float(hpz), float(dtlookahead)
         self.pair_capacity = int(pair_capacity)
+        self.los_capacity = int(pair_capacity if los_capacity is None else los_capacity)
         self.gpu_launches = 0
         self._buf = {}
 
@@ -61,8 +63,21 @@ class StateBasedCD:
         return rec, n
 
     # ---------------------------------------------------------------- detection on packed records
-    def detect_packed(self, rec, n_all, row0=0, n_rows=None, lon_wrap=False, want_pairs=True, cull=False, symmetric=False):
-        """Rows [row0, row0+n_rows) x all n_all columns.  Asynchronous; returns device tensors.
+    def _lists(self, want_pairs, want_attr=True):
+        """Device pair lists of one detection (include/bsg.h::bsg_cd_lists) and the ctypes view handed to the library."""
+        npairs = self._get("npairs", (2,), torch.int64)
+        pairs = self._get("pairs", (max(self.pair_capacity, 1), 2), torch.int32) if want_pairs else None
+        attr = self._get("attr", (max(self.pair_capacity, 1), len(_lib.CD_ATTR)), torch.float32) if want_pairs and want_attr else None
+        los = self._get("lospairs", (max(self.los_capacity, 1), 2), torch.int32) if want_pairs else None
+        lists = _lib.CdLists(d_conf_pairs=_ptr(pairs), d_conf_attr=_ptr(attr), conf_cap=self.pair_capacity if want_pairs else 0,
+                             d_los_pairs=_ptr(los), los_cap=self.los_capacity if want_pairs else 0, d_npairs=_ptr(npairs))
+        return lists, dict(pairs=pairs, attr=attr, lospairs=los, npairs=npairs)
+
+    def detect_packed(self, rec, n_all, row0=0, n_rows=None, lon_wrap=False, want_pairs=True, cull=False, symmetric=False,
+                      want_attr=True):
+        """Rows [row0, row0+n_rows) x all n_all columns.  Asynchronous; returns device tensors: per-row ``nconf_row``,
+        ``nlos_row``, ``tcpamax``, ``inconf``; ``npairs`` = (conflicts, LoS pairs) found; with ``want_pairs`` the lists
+        ``pairs`` [cap, 2] (+ ``attr`` [cap, 5] = qdr, dist, dcpa, tcpa, tinconf per conflict) and ``lospairs`` [cap, 2].
         ``cull=True``: bsg_cd_detect_culled (identical outputs; pays off on spatially sorted records).
         ``symmetric=True`` (full N x N only): each unordered tile pair is evaluated once and both ordered results are
         emitted (BSG_CD_SYMMETRIC; identical outputs, half the pair evaluations); combines with ``cull``."""
@@ -72,8 +87,7 @@ class StateBasedCD:
         nlos = self._get("nlos", (m,), torch.int32)
         tcpamax = self._get("tcpamax", (m,), torch.float32)
         inconf = self._get("inconf", (m,), torch.uint8)
-        npairs = self._get("npairs", (2,), torch.int64)
-        pairs = self._get("pairs", (max(self.pair_capacity, 1), 2), torch.int32) if want_pairs else None
+        lists, lt = self._lists(want_pairs, want_attr)
         flags = _lib.CD_LON_WRAP if lon_wrap else 0
         if symmetric:
             flags |= _lib.CD_SYMMETRIC | (0 if cull else _lib.CD_ALLTILES)
@@ -83,17 +97,15 @@ class StateBasedCD:
                 work = self._get("cull_work", (nbytes,), torch.uint8)
                 _lib.check(self.lib.bsg_cd_detect_culled(_ptr(rec), n_all, row0, n_rows, self.rpz, self.hpz, self.dtlookahead,
                                                          flags, _ptr(nconf), _ptr(nlos), _ptr(tcpamax), _ptr(inconf),
-                                                         _ptr(pairs), self.pair_capacity if want_pairs else 0, _ptr(npairs),
-                                                         _ptr(work), nbytes, self._stream()))
+                                                         C.byref(lists), _ptr(work), nbytes, self._stream()))
                 self.gpu_launches += 5 if n_rows else 0
             else:
                 _lib.check(self.lib.bsg_cd_detect(_ptr(rec), n_all, row0, n_rows, self.rpz, self.hpz, self.dtlookahead,
                                                   flags, _ptr(nconf), _ptr(nlos), _ptr(tcpamax), _ptr(inconf),
-                                                  _ptr(pairs), self.pair_capacity if want_pairs else 0, _ptr(npairs),
-                                                  self._stream()))
+                                                  C.byref(lists), self._stream()))
                 self.gpu_launches += 2 if n_rows else 0
         return dict(nconf_row=nconf[:n_rows], nlos_row=nlos[:n_rows], tcpamax=tcpamax[:n_rows],
-                    inconf=inconf[:n_rows], pairs=pairs, npairs=npairs)
+                    inconf=inconf[:n_rows], **lt)
 
     # ---------------------------------------------------------------- spatial order for the culled form
     @staticmethod
@@ -126,8 +138,9 @@ class StateBasedCD:
         n = lat_d.numel()
         if n == 0:
             z = np.zeros(0)
-            return dict(confpairs=np.zeros((0, 2), np.int32), inconf=z.astype(bool), tcpamax=z,
-                        nconf_row=z.astype(np.int64), nlos_row=z.astype(np.int64), n_conf=0, n_los=0, truncated=False)
+            return dict(confpairs=np.zeros((0, 2), np.int32), lospairs=np.zeros((0, 2), np.int32), inconf=z.astype(bool),
+                        tcpamax=z, nconf_row=z.astype(np.int64), nlos_row=z.astype(np.int64), n_conf=0, n_los=0,
+                        truncated=False, **{k: z.copy() for k in _lib.CD_ATTR})
         if lat0 is None:
             lat0 = float(lat_d.mean())
         if lon0 is None:
@@ -143,21 +156,30 @@ class StateBasedCD:
         out = self.detect_packed(rec, n, lon_wrap=span >= 90.0, cull=cull, symmetric=symmetric and span < 90.0)
         torch.cuda.synchronize(self.device)
         n_conf, n_los = (int(v) for v in out["npairs"].cpu())
-        k = min(n_conf, self.pair_capacity)
-        pairs, inconf, tcpamax = out["pairs"][:k], out["inconf"], out["tcpamax"]
+        k, kl = min(n_conf, self.pair_capacity), min(n_los, self.los_capacity)
+        pairs, lospairs, attr = out["pairs"][:k], out["lospairs"][:kl], out["attr"][:k]
+        inconf, tcpamax = out["inconf"], out["tcpamax"]
         nconf_row, nlos_row = out["nconf_row"], out["nlos_row"]
         if perm is not None:                              # back to the caller's aircraft order
             pairs = perm[pairs.long()].to(torch.int32)
+            lospairs = perm[lospairs.long()].to(torch.int32)
             def unperm(x):
                 y = torch.empty_like(x)
                 y[perm] = x
                 return y
             inconf, tcpamax, nconf_row, nlos_row = (unperm(x) for x in (inconf, tcpamax, nconf_row, nlos_row))
-        return dict(confpairs=pairs.cpu().numpy(), inconf=inconf.cpu().numpy().astype(bool),
-                    tcpamax=tcpamax.cpu().numpy().astype(np.float64),
-                    nconf_row=nconf_row.cpu().numpy().astype(np.int64),
-                    nlos_row=nlos_row.cpu().numpy().astype(np.int64),
-                    n_conf=n_conf, n_los=n_los, truncated=n_conf > self.pair_capacity)
+        # upstream's order: row-major np.where (own index, then intruder index)
+        pairs, lospairs, attr = pairs.cpu().numpy(), lospairs.cpu().numpy(), attr.cpu().numpy().astype(np.float64)
+        o = np.lexsort((pairs[:, 1], pairs[:, 0]))
+        ol = np.lexsort((lospairs[:, 1], lospairs[:, 0]))
+        res = dict(confpairs=pairs[o], lospairs=lospairs[ol], inconf=inconf.cpu().numpy().astype(bool),
+                   tcpamax=tcpamax.cpu().numpy().astype(np.float64),
+                   nconf_row=nconf_row.cpu().numpy().astype(np.int64),
+                   nlos_row=nlos_row.cpu().numpy().astype(np.int64),
+                   n_conf=n_conf, n_los=n_los, truncated=n_conf > self.pair_capacity or n_los > self.los_capacity)
+        for c, name in enumerate(_lib.CD_ATTR):           # qdr, dist, dcpa, tcpa, tinconf of each conflict (detect()'s tail)
+            res[name] = attr[o, c]
+        return res
 
     # ---------------------------------------------------------------- multi-GPU: rows sharded over ranks
     def detect_sharded(self, rec_local, n_local, group=None, lon_wrap=False, want_pairs=False, cull=False):
@@ -202,8 +224,7 @@ class StateBasedCD:
         nlos = self._get("nlos", (m,), torch.int32)
         tcpamax = self._get("tcpamax", (m,), torch.float32)
         inconf = self._get("inconf", (m,), torch.uint8)
-        npairs = self._get("npairs", (2,), torch.int64)
-        pairs = self._get("pairs", (max(self.pair_capacity, 1), 2), torch.int32) if want_pairs else None
+        lists, lt = self._lists(want_pairs)
         work, nbytes = None, 0
         if cull:
             nbytes = int(self.lib.bsg_cd_cull_workspace(n_local * world, n_local))
@@ -211,11 +232,10 @@ class StateBasedCD:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.bsg_cd_detect_peers(ptrs, world, rank, n_local, self.rpz, self.hpz, self.dtlookahead,
                                                     _lib.CD_CULL if cull else 0, _ptr(nconf), _ptr(nlos), _ptr(tcpamax),
-                                                    _ptr(inconf), _ptr(pairs), self.pair_capacity if want_pairs else 0,
-                                                    _ptr(npairs), _ptr(work), nbytes, self._stream()))
+                                                    _ptr(inconf), C.byref(lists), _ptr(work), nbytes, self._stream()))
         hdl.barrier(channel=1)                  # nobody overwrites a block that a peer may still be reading
         self.gpu_launches += 5 if cull else 2
-        return dict(nconf_row=nconf, nlos_row=nlos, tcpamax=tcpamax, inconf=inconf, pairs=pairs, npairs=npairs)
+        return dict(nconf_row=nconf, nlos_row=nlos, tcpamax=tcpamax, inconf=inconf, **lt)
 
 
 def shard_rows(n_all, world, rank):

@@ -47,6 +47,7 @@ struct bsg_handle {
     cudaEvent_t ev[4];      // chunk-arrival events of bsg_step_host_copy (created on first use)
     bool have_ev;
     bool pending;           // a bsg_step_host_begin without its bsg_step_host_wait
+    int fc_slot;            // final_count slot of the last step launch (two counters take turns, see env_kernel)
     float obs_noise;        // NoisyObservationWrapper sigma (0 = off)
     uint32_t noise_calls;   // reset / step calls so far: the noise stream's call index
 };
@@ -60,6 +61,7 @@ extern "C" int bsg_abi_struct_size(int which) {
         case 3: return (int)sizeof(bsg_wind);
         case 4: return (int)sizeof(bsg_perf);
         case 5: return (int)sizeof(bsg_ac_state);
+        case 6: return (int)sizeof(bsg_cd_lists);
     }
     return -1;
 }
@@ -112,6 +114,7 @@ extern "C" int bsg_create(const bsg_config* cfg, bsg_handle** out) {
     int rc = bsg_query_layout(cfg, &lay);
     if (rc != BSG_OK) return rc;
     if (cfg->autoreset_mode < 0 || cfg->autoreset_mode > 2) return bsg_fail(BSG_EINVAL, "bad autoreset_mode");
+    if (cfg->cd_pair_cap < 0) return bsg_fail(BSG_EINVAL, "cd_pair_cap must be >= 0");
     int ndev = bsg_device_count();
     if (ndev <= 0) return bsg_fail(BSG_ECUDA, "no CUDA device: libbsg_b200 has no CPU fallback");
     if (cfg->device < 0 || cfg->device >= ndev) return bsg_fail(BSG_EINVAL, "device ordinal out of range");
@@ -131,11 +134,12 @@ extern "C" int bsg_create(const bsg_config* cfg, bsg_handle** out) {
     P.R2 = rpz * rpz;
     P.rpz = rpz;
     P.init_alt = cfg->init_alt;
-    {   // ISA at init_alt (bluesky/tools/aero.py::vatmos as restated in oracle/aero.py), evaluated once here
+    {   // vcas2tas(150 m/s, init_alt) (bluesky/tools/aero.py::vatmos / vcas2tas as restated in oracle/aero.py), once, here
         const double hh = (double)cfg->init_alt, T = fmax(288.15 - 0.0065 * hh, 216.65);
         const double rhotrop = 1.225 * pow(T / 288.15, 4.256848030018761);
-        P.init_rho = rhotrop * exp(-fmax(0.0, hh - 11000.0) / 6341.552161);
-        P.init_p = P.init_rho * 287.05287 * T;
+        const double rho = rhotrop * exp(-fmax(0.0, hh - 11000.0) / 6341.552161), p = rho * 287.05287 * T;
+        const double q = 101325.0 * (pow(1.0 + 1.225 * 150.0 * 150.0 / (7.0 * 101325.0), 3.5) - 1.0);
+        P.init_tas0 = sqrt(7.0 * p / rho * (pow(q / p + 1.0, 2.0 / 7.0) - 1.0));
     }
     P.hpz = cfg->hpz > 0.0f ? cfg->hpz : 1000.0f * 0.3048f;
     P.dtlook = cfg->dtlookahead > 0.0f ? cfg->dtlookahead : 300.0f;
@@ -175,6 +179,10 @@ extern "C" int bsg_bind_state(bsg_handle* h, const bsg_tensor_table* t) {
     P.ef64 = t->env_f64; P.ef32 = t->env_f32; P.ei32 = t->env_i32; P.poly = t->poly;
     P.obs = t->obs; P.final_obs = t->final_obs; P.final_ids = t->final_ids; P.final_count = t->final_count; P.reward = t->reward; P.term = t->terminated; P.trunc = t->truncated;
     P.info = t->info;
+    if (h->cfg.cd_pair_cap > 0 && h->cfg.cd_enabled && !t->cd_pairs) return bsg_fail(BSG_EINVAL, "cd_pair_cap > 0 needs tensor_table.cd_pairs");
+    P.cd_pairs = (h->cfg.cd_pair_cap > 0 && h->cfg.cd_enabled) ? t->cd_pairs : nullptr;
+    P.cd_attr = P.cd_pairs ? t->cd_attr : nullptr;
+    P.cd_pair_cap = h->cfg.cd_pair_cap;
     h->bound = true;
     return BSG_OK;
 }
@@ -186,8 +194,8 @@ static int run_mode(bsg_handle* h, int mode, const float* d_actions, const uint8
     bsg::EnvParams P = h->P;
     P.mode = mode; P.actions = d_actions; P.reset_mask = d_mask;
     if (n_sub > 0) P.n_sub = n_sub;
-    if (mode == bsg::kModeStep && P.final_count)
-        BSG_CUDA(cudaMemsetAsync(P.final_count, 0, sizeof(int32_t), (cudaStream_t)stream));
+    if (mode == bsg::kModeStep) h->fc_slot ^= 1;
+    P.fc_slot = h->fc_slot;
     int rc = bsg_launch_env(P, h->lay.slots, (cudaStream_t)stream);
     if (rc != BSG_OK || mode == bsg::kModeTraf || !(h->obs_noise > 0.0f)) return rc;
     return bsg_launch_obs_noise(P, h->obs_noise, h->noise_calls++, mode == bsg::kModeStep, (cudaStream_t)stream);
@@ -331,7 +339,7 @@ extern "C" int bsg_step_host(bsg_handle* h, const float* h_actions, float* h_obs
             if (h_truncated) BSG_CUDA(cudaMemcpyAsync(h_truncated, h->t.truncated, E, cudaMemcpyDeviceToHost, st));
             if (h_info) BSG_CUDA(cudaMemcpyAsync(h_info, h->t.info, n_info, cudaMemcpyDeviceToHost, st));
             if (h_final_count && h->t.final_count)
-                BSG_CUDA(cudaMemcpyAsync(h_final_count, h->t.final_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                BSG_CUDA(cudaMemcpyAsync(h_final_count, h->t.final_count + h->fc_slot, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         }
     }
     BSG_CUDA(cudaStreamSynchronize(st));

@@ -167,6 +167,12 @@ template <int G, typename T> __device__ __forceinline__ T group_bcast(T v, int s
     if (G == 1) return v;
     return __shfl_sync(group_mask<G>(), v, src, G);
 }
+template <int G> __device__ __forceinline__ bool group_all(bool v) {
+    if (G == 1) return v;
+    if (G >= 32) return __all_sync(0xffffffffu, v);
+    const unsigned m = group_mask<G>();
+    return (__ballot_sync(m, v) & m) == m;
+}
 template <int G> __device__ __forceinline__ int group_sum(int v) {
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(group_mask<G>(), v, o, G);

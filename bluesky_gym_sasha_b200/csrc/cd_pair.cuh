@@ -63,6 +63,9 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
 struct CdPair {
     bool conf, los;
     float tcpa;
+    // what upstream's detect() returns per conflict besides the pair (qdr, dist, dcpa, tcpa, tinconf): dx, dy give
+    // qdr = atan2(dx, dy) and dist on the (rare) emitting path; unused fields are dropped by the compiler
+    float tinconf, dcpa2, dist2, dx, dy;
 };
 
 // (i) = own row, (j) = intruder column.  `same` marks the diagonal (upstream adds 1e9*eye).
@@ -102,7 +105,7 @@ __device__ __forceinline__ CdPair cd_pair_eval(const float4 Ai, const float4 Bi,
     CdPair o;
     o.conf = swhor && (tinconf <= toutconf) && (toutconf > 0.0f) && (tinconf < dtlook) && !same;
     o.los = (dist2 < R2) && (fabsf(dalt) < hpz) && !same;
-    o.tcpa = tcpa;
+    o.tcpa = tcpa; o.tinconf = tinconf; o.dcpa2 = dcpa2; o.dist2 = dist2; o.dx = dx; o.dy = dy;
     return o;
 }
 
@@ -112,6 +115,7 @@ __device__ __forceinline__ CdPair cd_pair_eval(const float4 Ai, const float4 Bi,
 struct CdSym {
     bool conf_ij, conf_ji, los;
     float tcpa;
+    float tin_ij, tin_ji, dcpa2, dist2, dx, dy;      // attributes of the pair (dx, dy as seen from i; (j, i): negated)
 };
 __device__ __forceinline__ CdSym cd_pair_sym(const float4 Ai, const float4 Bi, const float4 Aj, const float4 Bj,
                                              float R2, float hpz, float dtlook) {
@@ -150,8 +154,9 @@ __device__ __forceinline__ CdSym cd_pair_sym(const float4 Ai, const float4 Bi, c
     o.conf_ij = swhor && (tin <= tout) && (tout > 0.0f) && (tin < dtlook);
     o.conf_ji = swhor && (tinr <= toutr) && (toutr > 0.0f) && (tinr < dtlook);
     // LoS (dist < R and |dalt| < hpz) implies dcpa < R: only looked at under swhor
-    o.los = swhor && (fmaf(dx, dx, dy * dy) < R2) && (fabsf(dalt) < hpz);
-    o.tcpa = tcpa;
+    const float d2 = fmaf(dx, dx, dy * dy);
+    o.los = swhor && (d2 < R2) && (fabsf(dalt) < hpz);
+    o.tcpa = tcpa; o.tin_ij = tin; o.tin_ji = tinr; o.dcpa2 = dcpa2; o.dist2 = d2; o.dx = dx; o.dy = dy;
     return o;
 }
 

@@ -77,8 +77,11 @@ struct CdArgs {
     uint32_t* nconf_row;
     uint32_t* nlos_row;
     float* tcpamax;
-    int32_t* pairs;
+    int32_t* pairs;        // conflict pairs [cap][2], attributes [cap][BSG_CD_ATTR_COUNT], LoS pairs [los_cap][2]
+    float* attr;
     long long cap;
+    int32_t* lospairs;
+    long long los_cap;
     unsigned long long* npairs;
     int n_rowblocks, n_colgroups, n_tiles;
     // culled form (bsg_cd_detect_culled): per row block the column tiles that can hold a conflict partner
@@ -107,24 +110,35 @@ __device__ __forceinline__ const float* tile_base(const CdArgs& a, int t) {
     return a.peer_rec[p] + (size_t)(t - p * a.tiles_per_peer) * kTileFloats;
 }
 
-// Exact (reference-order) evaluation of one candidate pair, out of line.  bit0 = conflict, bit1 = LoS.
+// Exact (reference-order) evaluation of one candidate pair, out of line, on records already at hand (own row from its
+// packed registers, column from the shared-memory tile: no global loads on the rare path, which matters once culling
+// has concentrated the candidates).  Returns bit0 = conflict, bit1 = LoS for the caller's per-row counters and appends
+// the ordered pair (ri, cj) to the lists of upstream's detect(): confpairs (+ qdr, dist, dcpa, tcpa, tinconf) and lospairs.
 template <bool WRAP>
-__device__ __noinline__ uint32_t cd_candidate(const CdArgs& a, int ri, int cj, float& tcpa) {
-    float4 Ai, Bi, Aj, Bj;
-    load_record(a.rec, ri, Ai, Bi);
-    load_record(a.rec, cj, Aj, Bj);
-    CdPair p = cd_pair_eval<WRAP>(Ai, Bi, Aj, Bj, a.R2, a.hpz, a.dtlook, ri == cj);
+__device__ __noinline__ uint32_t cd_candidate_rec(const CdArgs& a, const int ri, const int cj, const float4 Ai, const float4 Bi,
+                                                  const float4 Aj, const float4 Bj, float& tcpa) {
+    const CdPair p = cd_pair_eval<WRAP>(Ai, Bi, Aj, Bj, a.R2, a.hpz, a.dtlook, ri == cj);
     tcpa = p.tcpa;
-    return (p.conf ? 1u : 0u) | (p.los ? 2u : 0u);
-}
-
-// Same, on records already at hand (own row from its packed registers, column from the shared-memory tile): no
-// global loads on the rare path, which matters once culling has concentrated the candidates.
-template <bool WRAP>
-__device__ __noinline__ uint32_t cd_candidate_rec(const float4 Ai, const float4 Bi, const float4 Aj, const float4 Bj,
-                                                  float R2, float hpz, float dtlook, bool same, float& tcpa) {
-    CdPair p = cd_pair_eval<WRAP>(Ai, Bi, Aj, Bj, R2, hpz, dtlook, same);
-    tcpa = p.tcpa;
+    if (a.npairs) {
+        if (p.los) {
+            const unsigned long long k = atomicAdd(a.npairs + 1, 1ULL);
+            if (a.lospairs && (long long)k < a.los_cap) { a.lospairs[2 * k] = ri; a.lospairs[2 * k + 1] = cj; }
+        }
+        if (p.conf) {
+            const unsigned long long k = atomicAdd(a.npairs, 1ULL);
+            if ((long long)k < a.cap) {
+                if (a.pairs) { a.pairs[2 * k] = ri; a.pairs[2 * k + 1] = cj; }
+                if (a.attr) {
+                    float* q = a.attr + BSG_CD_ATTR_COUNT * k;
+                    q[BSG_CD_ATTR_QDR] = mod360(kRad2Deg * atan2f(p.dx, p.dy));
+                    q[BSG_CD_ATTR_DIST] = sqrtf(p.dist2);
+                    q[BSG_CD_ATTR_DCPA] = sqrtf(p.dcpa2);
+                    q[BSG_CD_ATTR_TCPA] = p.tcpa;
+                    q[BSG_CD_ATTR_TINCONF] = p.tinconf;
+                }
+            }
+        }
+    }
     return (p.conf ? 1u : 0u) | (p.los ? 2u : 0u);
 }
 
@@ -243,67 +257,79 @@ __device__ __forceinline__ void cd_process_item(const CdArgs& a, float (*s_tile)
         parity[s] ^= 1u;
         const float* tile = s_tile[s];
         const int c0 = t * kTJ;
+        // Hot loop: no branch besides the loop itself.  Each iteration tests 4 columns against the thread's rows and drops
+        // one bit per row into a mask (bit g of half h = columns 4 (32 h + g) .. + 3 hold a candidate); the flagged groups
+        // are re-evaluated exactly after the half-tile, from the tile that is still in shared memory.
 #pragma unroll 1
-        for (int j = 0; j < kTJ; j += 4) {
-            // 8 broadcast LDS.128: four consecutive columns of each field = two packed operands
-            const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(tile + FX * kTJ + j);
-            const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(tile + FY * kTJ + j);
-            const ulonglong2 CH = *reinterpret_cast<const ulonglong2*>(tile + FCH * kTJ + j);
-            const ulonglong2 SH = *reinterpret_cast<const ulonglong2*>(tile + FSH * kTJ + j);
-            const ulonglong2 U = *reinterpret_cast<const ulonglong2*>(tile + FU * kTJ + j);
-            const ulonglong2 V = *reinterpret_cast<const ulonglong2*>(tile + FV * kTJ + j);
-            const ulonglong2 AL = *reinterpret_cast<const ulonglong2*>(tile + FALT * kTJ + j);
-            const ulonglong2 VS = *reinterpret_cast<const ulonglong2*>(tile + FVS * kTJ + j);
-            bool hit[kR];               // per own row: any of the four columns j .. j+3 flagged
+        for (int half = 0; half < 2; ++half) {
+            uint32_t mask[kR];
 #pragma unroll
-            for (int k = 0; k < kR; ++k) {
-                hit[k] = cd_hot2<WRAP, SYM>(rp[k], X.x, Y.x, CH.x, SH.x, U.x, V.x, AL.x, VS.x, R2P, HPZP, NEG1, dtlh);
-                hit[k] |= cd_hot2<WRAP, SYM>(rp[k], X.y, Y.y, CH.y, SH.y, U.y, V.y, AL.y, VS.y, R2P, HPZP, NEG1, dtlh);
+            for (int k = 0; k < kR; ++k) mask[k] = 0u;
+            uint32_t bit = 1u;
+            const float* th = tile + half * (kTJ / 2);
+#pragma unroll 1
+            for (int j = 0; j < kTJ / 2; j += 4, bit <<= 1) {
+                // 8 broadcast LDS.128: four consecutive columns of each field = two packed operands
+                const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(th + FX * kTJ + j);
+                const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(th + FY * kTJ + j);
+                const ulonglong2 CH = *reinterpret_cast<const ulonglong2*>(th + FCH * kTJ + j);
+                const ulonglong2 SH = *reinterpret_cast<const ulonglong2*>(th + FSH * kTJ + j);
+                const ulonglong2 U = *reinterpret_cast<const ulonglong2*>(th + FU * kTJ + j);
+                const ulonglong2 V = *reinterpret_cast<const ulonglong2*>(th + FV * kTJ + j);
+                const ulonglong2 AL = *reinterpret_cast<const ulonglong2*>(th + FALT * kTJ + j);
+                const ulonglong2 VS = *reinterpret_cast<const ulonglong2*>(th + FVS * kTJ + j);
+                bool hit[kR];
+#pragma unroll
+                for (int k = 0; k < kR; ++k) {
+                    hit[k] = cd_hot2<WRAP, SYM>(rp[k], X.x, Y.x, CH.x, SH.x, U.x, V.x, AL.x, VS.x, R2P, HPZP, NEG1, dtlh);
+                    hit[k] |= cd_hot2<WRAP, SYM>(rp[k], X.y, Y.y, CH.y, SH.y, U.y, V.y, AL.y, VS.y, R2P, HPZP, NEG1, dtlh);
+                }
+                bool anyhit = false;
+#pragma unroll
+                for (int k = 0; k < kR; ++k) anyhit |= hit[k];
+                if (anyhit) {                // rarely taken; the empty asm keeps it a branch (the predicates stay predicates)
+                    asm volatile("" ::: "memory");
+#pragma unroll
+                    for (int k = 0; k < kR; ++k) mask[k] |= hit[k] ? bit : 0u;
+                }
             }
             bool any = false;
 #pragma unroll
-            for (int k = 0; k < kR; ++k) any |= hit[k];
-            if (any) for (int b = 0; b < 4 * kR; ++b) {  // rare: exact re-evaluation of the flagged rows' four pairs
-                const int k = b >> 2, jc = j + (b & 3), cj = c0 + jc;
-                if (!(k == 0 ? hit[0] : hit[kR - 1]) || ri[k] >= row_end || cj >= a.n_all) continue;
-                float nx, ny, chh, nsh, nu, nv, nal, nvs, dummy;
-                up2(rp[k].nX, nx, dummy); up2(rp[k].nY, ny, dummy); up2(rp[k].CH, chh, dummy); up2(rp[k].nSH, nsh, dummy);
-                up2(rp[k].nU, nu, dummy); up2(rp[k].nV, nv, dummy); up2(rp[k].nALT, nal, dummy); up2(rp[k].nVS, nvs, dummy);
-                float tc;
-                const float4 Ai = make_float4(-nx, -ny, chh, -nsh), Bi = make_float4(-nu, -nv, -nal, -nvs);
-                const float4 Aj = make_float4(tile[FX * kTJ + jc], tile[FY * kTJ + jc], tile[FCH * kTJ + jc], tile[FSH * kTJ + jc]);
-                const float4 Bj = make_float4(tile[FU * kTJ + jc], tile[FV * kTJ + jc], tile[FALT * kTJ + jc], tile[FVS * kTJ + jc]);
-                const uint32_t f = cd_candidate_rec<WRAP>(Ai, Bi, Aj, Bj, a.R2, a.hpz, a.dtlook, ri[k] == cj, tc);
-                if (SYM && t > own_tile) {       // the mirrored ordered pair (cj, ri): its row lives in another tile
-                    float tcr;
-                    const uint32_t fr = cd_candidate_rec<WRAP>(Aj, Bj, Ai, Bi, a.R2, a.hpz, a.dtlook, false, tcr);
-                    const int o = cj - a.row0;
-                    if ((fr & 2u) && a.nlos_row) atomicAdd(&a.nlos_row[o], 1u);
-                    if ((fr & 2u) && a.npairs) atomicAdd(a.npairs + 1, 1ULL);
-                    if (fr & 1u) {
-                        atomicAdd(&a.nconf_row[o], 1u);
-                        if (a.tcpamax && tcr > 0.0f) atomicMax((int*)&a.tcpamax[o], __float_as_int(tcr));
-                        if (a.npairs) {
-                            unsigned long long slot = atomicAdd(a.npairs, 1ULL);
-                            if (a.pairs && (long long)slot < a.cap) {
-                                a.pairs[2 * slot] = cj;
-                                a.pairs[2 * slot + 1] = ri[k];
+            for (int k = 0; k < kR; ++k) any |= mask[k] != 0u;
+            if (any) {                       // rare: exact re-evaluation of the flagged groups' four pairs per row
+#pragma unroll
+                for (int k = 0; k < kR; ++k) {       // (unrolled: a runtime k would push the row registers to local memory)
+                    if (ri[k] >= row_end) continue;
+                    float nx, ny, chh, nsh, nu, nv, nal, nvs, dummy;
+                    up2(rp[k].nX, nx, dummy); up2(rp[k].nY, ny, dummy); up2(rp[k].CH, chh, dummy); up2(rp[k].nSH, nsh, dummy);
+                    up2(rp[k].nU, nu, dummy); up2(rp[k].nV, nv, dummy); up2(rp[k].nALT, nal, dummy); up2(rp[k].nVS, nvs, dummy);
+                    const float4 Ai = make_float4(-nx, -ny, chh, -nsh), Bi = make_float4(-nu, -nv, -nal, -nvs);
+#pragma unroll 1
+                    for (uint32_t m = mask[k]; m; m &= m - 1u) {
+                        const int g = __ffs((int)m) - 1;
+#pragma unroll 1
+                        for (int q = 0; q < 4; ++q) {
+                            const int jc = half * (kTJ / 2) + 4 * g + q, cj = c0 + jc;
+                            if (cj >= a.n_all) continue;
+                            float tc;
+                            const float4 Aj = make_float4(tile[FX * kTJ + jc], tile[FY * kTJ + jc], tile[FCH * kTJ + jc], tile[FSH * kTJ + jc]);
+                            const float4 Bj = make_float4(tile[FU * kTJ + jc], tile[FV * kTJ + jc], tile[FALT * kTJ + jc], tile[FVS * kTJ + jc]);
+                            const uint32_t f = cd_candidate_rec<WRAP>(a, ri[k], cj, Ai, Bi, Aj, Bj, tc);
+                            if (SYM && t > own_tile) {       // the mirrored ordered pair (cj, ri): its row lives in another tile
+                                float tcr;
+                                const uint32_t fr = cd_candidate_rec<WRAP>(a, cj, ri[k], Aj, Bj, Ai, Bi, tcr);
+                                const int o = cj - a.row0;
+                                if ((fr & 2u) && a.nlos_row) atomicAdd(&a.nlos_row[o], 1u);
+                                if (fr & 1u) {
+                                    atomicAdd(&a.nconf_row[o], 1u);
+                                    if (a.tcpamax && tcr > 0.0f) atomicMax((int*)&a.tcpamax[o], __float_as_int(tcr));
+                                }
                             }
-                        }
-                    }
-                }
-                if (f & 2u) {
-                    nlos[k]++;
-                    if (a.npairs) atomicAdd(a.npairs + 1, 1ULL);
-                }
-                if (f & 1u) {
-                    nconf[k]++;
-                    tmax[k] = fmaxf(tmax[k], tc);
-                    if (a.npairs) {
-                        unsigned long long slot = atomicAdd(a.npairs, 1ULL);
-                        if (a.pairs && (long long)slot < a.cap) {
-                            a.pairs[2 * slot] = ri[k];
-                            a.pairs[2 * slot + 1] = cj;
+                            if (f & 2u) nlos[k]++;
+                            if (f & 1u) {
+                                nconf[k]++;
+                                tmax[k] = fmaxf(tmax[k], tc);
+                            }
                         }
                     }
                 }
@@ -328,7 +354,9 @@ __device__ __forceinline__ void cd_process_item(const CdArgs& a, float (*s_tile)
 #define BSG_CD_MINBLOCKS 4
 #endif
 template <bool WRAP, bool LIST, bool SYM>
-__global__ void __launch_bounds__(kNT, BSG_CD_MINBLOCKS) cd_tiled_kernel(const CdArgs a) {
+// (__grid_constant__: the rare path hands `a` to out-of-line routines by reference; without it taking the parameter's
+// address would make the compiler keep a local-memory copy of the whole structure and read the hot loop's operands from it)
+__global__ void __launch_bounds__(kNT, BSG_CD_MINBLOCKS) cd_tiled_kernel(const __grid_constant__ CdArgs a) {
     __shared__ __align__(128) float s_tile[2][kTileFloats];
     __shared__ __align__(8) uint64_t s_full[2];
     __shared__ int s_item[3];
@@ -521,12 +549,14 @@ extern "C" int bsg_cd_pack(const double* d_lat, const double* d_lon, const doubl
 
 // ---- launch plumbing shared by the three entry points ------------------------------------------------
 static int cd_fill_args(CdArgs& a, int64_t n_all, int64_t row0, int64_t n_rows, float rpz, float hpz, float dtlookahead,
-                        uint32_t* d_nconf_row, uint32_t* d_nlos_row, float* d_tcpamax, int32_t* d_pairs, int64_t cap,
-                        unsigned long long* d_npairs) {
+                        uint32_t* d_nconf_row, uint32_t* d_nlos_row, float* d_tcpamax, const bsg_cd_lists* lists) {
+    static const bsg_cd_lists none = {nullptr, nullptr, 0, nullptr, 0, nullptr};
+    const bsg_cd_lists& L = lists ? *lists : none;
     if (n_all < 0 || row0 < 0 || n_rows < 0 || row0 + n_rows > n_all) return bsg_fail(BSG_EINVAL, "CD: row range outside [0, n_all)");
     if (n_all > 0x7fffff00LL) return bsg_fail(BSG_EINVAL, "CD: n_all exceeds int32 pair indices");
     if (n_rows > 0 && !d_nconf_row) return bsg_fail(BSG_EINVAL, "CD: null d_nconf_row");
-    if (d_pairs && (!d_npairs || cap < 0)) return bsg_fail(BSG_EINVAL, "CD: pair list needs d_npairs and cap >= 0");
+    if ((L.d_conf_pairs || L.d_conf_attr || L.d_los_pairs) && !L.d_npairs) return bsg_fail(BSG_EINVAL, "CD: pair lists need d_npairs");
+    if (L.conf_cap < 0 || L.los_cap < 0) return bsg_fail(BSG_EINVAL, "CD: negative list capacity");
     memset(&a, 0, sizeof(a));
     a.n_all = (int)n_all; a.row0 = (int)row0; a.n_rows = (int)n_rows;
     if (rpz <= 0.0f) rpz = 5.0f * 1852.0f;
@@ -534,7 +564,8 @@ static int cd_fill_args(CdArgs& a, int64_t n_all, int64_t row0, int64_t n_rows, 
     if (dtlookahead <= 0.0f) dtlookahead = 300.0f;
     a.R2 = rpz * rpz; a.hpz = hpz; a.dtlook = dtlookahead;
     a.nconf_row = d_nconf_row; a.nlos_row = d_nlos_row; a.tcpamax = d_tcpamax;
-    a.pairs = d_pairs; a.cap = cap; a.npairs = d_npairs;
+    a.pairs = L.d_conf_pairs; a.attr = L.d_conf_attr; a.cap = L.conf_cap;
+    a.lospairs = L.d_los_pairs; a.los_cap = L.los_cap; a.npairs = L.d_npairs;
     a.n_tiles = (int)(bsg_cd_padded(n_all) / kTJ);
     a.n_rowblocks = (int)((n_rows + kRowsPerCta - 1) / kRowsPerCta);
     a.n_colgroups = (a.n_tiles + kTilesPerItem - 1) / kTilesPerItem;
@@ -597,11 +628,10 @@ static int cd_launch(CdArgs& a, bool wrap, bool cull, bool sym, bool alltiles, v
 
 extern "C" int bsg_cd_detect(const float* d_rec, int64_t n_all, int64_t row0, int64_t n_rows, float rpz, float hpz,
                              float dtlookahead, uint32_t flags, uint32_t* d_nconf_row, uint32_t* d_nlos_row,
-                             float* d_tcpamax, uint8_t* d_inconf, int32_t* d_pairs, int64_t cap,
-                             unsigned long long* d_npairs, void* stream) {
+                             float* d_tcpamax, uint8_t* d_inconf, const bsg_cd_lists* lists, void* stream) {
     if (flags & BSG_CD_SYMMETRIC) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: BSG_CD_SYMMETRIC is served by bsg_cd_detect_culled (it needs the work-list scratch)");
     CdArgs a;
-    int rc = cd_fill_args(a, n_all, row0, n_rows, rpz, hpz, dtlookahead, d_nconf_row, d_nlos_row, d_tcpamax, d_pairs, cap, d_npairs);
+    int rc = cd_fill_args(a, n_all, row0, n_rows, rpz, hpz, dtlookahead, d_nconf_row, d_nlos_row, d_tcpamax, lists);
     if (rc != BSG_OK) return rc;
     if (n_rows > 0 && !d_rec) return bsg_fail(BSG_EINVAL, "bsg_cd_detect: null d_rec");
     a.rec = d_rec; a.rec_rows = d_rec; a.rows_base = 0;
@@ -617,10 +647,10 @@ extern "C" int64_t bsg_cd_cull_workspace(int64_t n_all, int64_t n_rows) {
 
 extern "C" int bsg_cd_detect_culled(const float* d_rec, int64_t n_all, int64_t row0, int64_t n_rows, float rpz, float hpz,
                                     float dtlookahead, uint32_t flags, uint32_t* d_nconf_row, uint32_t* d_nlos_row,
-                                    float* d_tcpamax, uint8_t* d_inconf, int32_t* d_pairs, int64_t cap,
-                                    unsigned long long* d_npairs, void* d_work, int64_t work_bytes, void* stream) {
+                                    float* d_tcpamax, uint8_t* d_inconf, const bsg_cd_lists* lists,
+                                    void* d_work, int64_t work_bytes, void* stream) {
     CdArgs a;
-    int rc = cd_fill_args(a, n_all, row0, n_rows, rpz, hpz, dtlookahead, d_nconf_row, d_nlos_row, d_tcpamax, d_pairs, cap, d_npairs);
+    int rc = cd_fill_args(a, n_all, row0, n_rows, rpz, hpz, dtlookahead, d_nconf_row, d_nlos_row, d_tcpamax, lists);
     if (rc != BSG_OK) return rc;
     if (n_rows > 0 && !d_rec) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: null d_rec");
     a.rec = d_rec; a.rec_rows = d_rec; a.rows_base = 0;
@@ -630,8 +660,8 @@ extern "C" int bsg_cd_detect_culled(const float* d_rec, int64_t n_all, int64_t r
 
 extern "C" int bsg_cd_detect_peers(const float* const* h_peer_rec, int32_t n_peers, int32_t my_rank, int64_t n_per_peer,
                                    float rpz, float hpz, float dtlookahead, uint32_t flags, uint32_t* d_nconf_row,
-                                   uint32_t* d_nlos_row, float* d_tcpamax, uint8_t* d_inconf, int32_t* d_pairs, int64_t cap,
-                                   unsigned long long* d_npairs, void* d_work, int64_t work_bytes, void* stream) {
+                                   uint32_t* d_nlos_row, float* d_tcpamax, uint8_t* d_inconf, const bsg_cd_lists* lists,
+                                   void* d_work, int64_t work_bytes, void* stream) {
     if (!h_peer_rec || n_peers < 1 || n_peers > 8 || my_rank < 0 || my_rank >= n_peers)
         return bsg_fail(BSG_EINVAL, "bsg_cd_detect_peers: need 1..8 peer buffers and a rank among them");
     if (n_per_peer <= 0 || n_per_peer % kTJ) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_peers: n_per_peer must be a positive multiple of 256");
@@ -639,7 +669,7 @@ extern "C" int bsg_cd_detect_peers(const float* const* h_peer_rec, int32_t n_pee
         if (!h_peer_rec[p]) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_peers: null peer buffer");
     CdArgs a;
     int rc = cd_fill_args(a, n_per_peer * n_peers, n_per_peer * my_rank, n_per_peer, rpz, hpz, dtlookahead, d_nconf_row, d_nlos_row,
-                          d_tcpamax, d_pairs, cap, d_npairs);
+                          d_tcpamax, lists);
     if (rc != BSG_OK) return rc;
     a.rec = nullptr;
     for (int p = 0; p < n_peers; ++p) a.peer_rec[p] = h_peer_rec[p];

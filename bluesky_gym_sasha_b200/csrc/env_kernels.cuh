@@ -38,8 +38,9 @@ enum { PH_NA = 0, PH_TO = 1, PH_IC = 2, PH_CL = 3, PH_CR = 4, PH_DE = 5, PH_AP =
 struct EnvParams {
     int env_type, E, n_int, cd_enabled, autoreset, max_steps, hdg_random, n_sub, fms_rel_freq, mode;
     int obs_dim, act_dim, info_dim;
+    int fc_slot;                  // which of final_count[0..1] counts this launch's finished envs (the other is zeroed for the next)
     float simdt, R2, hpz, dtlook, rpz, init_alt;
-    double init_p, init_rho;      // ISA pressure / density at init_alt (host-evaluated, HorizontalCR scenario generator)
+    double init_tas0;             // vcas2tas(150 m/s, init_alt), host-evaluated (HorizontalCR scenario generator)
     double fix_lat, fix_lon;      // MergeEnv FIX (merge_env.py:43-46), evaluated on the host in double
     uint64_t seed;
     long long gid0;
@@ -49,6 +50,7 @@ struct EnvParams {
     double* ef64; float* ef32; int32_t* ei32; double* poly;
     float* obs; float* final_obs; int32_t* final_ids; int32_t* final_count; float* reward; uint8_t* term; uint8_t* trunc; float* info;
     const float* actions; const uint8_t* reset_mask;
+    uint32_t* cd_pairs; float* cd_attr; int cd_pair_cap;      // in-sim ASAS pair lists of the last substep (may be null)
     // WindFieldWrapper (bsg_set_wind): wind_n == 0 <=> no wind
     int wind_n, wind_nalt, wind_obs, sector_uniform;
     float wind_altstep;
@@ -125,6 +127,18 @@ __device__ inline void ac_create_tas(Ac& a, double lat, double lon, double hdg, 
     double hr = hdg * kDeg2RadD;
     a.gsn = (float)(tas * cos(hr)); a.gse = (float)(tas * sin(hr));
     a.coslat = (float)cos(a.lat * kDeg2RadD);
+    a.tcpamax = 0.0f; a.inconf = false;
+}
+// same with the cosine / sine of the heading at hand (the generator just computed them)
+__device__ inline void ac_create_dir(Ac& a, double lat, double lon, double hdg, double alt, double cas_cmd, double tas,
+                                     double ch, double sh) {
+    a.lat = lat; a.lon = lon > 180.0 ? lon - 360.0 : (lon < -180.0 ? lon + 360.0 : lon);
+    a.alt = (float)alt; a.tas = (float)tas; a.hdg = (float)hdg; a.vs = 0.0f;
+    a.selspd = (float)cas_cmd; a.selalt = (float)alt; a.selvs = 0.0f; a.aptrk = (float)hdg;
+    a.ax = 0.0f; a.curlegdir = -999.0f; a.cas = (float)cas_cmd;
+    a.flags = kFlAlive;
+    a.gsn = (float)(tas * ch); a.gse = (float)(tas * sh);
+    a.coslat = __cosf((float)a.lat * kDeg2Rad);                // (the expression ac_load rebuilds it with)
     a.tcpamax = 0.0f; a.inconf = false;
 }
 __device__ inline void ac_create(Ac& a, double lat, double lon, double hdg, double alt, double cas_cmd) {
@@ -458,10 +472,12 @@ __device__ __forceinline__ u64 abs2(u64 v) { return v & 0x7fffffff7fffffffULL; }
 __device__ __forceinline__ u64 neg2(u64 v) { return v ^ 0x8000000080000000ULL; }
 
 // `horizon`: simulated seconds between this substep and the last one of the env step (what a kept (B) list must cover)
+// `emit`: this is the last substep of the launch and the caller bound pair lists: the exact phase also appends every
+// conflicting / LoS pair to the env's list (entry format in include/bsg.h), count left in s_np[grp] for the caller.
 template <int G>
 __device__ __forceinline__ void group_cd(const int tid, Ac& a, bool alive, int nac, const EnvParams& P, float horizon, float4* s_rec,
                                          float* s_hot, uint16_t* s_queue, int* s_tmax, int* s_cnt, int* s_nb,
-                                         const uint16_t* s_pairs, int& nconf_env, int& nlos_env) {
+                                         const uint16_t* s_pairs, int& nconf_env, int& nlos_env, const bool emit, const long long e, int* s_np) {
     const int lane = tid & 31;
     const int lane_g = tid & (G - 1);
     const int gbase = tid - lane_g;           // first thread of this group in the block
@@ -477,6 +493,7 @@ __device__ __forceinline__ void group_cd(const int tid, Ac& a, bool alive, int n
     s_rec[2 * tid] = make_float4(x, y, ch, sh);
     s_rec[2 * tid + 1] = make_float4(a.gse, a.gsn, a.alt, a.vs);
     s_tmax[tid] = 0;
+    if (emit && lane_g == 0) s_np[grp] = 0;
     unsigned confmask = 0u;       // bit = warp lane of an aircraft that is in conflict (this lane's pairs only)
     int counts = 0;               // ordered conflict pairs (low half) / ordered LoS pairs (high half) found by this lane
     bool found = true;
@@ -489,6 +506,23 @@ __device__ __forceinline__ void group_cd(const int tid, Ac& a, bool alive, int n
             const int tb = __float_as_int(fmaxf(r.tcpa, 0.0f));
             if (r.conf_ij) atomicMax(&s_tmax[gbase + i], tb);
             if (r.conf_ji) atomicMax(&s_tmax[gbase + j], tb);
+        }
+        if (emit && (r.conf_ij | r.conf_ji | r.los)) {        // rare: the pair goes to the env's list
+            const int k = atomicAdd(&s_np[grp], 1);
+            if (k < P.cd_pair_cap) {
+                const long long o = e * P.cd_pair_cap + k;
+                P.cd_pairs[o] = (uint32_t)i | ((uint32_t)j << 8) | (r.conf_ij ? (uint32_t)BSG_PAIR_CONF_IJ : 0u) |
+                                (r.conf_ji ? (uint32_t)BSG_PAIR_CONF_JI : 0u) | (r.los ? (uint32_t)BSG_PAIR_LOS : 0u);
+                if (P.cd_attr) {
+                    float* q = P.cd_attr + o * BSG_PAIR_ATTR_COUNT;
+                    q[BSG_PAIR_ATTR_QDR] = mod360(kRad2Deg * atan2f(r.dx, r.dy));
+                    q[BSG_PAIR_ATTR_DIST] = sqrtf(r.dist2);
+                    q[BSG_PAIR_ATTR_DCPA] = sqrtf(r.dcpa2);
+                    q[BSG_PAIR_ATTR_TCPA] = r.tcpa;
+                    q[BSG_PAIR_ATTR_TINCONF_IJ] = r.tin_ij;
+                    q[BSG_PAIR_ATTR_TINCONF_JI] = r.tin_ji;
+                }
+            }
         }
     };
     if (G <= 8) {

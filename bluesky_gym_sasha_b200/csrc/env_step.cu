@@ -70,44 +70,62 @@ __device__ inline void descent_info(const EnvS& s, float* info) {           // d
 // =====================================================================================================
 // HorizontalCREnv (horizontal_cr_env.py) -- slot 0 = ownship, slots 1..n = creconfs intruders
 // =====================================================================================================
+// The generator of an env that finishes runs at the END of a launch, on one warp, when the rest of the batch is done:
+// its dependent chain of float64 special functions IS the tail of the launch (25 us of a 45 us launch before this form;
+// scripts/phase_timing.py).  So: the ISA / CAS conversions at the configured altitude come from the host (init_tas0),
+// upstream's vtas2cas -> cre -> vcas2tas round trip of an intruder's speed is taken as the identity it is (the intruder
+// flies the reference ground speed to 2e-16: |cas - 150| ~ 1e-14 << half an ulp of the float32 state), headings come from
+// the track angle instead of atan2 of its own sine / cosine, sines and cosines are evaluated in pairs (sincos), and the
+// waypoint straight north of the ownship (bearing 0 in functions.py:24-42) is lat0 + distance / R.
 template <int G>
 __device__ inline void horizontal_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot) {
     Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);      // horizontal_cr_env.py:82-101
     const int n = P.n_int;
     const double hdg0 = P.hdg_random ? (double)rng.randint(0, 1, 360) : 0.0;
     const double lat0 = 52.0, lon0 = 4.0, alt0 = (double)P.init_alt;     // reference: cre without acalt => 0
-    const double tas0 = d_cas2tas_at(150.0, P.init_p, P.init_rho);
+    const double tas0 = P.init_tas0;                                      // vcas2tas(150, init_alt), host-evaluated
+    const double trkref = hdg0 * kDeg2RadD, gsref = tas0;
+    double sr, cr;
+    sincos(trkref, &sr, &cr);
     if (slot == 0) {
-        ac_create_tas(a, lat0, lon0, hdg0, alt0, 150.0, tas0);
+        ac_create_dir(a, lat0, lon0, hdg0, alt0, 150.0, tas0, cr, sr);
     } else if (slot <= n) {
         // Traffic.creconfs (oracle/traffic.py::creconfs), horizontal_cr_env.py:127-133
         const uint32_t d = 1u + 3u * (uint32_t)(slot - 1);
-        double dpsi = (double)rng.randint(d, 45, 315);
-        double cpa = (double)rng.randint(d + 1, 0, 5) * 1852.0;
-        double tlosh = (double)rng.randint(d + 2, 100, 1000);
+        const double dpsi = (double)rng.randint(d, 45, 315);
+        const double cpa = (double)rng.randint(d + 1, 0, 5) * 1852.0;
+        const double tlosh = (double)rng.randint(d + 2, 100, 1000);
         const double pzr = 5.0 * 1852.0;
-        double trkref = hdg0 * kDeg2RadD, gsref = tas0;
-        double trk = trkref + dpsi * kDeg2RadD;
-        double gsn = gsref * cos(trk), gse = gsref * sin(trk);
-        double vreln = gsref * cos(trkref) - gsn, vrele = gsref * sin(trkref) - gse;
-        double vrel = sqrt(vreln * vreln + vrele * vrele);
-        double drelcpa = tlosh * vrel + (cpa > pzr ? 0.0 : sqrt(pzr * pzr - cpa * cpa));
-        double dist = sqrt(drelcpa * drelcpa + cpa * cpa);
-        double rd = drelcpa / dist, rx = cpa / dist;
-        double brn = kRad2DegD * atan2(-rx * vreln + rd * vrele, rd * vreln + rx * vrele);
+        const double trk = trkref + dpsi * kDeg2RadD;
+        double st, ct;
+        sincos(trk, &st, &ct);
+        const double gsn = gsref * ct, gse = gsref * st;
+        const double vreln = gsref * cr - gsn, vrele = gsref * sr - gse;
+        const double vrel = sqrt(vreln * vreln + vrele * vrele);
+        const double drelcpa = tlosh * vrel + (cpa > pzr ? 0.0 : sqrt(pzr * pzr - cpa * cpa));
+        const double dist = sqrt(drelcpa * drelcpa + cpa * cpa);
+        const double rd = drelcpa / dist, rx = cpa / dist;
+        const double brn = atan2(-rx * vreln + rd * vrele, rd * vreln + rx * vrele);      // [rad]
+        double sb, cb;
+        sincos(brn, &sb, &cb);
         // geo.kwikpos
-        double dnm = dist / 1852.0;
-        double lat = lat0 + dnm * cos(brn * kDeg2RadD) / 60.0;
-        double lon = lon0 + dnm * sin(brn * kDeg2RadD) / fmax(0.01, 60.0 * cos(lat0 * kDeg2RadD));
+        const double dnm = dist / 1852.0;
+        const double lat = lat0 + dnm * cb / 60.0;
+        double lon = lon0 + dnm * sb / fmax(0.01, 60.0 * 0.6156614753256583);           // cos(52 deg)
         lon = fmod(lon + 180.0, 360.0); if (lon < 0.0) lon += 360.0; lon -= 180.0;
-        double acspd = d_tas2cas_at(sqrt(gsn * gsn + gse * gse), P.init_p, P.init_rho);
-        double achdg = kRad2DegD * atan2(gse, gsn);
-        ac_create_tas(a, lat, lon, achdg, alt0, acspd, d_cas2tas_at(acspd, P.init_p, P.init_rho));
+        const double gs = sqrt(gsn * gsn + gse * gse);
+        const double acspd = 150.0 * (gs / tas0);              // vtas2cas(gs) to first order in (gs / tas0 - 1) ~ 1e-16
+        // achdg = degrees(atan2(gse, gsn)): the track angle folded into (-180, 180]
+        double achdg = hdg0 + dpsi;
+        achdg = achdg > 180.0 ? achdg - 360.0 : achdg;
+        achdg = achdg > 180.0 ? achdg - 360.0 : achdg;
+        ac_create_dir(a, lat, lon, achdg, alt0, acspd, gs, ct, st);
     } else {
         ac_clear(a);
     }
-    int wpt_dis = rng.randint(1u + 3u * (uint32_t)n, 100, 150);             // horizontal_cr_env.py:135-148
-    d_point_at_distance(lat0, lon0, (double)wpt_dis, 0.0, s.wpt_lat, s.wpt_lon);
+    const int wpt_dis = rng.randint(1u + 3u * (uint32_t)n, 100, 150);       // horizontal_cr_env.py:135-148
+    s.wpt_lat = lat0 + ((double)wpt_dis / 6371.0) * kRad2DegD;              // get_point_at_distance(lat0, lon0, d, bearing 0)
+    s.wpt_lon = lon0;
     s.wpt_reach = 0; s.total_reward = 0.0f; s.intrusions = 0; s.drift_sum = 0.0f; s.drift_n = 0;
     s.num_ac = n + 1;
 }
@@ -786,6 +804,7 @@ __device__ __forceinline__ void do_reset(Ac& a, EnvS& s, const EnvParams& P, lon
     if (ENV == BSG_ENV_VERTICAL_CR) vertical_reset<G>(a, s, P, e, slot);
     if (ENV == BSG_ENV_STATIC_OBSTACLE) static_reset<G>(a, s, P, e, slot, scratch);
     s.step = 0; s.needs_reset = 0; s.episode += 1; s.nconf = 0; s.nlos = 0;
+    if (P.cd_pairs && slot == 0) P.ei32[e * BSG_I32_COUNT + BSG_I32_NPAIRS] = 0;      // no detection yet in the new episode
 }
 template <int ENV, int G>
 __device__ __forceinline__ StepOut do_obs(const Ac& a, EnvS& s, const EnvParams& P, float* obs, int slot, long long e,
@@ -816,6 +835,17 @@ __device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float
 // =====================================================================================================
 // K6: the env-step megakernel (also serves reset and the kinematics-only parity entry point)
 // =====================================================================================================
+// Phase stamps of a profiling build (-DBSG_PHASE_TIMING, scripts/phase_timing.py): %globaltimer at the phase boundaries of
+// every env's lane 0, parked in the unused tail of the final_obs buffer.  Not compiled into the product library.
+#ifndef BSG_FAST_STEADY
+#define BSG_FAST_STEADY 1
+#endif
+#ifdef BSG_PHASE_TIMING
+#define BSG_STAMP(k) do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(stamps[k]) :: "memory"); } while (0)
+#else
+#define BSG_STAMP(k) do { } while (0)
+#endif
+
 template <int ENV, int G, bool WIND>
 __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const EnvParams P) {
     __shared__ __align__(16) float4 s_rec[(G > 1) ? kEnvThreads * 2 : 1];
@@ -824,6 +854,7 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
     __shared__ int s_tmax[(G > 1) ? kEnvThreads : 1];
     __shared__ int s_cnt[(G > 8) ? kEnvThreads / G : 1];
     __shared__ int s_nb[(G > 8) ? kEnvThreads / G : 1];       // candidates kept from the last (B) filter pass, -1 = none
+    __shared__ int s_np[(G > 1) ? kEnvThreads / G : 1];       // entries appended to the env's ASAS pair list (last substep)
     __shared__ uint16_t s_pairs[(G > 1 && G <= 8) ? kSmallPairs : 1];
     if (G > 1 && G <= 8 && P.cd_enabled && P.mode != kModeReset) {
         build_pair_table(s_pairs);
@@ -833,12 +864,22 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
                                 : (ENV == BSG_ENV_STATIC_OBSTACLE) ? (kEnvThreads / G) * kStaticScratch : 1];
     const int tid = threadIdx.x;
     const long long gt = (long long)blockIdx.x * kEnvThreads + tid;
+    if (gt == 0 && P.mode == kModeStep && P.final_count) {
+        // two counters take turns (no memset node between launches): this launch counts in [fc_slot], clears the other one
+        // for the next launch and publishes which is live in [2]
+        P.final_count[P.fc_slot ^ 1] = 0;
+        P.final_count[2] = P.fc_slot;
+    }
     const long long e = gt / G;
     const int slot = (int)(gt % G);
     if (e >= P.E) return;                       // group-uniform (G divides the block size)
     double* scratch = (ENV == BSG_ENV_SECTOR_CR) ? &s_scratch[(threadIdx.x / 32) * kSectorScratch]
                     : (ENV == BSG_ENV_STATIC_OBSTACLE) ? &s_scratch[(threadIdx.x / G) * kStaticScratch] : s_scratch;
 
+#ifdef BSG_PHASE_TIMING
+    unsigned long long stamps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    BSG_STAMP(0);
     EnvS s;
     env_load_pre(s, P, e);
     Ac a;
@@ -879,8 +920,17 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
             if (slot == 0) s_nb[threadIdx.x / G] = -1;
             __syncwarp(group_mask<G>());
         }
+        BSG_STAMP(1);
         Targets T;
         compute_targets(a, P, T);
+        BSG_STAMP(2);
+        // `fixed`: the last full kinematics update left (tas, hdg, vs, alt, ax, ground-speed components) exactly as they
+        // were.  They are a pure function of themselves, the targets T (recomputed only when alt / vs move) and the
+        // commands (which change only between env steps, or through LNAV in MergeEnv, or with the wind): the next update
+        // would reproduce them bit for bit, so while EVERY aircraft of the env is fixed -- intruders always, the ownship
+        // once it has finished its turn -- a substep only advances the positions, with the very expressions of
+        // ac_kinematics (BSG_FAST_STEADY=0 switches the shortcut off: identical outputs, scripts/ab_identical.py).
+        bool fixed = false;
 #pragma unroll 1
         for (int k = 0; k < P.n_sub; ++k) {                 // n_sub x bs.sim.step()
             s.simk += 1;
@@ -889,13 +939,33 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
                 if (a.alt != T.k_alt || a.vs != T.k_vs) compute_targets(a, P, T);
                 ac_autopilot<ENV>(a, P, fms_ready);
             }
-            if (G > 1 && P.cd_enabled) group_cd<G>(tid, a, alive, s.num_ac, P, (float)(P.n_sub - 1 - k) * P.simdt, s_rec, s_hot, s_queue, s_tmax, s_cnt, s_nb, s_pairs, nconf, nlos);
-            if (alive) ac_kinematics<WIND>(a, P, T);
+            if (G > 1 && P.cd_enabled) {
+                const bool emit = P.cd_pairs != nullptr && (k == P.n_sub - 1 || ENV == BSG_ENV_STATIC_OBSTACLE);
+                group_cd<G>(tid, a, alive, s.num_ac, P, (float)(P.n_sub - 1 - k) * P.simdt, s_rec, s_hot, s_queue, s_tmax, s_cnt, s_nb,
+                            s_pairs, nconf, nlos, emit, e, s_np);
+                if (emit && slot == 0) P.ei32[e * BSG_I32_COUNT + BSG_I32_NPAIRS] = s_np[tid / G];
+            }
+            if (BSG_FAST_STEADY && !WIND && ENV != BSG_ENV_MERGE && group_all<G>(fixed || !alive)) {
+                if (alive) {                                // update_pos alone (same expressions as ac_kinematics)
+                    a.lat += (double)(kRad2Deg * (P.simdt * a.gsn * (1.0f / kRearth)));
+                    a.coslat = __cosf((float)a.lat * kDeg2Rad);
+                    a.lon += (double)(kRad2Deg * (P.simdt * a.gse * rcp_approx(a.coslat) * (1.0f / kRearth)));
+                }
+            } else if (alive) {
+                const float o_tas = a.tas, o_hdg = a.hdg, o_vs = a.vs, o_alt = a.alt, o_ax = a.ax, o_gsn = a.gsn, o_gse = a.gse;
+                ac_kinematics<WIND>(a, P, T);
+                fixed = a.tas == o_tas && a.hdg == o_hdg && a.vs == o_vs && a.alt == o_alt && a.ax == o_ax && a.gsn == o_gsn &&
+                        a.gse == o_gse;
+            }
             if (ENV == BSG_ENV_STATIC_OBSTACLE && P.mode == kModeStep) {   // per-substep reward / termination
                 if (k == 0) env_load_post(s, P, e);
                 if (static_substep_check<G>(a, s, P, e, slot)) break;
             }
+#ifdef BSG_PHASE_TIMING
+            if (k == 0) BSG_STAMP(3);
+#endif
         }
+        BSG_STAMP(4);
         // update_airspeed's cas = vtas2cas(tas, alt) uses the altitude from before update_pos: T.at of the last substep
         // (only the envs whose action reads traf.cas need it: Sector, Merge, StaticObstacle)
         if ((ENV == BSG_ENV_SECTOR_CR || ENV == BSG_ENV_MERGE || ENV == BSG_ENV_STATIC_OBSTACLE || P.mode == kModeTraf) &&
@@ -921,6 +991,9 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
             obs[P.obs_dim - 2] = (wn * ch + we * sh) * (1.0f / 50.0f);
             obs[P.obs_dim - 1] = (-wn * sh + we * ch) * (1.0f / 50.0f);
         }
+#ifdef BSG_PHASE_TIMING
+        if (pass == 0) BSG_STAMP(5);
+#endif
         if (pass == 1) break;                            // SAME_STEP: the step's reward / flags / info stay
         if (fresh) {
             if (slot == 0) { P.reward[e] = 0.0f; P.term[e] = 0; P.trunc[e] = 0; do_info<ENV>(s, P, info); }
@@ -937,7 +1010,7 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
         if (P.autoreset != BSG_AUTORESET_SAME_STEP) break;
         if (P.final_obs) {                               // the terminal observation survives, compacted
             int k = 0;
-            if (slot == 0) { k = atomicAdd(P.final_count, 1); P.final_ids[k] = (int32_t)e; }
+            if (slot == 0) { k = atomicAdd(P.final_count + P.fc_slot, 1); P.final_ids[k] = (int32_t)e; }
             k = group_bcast<G>(k, 0);
             __syncwarp(group_mask<G>());
             float* fo = P.final_obs + (long long)k * P.obs_dim;
@@ -946,8 +1019,16 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
         }
         resetting = true;
     }
+    BSG_STAMP(6);
     ac_store(a, P, gt);
     if (slot == 0) env_store(s, P, e);
+#ifdef BSG_PHASE_TIMING
+    BSG_STAMP(7);
+    if (slot == 0 && P.final_obs && P.mode == kModeStep) {
+        unsigned long long* out = reinterpret_cast<unsigned long long*>(P.final_obs + (long long)P.E * P.obs_dim) - 8LL * P.E;
+        for (int k = 0; k < 8; ++k) out[8 * e + k] = stamps[k];
+    }
+#endif
 }
 
 }  // namespace bsg

@@ -61,7 +61,7 @@ int bsg_launch_obs_noise(const bsg::EnvParams& P, float sigma, uint32_t call, bo
     bsg::obs_noise_kernel<<<blocks, 256, 0, st>>>(P.obs, nullptr, nullptr, P.E, P.obs_dim, P.reset_mask, sigma, P.seed, P.gid0,
                                                    call, bsg::kTagNoise);
     if (with_final && P.final_obs && P.final_ids && P.final_count)
-        bsg::obs_noise_kernel<<<blocks, 256, 0, st>>>(P.final_obs, P.final_ids, P.final_count, 0, P.obs_dim, nullptr, sigma,
+        bsg::obs_noise_kernel<<<blocks, 256, 0, st>>>(P.final_obs, P.final_ids, P.final_count + P.fc_slot, 0, P.obs_dim, nullptr, sigma,
                                                        P.seed, P.gid0, call, bsg::kTagNoiseTerminal);
     return bsg_cuda_check(cudaGetLastError(), "obs_noise_kernel launch");
 }

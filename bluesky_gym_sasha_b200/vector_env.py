@@ -34,7 +34,7 @@ class BlueSkyVectorEnv(VectorEnv):
                  autoreset_mode="next_step", env_id_offset=0, max_episode_steps=None, perf=None,
                  default_hdg="random", rpz=0.0, hpz=0.0, dtlookahead=0.0, render_mode=None,
                  obs_dtype=np.float32, copy=True, obs_noise=0.0, wind=None, wind_obs=False,
-                 ac_density_mode="normal", init_alt=0.0):
+                 ac_density_mode="normal", init_alt=0.0, cd_pairs=False):
         if env_id in NOT_ACCELERATED:
             raise NotImplementedError(f"{env_id} is registered by the reference but is not on the accelerated "
                                       "path yet (SURVEY.md section 8f)")
@@ -71,6 +71,12 @@ class BlueSkyVectorEnv(VectorEnv):
         self.layout = _lib.query_layout(self.cfg)
         L, E, G = self.layout, self.num_envs, self.layout.slots
         self.slots = G
+        # in-sim ASAS pair lists (bs.traf.cd.confpairs / lospairs + per-conflict attributes of the last substep):
+        # cd_pairs=True keeps up to 128 unordered pairs per env (or all of them when there are fewer), an int = that many
+        self.cd_pair_cap = 0
+        if cd_pairs and cd_enabled and G > 1:
+            self.cd_pair_cap = min(G * (G - 1) // 2, 128) if cd_pairs is True else int(cd_pairs)
+        self.cfg.cd_pair_cap = self.cd_pair_cap
 
         # ---- spaces (identical keys / shapes / dtype to the reference declarations)
         self.obs_layout, obs_dim = self.spec_b200.obs_layout(n_int)
@@ -122,7 +128,9 @@ class BlueSkyVectorEnv(VectorEnv):
             poly=z((E, max(L.poly_f64, 1)), torch.float64) if L.poly_f64 else None,
             obs=d_obs, final_obs=d_fobs, final_ids=d_fids, final_count=d_cnt,
             reward=d_rew, terminated=d_term, truncated=d_trunc,
-            info=d_info, actions_staging=z((E, L.act_dim), torch.float32))
+            info=d_info, actions_staging=z((E, L.act_dim), torch.float32),
+            cd_pairs=z((E, self.cd_pair_cap), torch.int32) if self.cd_pair_cap else None,
+            cd_attr=z((E, self.cd_pair_cap, _lib.PAIR_ATTR_COUNT), torch.float32) if self.cd_pair_cap else None)
         # pinned host mirrors for the numpy API: two rotating blocks with the device block's layout; the numpy
         # views are made once (torch -> numpy conversion per step costs more than the small copies themselves)
         ph = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
@@ -334,7 +342,8 @@ class BlueSkyVectorEnv(VectorEnv):
         trunc = h["truncated"].astype(bool)
         infos = self._infos_np(h["info"])
         if self.autoreset_mode == "same_step":
-            n_fin = int(h["final_count"][0])
+            fc = h["final_count"]
+            n_fin = int(fc[fc[2]])              # two counters take turns; [2] names the live one (include/bsg.h)
             if n_fin:                   # compacted terminal observations of the envs that finished in this step
                 ids = h["final_ids"][:n_fin]
                 cap = self._final_cap
@@ -352,6 +361,32 @@ class BlueSkyVectorEnv(VectorEnv):
                 infos["_final_obs"] = term | trunc
         return obs, rew, term, trunc, infos
 
+    def asas_pairs(self, e):
+        """In-sim ASAS pair lists of env ``e`` after the last simulator substep, shaped like upstream's
+        ``StateBased.detect`` outputs (what ``bs.traf.cd`` holds after ``bs.sim.step()``): ``confpairs`` / ``lospairs`` as
+        ordered (own slot, intruder slot) pairs in row-major order, and per conflict ``qdr, dist, dcpa, tcpa, tinconf``.
+        Needs ``cd_enabled`` and ``cd_pairs`` at construction.  ``truncated`` tells that the env had more pairs than the
+        list holds."""
+        if not self.cd_pair_cap:
+            raise _lib.BsgError("asas_pairs(): construct the env with cd_enabled=True, cd_pairs=True")
+        n = int(self.t["env_i32"][e, _lib.I32_NPAIRS])
+        k = min(n, self.cd_pair_cap)
+        ent = self.t["cd_pairs"][e, :k].cpu().numpy().view(np.uint32)
+        att = self.t["cd_attr"][e, :k].cpu().numpy().astype(np.float64)
+        i, j = (ent & 0xff).astype(np.int64), ((ent >> 8) & 0xff).astype(np.int64)
+        cij, cji, los = (ent & _lib.PAIR_CONF_IJ) != 0, (ent & _lib.PAIR_CONF_JI) != 0, (ent & _lib.PAIR_LOS) != 0
+        own = np.concatenate([i[cij], j[cji]])
+        intr = np.concatenate([j[cij], i[cji]])
+        qdr = np.concatenate([att[cij, 0], (att[cji, 0] + 180.0) % 360.0])
+        cols = {"dist": 1, "dcpa": 2, "tcpa": 3}
+        vals = {name: np.concatenate([att[cij, c], att[cji, c]]) for name, c in cols.items()}
+        tin = np.concatenate([att[cij, 4], att[cji, 5]])
+        o = np.lexsort((intr, own))
+        lown, lintr = np.concatenate([i[los], j[los]]), np.concatenate([j[los], i[los]])
+        ol = np.lexsort((lintr, lown))
+        return dict(confpairs=np.stack([own[o], intr[o]], axis=1), lospairs=np.stack([lown[ol], lintr[ol]], axis=1),
+                    qdr=qdr[o], tinconf=tin[o], truncated=n > self.cd_pair_cap, **{k_: v[o] for k_, v in vals.items()})
+
     def reset_flags(self):
         """Per-env bit mask left by the last scenario generation (include/bsg.h BSG_I32_RESET_FLAGS): 1 = polygon area
         below the reference's threshold when the vertex cap was hit, 2 = aircraft count clipped to the slot count,
@@ -364,7 +399,8 @@ class BlueSkyVectorEnv(VectorEnv):
         return dict(env_id=self.env_id, num_envs=self.num_envs, n_intruders=self.n_intruders, seed=int(c.seed),
                     env_id_offset=int(c.env_id_offset), cd_enabled=int(c.cd_enabled), autoreset_mode=self.autoreset_mode,
                     max_episode_steps=int(c.max_episode_steps), wind_obs=int(c.wind_obs), init_alt=float(c.init_alt),
-                    sector_density_uniform=int(c.sector_density_uniform), default_hdg_random=int(c.default_hdg_random))
+                    sector_density_uniform=int(c.sector_density_uniform), default_hdg_random=int(c.default_hdg_random),
+                    cd_pair_cap=int(c.cd_pair_cap))
 
     def state_dict(self):
         """Checkpoint: clones of every device tensor that carries simulator state (aircraft SoA, per-env records,
@@ -400,7 +436,7 @@ class BlueSkyVectorEnv(VectorEnv):
         elif cfg is not None and self._wind_t is not None:
             self.set_wind()
         for k, v in sd.items():
-            if k in self.t and self.t[k] is not None:
+            if k in self.t and self.t[k] is not None and k != "final_count":      # (an output whose slot parity lives in the handle)
                 self.t[k].copy_(v)
         if "obs_noise" in sd:
             self.set_obs_noise(sd["obs_noise"]["sigma"])

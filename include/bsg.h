@@ -72,6 +72,8 @@ typedef struct bsg_config {
     float init_alt;             /* HorizontalCR: altitude [m] every aircraft is created at.  Reference: 0
                                  * (horizontal_cr_env.py:91, cre without acalt => ground phase, CAS capped near
                                  * 88 m/s); SURVEY 8d also measures a 3000 m variant (aircraft keep 150 m/s CAS) */
+    int32_t cd_pair_cap;        /* in-sim ASAS pair list: entries per env in tensor_table.cd_pairs / cd_attr
+                                 * (0 = lists off; slots*(slots-1)/2 holds every pair)                         */
 } bsg_config;
 
 /* What the caller must allocate (all device memory, zero-initialised) for a given config. */
@@ -101,15 +103,28 @@ typedef struct bsg_tensor_table {
     double *poly;       /* [E*poly_f64] or NULL                                                      */
     float *obs;         /* [E*obs_dim]   Env._get_obs, keys concatenated in declaration order        */
     float *final_obs;   /* [E*obs_dim]   SAME_STEP autoreset: terminal observations, COMPACT -- row k is the */
-                        /*               terminal obs of env final_ids[k], k < final_count[0]; may be NULL  */
+                        /*               terminal obs of env final_ids[k], k < final_count[final_count[2]]; may be NULL */
     int32_t *final_ids; /* [E]           env index of each compact final_obs row (needed with final_obs)    */
-    int32_t *final_count;/* [4]          [0] = number of envs that finished in the last step                */
+    int32_t *final_count;/* [4]          [2] = s in {0, 1}; [s] = number of envs that finished in the last step (two  */
+                        /*               counters take turns so that no memset sits between two step launches) */
     float *reward;      /* [E]                                                                       */
     uint8_t *terminated;/* [E]                                                                       */
     uint8_t *truncated; /* [E]                                                                       */
     float *info;        /* [E*info_dim]  Env._get_info values at the end of the step (pre-autoreset) */
     float *actions_staging; /* [E*act_dim] device staging buffer used by bsg_step_host, may be NULL  */
+    /* in-sim ASAS pair lists of the LAST simulator substep (bs.traf.cd.confpairs / lospairs and the per-conflict
+     * qdr, dist, dcpa, tcpa, tinconf of upstream's detect()), cfg.cd_pair_cap entries per env, count in
+     * env_i32[BSG_I32_NPAIRS] (true number found; entries beyond the capacity are dropped).  One entry per UNORDERED
+     * pair i < j that is a conflict in either order or a LoS:
+     *   cd_pairs: i | j << 8 | BSG_PAIR_CONF_IJ | BSG_PAIR_CONF_JI | BSG_PAIR_LOS
+     *   cd_attr : BSG_PAIR_ATTR_COUNT floats (qdr i->j [deg], dist [m], dcpa [m], tcpa [s], tinconf (i,j), tinconf (j,i))
+     * Both may be NULL (cd_attr alone may be NULL too). */
+    uint32_t *cd_pairs;     /* [E*cd_pair_cap]                                                          */
+    float *cd_attr;         /* [E*cd_pair_cap*BSG_PAIR_ATTR_COUNT]                                       */
 } bsg_tensor_table;
+enum { BSG_PAIR_CONF_IJ = 1 << 16, BSG_PAIR_CONF_JI = 1 << 17, BSG_PAIR_LOS = 1 << 18 };
+enum { BSG_PAIR_ATTR_QDR = 0, BSG_PAIR_ATTR_DIST = 1, BSG_PAIR_ATTR_DCPA = 2, BSG_PAIR_ATTR_TCPA = 3,
+       BSG_PAIR_ATTR_TINCONF_IJ = 4, BSG_PAIR_ATTR_TINCONF_JI = 5, BSG_PAIR_ATTR_COUNT = 6 };
 
 /* indices into the per-env records (shared by all env types; unused slots stay zero) */
 enum { BSG_F64_WPT_LAT = 0, BSG_F64_WPT_LON = 1, BSG_F64_TARGET_ALT = 2, BSG_F64_POLY_AREA = 3,
@@ -119,14 +134,15 @@ enum { BSG_F32_TOTAL_REWARD = 0, BSG_F32_DRIFT_SUM = 1, BSG_F32_FINAL_ALT = 2, B
 enum {
     BSG_I32_STEP = 0, BSG_I32_EPISODE = 1, BSG_I32_SIMK = 2, BSG_I32_WPT_REACH = 3, BSG_I32_DRIFT_N = 4,
     BSG_I32_INTRUSIONS = 5, BSG_I32_NUM_AC = 6, BSG_I32_NVERT = 7, BSG_I32_NEEDS_RESET = 8,
-    BSG_I32_FAF = 9, BSG_I32_NCONF = 10, BSG_I32_NLOS = 11, BSG_I32_RESET_FLAGS = 12, BSG_I32_COUNT = 16
+    BSG_I32_FAF = 9, BSG_I32_NCONF = 10, BSG_I32_NLOS = 11, BSG_I32_RESET_FLAGS = 12, BSG_I32_NPAIRS = 13,
+    BSG_I32_COUNT = 16
 };
 
 typedef struct bsg_handle bsg_handle;
 
 int bsg_abi_version(void);
 /* sizeof of the library's view of an interface structure (which: 0 bsg_config, 1 bsg_layout, 2 bsg_tensor_table,
- * 3 bsg_wind, 4 bsg_perf, 5 bsg_ac_state; anything else -1): a binding in another language checks its own declarations against it */
+ * 3 bsg_wind, 4 bsg_perf, 5 bsg_ac_state, 6 bsg_cd_lists; anything else -1): a binding in another language checks its own declarations against it */
 int bsg_abi_struct_size(int which);
 const char *bsg_last_error(void);
 int bsg_device_count(void);
@@ -253,14 +269,31 @@ enum { BSG_CD_LON_WRAP = 1,     /* pairs may straddle the +-180 deg meridian rel
        BSG_CD_ALLTILES = 8 };   /* bsg_cd_detect_culled: keep every tile pair (no culling; with
                                  * BSG_CD_SYMMETRIC = brute force over unordered pairs)              */
 
+/* Pair lists of a detection = what upstream's StateBased.detect returns besides the per-aircraft flags:
+ * confpairs, lospairs and, per conflict, qdr / dist / dcpa / tcpa / tinconf.  All DEVICE memory owned by the caller;
+ * any pointer may be NULL (that output is then only counted).  Entries are written in arbitrary order (upstream's
+ * order is row-major np.where; sort on the host if needed); conf_attr row k belongs to conf_pairs row k.  When more
+ * pairs exist than the capacity holds the lists are truncated, d_npairs keeps the true totals. */
+enum { BSG_CD_ATTR_QDR = 0 /* deg [0, 360) own -> intruder */, BSG_CD_ATTR_DIST = 1 /* m */, BSG_CD_ATTR_DCPA = 2 /* m */,
+       BSG_CD_ATTR_TCPA = 3 /* s */, BSG_CD_ATTR_TINCONF = 4 /* s */, BSG_CD_ATTR_COUNT = 5 };
+typedef struct bsg_cd_lists {
+    int32_t *d_conf_pairs;              /* [conf_cap][2] ordered (own, intruder) global indices             */
+    float *d_conf_attr;                 /* [conf_cap][BSG_CD_ATTR_COUNT]                                    */
+    int64_t conf_cap;
+    int32_t *d_los_pairs;               /* [los_cap][2]                                                     */
+    int64_t los_cap;
+    unsigned long long *d_npairs;       /* [2]: conflicts found, LoS pairs found (required with any list)   */
+} bsg_cd_lists;
+
 /* Rows [row0, row0+n_rows) of d_rec against all n_all aircraft (row sharding for multi-GPU).
- * Outputs (caller-owned, device): per-row nconf / nlos counts and tcpamax, inconf flags, and a pair
- * list of capacity `cap` ordered pairs (i, j) with its true length in d_npairs[0] (conflicts) and
- * d_npairs[1] (LoS pairs found; only counted).  Any output pointer except d_nconf_row may be NULL. */
+ * Outputs (caller-owned, device): per-row nconf / nlos counts and tcpamax, inconf flags, and the pair lists
+ * (`lists` may be NULL).  Any output pointer except d_nconf_row may be NULL.
+ * replaces: StateBased.detect(ownship, intruder, rpz, hpz, dtlookahead) -> confpairs, lospairs, inconf, tcpamax,
+ * qdr, dist, dcpa, tcpa, tLOS (upstream bluesky/traffic/asas/statebased.py). */
 int bsg_cd_detect(const float *d_rec, int64_t n_all, int64_t row0, int64_t n_rows,
                   float rpz, float hpz, float dtlookahead, uint32_t flags,
                   uint32_t *d_nconf_row, uint32_t *d_nlos_row, float *d_tcpamax, uint8_t *d_inconf,
-                  int32_t *d_pairs, int64_t cap, unsigned long long *d_npairs, void *stream);
+                  const bsg_cd_lists *lists, void *stream);
 
 /* bsg_cd_detect with spatial culling: identical outputs, but column tiles that cannot contain a conflict or LoS
  * partner of a row block (farther apart at time 0 than rpz + (v_a + v_b) * dtlookahead, or vertically beyond
@@ -272,8 +305,8 @@ int bsg_cd_detect(const float *d_rec, int64_t n_all, int64_t row0, int64_t n_row
 int64_t bsg_cd_cull_workspace(int64_t n_all, int64_t n_rows);
 int bsg_cd_detect_culled(const float *d_rec, int64_t n_all, int64_t row0, int64_t n_rows, float rpz, float hpz,
                          float dtlookahead, uint32_t flags, uint32_t *d_nconf_row, uint32_t *d_nlos_row,
-                         float *d_tcpamax, uint8_t *d_inconf, int32_t *d_pairs, int64_t cap,
-                         unsigned long long *d_npairs, void *d_work, int64_t work_bytes, void *stream);
+                         float *d_tcpamax, uint8_t *d_inconf, const bsg_cd_lists *lists,
+                         void *d_work, int64_t work_bytes, void *stream);
 
 /* Multi-GPU form without a gather: every GPU of the node packs its block of n_per_peer aircraft (a multiple of 256)
  * into a buffer that its peers can address (CUDA peer access / symmetric memory: torch.distributed._symmetric_memory
@@ -286,8 +319,8 @@ int bsg_cd_detect_culled(const float *d_rec, int64_t n_all, int64_t row0, int64_
  * Replaces: ncclAllGather + bsg_cd_detect(row0 = my_rank * n_per_peer, n_rows = n_per_peer). */
 int bsg_cd_detect_peers(const float *const *h_peer_rec, int32_t n_peers, int32_t my_rank, int64_t n_per_peer,
                         float rpz, float hpz, float dtlookahead, uint32_t flags, uint32_t *d_nconf_row,
-                        uint32_t *d_nlos_row, float *d_tcpamax, uint8_t *d_inconf, int32_t *d_pairs, int64_t cap,
-                        unsigned long long *d_npairs, void *d_work, int64_t work_bytes, void *stream);
+                        uint32_t *d_nlos_row, float *d_tcpamax, uint8_t *d_inconf, const bsg_cd_lists *lists,
+                        void *d_work, int64_t work_bytes, void *stream);
 
 /* ---- roofline denominators measured on the spot (bench.py) ------------------------------------- */
 /* Dense FP32 FMA throughput [FLOP/s] of this device, timed with CUDA events. */

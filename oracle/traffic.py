@@ -196,6 +196,13 @@ class Traffic:
             self.swlastwp[idx] = False
 
     # ------------------------------------------------------------------ simulation
+    def near_band(self):
+        """Ordered pairs whose conflict / LoS decision sits inside the comparison band of SURVEY 8c for the traffic state
+        the LAST detection saw (a float32 kernel may decide them either way): (near_conf, near_los) boolean matrices."""
+        m = statebased.detect_rows(np.arange(self.ntraf), *self._cd_inputs, self.rpz, self.hpz, self.dtlookahead,
+                                   with_margins=True)
+        return m["near_conf"], m["near_los"]
+
     def simstep(self):
         """Simulation.step(): stack.process(); timers step; traf.update()."""
         q, self.queue = self.queue, []
@@ -222,9 +229,12 @@ class Traffic:
         self.ap_tas = aero.vcasormach2tas(self.selspd, self.alt)
         # ---- ASAS (detection only; resolution is off) ------------------------------------
         if self.cd_enabled:
-            (self.confpairs, self.lospairs, self.inconf, self.tcpamax, *_rest) = statebased.detect(
+            self._cd_inputs = tuple(np.array(x, dtype=np.float64) for x in (self.lat, self.lon, self.trk, self.gs, self.alt, self.vs))
+            (self.confpairs, self.lospairs, self.inconf, self.tcpamax, *rest) = statebased.detect(
                 self.lat, self.lon, self.trk, self.gs, self.alt, self.vs,
                 self.rpz, self.hpz, self.dtlookahead)
+            # per conflict, aligned with confpairs (upstream ConflictDetection.update keeps them as cd.qdr, cd.dist, ...)
+            self.cd_qdr, self.cd_dist, self.cd_dcpa, self.cd_tcpa, self.cd_tinconf = rest
         # ---- APorASAS.update --------------------------------------------------------------
         p_trk, p_tas, p_alt = self.ap_trk, self.ap_tas, self.ap_alt
         p_vs = np.abs(self.ap_vs)

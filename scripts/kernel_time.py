@@ -22,8 +22,9 @@ def run(env_id, E, cd, steps=100, **kw):
         v.step_torch(a[10 + i])
         ev[i][1].record()
     torch.cuda.synchronize()
-    ms = sorted(x.elapsed_time(y) for x, y in ev)[steps // 2]
-    print(f"{env_id:22s} E={E:6d} cd={int(cd)} {kw}: median {ms * 1e3:8.1f} us/step  {E / ms * 1e3:.3e} env-steps/s")
+    ts = sorted(x.elapsed_time(y) for x, y in ev)
+    ms, mean = ts[steps // 2], sum(ts) / steps
+    print(f"{env_id:22s} E={E:6d} cd={int(cd)} {kw}: median {ms * 1e3:8.1f} mean {mean * 1e3:8.1f} us/step  {E / mean * 1e3:.3e} env-steps/s")
     v.close()
 
 

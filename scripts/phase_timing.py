@@ -1,0 +1,65 @@
+"""Where does the time of one env-step launch go?  Needs a profiling build of the library:
+
+    BSG_LIB_OUT=ab_libs/libbsg_phase.so BSG_EXTRA_NVCC_FLAGS=-DBSG_PHASE_TIMING python -m bluesky_gym_sasha_b200.build --force
+    BSG_B200_LIB=ab_libs/libbsg_phase.so python scripts/phase_timing.py [env_id] [E]
+
+Every env's lane 0 stamps %globaltimer at 8 phase boundaries (env_step.cu, BSG_STAMP); the stamps land in the unused
+tail of the final_obs buffer.  Printed: per phase the median / p95 / max duration over the envs, when the first and the
+last warp started and ended relative to the first start, and the CUDA-event time of the same launch (L2 flushed)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv  # noqa: E402
+
+NAMES = ["load ei32 + state + action", "compute_targets", "substep 0", "substeps 1..n-1", "load env record + obs/reward",
+         "autoreset (generator + obs)", "stores"]
+
+
+def main():
+    env_id = sys.argv[1] if len(sys.argv) > 1 else "HorizontalCREnv-v0"
+    E = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+    kw = dict(cd_enabled=True, n_intruders=20) if env_id == "HorizontalCREnv-v0" else dict(cd_enabled=True)
+    v = BlueSkyVectorEnv(env_id, E, seed=0, autoreset_mode="same_step", **kw)
+    v.reset_torch()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    rows = []
+    for i in range(60):
+        a = torch.rand((E, v.layout.act_dim), device="cuda", generator=g) * 2 - 1
+        flush.fill_(float(i))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        v.step_torch(a)
+        e1.record()
+        torch.cuda.synchronize()
+        if i < 20:
+            continue
+        st = v.t["final_obs"].view(-1).view(torch.int64)[-8 * E:].view(E, 8).cpu().numpy().astype(np.float64)
+        t0 = st[:, 0].min()
+        st = (st - t0) * 1e-3                                    # us since the first warp started
+        rows.append((e0.elapsed_time(e1) * 1e3, st, int(v.t["final_count"][int(v.t["final_count"][2])])))
+    ev = np.median([r[0] for r in rows])
+    print(f"{env_id} E={E}: CUDA-event time per launch {ev:.1f} us (median of {len(rows)}), envs finishing per step "
+          f"{np.mean([r[2] for r in rows]):.0f}")
+    st = np.stack([r[1] for r in rows])                          # [launch, env, stamp]
+    d = np.diff(st, axis=2)
+    print(f"{'phase':34s} {'median':>8s} {'p95':>8s} {'max':>8s}   [us per env]")
+    for k, name in enumerate(NAMES):
+        x = d[:, :, k].reshape(-1)
+        if k == 5:
+            x = x[x > 0.5] if (x > 0.5).any() else x              # only the envs that reset
+        print(f"{name:34s} {np.median(x):8.2f} {np.percentile(x, 95):8.2f} {x.max():8.2f}")
+    start, end = st[:, :, 0], st[:, :, 7]
+    print(f"warp start: median {np.median(start):.2f}  p95 {np.percentile(start, 95):.2f}  max {start.max(axis=1).mean():.2f} us after the first")
+    print(f"warp end  : median {np.median(end):.2f}  p95 {np.percentile(end, 95):.2f}  max {end.max(axis=1).mean():.2f} us after the first start")
+    print(f"lifetime of a warp: median {np.median(end - start):.2f}  p95 {np.percentile(end - start, 95):.2f}  max {(end - start).max():.2f} us")
+    fin = d[:, :, 5] > 0.5
+    print(f"envs that reset: {fin.mean() * 100:.1f} %; their lifetime median {np.median((end - start)[fin]) if fin.any() else 0:.2f} us")
+
+
+if __name__ == "__main__":
+    main()

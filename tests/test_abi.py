@@ -24,7 +24,7 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, n), f"{n} declared in include/bsg.h but not exported"
     assert set(_lib.SYMBOLS) == set(names)
     assert lib.bsg_abi_version() == 4
-    for which, st in enumerate((_lib.Config, _lib.Layout, _lib.TensorTable, _lib.Wind, _lib.Perf)):
+    for which, st in enumerate((_lib.Config, _lib.Layout, _lib.TensorTable, _lib.Wind, _lib.Perf, _lib.AcState, _lib.CdLists)):
         assert lib.bsg_abi_struct_size(which) == C.sizeof(st), st.__name__          # the ctypes mirror of include/bsg.h
     assert lib.bsg_abi_struct_size(99) == -1
 
@@ -69,7 +69,7 @@ def test_no_cpu_fallback(lib):
 
 def test_argument_validation(lib):
     from bluesky_gym_sasha_b200 import _lib
-    assert lib.bsg_cd_detect(None, 10, 5, 10, 0.0, 0.0, 0.0, 0, None, None, None, None, None, 0, None, None) == _lib.BSG_EINVAL
+    assert lib.bsg_cd_detect(None, 10, 5, 10, 0.0, 0.0, 0.0, 0, None, None, None, None, None, None) == _lib.BSG_EINVAL
     assert b"row range" in lib.bsg_last_error()
     assert lib.bsg_cd_pack(None, None, None, None, None, None, 4, 0.0, 0.0, None, None) == _lib.BSG_EINVAL
     assert lib.bsg_reset(None, None, None) == _lib.BSG_EINVAL

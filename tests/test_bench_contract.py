@@ -21,6 +21,9 @@ def test_reference_arm_prints_one_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # exactly K timed steps: ms_per_step is the measured wall time of a step (nothing extrapolated)
+    per_step = int(d["step_definition"].split("(")[1].split()[0])
+    assert abs(d["value"] - per_step * d["steps"] / (d["ms_per_step"] * d["steps"] * 1e-3)) < 1e-6 * d["value"]
 
 
 def test_reference_arm_other_ranks_stay_silent():

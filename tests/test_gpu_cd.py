@@ -14,7 +14,9 @@ pytestmark = pytest.mark.gpu
 RPZ, HPZ, DTL = 9260.0, 304.8, 300.0
 
 
-def _check_against_oracle(s, g, rows=None):
+def _check_against_oracle(s, g, rows=None, stats=None, pos_quant=0.5):
+    """Conflict AND LoS pair sets (as sets of ordered index pairs) identical to the float64 oracle outside the epsilon
+    band; per-row outputs for rows with no banded pair; qdr / dist / dcpa / tcpa / tinconf of every common conflict."""
     n = len(s[0])
     rows = np.arange(n) if rows is None else rows
     o = statebased.detect_rows(rows, *s, RPZ, HPZ, DTL, with_margins=True)
@@ -26,6 +28,12 @@ def _check_against_oracle(s, g, rows=None):
     bad = [p for p in gp ^ op if not near[row_of[p[0]], p[1]]]
     assert not bad, f"{len(bad)} pair mismatches outside the epsilon band, e.g. {bad[:5]}"
     n_exempt = len(gp ^ op)
+    # LoS pairs as a set
+    gl = {p for p in map(tuple, g["lospairs"].tolist()) if p[0] in row_of}
+    ol = {(int(rows[i]), int(j)) for i, j in zip(*np.where(o["swlos"]))}
+    badl = [p for p in gl ^ ol if not o["near_los"][row_of[p[0]], p[1]]]
+    assert not badl, f"{len(badl)} LoS pair mismatches outside the epsilon band, e.g. {badl[:5]}"
+    assert len(g["lospairs"]) == g["n_los"] and len(set(map(tuple, g["lospairs"].tolist()))) == g["n_los"]
     # per-row outputs, for rows with no banded pair
     clean = ~(near.any(axis=1) | o["near_los"].any(axis=1))
     nconf_o = sw.sum(axis=1)
@@ -36,6 +44,29 @@ def _check_against_oracle(s, g, rows=None):
     assert np.array_equal(g["inconf"][gi][clean], nconf_o[clean] > 0)
     tmax_o = np.max(o["tcpa"] * sw, axis=1)
     np.testing.assert_allclose(g["tcpamax"][gi][clean], tmax_o[clean], rtol=2e-4, atol=0.05)
+    # attributes of the conflicts both sides report (float32 kernel vs float64 oracle; tolerances stated here):
+    #   qdr 2e-3 deg (+ 2 pos_quant / dist), dist 1e-5 rel + pos_quant, dcpa 1e-4 rel + 4 pos_quant, tcpa 1e-4 rel + 0.05 s,
+    #   tinconf 1e-4 rel + 0.05 s + 1e-2 of the half-width of the horizontal window (sqrt near dcpa = R), banded pairs skipped.
+    #   pos_quant = resolution of the float32 record positions: 0.5 m within ~40 deg of the airspace origin; the antimeridian
+    #   test puts the origin half a world away (x ~ 2e7 m: 2 m steps) on purpose
+    err = dict(qdr=0.0, dist=0.0, dcpa=0.0, tcpa=0.0, tinconf=0.0)
+    for k, (i, j) in enumerate(map(tuple, g["confpairs"].tolist())):
+        if i not in row_of or (i, j) not in op or near[row_of[i], j]:
+            continue
+        r = row_of[i]
+        dist, dcpa, tcpa, tin = o["dist"][r, j], np.sqrt(o["dcpa2"][r, j]), o["tcpa"][r, j], o["tinconf"][r, j]
+        dq = abs((g["qdr"][k] - o["qdr"][r, j] + 180.0) % 360.0 - 180.0)
+        assert dq < 2e-3 + np.degrees(2.0 * pos_quant / max(dist, 1.0)), (i, j, "qdr", g["qdr"][k], o["qdr"][r, j])
+        assert abs(g["dist"][k] - dist) < pos_quant + 1e-5 * dist, (i, j, "dist")
+        assert abs(g["dcpa"][k] - dcpa) < 4.0 * pos_quant + 1e-4 * dcpa, (i, j, "dcpa", g["dcpa"][k], dcpa)
+        assert abs(g["tcpa"][k] - tcpa) < 0.05 * max(1.0, 2.0 * pos_quant) + 1e-4 * abs(tcpa), (i, j, "tcpa")
+        half = abs(tcpa - tin)
+        assert abs(g["tinconf"][k] - tin) < 0.05 * max(1.0, 2.0 * pos_quant) + 1e-4 * abs(tin) + 1e-2 * half, (i, j, "tinconf", g["tinconf"][k], tin)
+        for name, e in (("qdr", dq), ("dist", abs(g["dist"][k] - dist)), ("dcpa", abs(g["dcpa"][k] - dcpa)),
+                        ("tcpa", abs(g["tcpa"][k] - tcpa)), ("tinconf", abs(g["tinconf"][k] - tin))):
+            err[name] = max(err[name], float(e))
+    if stats is not None:
+        stats.update(err, n_los=len(ol), n_los_exempt=len(gl ^ ol))
     return n_exempt, len(op)
 
 
@@ -43,10 +74,15 @@ def _check_against_oracle(s, g, rows=None):
 def test_dense_parity(cuda, n, box):
     from bluesky_gym_sasha_b200.cd import StateBasedCD
     s = synth_airspace(n, box_deg=box, seed=n)
-    g = StateBasedCD(rpz=RPZ, hpz=HPZ, dtlookahead=DTL).detect(*s)
-    n_exempt, n_conf = _check_against_oracle(s, g)
-    assert g["n_conf"] == len(g["confpairs"])
-    assert n_exempt <= max(2, n_conf // 200), (n_exempt, n_conf)       # the band must stay a rarity
+    stats = {}
+    for kw in (dict(cull=False, symmetric=False), dict()):             # every ordered pair / the default (culled + symmetric) form
+        g = StateBasedCD(rpz=RPZ, hpz=HPZ, dtlookahead=DTL).detect(*s, **kw)
+        n_exempt, n_conf = _check_against_oracle(s, g, stats=stats)
+        assert g["n_conf"] == len(g["confpairs"]) == len(g["tcpa"])
+        assert n_exempt <= max(2, n_conf // 200), (n_exempt, n_conf)       # the band must stay a rarity
+        assert stats["n_los_exempt"] <= max(2, stats["n_los"] // 100)
+    print(f"N={n}: {n_conf} conflicts ({n_exempt} banded), {stats['n_los']} LoS pairs ({stats['n_los_exempt']} banded); max |error| "
+          + ", ".join(f"{k} {stats[k]:.3g}" for k in ("qdr", "dist", "dcpa", "tcpa", "tinconf")))
 
 
 def test_empty_and_single(cuda):
@@ -68,11 +104,22 @@ def test_known_geometry(cuda):
     alt = np.array([9000.0, 9000.0, 5000.0, 5000.0 + 2 * HPZ])
     vs = np.zeros(4)
     g = StateBasedCD().detect(lat, lon, trk, gs, alt, vs)
-    assert set(map(tuple, g["confpairs"].tolist())) == {(0, 1), (1, 0)}
+    assert g["confpairs"].tolist() == [[0, 1], [1, 0]]                 # row-major, like upstream's np.where
     d = 6371000.0 * np.radians(1.0)
     assert abs(g["tcpamax"][0] - d / 400.0) < 0.05
     assert list(g["inconf"]) == [True, True, False, False]
-    assert g["n_los"] == 0
+    assert g["n_los"] == 0 and g["lospairs"].shape == (0, 2)
+    # attributes of the two conflicts: bearing east / west, distance of one degree of longitude on the equator,
+    # closest approach 0, entry into the zone (d - rpz) / 400 s from now
+    np.testing.assert_allclose(g["qdr"], [90.0, 270.0], atol=1e-3)
+    np.testing.assert_allclose(g["dist"], [d, d], rtol=1e-6)
+    np.testing.assert_allclose(g["dcpa"], [0.0, 0.0], atol=1.0)
+    np.testing.assert_allclose(g["tcpa"], [d / 400.0] * 2, atol=0.05)
+    np.testing.assert_allclose(g["tinconf"], [(d - RPZ) / 400.0] * 2, atol=0.05)
+    # two aircraft inside each other's zone: one LoS pair in each order
+    lat2, lon2 = np.array([52.0, 52.02]), np.array([4.0, 4.0])
+    g2 = StateBasedCD().detect(lat2, lon2, np.array([90.0, 90.0]), np.array([200.0, 210.0]), np.array([9000.0, 9100.0]), np.zeros(2))
+    assert g2["lospairs"].tolist() == [[0, 1], [1, 0]] and g2["n_los"] == 2
 
 
 def test_lon_wrap(cuda):
@@ -81,7 +128,7 @@ def test_lon_wrap(cuda):
     s = list(synth_airspace(600, box_deg=3.0, seed=5, lat0=10.0, lon0=179.9))
     s[1] = (s[1] + 180.0) % 360.0 - 180.0
     g = StateBasedCD().detect(*s, lon0=0.0)        # origin far away -> the wrap path is taken
-    _check_against_oracle(tuple(s), g)
+    _check_against_oracle(tuple(s), g, pos_quant=4.0)
 
 
 def test_row_shards_union(cuda):
@@ -119,12 +166,27 @@ def test_full_size_sampled_rows(cuda):
     ps = set(map(tuple, g["confpairs"].tolist()))
     asym = [p for p in ps if (p[1], p[0]) not in ps]
     assert len(asym) <= max(2, len(ps) // 500)         # uniform zones => symmetric up to the epsilon band
-    rows = np.random.default_rng(0).choice(n, 48, replace=False)
+    assert g["nlos_row"].sum() == g["n_los"] == len(g["lospairs"])
+    ls = set(map(tuple, g["lospairs"].tolist()))
+    assert len([p for p in ls if (p[1], p[0]) not in ls]) <= max(2, len(ls) // 200)       # LoS is symmetric
+    conf_of, los_of = {}, {}
+    for i, j in g["confpairs"].tolist():
+        conf_of.setdefault(i, set()).add(j)
+    for i, j in g["lospairs"].tolist():
+        los_of.setdefault(i, set()).add(j)
+    # sampled rows: every row that has a LoS pair (they are few) + 48 random ones, as SETS against the C restatement
+    rows = sorted(set(np.random.default_rng(0).choice(n, 48, replace=False).tolist()) | set(list(los_of)[:64]))
+    n_los_rows = 0
     for r in rows:
-        c = cbind.detect_rows(*s, RPZ, HPZ, DTL, row0=int(r), nrows=1)
-        if abs(int(c["nconf_row"][0]) - int(g["nconf_row"][r])) > 0 or abs(int(c["nlos_row"][0]) - int(g["nlos_row"][r])) > 0:
+        c = cbind.detect_rows(*s, RPZ, HPZ, DTL, row0=int(r), nrows=1, pair_cap=4096)
+        oc = {int(j) for _, j in c["confpairs"].tolist()}
+        ol = {int(j) for _, j in c["lospairs"].tolist()}
+        n_los_rows += bool(ol)
+        if oc != conf_of.get(r, set()) or ol != los_of.get(r, set()):
             o = statebased.detect_rows(np.array([r]), *s, RPZ, HPZ, DTL, with_margins=True)
-            assert o["near_conf"].any() or o["near_los"].any(), f"row {r}: counts differ with no banded pair"
+            assert all(o["near_conf"][0, j] for j in oc ^ conf_of.get(r, set())), f"row {r}: conflict sets differ outside the band"
+            assert all(o["near_los"][0, j] for j in ol ^ los_of.get(r, set())), f"row {r}: LoS sets differ outside the band"
+    assert n_los_rows > 0 or g["n_los"] == 0
 
 
 @pytest.mark.parametrize("n,box,seed", [(20000, 40.0, 3), (5000, 3.0, 4), (1, 1.0, 5), (257, 60.0, 6), (40001, 25.0, 7)])
@@ -137,7 +199,9 @@ def test_culled_form_is_identical_to_plain(cuda, n, box, seed):
     plain = cd.detect(*s, cull=False, symmetric=False)
     culled = cd.detect(*s, cull=True, symmetric=False)
     assert plain["n_conf"] == culled["n_conf"] and plain["n_los"] == culled["n_los"]
-    assert set(map(tuple, plain["confpairs"].tolist())) == set(map(tuple, culled["confpairs"].tolist()))
+    assert np.array_equal(plain["confpairs"], culled["confpairs"]) and np.array_equal(plain["lospairs"], culled["lospairs"])
+    for k in ("qdr", "dist", "dcpa", "tcpa", "tinconf"):          # the same exact routine decides in every form
+        assert np.array_equal(plain[k], culled[k]), k
     assert np.array_equal(plain["nconf_row"], culled["nconf_row"]) and np.array_equal(plain["nlos_row"], culled["nlos_row"])
     assert np.array_equal(plain["inconf"], culled["inconf"])
     assert np.array_equal(plain["tcpamax"], culled["tcpamax"])
@@ -147,7 +211,9 @@ def test_culled_form_is_identical_to_plain(cuda, n, box, seed):
     for kw in (dict(symmetric=True), dict(symmetric=True, cull=True)):
         sym = cd.detect(*s, **kw)
         assert plain["n_conf"] == sym["n_conf"] and plain["n_los"] == sym["n_los"], kw
-        assert set(map(tuple, plain["confpairs"].tolist())) == set(map(tuple, sym["confpairs"].tolist())), kw
+        assert np.array_equal(plain["confpairs"], sym["confpairs"]) and np.array_equal(plain["lospairs"], sym["lospairs"]), kw
+        for k in ("qdr", "dist", "dcpa", "tcpa", "tinconf"):
+            assert np.array_equal(plain[k], sym[k]), (kw, k)
         assert np.array_equal(plain["nconf_row"], sym["nconf_row"]) and np.array_equal(plain["nlos_row"], sym["nlos_row"]), kw
         assert np.array_equal(plain["inconf"], sym["inconf"]) and np.array_equal(plain["tcpamax"], sym["tcpamax"]), kw
 
@@ -222,15 +288,20 @@ def test_peer_form_equals_gathered_form(cuda, cull):
         inconf = torch.zeros(per, dtype=torch.uint8, device="cuda")
         npairs = torch.zeros(2, dtype=torch.int64, device="cuda")
         pairs = torch.zeros((1 << 16, 2), dtype=torch.int32, device="cuda")
+        los = torch.zeros((1 << 12, 2), dtype=torch.int32, device="cuda")
+        lists = _lib.CdLists(d_conf_pairs=pairs.data_ptr(), d_conf_attr=None, conf_cap=1 << 16, d_los_pairs=los.data_ptr(),
+                             los_cap=1 << 12, d_npairs=npairs.data_ptr())
         nbytes = int(lib.bsg_cd_cull_workspace(n, per))
         work = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
         _lib.check(lib.bsg_cd_detect_peers(ptrs, W, r, per, RPZ, HPZ, DTL, _lib.CD_CULL if cull else 0, nconf.data_ptr(),
-                                           nlos.data_ptr(), tmax.data_ptr(), inconf.data_ptr(), pairs.data_ptr(), 1 << 16,
-                                           npairs.data_ptr(), work.data_ptr(), nbytes, None))
+                                           nlos.data_ptr(), tmax.data_ptr(), inconf.data_ptr(), C.byref(lists),
+                                           work.data_ptr(), nbytes, None))
         torch.cuda.synchronize()
         assert torch.equal(nconf, ref["nconf_row"]) and torch.equal(nlos, ref["nlos_row"]) and torch.equal(tmax, ref["tcpamax"])
         k = int(npairs[0])
         assert k == int(ref["npairs"][0])
         assert set(map(tuple, pairs[:k].tolist())) == set(map(tuple, ref["pairs"][:k].tolist()))
+        kl = int(npairs[1])
+        assert kl == int(ref["npairs"][1]) and set(map(tuple, los[:kl].tolist())) == set(map(tuple, ref["lospairs"][:kl].tolist()))
         tot += k
     assert tot > 100

@@ -26,6 +26,21 @@ pytestmark = pytest.mark.gpu
 TOL = dict(pos=2e-5, alt=0.5, tas=2e-2, vs=2e-2, hdg=5e-3)
 
 
+class ErrStats:
+    """Largest observed |device - oracle| per quantity (printed by the parity tests: the evidence behind the tolerances)."""
+
+    def __init__(self):
+        self.m = {}
+
+    def add(self, name, err):
+        err = float(np.max(err)) if np.size(err) else 0.0
+        if np.isfinite(err):
+            self.m[name] = max(self.m.get(name, 0.0), err)
+
+    def __str__(self):
+        return ", ".join(f"{k} {v:.3g}" for k, v in sorted(self.m.items()))
+
+
 def _make_oracle(env_id, draws=None, cd=False, n_int=5, density="normal", init_alt=0.0):
     if env_id == "HorizontalCREnv-v0":
         return oenvs.HorizontalCREnv(n_intruders=n_int, draws=draws, cd_enabled=cd, init_alt=init_alt)
@@ -74,7 +89,7 @@ def _inject(venv, e, oenv, env_id):
     inject_oracle_env(venv, e, oenv, extra_f64=f64, extra_i32=i32, poly=poly, extra_f32=f32)
 
 
-def _compare_traffic(venv, oracles, alive_mask, step, exempt=None):
+def _compare_traffic(venv, oracles, alive_mask, step, exempt=None, stats=None):
     d = device_traffic(venv)
     for e, o in enumerate(oracles):
         if not alive_mask[e]:
@@ -97,16 +112,79 @@ def _compare_traffic(venv, oracles, alive_mask, step, exempt=None):
         d2wp = np.asarray(ogeo.kwikdist(t.lat, t.lon, t.actwp_lat, t.actwp_lon)) * 1852.0
         hdg_tol = TOL["hdg"] + np.where(t.swlnav, np.degrees(2.0 / np.maximum(d2wp, 1.0)) * 3.0, 0.0)
         assert np.all((angdiff(d["hdg"][e, :n], t.hdg) < hdg_tol)[ok]), (step, e, "hdg", angdiff(d["hdg"][e, :n], t.hdg).max())
+        if stats is not None and ok.any():
+            plain = ok & (np.asarray(t.iactwp) < 1)                # (aircraft past a waypoint carry the documented offset)
+            if plain.any():
+                stats.add("pos_deg", np.maximum(np.abs(d["lat"][e, :n] - t.lat), np.abs(d["lon"][e, :n] - t.lon))[plain])
+            stats.add("alt_m", np.abs(d["alt"][e, :n] - t.alt)[ok])
+            stats.add("tas", np.abs(d["tas"][e, :n] - t.tas)[ok])
+            stats.add("vs", np.abs(d["vs"][e, :n] - t.vs)[ok])
+            stats.add("hdg_deg", angdiff(d["hdg"][e, :n], t.hdg)[ok & ~t.swlnav])
+
+
+def _compare_asas_pairs(g, t, where):
+    """In-sim ASAS pair lists of one env (``BlueSkyVectorEnv.asas_pairs``) against the oracle traffic's last detection:
+    conflict and LoS pair SETS identical outside the epsilon band of SURVEY 8c, and qdr / dist / dcpa / tcpa / tinconf of
+    every common conflict (same tolerances as tests/test_gpu_cd.py).  Returns the number of conflicts compared."""
+    assert not g["truncated"], where
+    gp, op = set(map(tuple, g["confpairs"].tolist())), set(t.confpairs)
+    gl, ol = set(map(tuple, g["lospairs"].tolist())), set(t.lospairs)
+    if gp != op or gl != ol:
+        near_conf, near_los = t.near_band()
+        assert all(near_conf[i, j] for i, j in gp ^ op), (where, "confpairs", sorted(gp ^ op))
+        assert all(near_los[i, j] for i, j in gl ^ ol), (where, "lospairs", sorted(gl ^ ol))
+    o_idx = {p: k for k, p in enumerate(t.confpairs)}
+    n = 0
+    for k, p in enumerate(map(tuple, g["confpairs"].tolist())):
+        if p not in o_idx:
+            continue
+        q = o_idx[p]
+        dist, dcpa, tcpa, tin = t.cd_dist[q], t.cd_dcpa[q], t.cd_tcpa[q], t.cd_tinconf[q]
+        if abs(dcpa * dcpa - t.rpz ** 2) / t.rpz ** 2 < 1e-3:
+            continue                                            # near-banded: the entry time is a square root near zero
+        # The device evaluates ITS OWN float32 traffic state, which follows the oracle's within the trajectory tolerances
+        # (TOL: 2 m in position, 2e-2 m/s per velocity component): the attributes inherit that -- a relative velocity known
+        # to dv = 4e-2 m/s out of vrel turns into tcpa * dv / vrel seconds and dist * dv / vrel metres of closest approach
+        i, j = p
+        _, _, trk_, gs_, _, _ = t._cd_inputs                      # the traffic state the last detection saw
+        vrel = max(np.hypot(gs_[j] * np.sin(np.radians(trk_[j])) - gs_[i] * np.sin(np.radians(trk_[i])),
+                            gs_[j] * np.cos(np.radians(trk_[j])) - gs_[i] * np.cos(np.radians(trk_[i]))), 1e-3)
+        rel = 2.0 * TOL["tas"] / vrel + 1e-4
+        dpos = 2.0 * TOL["pos"] * 111e3
+        assert abs((g["qdr"][k] - t.cd_qdr[q] + 180.0) % 360.0 - 180.0) < 2e-3 + np.degrees(dpos / max(dist, 1.0)), (where, p, "qdr")
+        assert abs(g["dist"][k] - dist) < dpos + 1e-5 * dist, (where, p, "dist")
+        assert abs(g["dcpa"][k] - dcpa) < 2.0 * dpos + rel * max(dist, dcpa), (where, p, "dcpa", g["dcpa"][k], dcpa)
+        assert abs(g["tcpa"][k] - tcpa) < 0.05 + dpos / vrel + rel * abs(tcpa), (where, p, "tcpa", g["tcpa"][k], tcpa)
+        half = abs(tcpa - tin)
+        assert abs(g["tinconf"][k] - tin) < 0.05 + dpos / vrel + rel * (abs(tin) + abs(tcpa)) + 0.05 * half, (where, p, "tinconf", g["tinconf"][k], tin)
+        n += 1
+    return n
+
+
+def _compare_tcpamax(g_tcpamax, t, where):
+    """Per-aircraft tcpamax (max of tcpa over the aircraft's conflicts) against the oracle's.  A time to closest approach is
+    distance over closing speed: with the device's own float32 traffic state following the oracle's within TOL (2 m, 2e-2 m/s
+    per velocity component) it is known to 2 TOL_pos / vrel + tcpa * 2 TOL_tas / vrel -- slowly converging pairs (two MergeEnv
+    intruders on almost the same track: vrel of a few m/s, tcpa of thousands of seconds) inherit percents, not 1e-3."""
+    _, _, trk_, gs_, _, _ = t._cd_inputs
+    u, v = gs_ * np.sin(np.radians(trk_)), gs_ * np.cos(np.radians(trk_))
+    tol = np.full(t.ntraf, 0.05)
+    for (i, j), tc in zip(t.confpairs, t.cd_tcpa):
+        vrel = max(np.hypot(u[j] - u[i], v[j] - v[i]), 1e-3)
+        tol[i] = max(tol[i], 0.05 + 2.0 * TOL["pos"] * 111e3 / vrel + abs(tc) * (2.0 * TOL["tas"] / vrel + 1e-3))
+    assert np.all(np.abs(g_tcpamax - t.tcpamax) <= tol), (where, "tcpamax", g_tcpamax, t.tcpamax, tol)
 
 
 OWNSHIP_KEYS = ("cos(drift)", "sin(drift)", "airspeed", "waypoint_dist", "faf_reached")
 
 
-def _compare_obs(gobs, oobs, e, step, vnorm=None, ownship_only=False):
+def _compare_obs(gobs, oobs, e, step, vnorm=None, ownship_only=False, stats=None):
     for k, v in oobs.items():
         if ownship_only and k not in OWNSHIP_KEYS:
             continue
         atol = 5e-4
+        if stats is not None and k not in ("cos(track)", "sin(track)"):
+            stats.add("obs", np.abs(gobs[k][e] - v) / (1.0 + np.abs(v)))
         if k in ("cos(track)", "sin(track)") and vnorm is not None:
             # direction of the relative velocity: ill-conditioned when the two aircraft fly almost the same
             # vector; allow the stated TAS tolerance (2e-2 m/s) divided by the relative speed
@@ -124,6 +202,7 @@ def _compare_obs(gobs, oobs, e, step, vnorm=None, ownship_only=False):
     ("HorizontalCREnv-v0", 31, True, 12),          # a full 32-aircraft group (even n: the doubled offset n/2)
     ("SectorCREnv-v0", 0, True, 40),
     ("MergeEnv-v0", 0, False, 50),
+    ("MergeEnv-v0", 0, True, 50),                  # the configuration bench.py times (FMS-guided intruders + CD every substep)
     ("PlanWaypointEnv-v0", 0, False, 60),
     ("VerticalCREnv-v0", 0, True, 45),
     ("StaticObstacleEnv-v0", 0, False, 100),
@@ -134,7 +213,7 @@ def test_step_parity_injected_state(cuda, env_id, n_int, cd, steps):
     np.random.seed(1234)
     random.seed(1234)
     kw = dict(n_intruders=n_int) if n_int else {}
-    venv = BlueSkyVectorEnv(env_id, E, seed=7, cd_enabled=cd, autoreset_mode="disabled", max_episode_steps=0, **kw)
+    venv = BlueSkyVectorEnv(env_id, E, seed=7, cd_enabled=cd, autoreset_mode="disabled", max_episode_steps=0, cd_pairs=cd, **kw)
     venv.reset()
     oracles = [_make_oracle(env_id, cd=cd, n_int=n_int) for _ in range(E)]
     o_obs = [o.reset()[0] for o in oracles]
@@ -150,6 +229,8 @@ def test_step_parity_injected_state(cuda, env_id, n_int, cd, steps):
     # aircraft is excluded, and for its env only the ownship quantities are compared.  Counted below.
     exempt = [set() for _ in range(E)]
     compared_full = 0
+    n_pairs_checked = 0
+    stats = ErrStats()
     for step in range(steps):
         a = rng.uniform(-1.0, 1.0, size=(E, act_dim)).astype(np.float32)
         gobs, grew, gterm, gtrunc, ginfo = venv.step(a)
@@ -159,13 +240,14 @@ def test_step_parity_injected_state(cuda, env_id, n_int, cd, steps):
             lnav_before = o.traf.swlnav.copy()
             oobs, orew, oterm, otrunc, oinfo = o.step(a[e].astype(np.float64))
             exempt[e] |= set(np.where(lnav_before & ~o.traf.swlnav)[0].tolist())
-            _compare_obs(gobs, oobs, e, step, vnorm, ownship_only=bool(exempt[e]))
+            _compare_obs(gobs, oobs, e, step, vnorm, ownship_only=bool(exempt[e]), stats=stats)
             if exempt[e]:
                 if oterm or otrunc:
                     alive[e] = False
                 continue
             compared_full += 1
             assert abs(grew[e] - orew) < 1e-3, (step, e, grew[e], orew)
+            stats.add("reward", abs(grew[e] - orew))
             assert bool(gterm[e]) == bool(oterm), (step, e, "terminated")
             assert bool(gtrunc[e]) == bool(otrunc), (step, e, "truncated")
             for k, v in oinfo.items():
@@ -178,12 +260,17 @@ def test_step_parity_injected_state(cuda, env_id, n_int, cd, steps):
                 assert ginfo["asas_nconf"][e] == len(t.confpairs), (step, e, "nconf", ginfo["asas_nconf"][e], len(t.confpairs))
                 assert ginfo["asas_nlos"][e] == len(t.lospairs), (step, e, "nlos")
                 assert np.array_equal(d["inconf"][e, :t.ntraf], t.inconf), (step, e, "inconf")
-                np.testing.assert_allclose(d["tcpamax"][e, :t.ntraf], t.tcpamax, rtol=1e-3, atol=0.05)
+                _compare_tcpamax(d["tcpamax"][e, :t.ntraf], t, (step, e))
+                n_pairs_checked += _compare_asas_pairs(venv.asas_pairs(e), t, (step, e))
             if oterm or otrunc:
                 alive[e] = False
-        _compare_traffic(venv, oracles, alive, step, exempt)
+        _compare_traffic(venv, oracles, alive, step, exempt, stats)
     n_ex = sum(1 for x in exempt if x)
-    print(f"{env_id}: {compared_full} env-steps compared in full, {n_ex}/{E} envs ended with an exempted aircraft")
+    print(f"{env_id}: {compared_full} env-steps compared in full, {n_ex}/{E} envs ended with an exempted aircraft"
+          + (f", {n_pairs_checked} in-sim ASAS conflict pairs compared with their attributes" if cd else "")
+          + f"; max |error|: {stats}")
+    if cd:
+        assert n_pairs_checked > 0
     assert compared_full >= (steps * E) // 4
     if env_id != "MergeEnv-v0":
         assert n_ex == 0
