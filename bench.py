@@ -326,8 +326,9 @@ def run_b200(args):
     h2d = E * L.act_dim * 4
     d2h = venv._out_bytes          # the mirrored head of the output block: obs, reward, info, flags, terminal-obs window
     e2e = {"value": E * world * K / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "api": "BlueSkyVectorEnv.step, default arguments (numpy in; fresh float32 numpy arrays out; bsg_step_host_copy: one H2D, "
-                  "one launch, one D2H of the output block, pooled host copy into the fresh array)"}
+           "api": "BlueSkyVectorEnv.step, default arguments (numpy in; float32 numpy arrays out that the caller owns; "
+                  "bsg_step_host_block: one H2D, one launch, one D2H of the output block straight into a pinned block leased to "
+                  "the caller until the arrays are dropped -- no host copy)"}
     # same call with copy=False (views of two rotating pinned buffers instead of fresh copies), for context
     venv.copy = False
     barrier()

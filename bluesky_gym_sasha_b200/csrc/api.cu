@@ -115,6 +115,7 @@ extern "C" int bsg_create(const bsg_config* cfg, bsg_handle** out) {
     if (rc != BSG_OK) return rc;
     if (cfg->autoreset_mode < 0 || cfg->autoreset_mode > 2) return bsg_fail(BSG_EINVAL, "bad autoreset_mode");
     if (cfg->cd_pair_cap < 0) return bsg_fail(BSG_EINVAL, "cd_pair_cap must be >= 0");
+    if ((long long)cfg->num_envs * lay.slots > 0x7fffff00LL) return bsg_fail(BSG_EINVAL, "num_envs * slots exceeds the 32-bit thread index");
     int ndev = bsg_device_count();
     if (ndev <= 0) return bsg_fail(BSG_ECUDA, "no CUDA device: libbsg_b200 has no CPU fallback");
     if (cfg->device < 0 || cfg->device >= ndev) return bsg_fail(BSG_EINVAL, "device ordinal out of range");

@@ -29,7 +29,7 @@ namespace bsg {
 #endif
 constexpr int kEnvThreads = BSG_ENV_THREADS;
 constexpr int kEnvBlocksPerSm = 896 / BSG_ENV_THREADS;      // 28 warps per SM: what 72 registers per thread allow
-constexpr uint32_t kFlAlive = 1u, kFlLnav = 2u, kFlLastWp = 4u, kFlWpShift = 8u;
+constexpr uint32_t kFlAlive = 1u, kFlLnav = 2u, kFlLastWp = 4u, kFlTgt = 8u /* aux.w caches allow_tas */, kFlWpShift = 8u;
 enum { kModeStep = 0, kModeReset = 1, kModeTraf = 2 };
 
 // bluesky.traffic.performance.openap.phase constants
@@ -63,6 +63,7 @@ struct Ac {
     float alt, tas, hdg, vs;
     float selspd, selalt, selvs, aptrk;
     float ax, curlegdir, cas;
+    float tgt;                // allow_tas of the last launch's targets (valid with kFlTgt; see env_kernel)
     uint32_t flags;
     float gsn, gse;           // cached tas*cos(hdg), tas*sin(hdg) of the last groundspeed update
     float coslat;             // cached cos(lat) of the last position update
@@ -122,7 +123,7 @@ __device__ inline void ac_create_tas(Ac& a, double lat, double lon, double hdg, 
     a.lat = lat; a.lon = lon > 180.0 ? lon - 360.0 : (lon < -180.0 ? lon + 360.0 : lon);
     a.alt = (float)alt; a.tas = (float)tas; a.hdg = (float)hdg; a.vs = 0.0f;
     a.selspd = (float)cas_cmd; a.selalt = (float)alt; a.selvs = 0.0f; a.aptrk = (float)hdg;
-    a.ax = 0.0f; a.curlegdir = -999.0f; a.cas = (float)cas_cmd;
+    a.ax = 0.0f; a.curlegdir = -999.0f; a.cas = (float)cas_cmd; a.tgt = 0.0f;
     a.flags = kFlAlive;
     double hr = hdg * kDeg2RadD;
     a.gsn = (float)(tas * cos(hr)); a.gse = (float)(tas * sin(hr));
@@ -135,7 +136,7 @@ __device__ inline void ac_create_dir(Ac& a, double lat, double lon, double hdg, 
     a.lat = lat; a.lon = lon > 180.0 ? lon - 360.0 : (lon < -180.0 ? lon + 360.0 : lon);
     a.alt = (float)alt; a.tas = (float)tas; a.hdg = (float)hdg; a.vs = 0.0f;
     a.selspd = (float)cas_cmd; a.selalt = (float)alt; a.selvs = 0.0f; a.aptrk = (float)hdg;
-    a.ax = 0.0f; a.curlegdir = -999.0f; a.cas = (float)cas_cmd;
+    a.ax = 0.0f; a.curlegdir = -999.0f; a.cas = (float)cas_cmd; a.tgt = 0.0f;
     a.flags = kFlAlive;
     a.gsn = (float)(tas * ch); a.gse = (float)(tas * sh);
     a.coslat = __cosf((float)a.lat * kDeg2Rad);                // (the expression ac_load rebuilds it with)
@@ -147,7 +148,7 @@ __device__ inline void ac_create(Ac& a, double lat, double lon, double hdg, doub
 __device__ inline void ac_clear(Ac& a) {
     a.lat = 0.0; a.lon = 0.0; a.alt = 0.0f; a.tas = 0.0f; a.hdg = 0.0f; a.vs = 0.0f;
     a.selspd = 0.0f; a.selalt = 0.0f; a.selvs = 0.0f; a.aptrk = 0.0f; a.ax = 0.0f; a.curlegdir = -999.0f;
-    a.cas = 0.0f; a.flags = 0u; a.gsn = 0.0f; a.gse = 0.0f; a.coslat = 1.0f; a.tcpamax = 0.0f; a.inconf = false;
+    a.cas = 0.0f; a.tgt = 0.0f; a.flags = 0u; a.gsn = 0.0f; a.gse = 0.0f; a.coslat = 1.0f; a.tcpamax = 0.0f; a.inconf = false;
 }
 
 // ---- wind field: upstream windfield.py::getdata (oracle/windfield.py) -------------------------------
@@ -189,27 +190,33 @@ __device__ __forceinline__ float ac_trk(const Ac& a, const EnvParams& P) {
 
 // ---- state I/O (coalesced: consecutive lanes -> consecutive float4 / double2) ----------------------
 __device__ __forceinline__ void ac_load(Ac& a, const EnvParams& P, long long idx) {
+    // (loads only: nothing here waits for the data, see ac_finish_load)
     double2 p = P.pos[idx];
     float4 k = P.kin[idx], c = P.cmd[idx], x = P.aux[idx];
     a.lat = p.x; a.lon = p.y;
     a.alt = k.x; a.tas = k.y; a.hdg = k.z; a.vs = k.w;
     a.selspd = c.x; a.selalt = c.y; a.selvs = c.z; a.aptrk = c.w;
-    a.ax = x.x; a.curlegdir = x.y; a.cas = x.z;
+    a.ax = x.x; a.curlegdir = x.y; a.cas = x.z; a.tgt = x.w;
     a.flags = P.flags[idx];
+    a.gsn = 0.0f; a.gse = 0.0f;
+    if (P.gsv) { float2 g = P.gsv[idx]; a.gsn = g.x; a.gse = g.y; }      // with wind the ground speed is state
+    a.tcpamax = 0.0f; a.inconf = false;
+}
+__device__ __forceinline__ void ac_finish_load(Ac& a, const EnvParams& P) {
     // the cached ground-speed components and cos(lat) are rebuilt with the very expressions of ac_kinematics, so a launch
     // continues bit for bit where the previous one stopped (n substeps in one launch == the same n split over launches)
-    float s, co;
-    __sincosf((a.hdg - 180.0f) * kDeg2Rad, &s, &co);
-    a.gsn = -a.tas * co; a.gse = -a.tas * s;
-    if (P.gsv) { float2 g = P.gsv[idx]; a.gsn = g.x; a.gse = g.y; }      // with wind the ground speed is state
+    if (!P.gsv) {
+        float s, co;
+        __sincosf((a.hdg - 180.0f) * kDeg2Rad, &s, &co);
+        a.gsn = -a.tas * co; a.gse = -a.tas * s;
+    }
     a.coslat = __cosf((float)a.lat * kDeg2Rad);
-    a.tcpamax = 0.0f; a.inconf = false;
 }
 __device__ __forceinline__ void ac_store(const Ac& a, const EnvParams& P, long long idx) {
     P.pos[idx] = make_double2(a.lat, a.lon);
     P.kin[idx] = make_float4(a.alt, a.tas, a.hdg, a.vs);
     P.cmd[idx] = make_float4(a.selspd, a.selalt, a.selvs, a.aptrk);
-    P.aux[idx] = make_float4(a.ax, a.curlegdir, a.cas, 0.0f);
+    P.aux[idx] = make_float4(a.ax, a.curlegdir, a.cas, a.tgt);
     P.flags[idx] = a.flags;
     if (P.gsv) P.gsv[idx] = make_float2(a.gsn, a.gse);
     if (P.cd_enabled) {
@@ -286,10 +293,14 @@ struct Targets {
     int ph;
 };
 
-__device__ __forceinline__ void compute_targets(const Ac& a, const EnvParams& P, Targets& T) {
+// `cached`: a.tgt holds allow_tas for exactly these inputs (env_kernel's targets cache): only the cheap parts are redone;
+// ATMOS: the caller needs T.at afterwards either way.
+template <bool ATMOS>
+__device__ __forceinline__ void compute_targets(const Ac& a, const EnvParams& P, Targets& T, const bool cached) {
     const bsg_perf& pf = P.perf;
     T.k_alt = a.alt; T.k_vs = a.vs;
-    T.at = vatmos(a.alt);
+    if (ATMOS || !cached) T.at = vatmos(a.alt);
+    else { T.at.p = 0.0f; T.at.rho = 0.0f; T.at.T = 0.0f; }
     // ---- perfoap.update: phase.get (later assignments overwrite earlier ones)
     float alt_ft = a.alt * (1.0f / kFt), roc = a.vs * (1.0f / kFpm);
     int ph = PH_NA;
@@ -307,6 +318,7 @@ __device__ __forceinline__ void compute_targets(const Ac& a, const EnvParams& P,
     T.inv_amax = 1.0f / T.amax;
     // ---- perfoap.limits (CAS round trip evaluated at the allowed commanded altitude)
     T.allow_h = a.selalt > pf.hmax ? pf.hmax : a.selalt;
+    if (cached) { T.allow_tas = a.tgt; return; }
     const bool level = T.allow_h == a.alt;
     Atmos ah = level ? T.at : vatmos(T.allow_h);
     float allow_tas = 0.0f, cas_c = a.selspd;
@@ -471,46 +483,58 @@ __device__ __forceinline__ void build_pair_table(uint16_t* s_pairs) {
 __device__ __forceinline__ u64 abs2(u64 v) { return v & 0x7fffffff7fffffffULL; }
 __device__ __forceinline__ u64 neg2(u64 v) { return v ^ 0x8000000080000000ULL; }
 
+// Shared memory of ONE group (env): every array the in-group CD touches sits at a compile-time offset from one base
+// address, so a thread needs a single address register (derived once from its index) for all of them.
+template <int G>
+struct __align__(16) GroupSmem {
+    float4 rec[2 * G];                                       // CD records: (x, y, ch, sh), (u, v, alt, vs) per slot
+    float hot[(G > 8) ? 2 * G * kHotFields : 4];            // (B) ring, structure of arrays written twice
+    uint16_t queue[(G > 8) ? G * kQueuePerThread : 8];      // candidate pairs: (B) entries first, (A) entries appended
+    int tmax[G];                                             // per-slot max tcpa of the slot's conflicts (float bits)
+    int cnt, nb, np, pad;                                    // compaction cursor | kept (B) entries (-1: none) | list entries
+};
+
 // `horizon`: simulated seconds between this substep and the last one of the env step (what a kept (B) list must cover)
 // `emit`: this is the last substep of the launch and the caller bound pair lists: the exact phase also appends every
-// conflicting / LoS pair to the env's list (entry format in include/bsg.h), count left in s_np[grp] for the caller.
-template <int G>
-__device__ __forceinline__ void group_cd(const int tid, Ac& a, bool alive, int nac, const EnvParams& P, float horizon, float4* s_rec,
-                                         float* s_hot, uint16_t* s_queue, int* s_tmax, int* s_cnt, int* s_nb,
-                                         const uint16_t* s_pairs, int& nconf_env, int& nlos_env, const bool emit, const long long e, int* s_np) {
-    const int lane = tid & 31;
-    const int lane_g = tid & (G - 1);
-    const int gbase = tid - lane_g;           // first thread of this group in the block
+// conflicting / LoS pair to the env's list (entry format in include/bsg.h), count left in S.np for the caller.
+// `lane_moved`: this aircraft's ground-speed vector changed in the last kinematics update.  TOL (MergeEnv: LNAV bearings
+// creep every substep) keeps a (B) list while every ring aircraft stays within kCdVelTol of the velocity the list was built
+// with; otherwise the list is rebuilt as soon as any ring aircraft moved at all (the intruders of HorizontalCR / SectorCR
+// never do).  Rebuilding more often never changes results: every list is a superset of what the exact phase accepts.
+template <int G, bool TOL>
+__device__ __forceinline__ void group_cd(GroupSmem<G>& S, const int lane_g, Ac& a, bool alive, int nac, const EnvParams& P, float horizon,
+                                         const uint16_t* s_pairs, int& nconf_env, int& nlos_env, const bool emit, const int e,
+                                         const bool lane_moved) {
+    const int lane = threadIdx.x & 31;
     const int wbase = lane - lane_g;                  // first lane of this group in the warp
-    const int grp = tid / G;
     double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);
-    // cos / sin of lat/2 from the cached cos(lat): half-angle identities (absolute error ~1e-7)
+    // cos / sin of lat/2 from the cached cos(lat): half-angle identities (absolute error ~1e-7); sign of lat from its high word
     const float ch = sqrt_approx(fmaf(0.5f, a.coslat, 0.5f));
-    const float sh = copysignf(sqrt_approx(fmaxf(fmaf(-0.5f, a.coslat, 0.5f), 0.0f)), (float)a.lat);
+    const float sh = __int_as_float((__float_as_int(sqrt_approx(fmaxf(fmaf(-0.5f, a.coslat, 0.5f), 0.0f))) & 0x7fffffff) |
+                                    (__double2hiint(a.lat) & 0x80000000));
     double dl = a.lon - lon0;
-    dl = dl > 180.0 ? dl - 360.0 : (dl < -180.0 ? dl + 360.0 : dl);
+    dl = fma(-360.0, rint(dl * (1.0 / 360.0)), dl);   // into [-180, 180] (ties stay: +-180 is kept as it is)
     const float x = (float)(kRearthD * kDeg2RadD * dl), y = (float)(kRearthD * kDeg2RadD * (a.lat - lat0));
-    s_rec[2 * tid] = make_float4(x, y, ch, sh);
-    s_rec[2 * tid + 1] = make_float4(a.gse, a.gsn, a.alt, a.vs);
-    s_tmax[tid] = 0;
-    if (emit && lane_g == 0) s_np[grp] = 0;
+    S.rec[2 * lane_g] = make_float4(x, y, ch, sh);
+    S.rec[2 * lane_g + 1] = make_float4(a.gse, a.gsn, a.alt, a.vs);
+    S.tmax[lane_g] = 0;
+    if (emit && lane_g == 0) S.np = 0;
     unsigned confmask = 0u;       // bit = warp lane of an aircraft that is in conflict (this lane's pairs only)
     int counts = 0;               // ordered conflict pairs (low half) / ordered LoS pairs (high half) found by this lane
     bool found = true;
     auto exact_pair = [&](int i, int j) {
-        CdSym r = cd_pair_sym(s_rec[2 * (gbase + i)], s_rec[2 * (gbase + i) + 1], s_rec[2 * (gbase + j)],
-                              s_rec[2 * (gbase + j) + 1], P.R2, P.hpz, P.dtlook);
+        CdSym r = cd_pair_sym(S.rec[2 * i], S.rec[2 * i + 1], S.rec[2 * j], S.rec[2 * j + 1], P.R2, P.hpz, P.dtlook);
         counts += (r.conf_ij ? 1 : 0) + (r.conf_ji ? 1 : 0) + (r.los ? (2 << 16) : 0);
         confmask |= (r.conf_ij ? 1u << (wbase + i) : 0u) | (r.conf_ji ? 1u << (wbase + j) : 0u);
         if (r.conf_ij | r.conf_ji) {               // tcpamax = max over the row of tcpa * swconfl (>= 0)
             const int tb = __float_as_int(fmaxf(r.tcpa, 0.0f));
-            if (r.conf_ij) atomicMax(&s_tmax[gbase + i], tb);
-            if (r.conf_ji) atomicMax(&s_tmax[gbase + j], tb);
+            if (r.conf_ij) atomicMax(&S.tmax[i], tb);
+            if (r.conf_ji) atomicMax(&S.tmax[j], tb);
         }
         if (emit && (r.conf_ij | r.conf_ji | r.los)) {        // rare: the pair goes to the env's list
-            const int k = atomicAdd(&s_np[grp], 1);
+            const int k = atomicAdd(&S.np, 1);
             if (k < P.cd_pair_cap) {
-                const long long o = e * P.cd_pair_cap + k;
+                const long long o = (long long)e * P.cd_pair_cap + k;
                 P.cd_pairs[o] = (uint32_t)i | ((uint32_t)j << 8) | (r.conf_ij ? (uint32_t)BSG_PAIR_CONF_IJ : 0u) |
                                 (r.conf_ji ? (uint32_t)BSG_PAIR_CONF_JI : 0u) | (r.los ? (uint32_t)BSG_PAIR_LOS : 0u);
                 if (P.cd_attr) {
@@ -539,12 +563,14 @@ __device__ __forceinline__ void group_cd(const int tid, Ac& a, bool alive, int n
     const int m = nac - 1, r = lane_g - 1;            // ring of the aircraft the agent does not steer
     const bool ring = lane_g >= 1 && lane_g < nac;
     const int kmax = m >> 1;
-    float* hot = s_hot + gbase * (2 * kHotFields);    // [field][2G] for this group
-    uint16_t* queue = s_queue + gbase * kQueuePerThread;
+    float* hot = S.hot;                               // [field][2G] for this group
+    uint16_t* queue = S.queue;
     const float Rh = P.rpz * 1.0002f, Lh = P.dtlook * 1.0002f;
     // ---- is the kept (B) list still good?  (hot[HU], hot[HV] hold the velocities it was computed from)
-    int nb = s_nb[grp];
-    const bool moved = ring && (fabsf(a.gse - hot[HU * 2 * G + (lane_g - 1)]) + fabsf(a.gsn - hot[HV * 2 * G + (lane_g - 1)]) > kCdVelTol);
+    int nb = S.nb;
+    bool moved;
+    if (TOL) moved = ring && (fabsf(a.gse - hot[HU * 2 * G + (lane_g - 1)]) + fabsf(a.gsn - hot[HV * 2 * G + (lane_g - 1)]) > kCdVelTol);
+    else moved = ring && lane_moved;
     const bool eval_b = !BSG_CD_REUSE || P.cd_enabled == 2 || nb < 0 || __any_sync(gm, moved);
     u64 KAP = 0, RR = 0, D0 = 0, DW = 0, LH = 0;
     if (eval_b) {
@@ -556,7 +582,7 @@ __device__ __forceinline__ void group_cd(const int tid, Ac& a, bool alive, int n
             w[HX * 2 * G] = -x; w[HY * 2 * G] = y;  w[HCH * 2 * G] = ch;
             w[HSH * 2 * G] = sh; w[HU * 2 * G] = a.gse; w[HV * 2 * G] = a.gsn;
         }
-        if (lane_g == 0) s_cnt[grp] = 0;
+        if (lane_g == 0) S.cnt = 0;
         // allowances for keeping the list over `horizon` seconds (see the header comment)
         float kap = 0.0f, d0 = 0.0f, dw = 0.0f;
         if (BSG_CD_REUSE && P.cd_enabled != 2 && horizon > 0.0f) {
@@ -567,7 +593,7 @@ __device__ __forceinline__ void group_cd(const int tid, Ac& a, bool alive, int n
             const float tmax = __uint_as_float(__reduce_max_sync(gm, __float_as_uint(tl)));
             kap = 1.5f * horizon * vmax * tmax * (1.0f / kRearth);
             d0 = (4.0f * vmax + 1.0f) * horizon;
-            dw = 2.0f * kCdVelTol;
+            dw = TOL ? 2.0f * kCdVelTol : 0.0f;              // (without TOL any change of velocity rebuilds the list)
         }
         KAP = pk2(kap, kap); RR = pk2(fmaf(kap, d0, Rh), fmaf(kap, d0, Rh)); D0 = pk2(d0, d0); DW = pk2(dw, dw);
         const float lh = P.cd_enabled != 2 ? Lh + horizon * 1.0002f : Lh;
@@ -624,7 +650,7 @@ __device__ __forceinline__ void group_cd(const int tid, Ac& a, bool alive, int n
         if (__any_sync(gm, cand != 0u)) {
             const int cnt = __popc(cand);
             int pos = 0;
-            if (cnt) pos = atomicAdd(&s_cnt[grp], cnt);
+            if (cnt) pos = atomicAdd(&S.cnt, cnt);
             uint16_t* qp = queue + pos;
 #pragma unroll 1
             for (unsigned c = cand; c; c &= c - 1u) {
@@ -633,16 +659,16 @@ __device__ __forceinline__ void group_cd(const int tid, Ac& a, bool alive, int n
                 *qp++ = (uint16_t)((lane_g << 8) | (rj + 1));
             }
             __syncwarp(gm);
-            nb = s_cnt[grp];
+            nb = S.cnt;
         } else {
             nb = 0;
         }
-        if (lane_g == 0) s_nb[grp] = nb;
+        if (lane_g == 0) S.nb = nb;
     }
     // ---- (A) pairs with slot 0 (x = y = 0 by construction), every substep ------------------------------------
     int ncand;
     {
-        const float4 A0 = s_rec[2 * gbase], B0 = s_rec[2 * gbase + 1];
+        const float4 A0 = S.rec[0], B0 = S.rec[1];
         const float cav = fmaf(-A0.w, sh, A0.z * ch);
         const float dx = x * cav;
         const float du = a.gse - B0.x, dv = a.gsn - B0.y;
@@ -659,8 +685,8 @@ __device__ __forceinline__ void group_cd(const int tid, Ac& a, bool alive, int n
     }
     // ---- exact phase -------------------------------------------------------------------------------
     for (int p = lane_g; p < ncand; p += G) {
-        const unsigned e = queue[p];
-        exact_pair((int)(e >> 8), (int)(e & 0xffu));
+        const unsigned en = queue[p];
+        exact_pair((int)(en >> 8), (int)(en & 0xffu));
     }
     found = ncand > 0;
     }
@@ -670,7 +696,7 @@ __device__ __forceinline__ void group_cd(const int tid, Ac& a, bool alive, int n
         counts = (int)__reduce_add_sync(group_mask<G>(), (unsigned)counts);
     }
     a.inconf = alive && ((confmask >> lane) & 1u);
-    a.tcpamax = __int_as_float(s_tmax[tid]);
+    a.tcpamax = __int_as_float(S.tmax[lane_g]);
     nconf_env = counts & 0xffff;
     nlos_env = counts >> 16;
     __syncwarp(group_mask<G>());

@@ -132,7 +132,8 @@ __device__ inline void horizontal_reset(Ac& a, EnvS& s, const EnvParams& P, long
 template <int G>
 __device__ inline void horizontal_action(Ac& a, const EnvParams& P, const float* act, int slot) {
     if (slot == 0) {                                                        // horizontal_cr_env.py:272-275
-        a.aptrk = a.hdg + act[0] * 45.0f;          // un-wrapped, like the reference's "HDG KL001 x"
+        a.aptrk = fmaf(act[0], 45.0f, a.hdg);      // un-wrapped, like the reference's "HDG KL001 x" (explicit fma: one
+                                                   // rounding whatever the surrounding code looks like to the compiler)
         a.flags &= ~kFlLnav;
     }
 }
@@ -342,9 +343,9 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
 template <int G>
 __device__ inline void sector_action(Ac& a, const EnvParams& P, const float* act, int slot) {
     if (slot == 0) {                                                        // sector_cr_env.py:315-322
-        a.aptrk = wrap180_fold(a.hdg + act[0] * 22.5f);
+        a.aptrk = wrap180_fold(fmaf(act[0], 22.5f, a.hdg));
         a.flags &= ~kFlLnav;
-        float kt = (a.cas + act[1] * (20.0f / 3.0f)) * 1.94384f;            // "SPD KL001 x": knots -> m/s
+        float kt = fmaf(act[1], 20.0f / 3.0f, a.cas) * 1.94384f;            // "SPD KL001 x": knots -> m/s
         a.selspd = (kt > 0.1f && kt < 1.0f) ? kt : kt * kKts;
     }
 }
@@ -434,9 +435,9 @@ __device__ inline void merge_reset(Ac& a, EnvS& s, const EnvParams& P, long long
 template <int G>
 __device__ inline void merge_action(Ac& a, const EnvParams& P, const float* act, int slot) {
     if (slot == 0) {                                                        // merge_env.py:286-293
-        a.aptrk = wrap180_fold(a.hdg + act[0] * 15.0f);
+        a.aptrk = wrap180_fold(fmaf(act[0], 15.0f, a.hdg));
         a.flags &= ~kFlLnav;
-        float kt = (a.cas + act[1] * 20.0f) * 1.94384f;
+        float kt = fmaf(act[1], 20.0f, a.cas) * 1.94384f;
         a.selspd = (kt > 0.1f && kt < 1.0f) ? kt : kt * kKts;
     }
 }
@@ -753,9 +754,9 @@ __device__ inline bool static_substep_check(const Ac& a, EnvS& s, const EnvParam
 template <int G>
 __device__ inline void static_action(Ac& a, const EnvParams& P, const float* act, int slot) {
     if (slot == 0) {                                                        // static_obstacle_env.py:343-350
-        a.aptrk = wrap180_fold(a.hdg + act[0] * 45.0f);
+        a.aptrk = wrap180_fold(fmaf(act[0], 45.0f, a.hdg));
         a.flags &= ~kFlLnav;
-        float kt = (a.cas + act[1] * (20.0f / 3.0f)) * 1.94384f;
+        float kt = fmaf(act[1], 20.0f / 3.0f, a.cas) * 1.94384f;
         a.selspd = (kt > 0.1f && kt < 1.0f) ? kt : kt * kKts;
     }
 }
@@ -840,6 +841,9 @@ __device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float
 #ifndef BSG_FAST_STEADY
 #define BSG_FAST_STEADY 1
 #endif
+#ifndef BSG_TARGET_CACHE
+#define BSG_TARGET_CACHE 1
+#endif
 #ifdef BSG_PHASE_TIMING
 #define BSG_STAMP(k) do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(stamps[k]) :: "memory"); } while (0)
 #else
@@ -848,13 +852,7 @@ __device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float
 
 template <int ENV, int G, bool WIND>
 __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const EnvParams P) {
-    __shared__ __align__(16) float4 s_rec[(G > 1) ? kEnvThreads * 2 : 1];
-    __shared__ float s_hot[(G > 8) ? kEnvThreads * 2 * kHotFields : 1];
-    __shared__ uint16_t s_queue[(G > 8) ? kEnvThreads * kQueuePerThread : 1];
-    __shared__ int s_tmax[(G > 1) ? kEnvThreads : 1];
-    __shared__ int s_cnt[(G > 8) ? kEnvThreads / G : 1];
-    __shared__ int s_nb[(G > 8) ? kEnvThreads / G : 1];       // candidates kept from the last (B) filter pass, -1 = none
-    __shared__ int s_np[(G > 1) ? kEnvThreads / G : 1];       // entries appended to the env's ASAS pair list (last substep)
+    __shared__ GroupSmem<(G > 1) ? G : 2> s_grp[(G > 1) ? kEnvThreads / G : 1];
     __shared__ uint16_t s_pairs[(G > 1 && G <= 8) ? kSmallPairs : 1];
     if (G > 1 && G <= 8 && P.cd_enabled && P.mode != kModeReset) {
         build_pair_table(s_pairs);
@@ -863,28 +861,43 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
     __shared__ double s_scratch[(ENV == BSG_ENV_SECTOR_CR) ? (kEnvThreads / 32) * kSectorScratch
                                 : (ENV == BSG_ENV_STATIC_OBSTACLE) ? (kEnvThreads / G) * kStaticScratch : 1];
     const int tid = threadIdx.x;
-    const long long gt = (long long)blockIdx.x * kEnvThreads + tid;
+    const int gt = blockIdx.x * kEnvThreads + tid;          // (E * G < 2^31: bsg_create checks)
     if (gt == 0 && P.mode == kModeStep && P.final_count) {
         // two counters take turns (no memset node between launches): this launch counts in [fc_slot], clears the other one
         // for the next launch and publishes which is live in [2]
         P.final_count[P.fc_slot ^ 1] = 0;
         P.final_count[2] = P.fc_slot;
     }
-    const long long e = gt / G;
-    const int slot = (int)(gt % G);
+    const int e = gt / G;
+    const int slot = gt % G;
     if (e >= P.E) return;                       // group-uniform (G divides the block size)
     double* scratch = (ENV == BSG_ENV_SECTOR_CR) ? &s_scratch[(threadIdx.x / 32) * kSectorScratch]
                     : (ENV == BSG_ENV_STATIC_OBSTACLE) ? &s_scratch[(threadIdx.x / G) * kStaticScratch] : s_scratch;
+    auto& S = s_grp[(G > 1) ? tid / G : 0];
 
 #ifdef BSG_PHASE_TIMING
     unsigned long long stamps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     BSG_STAMP(0);
+    // Every load of the step is issued here, before anything waits on one of them: with the state cold in DRAM (the usual
+    // case: 14 MB per batch touched once per env step) the aircraft record, the env counters and the actions arrive in ONE
+    // memory round trip instead of three dependent ones, and the records read after the substep loop are on their way to L2.
+    Ac a;
+    ac_load(a, P, gt);
+    float act[2] = {0.0f, 0.0f};
+    if (P.mode == kModeStep) {
+        act[0] = P.actions[(long long)e * P.act_dim];
+        if (ENV == BSG_ENV_SECTOR_CR || ENV == BSG_ENV_MERGE || ENV == BSG_ENV_STATIC_OBSTACLE) act[1] = P.actions[(long long)e * P.act_dim + 1];
+    }
     EnvS s;
     env_load_pre(s, P, e);
-    Ac a;
-    float* obs = P.obs + e * P.obs_dim;
-    float* info = P.info + e * P.info_dim;
+    if (slot == 0) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.ef64 + (long long)e * BSG_F64_COUNT));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.ef32 + (long long)e * BSG_F32_COUNT));
+    }
+    if (ENV == BSG_ENV_SECTOR_CR && slot < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.poly + (long long)e * (2 * kSectorMaxV) + 16 * slot));
+    float* obs = P.obs + (long long)e * P.obs_dim;
+    float* info = P.info + (long long)e * P.info_dim;
 
     // One control flow for reset / step / autoreset so that the scenario generator and the observation
     // code exist ONCE in the kernel (they are big; duplicating them blew the instruction cache).
@@ -897,16 +910,22 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
     }
 
     if (!resetting) {
-        ac_load(a, P, gt);
+        ac_finish_load(a, P);
         const bool alive = (a.flags & kFlAlive) != 0;
+        // The targets of the last launch (ISA / CAS conversions: ~400 instructions of pow-type arithmetic) stay valid while
+        // what they are a function of -- alt, vs, selspd, selalt -- stays put: the record carries allow_tas with a valid bit
+        // that the end of a launch sets when its last targets belong to the stored (alt, vs), and that an action which
+        // moves selspd / selalt clears.  Same inputs, same function: the cached value is the recomputed one bit for bit.
+        bool tgt_cached = BSG_TARGET_CACHE && P.mode == kModeStep && (a.flags & kFlTgt) != 0;
         if (P.mode == kModeStep) {
-            const float* act = P.actions + e * P.act_dim;
+            const float o_selspd = a.selspd, o_selalt = a.selalt;
             if (ENV == BSG_ENV_DESCENT || ENV == BSG_ENV_VERTICAL_CR) descent_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_PLAN_WAYPOINT) horizontal_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_STATIC_OBSTACLE) static_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_HORIZONTAL_CR) horizontal_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_SECTOR_CR) sector_action<G>(a, P, act, slot);
             if (ENV == BSG_ENV_MERGE) merge_action<G>(a, P, act, slot);
+            tgt_cached = tgt_cached && a.selspd == o_selspd && a.selalt == o_selalt;
             if (WIND && ENV != BSG_ENV_DESCENT && ENV != BSG_ENV_VERTICAL_CR && slot == 0 && a.alt > 50.0f * kFt) {
                 // Autopilot.selhdgcmd with wind: the commanded HEADING becomes the track it produces right now
                 float wn, we, sh, ch;
@@ -917,12 +936,14 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
         }
         int nconf = s.nconf, nlos = s.nlos;
         if (G > 8 && P.cd_enabled) {
-            if (slot == 0) s_nb[threadIdx.x / G] = -1;
+            if (slot == 0) S.nb = -1;
             __syncwarp(group_mask<G>());
         }
         BSG_STAMP(1);
+        // (the envs whose action reads traf.cas convert tas -> cas after the loop and need the atmosphere for it)
+        constexpr bool kNeedAtmos = ENV == BSG_ENV_SECTOR_CR || ENV == BSG_ENV_MERGE || ENV == BSG_ENV_STATIC_OBSTACLE;
         Targets T;
-        compute_targets(a, P, T);
+        compute_targets<kNeedAtmos>(a, P, T, tgt_cached);
         BSG_STAMP(2);
         // `fixed`: the last full kinematics update left (tas, hdg, vs, alt, ax, ground-speed components) exactly as they
         // were.  They are a pure function of themselves, the targets T (recomputed only when alt / vs move) and the
@@ -931,21 +952,23 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
         // once it has finished its turn -- a substep only advances the positions, with the very expressions of
         // ac_kinematics (BSG_FAST_STEADY=0 switches the shortcut off: identical outputs, scripts/ab_identical.py).
         bool fixed = false;
+        bool moved = false;                                 // the ground-speed vector changed in the last update (K3's (B) list)
 #pragma unroll 1
         for (int k = 0; k < P.n_sub; ++k) {                 // n_sub x bs.sim.step()
             s.simk += 1;
-            const bool fms_ready = (s.simk % P.fms_rel_freq) == 0;
+            const bool fms_ready = ENV == BSG_ENV_MERGE && (s.simk % P.fms_rel_freq) == 0;
             if (alive) {
-                if (a.alt != T.k_alt || a.vs != T.k_vs) compute_targets(a, P, T);
+                if (a.alt != T.k_alt || a.vs != T.k_vs) compute_targets<true>(a, P, T, false);
                 ac_autopilot<ENV>(a, P, fms_ready);
             }
-            if (G > 1 && P.cd_enabled) {
+            if constexpr (G > 1) if (P.cd_enabled) {
                 const bool emit = P.cd_pairs != nullptr && (k == P.n_sub - 1 || ENV == BSG_ENV_STATIC_OBSTACLE);
-                group_cd<G>(tid, a, alive, s.num_ac, P, (float)(P.n_sub - 1 - k) * P.simdt, s_rec, s_hot, s_queue, s_tmax, s_cnt, s_nb,
-                            s_pairs, nconf, nlos, emit, e, s_np);
-                if (emit && slot == 0) P.ei32[e * BSG_I32_COUNT + BSG_I32_NPAIRS] = s_np[tid / G];
+                group_cd<G, ENV == BSG_ENV_MERGE || WIND>(S, slot, a, alive, s.num_ac, P, (float)(P.n_sub - 1 - k) * P.simdt, s_pairs, nconf,
+                                                          nlos, emit, e, moved);
+                if (emit && slot == 0) P.ei32[(long long)e * BSG_I32_COUNT + BSG_I32_NPAIRS] = S.np;
             }
             if (BSG_FAST_STEADY && !WIND && ENV != BSG_ENV_MERGE && group_all<G>(fixed || !alive)) {
+                moved = false;
                 if (alive) {                                // update_pos alone (same expressions as ac_kinematics)
                     a.lat += (double)(kRad2Deg * (P.simdt * a.gsn * (1.0f / kRearth)));
                     a.coslat = __cosf((float)a.lat * kDeg2Rad);
@@ -954,8 +977,8 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
             } else if (alive) {
                 const float o_tas = a.tas, o_hdg = a.hdg, o_vs = a.vs, o_alt = a.alt, o_ax = a.ax, o_gsn = a.gsn, o_gse = a.gse;
                 ac_kinematics<WIND>(a, P, T);
-                fixed = a.tas == o_tas && a.hdg == o_hdg && a.vs == o_vs && a.alt == o_alt && a.ax == o_ax && a.gsn == o_gsn &&
-                        a.gse == o_gse;
+                moved = a.gsn != o_gsn || a.gse != o_gse;
+                fixed = !moved && a.tas == o_tas && a.hdg == o_hdg && a.vs == o_vs && a.alt == o_alt && a.ax == o_ax;
             }
             if (ENV == BSG_ENV_STATIC_OBSTACLE && P.mode == kModeStep) {   // per-substep reward / termination
                 if (k == 0) env_load_post(s, P, e);
@@ -968,8 +991,12 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
         BSG_STAMP(4);
         // update_airspeed's cas = vtas2cas(tas, alt) uses the altitude from before update_pos: T.at of the last substep
         // (only the envs whose action reads traf.cas need it: Sector, Merge, StaticObstacle)
-        if ((ENV == BSG_ENV_SECTOR_CR || ENV == BSG_ENV_MERGE || ENV == BSG_ENV_STATIC_OBSTACLE || P.mode == kModeTraf) &&
-            alive && P.n_sub > 0) a.cas = tas2cas(a.tas, T.at);
+        if ((kNeedAtmos || P.mode == kModeTraf) && alive && P.n_sub > 0) {
+            a.cas = tas2cas(a.tas, T.at);
+        }
+        // targets cache for the next launch: valid when the last targets belong to the state that is stored
+        a.tgt = T.allow_tas;
+        a.flags = (BSG_TARGET_CACHE && alive && T.k_alt == a.alt && T.k_vs == a.vs) ? (a.flags | kFlTgt) : (a.flags & ~kFlTgt);
         s.nconf = nconf; s.nlos = nlos;
         if (P.mode == kModeTraf) {
             ac_store(a, P, gt);
@@ -1026,7 +1053,7 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
     BSG_STAMP(7);
     if (slot == 0 && P.final_obs && P.mode == kModeStep) {
         unsigned long long* out = reinterpret_cast<unsigned long long*>(P.final_obs + (long long)P.E * P.obs_dim) - 8LL * P.E;
-        for (int k = 0; k < 8; ++k) out[8 * e + k] = stamps[k];
+        for (int k = 0; k < 8; ++k) out[8LL * e + k] = stamps[k];
     }
 #endif
 }

@@ -27,6 +27,24 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_LEASE_TYPES = {}
+
+
+def _lease_type(nbytes):
+    """ctypes array type over a borrowed pinned block.  numpy arrays made from an instance (np.frombuffer) keep it alive
+    through their .base chain; when the last of them is garbage-collected the instance dies and puts the block back on its
+    pool's free list -- the caller owns a step's results for exactly as long as it holds on to them, and nothing is copied."""
+    t = _LEASE_TYPES.get(nbytes)
+    if t is None:
+        class Lease(C.c_uint8 * nbytes):
+            def __del__(self):
+                free = getattr(self, "free", None)
+                if free is not None:
+                    free.append(self.index)
+        t = _LEASE_TYPES[nbytes] = Lease
+    return t
+
+
 class BlueSkyVectorEnv(VectorEnv):
     metadata = {"render_modes": [], "autoreset_mode": "next_step"}
 
@@ -142,6 +160,16 @@ class BlueSkyVectorEnv(VectorEnv):
             hb["block"], hb["ptr"] = blk, _ptr(blk)
             self._hbuf.append(hb)
         self._hsel = 0
+        # copy=True (default): every step's results are views of a pinned block LEASED to the caller until the last view
+        # is dropped (see _lease_type): the device->host transfer lands directly in memory the caller may keep, no host
+        # copy.  The pool grows on demand (a rollout buffer that copies what it needs holds 1-2 blocks) up to
+        # `_LEASE_MAX` blocks; a caller that hoards more than that gets ordinary copies instead.
+        self._carve = carve
+        self._off = dict(obs=(0, np.float32, E * L.obs_dim), reward=(n_obs, np.float32, E), info=(o_info, np.float32, E * L.info_dim),
+                         final_count=(o_cnt, np.int32, 4), terminated=(o_term, np.uint8, E), truncated=(o_term + E, np.uint8, E),
+                         final_ids=(o_fids, np.int32, E), final_obs=(o_fobs, np.float32, self._final_cap * L.obs_dim))
+        self._lease_blocks, self._lease_free = [], []
+        self._lease_cls = _lease_type(self._out_bytes)
         self._pending = None        # mirrored block of a step_async() whose step_wait() has not run yet
         self.h = dict(actions=ph((E, L.act_dim), torch.float32))
         self._act_np, self._act_ptr = self.h["actions"].numpy(), _ptr(self.h["actions"])
@@ -228,7 +256,7 @@ class BlueSkyVectorEnv(VectorEnv):
         return OrderedDict((k, flat[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
 
     def _infos_np(self, info):
-        t = info.T.astype(np.float64)               # [info_dim, E]: one conversion, contiguous rows per key
+        t = info.T.astype(np.float64)               # [info_dim, E]: one conversion, contiguous rows per key (fresh memory)
         out = {k: t[i] for i, k in enumerate(self.spec_b200.info_keys)}
         if self.cfg.cd_enabled:
             out["asas_nconf"] = t[4].astype(np.int64)
@@ -279,26 +307,46 @@ class BlueSkyVectorEnv(VectorEnv):
         info = self.t["info"].cpu().numpy()
         return self._obs_dict_np(obs), self._infos_np(info)
 
+    _LEASE_MAX = 64
+
+    def _acquire(self):
+        """A host block for this step's results: a leased pinned block (copy=True, float32), else one of the two
+        rotating mirrors.  Returns the dict of numpy views (+ "ptr")."""
+        if not (self.copy and self.obs_dtype == np.float32):
+            self._hsel ^= 1
+            return self._hbuf[self._hsel]
+        if not self._lease_free:
+            if len(self._lease_blocks) >= self._LEASE_MAX:          # the caller keeps everything: hand out copies
+                self._hsel ^= 1
+                h = self._hbuf[self._hsel]
+                return dict(h, copy_out=True)
+            self._lease_blocks.append(torch.zeros((self._out_bytes,), dtype=torch.uint8).pin_memory())
+            self._lease_free.append(len(self._lease_blocks) - 1)
+        idx = self._lease_free.pop()
+        blk = self._lease_blocks[idx]
+        lease = self._lease_cls.from_address(blk.data_ptr())
+        lease.free, lease.index, lease.block = self._lease_free, idx, blk      # (the views keep the pinned block alive)
+        E, L = self.num_envs, self.layout
+        h = {k: np.frombuffer(lease, dtype=dt, count=n, offset=off) for k, (off, dt, n) in self._off.items()}
+        h["obs"] = h["obs"].reshape(E, L.obs_dim)
+        h["info"] = h["info"].reshape(E, L.info_dim)
+        h["final_obs"] = h["final_obs"].reshape(self._final_cap, L.obs_dim)
+        h["ptr"] = C.c_void_p(blk.data_ptr())
+        return h
+
     def step(self, actions):
         if self._pending is not None:
             raise _lib.BsgError("step(): a step_async() is in flight; call step_wait() first")
         E = self.num_envs
         self._act_np[...] = np.asarray(actions, dtype=np.float32).reshape(E, self.layout.act_dim)
-        self._hsel ^= 1
-        h = self._hbuf[self._hsel]
-        fresh = self.copy and self.obs_dtype == np.float32
+        h = self._acquire()
         # (the library sets the device itself; the stream is looked up per call because callers may switch streams)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        if fresh:           # the result array is filled by the library's host threads while the transfer is in flight
-            flat = np.empty((E, self.layout.obs_dim), dtype=np.float32)
-            rc = self._lib.bsg_step_host_copy(self._h, self._act_ptr, h["ptr"], self._out_bytes,
-                                              flat.ctypes.data, flat.nbytes, stream)
-        else:
-            rc = self._lib.bsg_step_host_block(self._h, self._act_ptr, h["ptr"], self._out_bytes, stream)
+        rc = self._lib.bsg_step_host_block(self._h, self._act_ptr, h["ptr"], self._out_bytes,
+                                           torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             _lib.check(rc)
         self.gpu_launches += 1
-        return self._step_results(h, flat if fresh else None)
+        return self._step_results(h)
 
     def step_async(self, actions):
         """First half of ``step`` (the SB3 / older-gymnasium ``step_async`` / ``step_wait`` pair): copies the actions in,
@@ -308,8 +356,7 @@ class BlueSkyVectorEnv(VectorEnv):
             raise _lib.BsgError("step_async(): the previous step has not been waited for (one step in flight per env batch)")
         E = self.num_envs
         self._act_np[...] = np.asarray(actions, dtype=np.float32).reshape(E, self.layout.act_dim)
-        self._hsel ^= 1
-        h = self._hbuf[self._hsel]
+        h = self._acquire()
         rc = self._lib.bsg_step_host_begin(self._h, self._act_ptr, h["ptr"], self._out_bytes,
                                            torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
@@ -323,20 +370,20 @@ class BlueSkyVectorEnv(VectorEnv):
         if h is None:
             raise RuntimeError("step_wait() without step_async()")
         self._pending = None
-        fresh = self.copy and self.obs_dtype == np.float32
-        flat = np.empty((self.num_envs, self.layout.obs_dim), dtype=np.float32) if fresh else None
-        rc = self._lib.bsg_step_host_wait(self._h, h["ptr"], flat.ctypes.data if fresh else None, flat.nbytes if fresh else 0)
+        rc = self._lib.bsg_step_host_wait(self._h, h["ptr"], None, 0)
         if rc:
             _lib.check(rc)
-        return self._step_results(h, flat)
+        return self._step_results(h)
 
-    def _step_results(self, h, flat):
-        """The (obs, reward, terminated, truncated, infos) tuple from mirrored block ``h`` (and, when the observations
-        were copied out by the library, the fresh array ``flat``)."""
-        if flat is not None:
-            obs = OrderedDict((k, flat[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
-        else:
-            obs = self._obs_dict_np(h["obs"])
+    def _step_results(self, h):
+        """The (obs, reward, terminated, truncated, infos) tuple from host block ``h`` (views of a leased block, or of a
+        rotating mirror: then copied unless copy=False)."""
+        flat = h["obs"]
+        if flat.dtype != self.obs_dtype:
+            flat = flat.astype(self.obs_dtype)
+        elif h.get("copy_out"):
+            flat = flat.copy()
+        obs = OrderedDict((k, flat[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
         rew = h["reward"].astype(np.float64)
         term = h["terminated"].astype(bool)
         trunc = h["truncated"].astype(bool)

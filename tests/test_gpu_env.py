@@ -6,9 +6,13 @@ Two families, per SURVEY.md section 0.6:
     same actions: trajectories, observations, rewards and termination flags must agree;
   * device reset -- the device's Philox-keyed scenario generator against the oracle env driven by the
     same Philox stream (oracle/philox.py).
-Tolerances (float32 kernels vs float64 oracle; stated here as the north_star requires):
-  lat/lon 2e-5 deg (~2 m), alt 0.5 m, tas / vs 2e-2 m/s, hdg 5e-3 deg, observations rtol 1e-3 + atol 5e-4,
-  reward atol 1e-3, terminated / truncated sequences identical.
+Tolerances (float32 kernels vs float64 oracle; stated here as the north_star requires) -- those SURVEY.md section 8c
+proposed or tighter, with the largest differences observed on a B200 over the whole suite in brackets (the parity tests
+print them per run: "max |error|"):
+  lat/lon 1e-5 deg = 1 m [4.9e-6; MergeEnv's LNAV-guided intruders 2e-5 (1.2e-5)], alt 0.1 m [0.049], tas 2e-3 m/s [6.4e-4],
+  vs 1e-3 m/s [4.8e-7], hdg 1e-3 deg [4.8e-4], observations 2e-4 (1 + |value|) [8.4e-5 (1 + |value|)],
+  reward 1e-4 [2.5e-6]; DescentEnv / VerticalCREnv 1e-3 [7.9e-4: the terminal reward is altitude * 50 / 3000],
+  terminated / truncated sequences identical.
 """
 import random
 
@@ -23,7 +27,16 @@ from tests.common import angdiff, device_traffic, inject_oracle_env
 
 pytestmark = pytest.mark.gpu
 
-TOL = dict(pos=2e-5, alt=0.5, tas=2e-2, vs=2e-2, hdg=5e-3)
+TOL = dict(pos=1e-5, alt=0.1, tas=2e-3, vs=1e-3, hdg=1e-3)
+OBS_TOL = 2e-4
+
+
+def pos_tol(env_id):
+    return 2.0 * TOL["pos"] if env_id == "MergeEnv-v0" else TOL["pos"]      # (LNAV: bearings to a waypoint feed back)
+
+
+def reward_tol(env_id):
+    return 1e-3 if env_id in ("DescentEnv-v0", "VerticalCREnv-v0") else 1e-4
 
 
 class ErrStats:
@@ -101,9 +114,10 @@ def _compare_traffic(venv, oracles, alive_mask, step, exempt=None, stats=None):
             ok[list(exempt[e])] = False
         # an FMS-guided aircraft that overflew a waypoint steered for a few substeps along a bearing to a
         # point metres away (see hdg_tol below): its track keeps a lateral offset of a few metres
-        pos_tol = np.where(np.asarray(t.iactwp) >= 1, 5.0 * TOL["pos"], TOL["pos"])
-        assert np.all((np.abs(d["lat"][e, :n] - t.lat) < pos_tol)[ok]), (step, e, "lat")
-        assert np.all((np.abs(d["lon"][e, :n] - t.lon) < pos_tol)[ok]), (step, e, "lon")
+        base = pos_tol(venv.env_id)
+        pos_tol_ = np.where(np.asarray(t.iactwp) >= 1, 5.0 * base, base)
+        assert np.all((np.abs(d["lat"][e, :n] - t.lat) < pos_tol_)[ok]), (step, e, "lat")
+        assert np.all((np.abs(d["lon"][e, :n] - t.lon) < pos_tol_)[ok]), (step, e, "lon")
         assert np.max(np.abs(d["alt"][e, :n] - t.alt)[ok]) < TOL["alt"], (step, e, "alt")
         assert np.max(np.abs(d["tas"][e, :n] - t.tas)[ok]) < TOL["tas"], (step, e, "tas")
         assert np.max(np.abs(d["vs"][e, :n] - t.vs)[ok]) < TOL["vs"], (step, e, "vs")
@@ -151,27 +165,38 @@ def _compare_asas_pairs(g, t, where):
                             gs_[j] * np.cos(np.radians(trk_[j])) - gs_[i] * np.cos(np.radians(trk_[i]))), 1e-3)
         rel = 2.0 * TOL["tas"] / vrel + 1e-4
         dpos = 2.0 * TOL["pos"] * 111e3
+        timed = vrel > 0.5        # (two aircraft on the same track at the same speed: closest approach is 0 / 0, any time goes)
         assert abs((g["qdr"][k] - t.cd_qdr[q] + 180.0) % 360.0 - 180.0) < 2e-3 + np.degrees(dpos / max(dist, 1.0)), (where, p, "qdr")
         assert abs(g["dist"][k] - dist) < dpos + 1e-5 * dist, (where, p, "dist")
-        assert abs(g["dcpa"][k] - dcpa) < 2.0 * dpos + rel * max(dist, dcpa), (where, p, "dcpa", g["dcpa"][k], dcpa)
-        assert abs(g["tcpa"][k] - tcpa) < 0.05 + dpos / vrel + rel * abs(tcpa), (where, p, "tcpa", g["tcpa"][k], tcpa)
         half = abs(tcpa - tin)
-        assert abs(g["tinconf"][k] - tin) < 0.05 + dpos / vrel + rel * (abs(tin) + abs(tcpa)) + 0.05 * half, (where, p, "tinconf", g["tinconf"][k], tin)
+        if timed:
+            assert abs(g["dcpa"][k] - dcpa) < 2.0 * dpos + rel * max(dist, dcpa), (where, p, "dcpa", g["dcpa"][k], dcpa)
+            assert abs(g["tcpa"][k] - tcpa) < 0.05 + dpos / vrel + rel * abs(tcpa), (where, p, "tcpa", g["tcpa"][k], tcpa)
+            assert abs(g["tinconf"][k] - tin) < 0.05 + dpos / vrel + rel * (abs(tin) + abs(tcpa)) + 0.05 * half, (where, p, "tinconf", g["tinconf"][k], tin)
         n += 1
     return n
 
 
-def _compare_tcpamax(g_tcpamax, t, where):
+def _compare_tcpamax(g_tcpamax, t, where, dev_hdg=None, dev_tas=None):
     """Per-aircraft tcpamax (max of tcpa over the aircraft's conflicts) against the oracle's.  A time to closest approach is
-    distance over closing speed: with the device's own float32 traffic state following the oracle's within TOL (2 m, 2e-2 m/s
-    per velocity component) it is known to 2 TOL_pos / vrel + tcpa * 2 TOL_tas / vrel -- slowly converging pairs (two MergeEnv
+    distance over closing speed: with the device's own float32 traffic state following the oracle's within TOL it is known
+    to 2 TOL_pos / vrel + tcpa * dv / vrel, dv = how far the two aircraft's velocity vectors are from the oracle's --
+    2 TOL_tas by default, or measured from the device state when given (a MergeEnv intruder turning over a waypoint
+    carries a larger heading difference for a few substeps, see _compare_traffic).  Slowly converging pairs (two MergeEnv
     intruders on almost the same track: vrel of a few m/s, tcpa of thousands of seconds) inherit percents, not 1e-3."""
     _, _, trk_, gs_, _, _ = t._cd_inputs
     u, v = gs_ * np.sin(np.radians(trk_)), gs_ * np.cos(np.radians(trk_))
+    verr = np.full(t.ntraf, TOL["tas"])
+    if dev_hdg is not None:
+        du = dev_tas * np.sin(np.radians(dev_hdg)) - t.tas * np.sin(np.radians(t.hdg))
+        dv = dev_tas * np.cos(np.radians(dev_hdg)) - t.tas * np.cos(np.radians(t.hdg))
+        verr = np.maximum(verr, 2.0 * np.hypot(du, dv))
     tol = np.full(t.ntraf, 0.05)
     for (i, j), tc in zip(t.confpairs, t.cd_tcpa):
         vrel = max(np.hypot(u[j] - u[i], v[j] - v[i]), 1e-3)
-        tol[i] = max(tol[i], 0.05 + 2.0 * TOL["pos"] * 111e3 / vrel + abs(tc) * (2.0 * TOL["tas"] / vrel + 1e-3))
+        if vrel < 0.5:            # same track, same speed: the time of closest approach is 0 / 0
+            tol[i] = np.inf
+        tol[i] = max(tol[i], 0.05 + 2.0 * TOL["pos"] * 111e3 / vrel + abs(tc) * ((verr[i] + verr[j]) / vrel + 1e-3))
     assert np.all(np.abs(g_tcpamax - t.tcpamax) <= tol), (where, "tcpamax", g_tcpamax, t.tcpamax, tol)
 
 
@@ -182,15 +207,15 @@ def _compare_obs(gobs, oobs, e, step, vnorm=None, ownship_only=False, stats=None
     for k, v in oobs.items():
         if ownship_only and k not in OWNSHIP_KEYS:
             continue
-        atol = 5e-4
+        atol = OBS_TOL
         if stats is not None and k not in ("cos(track)", "sin(track)"):
             stats.add("obs", np.abs(gobs[k][e] - v) / (1.0 + np.abs(v)))
         if k in ("cos(track)", "sin(track)") and vnorm is not None:
             # direction of the relative velocity: ill-conditioned when the two aircraft fly almost the same
             # vector; allow the stated TAS tolerance (2e-2 m/s) divided by the relative speed
             dv = np.hypot(oobs["vx_r"] * vnorm[0], oobs["vy_r"] * vnorm[1])
-            atol = 5e-4 + TOL["tas"] / np.maximum(dv, 1e-3)
-        assert np.all(np.abs(gobs[k][e] - v) <= atol + 1e-3 * np.abs(v)), \
+            atol = OBS_TOL + 2.0 * TOL["tas"] / np.maximum(dv, 1e-3)
+        assert np.all(np.abs(gobs[k][e] - v) <= atol + OBS_TOL * np.abs(v)), \
             f"step {step} env {e} key {k}: {gobs[k][e]} vs {v}"
 
 
@@ -246,7 +271,7 @@ def test_step_parity_injected_state(cuda, env_id, n_int, cd, steps):
                     alive[e] = False
                 continue
             compared_full += 1
-            assert abs(grew[e] - orew) < 1e-3, (step, e, grew[e], orew)
+            assert abs(grew[e] - orew) < reward_tol(env_id), (step, e, grew[e], orew)
             stats.add("reward", abs(grew[e] - orew))
             assert bool(gterm[e]) == bool(oterm), (step, e, "terminated")
             assert bool(gtrunc[e]) == bool(otrunc), (step, e, "truncated")
@@ -260,7 +285,7 @@ def test_step_parity_injected_state(cuda, env_id, n_int, cd, steps):
                 assert ginfo["asas_nconf"][e] == len(t.confpairs), (step, e, "nconf", ginfo["asas_nconf"][e], len(t.confpairs))
                 assert ginfo["asas_nlos"][e] == len(t.lospairs), (step, e, "nlos")
                 assert np.array_equal(d["inconf"][e, :t.ntraf], t.inconf), (step, e, "inconf")
-                _compare_tcpamax(d["tcpamax"][e, :t.ntraf], t, (step, e))
+                _compare_tcpamax(d["tcpamax"][e, :t.ntraf], t, (step, e), d["hdg"][e, :t.ntraf], d["tas"][e, :t.ntraf])
                 n_pairs_checked += _compare_asas_pairs(venv.asas_pairs(e), t, (step, e))
             if oterm or otrunc:
                 alive[e] = False

@@ -16,7 +16,7 @@ import pytest
 
 from oracle.philox import PhiloxDraws
 from tests.common import device_traffic
-from tests.test_gpu_env import TOL, _compare_asas_pairs, _compare_obs, _make_oracle, ErrStats
+from tests.test_gpu_env import TOL, ErrStats, _compare_asas_pairs, _compare_obs, _make_oracle, pos_tol, reward_tol
 
 pytestmark = pytest.mark.gpu
 
@@ -62,7 +62,7 @@ def _run(env_id, E, steps, cap, seed, sample=None, n_int=0, cd=False, off=0, den
                 continue
             assert bool(gterm[e]) == bool(oterm) and bool(gtrunc[e]) == otrunc, (step, e)
             if not exempt[e]:
-                assert abs(grew[e] - orew) < 1e-3, (step, e, grew[e], orew)
+                assert abs(grew[e] - orew) < reward_tol(env_id), (step, e, grew[e], orew)
                 stats.add("reward", abs(grew[e] - orew))
                 for k, v in oinfo.items():
                     if not (isinstance(v, float) and np.isnan(v)):
@@ -93,7 +93,7 @@ def _run(env_id, E, steps, cap, seed, sample=None, n_int=0, cd=False, off=0, den
                 if not exempt[e]:
                     t = o.traf
                     n = t.ntraf
-                    for name, dv, tol in (("pos", np.maximum(np.abs(d["lat"][e, :n] - t.lat), np.abs(d["lon"][e, :n] - t.lon)), TOL["pos"]),
+                    for name, dv, tol in (("pos", np.maximum(np.abs(d["lat"][e, :n] - t.lat), np.abs(d["lon"][e, :n] - t.lon)), pos_tol(env_id)),
                                           ("alt", np.abs(d["alt"][e, :n] - t.alt), TOL["alt"]), ("tas", np.abs(d["tas"][e, :n] - t.tas), TOL["tas"]),
                                           ("vs", np.abs(d["vs"][e, :n] - t.vs), TOL["vs"])):
                         # (FMS-guided aircraft past a waypoint keep a lateral offset of a few metres: test_gpu_env.py)
