@@ -242,6 +242,36 @@ class ClockSampler:
                 "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def pin_to_gpu_numa_node(index):
+    """One process per GPU: run this rank's host thread on the cores of the NUMA node its GPU hangs off, so the pinned
+    blocks it allocates (first touch) and the Python loop that fills / reads them sit next to the PCIe root of the GPU.
+    Returns a short description for the JSON line, or None when the topology cannot be read (then nothing is changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:                      # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if not ids:
+            return None
+        os.sched_setaffinity(0, ids)
+        return f"numa node {node} ({len(ids)} cores)"
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
     import torch
@@ -257,6 +287,7 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = pin_to_gpu_numa_node(local) if world > 1 else None     # each rank's host thread + pinned blocks next to its GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
@@ -315,17 +346,31 @@ def run_b200(args):
     # end to end through the public numpy API: pinned host actions in, obs/reward/flags/info out, every step
     host_actions = bank[W:].cpu().numpy()
     for i in range(3):
-        venv.step(host_actions[i % K])
+        obs, rew, term, trunc, info = venv.step(host_actions[i % K])       # (results held like in the timed loop)
     barrier()
+    prof = None
+    if os.environ.get("BSG_BENCH_PROFILE"):      # where does the host time of the e2e loop go? (stats to stderr)
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     t0 = time.perf_counter()
+    step_s = []
     for i in range(K):
+        t1 = time.perf_counter()
         obs, rew, term, trunc, info = venv.step(host_actions[i])
+        step_s.append(time.perf_counter() - t1)
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(18)
     L = venv.layout
     h2d = E * L.act_dim * 4
     d2h = venv._out_bytes          # the mirrored head of the output block: obs, reward, info, flags, terminal-obs window
+    ss = sorted(step_s)
     e2e = {"value": E * world * K / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "us_per_step_median": 1e6 * ss[len(ss) // 2], "us_per_step_max": 1e6 * ss[-1],
            "api": "BlueSkyVectorEnv.step, default arguments (numpy in; float32 numpy arrays out that the caller owns; "
                   "bsg_step_host_block: one H2D, one launch, one D2H of the output block straight into a pinned block leased to "
                   "the caller until the arrays are dropped -- no host copy)"}
@@ -336,6 +381,7 @@ def run_b200(args):
     for i in range(K):
         venv.step(host_actions[i])
     barrier()
+    e2e["host_affinity"] = affinity
     e2e["value_copy_false"] = E * world * K / max_over_ranks(time.perf_counter() - t0)
     venv.copy = True
     # same call returning float64 observations (the dtype the reference's spaces declare; what the scalar gym.make envs return)

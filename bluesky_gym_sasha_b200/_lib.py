@@ -74,7 +74,7 @@ class TensorTable(C.Structure):
 
 
 SYMBOLS = ("bsg_abi_version", "bsg_abi_struct_size", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
-           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_step_host_begin", "bsg_step_host_wait", "bsg_host_copy", "bsg_set_obs_noise", "bsg_get_noise_calls", "bsg_set_noise_calls", "bsg_load_state", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
+           "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_step_host_begin", "bsg_step_host_wait", "bsg_host_copy", "bsg_host_widen", "bsg_set_obs_noise", "bsg_get_noise_calls", "bsg_set_noise_calls", "bsg_load_state", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
            "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_cd_cull_workspace", "bsg_cd_detect_culled", "bsg_cd_detect_peers", "bsg_probe_fp32")
 
 _lib = None
@@ -128,6 +128,9 @@ def load():
         lib.bsg_set_noise_calls.restype = C.c_int
     lib.bsg_host_copy.argtypes = [vp, vp, C.c_size_t]
     lib.bsg_host_copy.restype = C.c_int
+    if hasattr(lib, "bsg_host_widen"):          # (absent only in older A/B builds loaded through BSG_B200_LIB)
+        lib.bsg_host_widen.argtypes = [vp, vp, C.c_size_t]
+        lib.bsg_host_widen.restype = C.c_int
     lib.bsg_step_host_copy.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp]
     lib.bsg_traf_update.argtypes = [vp, i32, vp]
     lib.bsg_cd_padded.argtypes = [i64]

@@ -12,7 +12,7 @@
 
 int bsg_launch_env(const bsg::EnvParams& P, int slots, cudaStream_t st);   // env_step.cu
 int bsg_launch_obs_noise(const bsg::EnvParams& P, float sigma, uint32_t call, bool with_final, cudaStream_t st);   // obs_noise.cu
-namespace bsg { void host_copy_mt(void* dst, const void* src, size_t n); void host_pool_prewake(); }   // host_pool.cu
+namespace bsg { void host_copy_mt(void* dst, const void* src, size_t n, bool widen = false); void host_pool_prewake(); }   // host_pool.cu
 
 static thread_local char g_err[512] = "";
 
@@ -446,6 +446,13 @@ extern "C" int bsg_host_copy(void* dst, const void* src, size_t nbytes) {
     if ((!dst || !src) && nbytes) return bsg_fail(BSG_EINVAL, "bsg_host_copy: null argument");
     bsg::host_pool_prewake();
     bsg::host_copy_mt(dst, src, nbytes);
+    return BSG_OK;
+}
+
+extern "C" int bsg_host_widen(double* dst, const float* src, size_t n) {
+    if ((!dst || !src) && n) return bsg_fail(BSG_EINVAL, "bsg_host_widen: null argument");
+    bsg::host_pool_prewake();
+    bsg::host_copy_mt(dst, src, n * sizeof(float), true);
     return BSG_OK;
 }
 

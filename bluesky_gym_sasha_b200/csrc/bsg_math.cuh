@@ -96,6 +96,18 @@ __device__ __forceinline__ void kwikqdrdist(double lata, double lona, double lat
     qdr = mod360(kRad2Deg * atan2f(dx, dlat));
 }
 
+// geo.kwikqdrdist without the bearing angle: the flat-earth offsets (radians of arc, north / east) and the distance [NM].
+// cos / sin of the bearing are dn / ang, de / ang: what an observation needs when it only takes the cosine and sine of
+// (heading - bearing) -- no atan2 followed by sincos.
+__device__ __forceinline__ void kwikoffsets(double lata, double lona, double latb, double lonb, float& dn, float& de, float& ang,
+                                            float& dist_nm) {
+    dn = (float)((latb - lata) * kDeg2RadD);
+    const float dlon = (float)((dmod360((lonb - lona) + 180.0) - 180.0) * kDeg2RadD);
+    de = dlon * __cosf((float)((lata + latb) * (0.5 * kDeg2RadD)));
+    ang = sqrtf(dn * dn + de * de);
+    dist_nm = (kRearth / kNm) * ang;
+}
+
 // sin / cos of a latitude in degrees (|lat| <= 90): MUFU.SIN / MUFU.COS, absolute error ~4e-7 on factors of order one
 __device__ __forceinline__ void sincos_lat(float latd, float& s, float& c) { __sincosf(latd * kDeg2Rad, &s, &c); }
 // sin / cos of an angle in degrees anywhere in (-540, 540) -- a difference of two headings / bearings: folded into

@@ -32,7 +32,7 @@ constexpr int kTJ = 256;                 // columns per tile
 constexpr int kNT = 128;                 // threads per CTA
 constexpr int kR = 2;                    // rows per thread
 constexpr int kRowsPerCta = kNT * kR;    // 256 = one tile of rows
-constexpr int kTilesPerItem = 8;
+constexpr int kTilesPerItem = 8;          // upper bound; the launch picks fewer when there are few items per CTA (tiles_per_item)
 // culled form: work item = one row block x up to kTilesPerChunk listed column tiles.  Measured at N = 100k (2.8 % of
 // the tile pairs kept): 1 -> 0.506 ms, 2 -> 0.539, 4 -> 0.574, 8 -> 0.626: balance beats the per-item set-up cost.
 constexpr int kTilesPerChunk = 1;
@@ -83,7 +83,7 @@ struct CdArgs {
     int32_t* lospairs;
     long long los_cap;
     unsigned long long* npairs;
-    int n_rowblocks, n_colgroups, n_tiles;
+    int n_rowblocks, n_colgroups, n_tiles, tiles_per_item;
     // culled form (bsg_cd_detect_culled): per row block the column tiles that can hold a conflict partner
     const int32_t* tile_list;     // [n_rowblocks][list_stride]
     const int32_t* list_cnt;      // [n_rowblocks]
@@ -379,8 +379,8 @@ __global__ void __launch_bounds__(kNT, BSG_CD_MINBLOCKS) cd_tiled_kernel(const C
         const long long n_items = (long long)a.n_rowblocks * a.n_colgroups;
         for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int rb = (int)(item / a.n_colgroups);
-            const int t_begin = (int)(item % a.n_colgroups) * kTilesPerItem;
-            const int n_t = min(kTilesPerItem, a.n_tiles - t_begin);
+            const int t_begin = (int)(item % a.n_colgroups) * a.tiles_per_item;
+            const int n_t = min(a.tiles_per_item, a.n_tiles - t_begin);
             cd_process_item<WRAP, false, false>(a, s_tile, s_full, parity, rb, t_begin, n_t, nullptr, R2P, HPZP, NEG1, dtlh, row_end);
         }
     } else {
@@ -567,6 +567,7 @@ static int cd_fill_args(CdArgs& a, int64_t n_all, int64_t row0, int64_t n_rows, 
     a.lospairs = L.d_los_pairs; a.los_cap = L.los_cap; a.npairs = L.d_npairs;
     a.n_tiles = (int)(bsg_cd_padded(n_all) / kTJ);
     a.n_rowblocks = (int)((n_rows + kRowsPerCta - 1) / kRowsPerCta);
+    a.tiles_per_item = kTilesPerItem;
     a.n_colgroups = (a.n_tiles + kTilesPerItem - 1) / kTilesPerItem;
     return BSG_OK;
 }
@@ -612,6 +613,22 @@ static int cd_launch(CdArgs& a, bool wrap, bool cull, bool sym, bool alltiles, v
         if (wrap) BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<true, false, false>, kNT, 0));
         else BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, false, false>, kNT, 0));
         if (occ < 1) occ = 1;
+        // Items are dealt to the persistent CTAs by a static stride, so the launch ends with a partial round: a row shard of
+        // 1/8 of 100k aircraft is 2401 eight-tile items on 592 CTAs = 4.06 rounds, i.e. a fifth round that is 6 % full
+        // (0.687 of the FP32 peak per GPU against 0.758 on one GPU).  The tiles per item are therefore chosen per launch:
+        // the count (1..8) that minimises rounds x (tiles + the pipeline bubble at the start of an item, ~6 % of a tile).
+        {
+            const long long slots = (long long)sms * occ;
+            double best = 1e30;
+            int best_t = kTilesPerItem;
+            for (int t = kTilesPerItem; t >= 1; --t) {
+                const long long items = (long long)a.n_rowblocks * ((a.n_tiles + t - 1) / t);
+                const double cost = (double)((items + slots - 1) / slots) * ((double)t + 0.06);
+                if (cost < best * 0.999) { best = cost; best_t = t; }
+            }
+            a.tiles_per_item = best_t;
+            a.n_colgroups = (a.n_tiles + best_t - 1) / best_t;
+        }
         const long long n_items = (long long)a.n_rowblocks * a.n_colgroups;
         const int grid = (int)((n_items < (long long)sms * occ) ? n_items : (long long)sms * occ);
         if (wrap) cd_tiled_kernel<true, false, false><<<grid, kNT, 0, st>>>(a);

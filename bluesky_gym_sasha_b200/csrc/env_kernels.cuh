@@ -504,17 +504,16 @@ struct __align__(16) GroupSmem {
 template <int G, bool TOL>
 __device__ __forceinline__ void group_cd(GroupSmem<G>& S, const int lane_g, Ac& a, bool alive, int nac, const EnvParams& P, float horizon,
                                          const uint16_t* s_pairs, int& nconf_env, int& nlos_env, const bool emit, const int e,
-                                         const bool lane_moved) {
+                                         const bool lane_moved, const double lat_ref, const double lon_ref) {
     const int lane = threadIdx.x & 31;
     const int wbase = lane - lane_g;                  // first lane of this group in the warp
-    double lat0 = group_bcast<G>(a.lat, 0), lon0 = group_bcast<G>(a.lon, 0);
     // cos / sin of lat/2 from the cached cos(lat): half-angle identities (absolute error ~1e-7); sign of lat from its high word
     const float ch = sqrt_approx(fmaf(0.5f, a.coslat, 0.5f));
     const float sh = __int_as_float((__float_as_int(sqrt_approx(fmaxf(fmaf(-0.5f, a.coslat, 0.5f), 0.0f))) & 0x7fffffff) |
                                     (__double2hiint(a.lat) & 0x80000000));
-    double dl = a.lon - lon0;
-    dl = fma(-360.0, rint(dl * (1.0 / 360.0)), dl);   // into [-180, 180] (ties stay: +-180 is kept as it is)
-    const float x = (float)(kRearthD * kDeg2RadD * dl), y = (float)(kRearthD * kDeg2RadD * (a.lat - lat0));
+    // metres of arc east / north of the env's reference point (the envs live within a few hundred km of it, far from the
+    // antimeridian: no +-180 fold)
+    const float x = (float)(kRearthD * kDeg2RadD * (a.lon - lon_ref)), y = (float)(kRearthD * kDeg2RadD * (a.lat - lat_ref));
     S.rec[2 * lane_g] = make_float4(x, y, ch, sh);
     S.rec[2 * lane_g + 1] = make_float4(a.gse, a.gsn, a.alt, a.vs);
     S.tmax[lane_g] = 0;
@@ -588,7 +587,9 @@ __device__ __forceinline__ void group_cd(GroupSmem<G>& S, const int lane_g, Ac& 
         if (BSG_CD_REUSE && P.cd_enabled != 2 && horizon > 0.0f) {
             const bool in = lane_g < nac;
             const float spd = in ? sqrtf(fmaf(a.gse, a.gse, a.gsn * a.gsn)) : 0.0f;
-            const float tl = in ? tanf(fminf(fabsf((float)a.lat), 89.0f) * kDeg2Rad) : 0.0f;
+            // tan |lat| from the cached cos(lat) (capped near the poles like tan(89 deg))
+            const float cl = fmaxf(a.coslat, 0.0175f);
+            const float tl = in ? sqrt_approx(fmaxf(fmaf(-cl, cl, 1.0f), 0.0f)) * rcp_approx(cl) * 1.0001f : 0.0f;
             const float vmax = __uint_as_float(__reduce_max_sync(gm, __float_as_uint(spd))) + kCdVelTol;
             const float tmax = __uint_as_float(__reduce_max_sync(gm, __float_as_uint(tl)));
             kap = 1.5f * horizon * vmax * tmax * (1.0f / kRearth);
@@ -665,19 +666,19 @@ __device__ __forceinline__ void group_cd(GroupSmem<G>& S, const int lane_g, Ac& 
         }
         if (lane_g == 0) S.nb = nb;
     }
-    // ---- (A) pairs with slot 0 (x = y = 0 by construction), every substep ------------------------------------
+    // ---- (A) pairs with slot 0, every substep ----------------------------------------------------------------
     int ncand;
     {
         const float4 A0 = S.rec[0], B0 = S.rec[1];
         const float cav = fmaf(-A0.w, sh, A0.z * ch);
-        const float dx = x * cav;
+        const float dx = (x - A0.x) * cav, dy = y - A0.y;
         const float du = a.gse - B0.x, dv = a.gsn - B0.y;
         const float dv2 = fmaf(du, du, dv * dv);
-        const float crs = fmaf(dx, dv, -y * du);
-        const float dot = fmaf(du, dx, dv * y);
+        const float crs = fmaf(dx, dv, -dy * du);
+        const float dot = fmaf(du, dx, dv * dy);
         const float w = sqrt_approx(dv2);
         const float t0 = fmaf(w, Rh, kCdAbsEps), reach = fmaf(w, Lh, Rh);
-        const bool pass = ring && fabsf(crs) < t0 && dot < t0 && fmaf(dx, dx, y * y) < reach * reach;
+        const bool pass = ring && fabsf(crs) < t0 && dot < t0 && fmaf(dx, dx, dy * dy) < reach * reach;
         const unsigned bm = (G >= 32) ? __ballot_sync(gm, pass) : ((__ballot_sync(gm, pass) >> wbase) & ((1u << (G & 31)) - 1u));
         if (pass) queue[nb + __popc(bm & ((1u << lane_g) - 1u))] = (uint16_t)lane_g;      // (i, j) = (0, lane_g)
         ncand = nb + __popc(bm);

@@ -145,11 +145,17 @@ __device__ inline StepOut horizontal_obs_reward(const Ac& a, EnvS& s, const EnvP
     const float gs_own = ac_gs(a, P);
     const float hdg0 = group_bcast<G>(a.hdg, 0), gs0 = group_bcast<G>(gs_own, 0);
     const bool intr = slot >= 1 && slot <= n;
-    float qdr = 0.0f, dis = 1e9f;
+    float dis = 1e9f;
     if (intr) {
-        kwikqdrdist(lat0, lon0, a.lat, a.lon, qdr, dis);
-        float sb, cb, sd, cd;
-        sincos_deg(wrap180_fold(hdg0 - qdr), sb, cb);
+        // cos / sin of (own heading - bearing to the intruder) from the flat-earth offsets themselves: cos(qdr) = dn / ang,
+        // sin(qdr) = de / ang (the reference goes through atan2 and back; same quantities, fewer roundings)
+        float dn, de, ang, sd, cd, sh0, ch0;
+        kwikoffsets(lat0, lon0, a.lat, a.lon, dn, de, ang, dis);
+        __sincosf((hdg0 - 180.0f) * kDeg2Rad, &sh0, &ch0);          // hdg0 in [0, 360): shifted into the MUFU's accurate range
+        sh0 = -sh0; ch0 = -ch0;
+        const float inv = ang > 0.0f ? 1.0f / ang : 0.0f;
+        const float cq = ang > 0.0f ? dn * inv : 1.0f, sq = de * inv;
+        const float cb = fmaf(ch0, cq, sh0 * sq), sb = fmaf(sh0, cq, -ch0 * sq);
         sincos_deg((hdg0 - a.hdg), sd, cd);
         const int k = slot - 1;
         obs[k] = dis * (1.852f / 150.0f);
@@ -609,10 +615,13 @@ __device__ inline StepOut vertical_obs_reward(const Ac& a, EnvS& s, const EnvPar
     const bool intr = slot >= 1 && slot <= 5;
     float dis = 1e9f;
     if (intr) {
-        float qdr;
-        kwikqdrdist(lat0, lon0, a.lat, a.lon, qdr, dis);
-        float sb, cb, sd, cd;
-        sincos_deg(wrap180_fold(hdg0 - qdr), sb, cb);
+        float dn, de, ang, sd, cd, sh0, ch0;                         // (as in horizontal_obs_reward: no atan2 / sincos round trip)
+        kwikoffsets(lat0, lon0, a.lat, a.lon, dn, de, ang, dis);
+        __sincosf((hdg0 - 180.0f) * kDeg2Rad, &sh0, &ch0);
+        sh0 = -sh0; ch0 = -ch0;
+        const float inv = ang > 0.0f ? 1.0f / ang : 0.0f;
+        const float cq = ang > 0.0f ? dn * inv : 1.0f, sq = de * inv;
+        const float cb = fmaf(ch0, cq, sh0 * sq), sb = fmaf(sh0, cq, -ch0 * sq);
         sincos_deg((hdg0 - a.hdg), sd, cd);
         const int k = slot - 1;
         obs[4 + k] = dis * (1.852f / 200.0f);
@@ -818,8 +827,10 @@ __device__ __forceinline__ StepOut do_obs(const Ac& a, EnvS& s, const EnvParams&
     if (ENV == BSG_ENV_STATIC_OBSTACLE) return static_obs_reward<G>(a, s, P, obs, slot, e, with_reward);
     return merge_obs_reward<G>(a, s, P, obs, slot, with_reward);
 }
+// Env._get_info values of env e, stored key-major -- info[k * E + e] -- so that the host sees one contiguous row per key
 template <int ENV>
-__device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float* info) {
+__device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, const int e) {
+    float info[6];
     if (ENV == BSG_ENV_DESCENT) descent_info(s, info);
     else if (ENV == BSG_ENV_MERGE) merge_info(s, info);
     else if (ENV == BSG_ENV_PLAN_WAYPOINT) {            // plan_waypoint_env.py:126-133
@@ -831,6 +842,8 @@ __device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, float
         info[3] = s.drift_sum / (float)s.drift_n;
     } else drift_info(s, info);
     info[4] = (float)s.nconf; info[5] = (float)s.nlos;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) P.info[(long long)k * P.E + e] = info[k];
 }
 
 // =====================================================================================================
@@ -897,7 +910,6 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
     }
     if (ENV == BSG_ENV_SECTOR_CR && slot < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.poly + (long long)e * (2 * kSectorMaxV) + 16 * slot));
     float* obs = P.obs + (long long)e * P.obs_dim;
-    float* info = P.info + (long long)e * P.info_dim;
 
     // One control flow for reset / step / autoreset so that the scenario generator and the observation
     // code exist ONCE in the kernel (they are big; duplicating them blew the instruction cache).
@@ -963,8 +975,12 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
             }
             if constexpr (G > 1) if (P.cd_enabled) {
                 const bool emit = P.cd_pairs != nullptr && (k == P.n_sub - 1 || ENV == BSG_ENV_STATIC_OBSTACLE);
+                // metric origin of the CD records: a fixed point of the env's airspace (aircraft stay within a few hundred km
+                // of it: float32 metres resolve 3 cm there), so no per-substep broadcast of the ownship position is needed
+                const double lat_ref = ENV == BSG_ENV_MERGE ? P.fix_lat : (ENV == BSG_ENV_SECTOR_CR ? kSectorLat0 : 52.0);
+                const double lon_ref = ENV == BSG_ENV_MERGE ? P.fix_lon : (ENV == BSG_ENV_SECTOR_CR ? kSectorLon0 : 4.0);
                 group_cd<G, ENV == BSG_ENV_MERGE || WIND>(S, slot, a, alive, s.num_ac, P, (float)(P.n_sub - 1 - k) * P.simdt, s_pairs, nconf,
-                                                          nlos, emit, e, moved);
+                                                          nlos, emit, e, moved, lat_ref, lon_ref);
                 if (emit && slot == 0) P.ei32[(long long)e * BSG_I32_COUNT + BSG_I32_NPAIRS] = S.np;
             }
             if (BSG_FAST_STEADY && !WIND && ENV != BSG_ENV_MERGE && group_all<G>(fixed || !alive)) {
@@ -1023,14 +1039,14 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
 #endif
         if (pass == 1) break;                            // SAME_STEP: the step's reward / flags / info stay
         if (fresh) {
-            if (slot == 0) { P.reward[e] = 0.0f; P.term[e] = 0; P.trunc[e] = 0; do_info<ENV>(s, P, info); }
+            if (slot == 0) { P.reward[e] = 0.0f; P.term[e] = 0; P.trunc[e] = 0; do_info<ENV>(s, P, e); }
             break;
         }
         s.step += 1;
         if (P.max_steps > 0 && s.step >= P.max_steps) o.truncated = 1;      // gymnasium TimeLimit
         if (slot == 0) {
             P.reward[e] = o.reward; P.term[e] = (uint8_t)o.terminated; P.trunc[e] = (uint8_t)o.truncated;
-            do_info<ENV>(s, P, info);
+            do_info<ENV>(s, P, e);
         }
         if (!(o.terminated || o.truncated)) break;
         if (P.autoreset == BSG_AUTORESET_NEXT_STEP) { s.needs_reset = 1; break; }
@@ -1053,6 +1069,9 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
     BSG_STAMP(7);
     if (slot == 0 && P.final_obs && P.mode == kModeStep) {
         unsigned long long* out = reinterpret_cast<unsigned long long*>(P.final_obs + (long long)P.E * P.obs_dim) - 8LL * P.E;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        stamps[7] = (stamps[7] & ~0xffULL) | (smid & 0xffu);      // SM id in the low byte of the last stamp (ns resolution lost: 256 ns)
         for (int k = 0; k < 8; ++k) out[8LL * e + k] = stamps[k];
     }
 #endif

@@ -32,8 +32,9 @@ constexpr int kSpinUs = 400;
 struct Job {
     char* dst = nullptr;
     const char* src = nullptr;
-    size_t n = 0;
+    size_t n = 0;               // source bytes
     int pieces = 0;
+    bool widen = false;         // float32 -> float64 conversion instead of a plain copy
     std::atomic<int> next{0}, done{0}, active{0};
 };
 
@@ -42,7 +43,13 @@ inline void work_on(Job& j) {
         int c = j.next.fetch_add(1, std::memory_order_acq_rel);
         if (c >= j.pieces) return;
         size_t lo = (size_t)c * kPiece, len = j.n - lo < kPiece ? j.n - lo : kPiece;
-        memcpy(j.dst + lo, j.src + lo, len);
+        if (j.widen) {
+            const float* s = (const float*)(j.src + lo);
+            double* d = (double*)(j.dst + 2 * lo);
+            for (size_t i = 0, m = len / sizeof(float); i < m; ++i) d[i] = (double)s[i];
+        } else {
+            memcpy(j.dst + lo, j.src + lo, len);
+        }
         j.done.fetch_add(1, std::memory_order_acq_rel);
     }
 }
@@ -136,19 +143,26 @@ void host_pool_prewake() {
     if (g_pool) g_pool->wake();
 }
 
-// memcpy(dst, src, n) shared between the calling thread and whichever pool workers are awake.
-void host_copy_mt(void* dst, const void* src, size_t n) {
+// memcpy(dst, src, n) -- or, with widen, dst[i] = (double)src[i] over n bytes of float32 -- shared between the calling
+// thread and whichever pool workers are awake.
+void host_copy_mt(void* dst, const void* src, size_t n, bool widen) {
     std::call_once(g_once, init_pool);
     bool expected = false;
     if (!g_pool || n < 4 * kPiece || !g_busy.compare_exchange_strong(expected, true)) {
-        memcpy(dst, src, n);                     // small, or another handle's thread is using the pool
+        if (widen) {                             // small, or another handle's thread is using the pool
+            const float* s = (const float*)src;
+            double* d = (double*)dst;
+            for (size_t i = 0, m = n / sizeof(float); i < m; ++i) d[i] = (double)s[i];
+        } else {
+            memcpy(dst, src, n);
+        }
         return;
     }
     Pool& p = *g_pool;
     const uint64_t g = p.job_gen.load(std::memory_order_acquire) + 1;
     Job& j = p.slot[g % kSlots];
     while (j.active.load(std::memory_order_acquire) != 0) { /* a straggler from kSlots jobs ago (never in practice) */ }
-    j.dst = (char*)dst; j.src = (const char*)src; j.n = n; j.pieces = (int)((n + kPiece - 1) / kPiece);
+    j.dst = (char*)dst; j.src = (const char*)src; j.n = n; j.pieces = (int)((n + kPiece - 1) / kPiece); j.widen = widen;
     j.done.store(0, std::memory_order_relaxed);
     j.next.store(0, std::memory_order_release);
     p.job_gen.store(g, std::memory_order_release);

@@ -121,7 +121,7 @@ def evaluate(venv, actor, episodes_per_env=1, max_steps=None):
         if bool(done.any()):
             rets.append(ret[done].cpu())
             lens.append(length[done].cpu())
-            infos.append(venv.t["info"][done].cpu())
+            infos.append(venv.t["info"][:, done].T.cpu())
             ret = torch.where(done, torch.zeros_like(ret), ret)
             length = torch.where(done, torch.zeros_like(length), length)
             left = left - done.int()

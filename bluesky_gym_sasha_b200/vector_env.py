@@ -128,7 +128,7 @@ class BlueSkyVectorEnv(VectorEnv):
         def carve(block, n_final):
             o = block[:n_obs].view(torch.float32).view(E, L.obs_dim)
             r = block[n_obs:o_info].view(torch.float32)
-            i = block[o_info:o_cnt].view(torch.float32).view(E, L.info_dim)
+            i = block[o_info:o_cnt].view(torch.float32).view(L.info_dim, E)          # key-major: one row per info key
             c = block[o_cnt:o_term].view(torch.int32)
             te = block[o_term:o_term + E]
             tr = block[o_term + E:o_term + 2 * E]
@@ -168,13 +168,15 @@ class BlueSkyVectorEnv(VectorEnv):
         self._off = dict(obs=(0, np.float32, E * L.obs_dim), reward=(n_obs, np.float32, E), info=(o_info, np.float32, E * L.info_dim),
                          final_count=(o_cnt, np.int32, 4), terminated=(o_term, np.uint8, E), truncated=(o_term + E, np.uint8, E),
                          final_ids=(o_fids, np.int32, E), final_obs=(o_fobs, np.float32, self._final_cap * L.obs_dim))
-        self._lease_blocks, self._lease_free = [], []
+        self._lease_blocks = [ph((self._out_bytes,), torch.uint8) for _ in range(2)] if self.copy else []
+        self._lease_free = list(range(len(self._lease_blocks)))
         self._lease_cls = _lease_type(self._out_bytes)
         self._pending = None        # mirrored block of a step_async() whose step_wait() has not run yet
         self.h = dict(actions=ph((E, L.act_dim), torch.float32))
         self._act_np, self._act_ptr = self.h["actions"].numpy(), _ptr(self.h["actions"])
         self._final_np = np.zeros((E, L.obs_dim), dtype=np.float32)
         self._h_final = ph((E, L.obs_dim), torch.float32)          # overflow beyond `_final_cap` rows (rare)
+        self._h_final_np = self._h_final.numpy()
 
         self._h = C.c_void_p(0)
         with torch.cuda.device(dev):
@@ -256,11 +258,11 @@ class BlueSkyVectorEnv(VectorEnv):
         return OrderedDict((k, flat[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
 
     def _infos_np(self, info):
-        t = info.T.astype(np.float64)               # [info_dim, E]: one conversion, contiguous rows per key (fresh memory)
-        out = {k: t[i] for i, k in enumerate(self.spec_b200.info_keys)}
+        """info: [info_dim, E] float32 (key-major, as the device writes it): one row view per key, no conversion."""
+        out = {k: info[i] for i, k in enumerate(self.spec_b200.info_keys)}
         if self.cfg.cd_enabled:
-            out["asas_nconf"] = t[4].astype(np.int64)
-            out["asas_nlos"] = t[5].astype(np.int64)
+            out["asas_nconf"] = info[4].astype(np.int64)
+            out["asas_nlos"] = info[5].astype(np.int64)
         return out
 
     # ------------------------------------------------------------------ device-tensor API (no host sync)
@@ -329,7 +331,7 @@ class BlueSkyVectorEnv(VectorEnv):
         E, L = self.num_envs, self.layout
         h = {k: np.frombuffer(lease, dtype=dt, count=n, offset=off) for k, (off, dt, n) in self._off.items()}
         h["obs"] = h["obs"].reshape(E, L.obs_dim)
-        h["info"] = h["info"].reshape(E, L.info_dim)
+        h["info"] = h["info"].reshape(L.info_dim, E)
         h["final_obs"] = h["final_obs"].reshape(self._final_cap, L.obs_dim)
         h["ptr"] = C.c_void_p(blk.data_ptr())
         return h
@@ -379,7 +381,11 @@ class BlueSkyVectorEnv(VectorEnv):
         """The (obs, reward, terminated, truncated, infos) tuple from host block ``h`` (views of a leased block, or of a
         rotating mirror: then copied unless copy=False)."""
         flat = h["obs"]
-        if flat.dtype != self.obs_dtype:
+        if self.obs_dtype == np.float64:         # the reference's declared dtype: widened by the library's host threads
+            wide = np.empty(flat.shape, dtype=np.float64)
+            _lib.check(self._lib.bsg_host_widen(wide.ctypes.data, flat.ctypes.data, flat.size))
+            flat = wide
+        elif flat.dtype != self.obs_dtype:
             flat = flat.astype(self.obs_dtype)
         elif h.get("copy_out"):
             flat = flat.copy()
@@ -397,13 +403,15 @@ class BlueSkyVectorEnv(VectorEnv):
                 # copy=True: a fresh array per step (callers such as SB3 read terminal observations later; np.zeros of
                 # this size is lazily mapped, so only the finished envs' rows are ever touched); copy=False: one
                 # persistent buffer, valid until the next step with a finished env
-                dst = np.zeros((self.num_envs, self.layout.obs_dim), dtype=np.float32) if self.copy else self._final_np
+                # (float64: only the finished rows are converted, on assignment)
+                dst = np.zeros((self.num_envs, self.layout.obs_dim), dtype=self.obs_dtype) if (self.copy or self.obs_dtype != np.float32) \
+                    else self._final_np
                 dst[ids[:cap]] = h["final_obs"][:min(n_fin, cap)]
                 if n_fin > cap:         # more finished than the mirrored window holds: fetch the rest
                     self._h_final[cap:n_fin].copy_(self.t["final_obs"][cap:n_fin], non_blocking=True)
                     torch.cuda.current_stream(self.device).synchronize()
-                    dst[ids[cap:]] = self._h_final.numpy()[cap:n_fin]
-                fo = dst.astype(self.obs_dtype) if self.obs_dtype != np.float32 else dst
+                    dst[ids[cap:]] = self._h_final_np[cap:n_fin]
+                fo = dst
                 infos["final_obs"] = OrderedDict((k, fo[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
                 infos["_final_obs"] = term | trunc
         return obs, rew, term, trunc, infos

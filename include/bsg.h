@@ -110,7 +110,8 @@ typedef struct bsg_tensor_table {
     float *reward;      /* [E]                                                                       */
     uint8_t *terminated;/* [E]                                                                       */
     uint8_t *truncated; /* [E]                                                                       */
-    float *info;        /* [E*info_dim]  Env._get_info values at the end of the step (pre-autoreset) */
+    float *info;        /* [info_dim][E] Env._get_info values at the end of the step (pre-autoreset), key-major: */
+                        /*               one contiguous row of E values per info key                          */
     float *actions_staging; /* [E*act_dim] device staging buffer used by bsg_step_host, may be NULL  */
     /* in-sim ASAS pair lists of the LAST simulator substep (bs.traf.cd.confpairs / lospairs and the per-conflict
      * qdr, dist, dcpa, tcpa, tinconf of upstream's detect()), cfg.cd_pair_cap entries per env, count in
@@ -194,6 +195,9 @@ int bsg_step_host_wait(bsg_handle *h, const void *h_block, void *dst, size_t dst
 
 /* The host-thread copy bsg_step_host_copy uses, on its own (pure host code; works without a GPU). */
 int bsg_host_copy(void *dst, const void *src, size_t nbytes);
+/* dst[i] = (double)src[i], i < n, with the same host threads: the float64 observations of the reference's spaces
+ * (e.g. horizontal_cr_env.py:49-62 declare np.float64) from the float32 block the device writes. */
+int bsg_host_widen(double *dst, const float *src, size_t n);
 
 /* replaces: Env.reset(seed=...) (gymnasium seeding, e.g. horizontal_cr_env.py:82-83 super().reset(seed=seed)):
  * re-keys the Philox streams of the scenario generators and of the observation noise; takes effect at the next

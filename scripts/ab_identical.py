@@ -38,7 +38,7 @@ for env_id, E, kw, nsub in CASES:
             v.load_state_dict(sd)
         v.step_torch(a)
         eat(("tcpamax", "inconf", "env_i32", "pos", "kin", "obs", "reward", "terminated", "truncated", "info"))
-        nconf_total += int(v.t["info"][:, 4].sum().item())
+        nconf_total += int(v.t["info"][4].sum().item())
     out["%%s %%s" %% (env_id, kw)] = [h.hexdigest()[:16], nconf_total]
     v.close()
 print(json.dumps(out))

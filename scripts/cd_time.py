@@ -32,7 +32,9 @@ def main(n=100_000, reps=7):
     print("package:", os.path.dirname(bluesky_gym_sasha_b200.__file__))
     for name, r, kw in (("every ordered pair", rec, {}), ("symmetric", rec_s, dict(symmetric=True)),
                         ("culled", rec_s, dict(cull=True)), ("culled + symmetric", rec_s, dict(cull=True, symmetric=True)),
-                        ("every ordered pair, no lists", rec, dict(want_pairs=False))):
+                        ("every ordered pair, no lists", rec, dict(want_pairs=False)),
+                        ("row shard 1/8 (12544 rows x all)", rec, dict(row0=12544 * 3, n_rows=12544)),
+                        ("row shard 1/8, culled", rec_s, dict(row0=12544 * 3, n_rows=12544, cull=True))):
         for _ in range(2):
             out = cd.detect_packed(r, n, **kw)
         torch.cuda.synchronize()

@@ -38,10 +38,12 @@ def main():
         torch.cuda.synchronize()
         if i < 20:
             continue
-        st = v.t["final_obs"].view(-1).view(torch.int64)[-8 * E:].view(E, 8).cpu().numpy().astype(np.float64)
+        raw = v.t["final_obs"].view(-1).view(torch.int64)[-8 * E:].view(E, 8).cpu().numpy()
+        smid = (raw[:, 7] & 0xff).astype(np.int64)
+        st = raw.astype(np.float64)
         t0 = st[:, 0].min()
         st = (st - t0) * 1e-3                                    # us since the first warp started
-        rows.append((e0.elapsed_time(e1) * 1e3, st, int(v.t["final_count"][int(v.t["final_count"][2])])))
+        rows.append((e0.elapsed_time(e1) * 1e3, st, int(v.t["final_count"][int(v.t["final_count"][2])]), smid))
     ev = np.median([r[0] for r in rows])
     print(f"{env_id} E={E}: CUDA-event time per launch {ev:.1f} us (median of {len(rows)}), envs finishing per step "
           f"{np.mean([r[2] for r in rows]):.0f}")
@@ -57,6 +59,23 @@ def main():
     print(f"warp start: median {np.median(start):.2f}  p95 {np.percentile(start, 95):.2f}  max {start.max(axis=1).mean():.2f} us after the first")
     print(f"warp end  : median {np.median(end):.2f}  p95 {np.percentile(end, 95):.2f}  max {end.max(axis=1).mean():.2f} us after the first start")
     print(f"lifetime of a warp: median {np.median(end - start):.2f}  p95 {np.percentile(end - start, 95):.2f}  max {(end - start).max():.2f} us")
+    # who are the stragglers?  phase breakdown of the slowest 2 % of the warps, and whether they sit on particular SMs
+    life = end - start
+    thr = np.percentile(life, 98)
+    slow = life >= thr
+    print(f"slowest 2 % of the warps (lifetime >= {thr:.1f} us): mean phase durations "
+          + ", ".join(f"{NAMES[k].split()[0]} {d[:, :, k][slow].mean():.1f}" for k in range(7))
+          + "  | all warps: " + ", ".join(f"{d[:, :, k].mean():.1f}" for k in range(7)))
+    sm = np.stack([r[3] for r in rows])
+    per_sm_load = np.array([[np.sum(sm[l] == k) for k in range(160)] for l in range(sm.shape[0])])      # envs (warps) per SM
+    ld = per_sm_load[0][per_sm_load[0] > 0]
+    print(f"warps per SM: min {ld.min()} max {ld.max()} (over {len(ld)} SMs)")
+    for cnt in sorted(set(ld.tolist())):
+        sel = np.isin(sm[0], np.where(per_sm_load[0] == cnt)[0])
+        print(f"   SMs holding {cnt} warps: mean lifetime {life[0][sel].mean():.2f} us, max {life[0][sel].max():.2f} us, share of slow warps "
+              f"{(slow[0] & sel).sum() / max(slow[0].sum(), 1) * 100:.0f} %")
+    sm_slow = np.bincount(sm[slow], minlength=160)
+    print("slow warps per SM (top 8 SMs):", sorted(sm_slow.tolist(), reverse=True)[:8], "of", int(slow.sum()))
     fin = d[:, :, 5] > 0.5
     print(f"envs that reset: {fin.mean() * 100:.1f} %; their lifetime median {np.median((end - start)[fin]) if fin.any() else 0:.2f} us")
 

@@ -102,3 +102,15 @@ def test_host_thread_copy(lib):
         dst = np.empty(1_687_552, dtype=np.uint8)
         lib.bsg_host_copy(C.c_void_p(dst.ctypes.data), C.c_void_p(src.ctypes.data), dst.nbytes)
         assert np.array_equal(dst, src[:dst.nbytes])
+
+
+def test_host_thread_widen(lib):
+    """bsg_host_widen (float32 -> float64 with the host threads) equals numpy's astype for ragged sizes."""
+    import ctypes as C
+    import numpy as np
+    rng = np.random.default_rng(1)
+    src = rng.standard_normal(1_300_003).astype(np.float32)
+    for n in (0, 1, 7, 16_384, 65_537, 421_888, 1_300_003):
+        dst = np.full(n + 4, -7.0)
+        assert lib.bsg_host_widen(C.c_void_p(dst.ctypes.data + 16), C.c_void_p(src.ctypes.data), n) == 0
+        assert np.array_equal(dst[2:2 + n], src[:n].astype(np.float64)) and (dst[:2] == -7.0).all() and (dst[2 + n:] == -7.0).all()
