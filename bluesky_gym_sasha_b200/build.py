@@ -46,7 +46,8 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libbsg_b200.so")
-    res = subprocess.run([nvcc, "-shared", "-o", LIB] + [o for _, o, _ in procs] + ["-lcudart"],
+    # (the arch is named at the link step too: without it nvcc adds an empty default-arch stub cubin to the fat binary)
+    res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + [o for _, o, _ in procs] + ["-lcudart"],
                          capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

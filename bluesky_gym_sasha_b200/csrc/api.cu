@@ -11,6 +11,7 @@
 #include "env_kernels.cuh"
 
 int bsg_launch_env(const bsg::EnvParams& P, int slots, cudaStream_t st);   // env_step.cu
+int bsg_upload_tas150_table(const double* h_tab);   // env_step.cu
 int bsg_launch_obs_noise(const bsg::EnvParams& P, float sigma, uint32_t call, bool with_final, cudaStream_t st);   // obs_noise.cu
 namespace bsg { void host_copy_mt(void* dst, const void* src, size_t n, bool widen = false); void host_pool_prewake(); }   // host_pool.cu
 
@@ -135,16 +136,39 @@ extern "C" int bsg_create(const bsg_config* cfg, bsg_handle** out) {
     P.R2 = rpz * rpz;
     P.rpz = rpz;
     P.init_alt = cfg->init_alt;
-    {   // vcas2tas(150 m/s, init_alt) (bluesky/tools/aero.py::vatmos / vcas2tas as restated in oracle/aero.py), once, here
-        const double hh = (double)cfg->init_alt, T = fmax(288.15 - 0.0065 * hh, 216.65);
+    {   // TAS every aircraft of the scenario generator is created with -- vcas2tas(cas, alt) of bluesky/tools/aero.py as
+        // restated in oracle/aero.py -- for the envs that create them at a fixed altitude and speed: evaluated once, here
+        double hh = (double)cfg->init_alt, cas = 150.0;              // HorizontalCR (horizontal_cr_env.py:91; init_alt: 0)
+        switch (cfg->env_type) {
+            case BSG_ENV_SECTOR_CR: case BSG_ENV_STATIC_OBSTACLE: hh = 350.0; break;     // sector_cr_env.py:211, static_obstacle_env.py:106
+            case BSG_ENV_MERGE: hh = 10000.0; cas = 100.0; break;                        // merge_env.py:119
+            case BSG_ENV_PLAN_WAYPOINT: hh = 0.0; break;                                 // plan_waypoint_env.py:162
+            default: break;
+        }
+        const double T = fmax(288.15 - 0.0065 * hh, 216.65);
         const double rhotrop = 1.225 * pow(T / 288.15, 4.256848030018761);
         const double rho = rhotrop * exp(-fmax(0.0, hh - 11000.0) / 6341.552161), p = rho * 287.05287 * T;
-        const double q = 101325.0 * (pow(1.0 + 1.225 * 150.0 * 150.0 / (7.0 * 101325.0), 3.5) - 1.0);
+        const double q = 101325.0 * (pow(1.0 + 1.225 * cas * cas / (7.0 * 101325.0), 3.5) - 1.0);
         P.init_tas0 = sqrt(7.0 * p / rho * (pow(q / p + 1.0, 2.0 / 7.0) - 1.0));
+    }
+    if (cfg->env_type == BSG_ENV_DESCENT || cfg->env_type == BSG_ENV_VERTICAL_CR) {
+        // descent_env.py:165,173 / vertical_cr_env.py:263,270: alt_init = randint(2000, 4000), cre(..., acspd=150): the TAS for
+        // every altitude the generator can draw, in float64, for this device's copy of the table
+        static double tab[2001];
+        const double q = 101325.0 * (pow(1.0 + 1.225 * 150.0 * 150.0 / (7.0 * 101325.0), 3.5) - 1.0);
+        for (int k = 0; k <= 2000; ++k) {
+            const double hh = 2000.0 + k, T = fmax(288.15 - 0.0065 * hh, 216.65);
+            const double rho = 1.225 * pow(T / 288.15, 4.256848030018761), p = rho * 287.05287 * T;
+            tab[k] = sqrt(7.0 * p / rho * (pow(q / p + 1.0, 2.0 / 7.0) - 1.0));
+        }
+        DeviceGuard guard(cfg->device);
+        const int rc2 = bsg_upload_tas150_table(tab);
+        if (rc2 != BSG_OK) { delete h; return rc2; }
     }
     P.hpz = cfg->hpz > 0.0f ? cfg->hpz : 1000.0f * 0.3048f;
     P.dtlook = cfg->dtlookahead > 0.0f ? cfg->dtlookahead : 300.0f;
     P.seed = cfg->seed; P.gid0 = cfg->env_id_offset; P.perf = cfg->perf;
+    P.inv_axmax_gd = 1.0f / cfg->perf.axmax_gd; P.inv_axmax_air = 1.0f / cfg->perf.axmax_air;
     {   // merge_env.py:43-46: FIX = get_point_at_distance(RWY, 200 km, bearing 0)
         const double d2r = 0.017453292519943295;
         double la = bsg::kRwyLat * d2r, lo = bsg::kRwyLon * d2r, ang = 200.0 / 6371.0;

@@ -39,8 +39,8 @@ struct EnvParams {
     int env_type, E, n_int, cd_enabled, autoreset, max_steps, hdg_random, n_sub, fms_rel_freq, mode;
     int obs_dim, act_dim, info_dim;
     int fc_slot;                  // which of final_count[0..1] counts this launch's finished envs (the other is zeroed for the next)
-    float simdt, R2, hpz, dtlook, rpz, init_alt;
-    double init_tas0;             // vcas2tas(150 m/s, init_alt), host-evaluated (HorizontalCR scenario generator)
+    float simdt, R2, hpz, dtlook, rpz, init_alt, inv_axmax_gd, inv_axmax_air;
+    double init_tas0;             // TAS the scenario generator creates aircraft with (fixed altitude / CAS envs), host-evaluated
     double fix_lat, fix_lon;      // MergeEnv FIX (merge_env.py:43-46), evaluated on the host in double
     uint64_t seed;
     long long gid0;
@@ -315,7 +315,7 @@ __device__ __forceinline__ void compute_targets(const Ac& a, const EnvParams& P,
     if (ph == PH_AP) { vmin = pf.vminap; vmax = pf.vmaxap; }
     if (ph == PH_GD) { vmin = 0.0f; vmax = pf.vmaxic; }
     T.amax = (ph == PH_GD) ? pf.axmax_gd : pf.axmax_air;
-    T.inv_amax = 1.0f / T.amax;
+    T.inv_amax = (ph == PH_GD) ? P.inv_axmax_gd : P.inv_axmax_air;       // (1 / amax, evaluated on the host)
     // ---- perfoap.limits (CAS round trip evaluated at the allowed commanded altitude)
     T.allow_h = a.selalt > pf.hmax ? pf.hmax : a.selalt;
     if (cached) { T.allow_tas = a.tgt; return; }
@@ -513,7 +513,8 @@ __device__ __forceinline__ void group_cd(GroupSmem<G>& S, const int lane_g, Ac& 
                                     (__double2hiint(a.lat) & 0x80000000));
     // metres of arc east / north of the env's reference point (the envs live within a few hundred km of it, far from the
     // antimeridian: no +-180 fold)
-    const float x = (float)(kRearthD * kDeg2RadD * (a.lon - lon_ref)), y = (float)(kRearthD * kDeg2RadD * (a.lat - lat_ref));
+    // (the difference in float64, the scaling in float32: 2 cm at 300 km from the origin)
+    const float x = (kRearth * kDeg2Rad) * (float)(a.lon - lon_ref), y = (kRearth * kDeg2Rad) * (float)(a.lat - lat_ref);
     S.rec[2 * lane_g] = make_float4(x, y, ch, sh);
     S.rec[2 * lane_g + 1] = make_float4(a.gse, a.gsn, a.alt, a.vs);
     S.tmax[lane_g] = 0;

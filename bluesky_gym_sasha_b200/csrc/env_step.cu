@@ -21,6 +21,11 @@ __device__ __forceinline__ int nearest_rank(float dist, bool cand, int K) {
     return rank;
 }
 
+// vcas2tas(150 m/s, h) for the integer altitudes h = 2000 .. 4000 m that the DescentEnv / VerticalCREnv generators draw
+// (alt_init = randint(2000, 4000)): float64, evaluated on the host when the handle is created (api.cu), so the generators
+// keep the oracle's float64 values without a float64 pow chain at the tail of every launch with a finishing env
+__device__ double g_tas150_tab[2001];
+
 // =====================================================================================================
 // DescentEnv (descent_env.py) -- 1 aircraft, G = 1
 // =====================================================================================================
@@ -30,7 +35,8 @@ __device__ inline void descent_reset(Ac& a, EnvS& s, const EnvParams& P, long lo
     int alt_init = rng.randint(0, 2000, 4000);
     s.target_alt = (double)(alt_init + rng.randint(1, -500, 500));
     double hdg = P.hdg_random ? (double)rng.randint(2, 1, 360) : 0.0;
-    if (slot == 0) ac_create(a, 52.0, 4.0, hdg, (double)alt_init, 150.0); else ac_clear(a);
+    if (slot == 0) ac_create_tas(a, 52.0, 4.0, hdg, (double)alt_init, 150.0, g_tas150_tab[alt_init - 2000]);
+    else ac_clear(a);
     s.total_reward = 0.0f; s.final_alt = 0.0f; s.num_ac = 1;
 }
 template <int G>
@@ -333,10 +339,10 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
         const double l1 = la * kDeg2RadD, l2 = wla * kDeg2RadD, dlo = (wlo - lo) * kDeg2RadD;
         const double hx = sin(dlo) * cos(l2), hy = cos(l1) * sin(l2) - sin(l1) * cos(l2) * cos(dlo);
         const double h = fmod(kRad2DegD * atan2(hx, hy) + 360.0, 360.0);
-        ac_create(a, la, lo, h, 350.0, 150.0);
+        ac_create_tas(a, la, lo, h, 350.0, 150.0, P.init_tas0);
         w0lat = wla; w0lon = wlo;
     } else if (slot < num_ac) {
-        ac_create(a, 0.0, 0.0, 0.0, 350.0, 150.0);      // (no point could be placed: flagged in rflags, as before)
+        ac_create_tas(a, 0.0, 0.0, 0.0, 350.0, 150.0, P.init_tas0);      // (no point could be placed: flagged in rflags, as before)
     } else {
         ac_clear(a);
     }
@@ -425,7 +431,7 @@ __device__ inline void merge_reset(Ac& a, EnvS& s, const EnvParams& P, long long
         double dist = slot == 0 ? rng.uniform(1u, 50.0, 200.0) : rng.uniform(2u * slot + 1u, 20.0, 500.0);
         double lat, lon;
         d_point_at_distance(P.fix_lat, P.fix_lon, dist, brg, lat, lon);
-        ac_create(a, lat, lon, brg - 180.0, 10000.0, 100.0);
+        ac_create_tas(a, lat, lon, brg - 180.0, 10000.0, 100.0, P.init_tas0);
         if (slot > 0) {     // "INTi addwpt FIX" -> Route.direct + LNAV on; "INTi dest RWY" appends the last wp
             float q, dm;
             qdrdist_wgs(a.lat, a.lon, P.fix_lat, P.fix_lon, q, dm);
@@ -511,7 +517,7 @@ template <int G>
 __device__ inline void planwp_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot) {
     Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);      // plan_waypoint_env.py:157-172,200-213
     double hdg = P.hdg_random ? (double)rng.randint(0, 1, 360) : 0.0;
-    if (slot == 0) ac_create(a, 52.0, 4.0, hdg, 0.0, 150.0); else ac_clear(a);
+    if (slot == 0) ac_create_tas(a, 52.0, 4.0, hdg, 0.0, 150.0, P.init_tas0); else ac_clear(a);
     double* w = P.ef64 + e * BSG_F64_COUNT + BSG_F64_WPTS;
     for (int k = 0; k < 5; ++k) {
         int dis = rng.randint(1u + 2u * k, 0, 75), brg = rng.randint(2u + 2u * k, 0, 359);
@@ -555,10 +561,12 @@ __device__ inline void vertical_reset(Ac& a, EnvS& s, const EnvParams& P, long l
     const double target = (double)(alt_init + rng.randint(1, -500, 500));
     const double hdg0 = P.hdg_random ? (double)rng.randint(2, 1, 360) : 0.0;
     const double lat0 = 52.0, lon0 = 4.0, alt0 = (double)alt_init;
-    const double tas0 = d_cas2tas(150.0, alt0);
+    // (the ownship's TAS from the host-evaluated float64 table: the float64 pow chains were 8 us of dependent latency at the
+    // tail of every launch with a finishing env; the intruders' commanded CAS below in float32, the precision of that state)
+    const double tas0 = g_tas150_tab[alt_init - 2000];
     s.target_alt = target;
     if (slot == 0) {
-        ac_create(a, lat0, lon0, hdg0, alt0, 150.0);
+        ac_create_tas(a, lat0, lon0, hdg0, alt0, 150.0, tas0);
     } else if (slot <= 5) {                                                  // _generate_conflicts :185-200
         const uint32_t d = 3u + 4u * (uint32_t)(slot - 1);
         double dpsi = (double)rng.randint(d, 45, 315);
@@ -586,8 +594,10 @@ __device__ inline void vertical_reset(Ac& a, EnvS& s, const EnvParams& P, long l
         double lat = lat0 + dnm * cos(brn * kDeg2RadD) / 60.0;
         double lon = lon0 + dnm * sin(brn * kDeg2RadD) / fmax(0.01, 60.0 * cos(lat0 * kDeg2RadD));
         lon = fmod(lon + 180.0, 360.0); if (lon < 0.0) lon += 360.0; lon -= 180.0;
-        double acspd = d_tas2cas(sqrt(gsn * gsn + gse * gse), acalt);
-        ac_create(a, lat, lon, kRad2DegD * atan2(gse, gsn), acalt, acspd);
+        // upstream: acspd = vtas2cas(gs, acalt), then cre: tas = vcas2tas(acspd, acalt) -- the round trip is the identity
+        const double gs = sqrt(gsn * gsn + gse * gse);
+        const double acspd = (double)tas2cas((float)gs, vatmos((float)acalt));
+        ac_create_tas(a, lat, lon, kRad2DegD * atan2(gse, gsn), acalt, acspd, gs);
         a.vs = (float)acvs;                 // creconfs: vs[-1] = acvs; the env then selaltcmd(alt + dH, 0)
         a.selalt = (float)acalt; a.selvs = 0.0f;
     } else {
@@ -741,7 +751,7 @@ __device__ inline void static_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
     }
     double hdg = 0.0, dnm;
     d_kwikqdrdist(lat0, lon0, wlat, wlon, hdg, dnm);                        // hdg = ap.trk = initial_wpt_qdr
-    if (slot == 0) ac_create(a, lat0, lon0, hdg, 350.0, 150.0); else ac_clear(a);
+    if (slot == 0) ac_create_tas(a, lat0, lon0, hdg, 350.0, 150.0, P.init_tas0); else ac_clear(a);
     s.wpt_lat = wlat; s.wpt_lon = wlon; s.rflags = rflags;
     s.wpt_reach = 0; s.intrusions = 0; s.total_reward = 0.0f; s.drift_sum = 0.0f; s.drift_n = 0; s.num_ac = 1;
 }
@@ -854,6 +864,12 @@ __device__ __forceinline__ void do_info(const EnvS& s, const EnvParams& P, const
 #ifndef BSG_FAST_STEADY
 #define BSG_FAST_STEADY 1
 #endif
+#ifndef BSG_PIN_SLOT
+#define BSG_PIN_SLOT 0
+#endif
+#ifndef BSG_PIN_GROUP
+#define BSG_PIN_GROUP 1
+#endif
 #ifndef BSG_TARGET_CACHE
 #define BSG_TARGET_CACHE 1
 #endif
@@ -882,11 +898,21 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
         P.final_count[2] = P.fc_slot;
     }
     const int e = gt / G;
-    const int slot = gt % G;
+    int slot_ = gt % G;
+#if BSG_PIN_SLOT
+    asm volatile("" : "+r"(slot_));
+#endif
+    const int slot = slot_;
     if (e >= P.E) return;                       // group-uniform (G divides the block size)
     double* scratch = (ENV == BSG_ENV_SECTOR_CR) ? &s_scratch[(threadIdx.x / 32) * kSectorScratch]
                     : (ENV == BSG_ENV_STATIC_OBSTACLE) ? &s_scratch[(threadIdx.x / G) * kStaticScratch] : s_scratch;
-    auto& S = s_grp[(G > 1) ? tid / G : 0];
+    // (group index made opaque: otherwise the compiler, short of registers, rebuilds the group's shared-memory address from
+    // the thread index -- S2R, shift, multiply-add -- at most of the dozen places per substep that use it)
+    int grp = (G > 1) ? tid / G : 0;
+#if BSG_PIN_GROUP
+    asm volatile("" : "+r"(grp));
+#endif
+    auto& S = s_grp[grp];
 
 #ifdef BSG_PHASE_TIMING
     unsigned long long stamps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -928,7 +954,7 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
         // what they are a function of -- alt, vs, selspd, selalt -- stays put: the record carries allow_tas with a valid bit
         // that the end of a launch sets when its last targets belong to the stored (alt, vs), and that an action which
         // moves selspd / selalt clears.  Same inputs, same function: the cached value is the recomputed one bit for bit.
-        bool tgt_cached = BSG_TARGET_CACHE && P.mode == kModeStep && (a.flags & kFlTgt) != 0;
+        bool tgt_cached = (BSG_TARGET_CACHE && P.mode == kModeStep && (a.flags & kFlTgt) != 0) || !alive;   // (empty slots: nothing to compute)
         if (P.mode == kModeStep) {
             const float o_selspd = a.selspd, o_selalt = a.selalt;
             if (ENV == BSG_ENV_DESCENT || ENV == BSG_ENV_VERTICAL_CR) descent_action<G>(a, P, act, slot);
@@ -1080,6 +1106,10 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
 }  // namespace bsg
 
 using namespace bsg;
+
+int bsg_upload_tas150_table(const double* h_tab) {
+    return bsg_cuda_check(cudaMemcpyToSymbol(g_tas150_tab, h_tab, sizeof(double) * 2001), "tas table upload");
+}
 
 template <int ENV, int G>
 static int launch_env_t(const EnvParams& P, cudaStream_t st) {
