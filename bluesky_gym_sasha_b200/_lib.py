@@ -57,6 +57,21 @@ class CdLists(C.Structure):
 
 CD_ATTR = ("qdr", "dist", "dcpa", "tcpa", "tinconf")          # BSG_CD_ATTR_* columns of d_conf_attr
 
+# single-airspace traffic (bsg_traf_*): BSG_TF_* flag bits, BSG_TRAF_* sizes
+(TF_ALIVE, TF_LNAV, TF_VNAV, TF_VNAVSPD, TF_LASTWP, TF_ASAS, TF_RESOOFF, TF_PH_GD, TF_PH_AP, TF_ACTIVATE) = (1 << b for b in range(10))
+TF_IWP_SHIFT, TF_NWP_SHIFT, TRAF_PARTNERS, TRAF_CTR_COUNT = 16, 24, 8, 4
+
+
+class TrafConfig(C.Structure):
+    _fields_ = [("n", C.c_int64), ("max_wpts", C.c_int32), ("reso", C.c_int32), ("reso_mode", C.c_int32), ("simdt", C.c_float),
+                ("rpz", C.c_float), ("hpz", C.c_float), ("dtlookahead", C.c_float), ("resofach", C.c_float),
+                ("resofacv", C.c_float), ("perf", Perf), ("lat0", C.c_double), ("lon0", C.c_double)]
+
+
+class TrafTensors(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("pos", "kin", "cmd", "aux", "actwp", "vnav1", "vnav2", "asas", "flags", "partners",
+                                          "rt_pos", "rt_con", "rt_dir", "counters")]
+
 
 class Layout(C.Structure):
     _fields_ = [("slots", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("info_dim", C.c_int32),
@@ -75,7 +90,8 @@ class TensorTable(C.Structure):
 
 SYMBOLS = ("bsg_abi_version", "bsg_abi_struct_size", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
            "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_step_host_begin", "bsg_step_host_wait", "bsg_host_copy", "bsg_host_widen", "bsg_set_obs_noise", "bsg_get_noise_calls", "bsg_set_noise_calls", "bsg_load_state", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
-           "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_cd_cull_workspace", "bsg_cd_detect_culled", "bsg_cd_detect_peers", "bsg_probe_fp32")
+           "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_cd_cull_workspace", "bsg_cd_detect_culled", "bsg_cd_detect_peers", "bsg_probe_fp32",
+           "bsg_traf_pack", "bsg_traf_activate", "bsg_traf_substep")
 
 _lib = None
 
@@ -133,6 +149,12 @@ def load():
         lib.bsg_host_widen.restype = C.c_int
     lib.bsg_step_host_copy.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp]
     lib.bsg_traf_update.argtypes = [vp, i32, vp]
+    if hasattr(lib, "bsg_traf_substep"):        # (absent only in older A/B builds loaded through BSG_B200_LIB)
+        lib.bsg_traf_pack.argtypes = [C.POINTER(TrafConfig), C.POINTER(TrafTensors), vp, vp]
+        lib.bsg_traf_activate.argtypes = [C.POINTER(TrafConfig), C.POINTER(TrafTensors), vp]
+        lib.bsg_traf_substep.argtypes = [C.POINTER(TrafConfig), C.POINTER(TrafTensors), vp, i32, vp, vp, vp, vp, i64, vp]
+        for f in (lib.bsg_traf_pack, lib.bsg_traf_activate, lib.bsg_traf_substep):
+            f.restype = C.c_int
     lib.bsg_cd_padded.argtypes = [i64]
     lib.bsg_cd_padded.restype = i64
     lib.bsg_cd_pack.argtypes = [vp, vp, vp, vp, vp, vp, i64, f64, f64, vp, vp]

@@ -63,6 +63,8 @@ extern "C" int bsg_abi_struct_size(int which) {
         case 4: return (int)sizeof(bsg_perf);
         case 5: return (int)sizeof(bsg_ac_state);
         case 6: return (int)sizeof(bsg_cd_lists);
+        case 7: return (int)sizeof(bsg_traf_config);
+        case 8: return (int)sizeof(bsg_traf_tensors);
     }
     return -1;
 }

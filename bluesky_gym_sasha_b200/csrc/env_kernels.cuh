@@ -371,14 +371,18 @@ __device__ __forceinline__ void ac_autopilot(Ac& a, const EnvParams& P, bool fms
     }
 }
 
-template <bool WIND>
-__device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const Targets& T) {
+// EXT (single-airspace traffic, traf_airspace.cu): the commanded track and vertical speed come from the caller -- VNAV or
+// the ASAS resolution may be in command (APorASAS.update) -- instead of the select modes; the env kernels never set it.
+template <bool WIND, bool EXT = false>
+__device__ __forceinline__ void ac_kinematics(Ac& a, const EnvParams& P, const Targets& T, const float ext_trk = 0.0f,
+                                              const float ext_vs = 0.0f) {
     const float dt = P.simdt;
     const bsg_perf& pf = P.perf;
     // ---- Autopilot select modes + APorASAS.update (resolution off)
     float selvs_eff = fabsf(a.selvs) > 0.1f ? a.selvs : kVsDef;
     float p_vs = fabsf(selvs_eff);
     float p_hdg = mod360(a.aptrk);
+    if (EXT) { p_vs = fabsf(ext_vs); p_hdg = mod360(ext_trk); }
     float wn = 0.0f, we = 0.0f;
     if (WIND) {
         // APorASAS.update with wind: the heading that makes good the commanded track (crab angle), from the

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BSG_ABI_VERSION 4
+#define BSG_ABI_VERSION 5
 
 enum { BSG_OK = 0, BSG_EINVAL = -1, BSG_ECUDA = -2, BSG_ESTATE = -3, BSG_ENOMEM = -4 };
 
@@ -143,7 +143,7 @@ typedef struct bsg_handle bsg_handle;
 
 int bsg_abi_version(void);
 /* sizeof of the library's view of an interface structure (which: 0 bsg_config, 1 bsg_layout, 2 bsg_tensor_table,
- * 3 bsg_wind, 4 bsg_perf, 5 bsg_ac_state, 6 bsg_cd_lists; anything else -1): a binding in another language checks its own declarations against it */
+ * 3 bsg_wind, 4 bsg_perf, 5 bsg_ac_state, 6 bsg_cd_lists, 7 bsg_traf_config, 8 bsg_traf_tensors; anything else -1): a binding in another language checks its own declarations against it */
 int bsg_abi_struct_size(int which);
 const char *bsg_last_error(void);
 int bsg_device_count(void);
@@ -325,6 +325,62 @@ int bsg_cd_detect_peers(const float *const *h_peer_rec, int32_t n_peers, int32_t
                         float rpz, float hpz, float dtlookahead, uint32_t flags, uint32_t *d_nconf_row,
                         uint32_t *d_nlos_row, float *d_tcpamax, uint8_t *d_inconf, const bsg_cd_lists *lists,
                         void *d_work, int64_t work_bytes, void *stream);
+
+/* ---- single-airspace traffic with routes, VNAV and ASAS resolution ---------------------------------
+ * One airspace of n aircraft (the bs.traf of a BlueSky scenario at N = 1e5 instead of the handful a NumPy Traffic
+ * can step): per simulator substep  bsg_traf_pack -> bsg_cd_detect[_culled] with pair lists -> (caller sorts the
+ * conflict keys) -> bsg_traf_substep, which fuses per aircraft: Autopilot.update (LNAV, update_fms over multi-waypoint
+ * routes with altitude / speed constraints, ComputeVNAV, the continuous VNAV / speed guidance), ConflictResolution.update
+ * (MVP.resolve over the aircraft's own conflicts in intruder order, resumenav with waypoint recovery), APorASAS.update,
+ * perfoap.limits and Traffic.update_airspeed / update_groundspeed / update_pos.
+ * Replaces upstream bluesky/traffic/{autopilot,route,aporasas}.py, asas/{resolution,mvp}.py as restated in
+ * oracle/traffic_ext.py (the reference only ever says `reso off`, merge_env.py:157, and builds unconstrained two-waypoint
+ * routes, merge_env.py:155-156).  Stateless: every call takes the configuration and the caller-owned DEVICE tensors. */
+enum { BSG_TRAF_PARTNERS = 8 };         /* resopairs kept per aircraft (ConflictResolution.resopairs as rows)      */
+enum { BSG_TF_ALIVE = 1, BSG_TF_LNAV = 2, BSG_TF_VNAV = 4, BSG_TF_VNAVSPD = 8, BSG_TF_LASTWP = 16, BSG_TF_ASAS = 32 /* cr.active */,
+       BSG_TF_RESOOFF = 64, BSG_TF_PH_GD = 128 /* phase of the last perf.update: ground */, BSG_TF_PH_AP = 256 /* approach */,
+       BSG_TF_ACTIVATE = 512 /* route uploaded, Route.direct(first waypoint) still to run */,
+       BSG_TF_IWP_SHIFT = 16 /* active waypoint index, 8 bits */, BSG_TF_NWP_SHIFT = 24 /* waypoints in the route, 8 bits */ };
+enum { BSG_TRAF_CTR_OVERFLOW = 0 /* resopairs that did not fit BSG_TRAF_PARTNERS */, BSG_TRAF_CTR_SWITCH = 1 /* waypoint switches */,
+       BSG_TRAF_CTR_ACTIVE = 2 /* aircraft under ASAS command after the last substep */, BSG_TRAF_CTR_COUNT = 4 };
+typedef struct bsg_traf_config {
+    int64_t n;                  /* aircraft                                                               */
+    int32_t max_wpts;           /* W: waypoint slots per route (<= 255)                                   */
+    int32_t reso;               /* 0: detection only (RESO OFF); 1: MVP                                   */
+    int32_t reso_mode;          /* 0: horizontal + vertical (upstream default); 1: horizontal only        */
+    float simdt;
+    float rpz, hpz, dtlookahead;
+    float resofach, resofacv;   /* settings.asas_mar (1.01)                                               */
+    bsg_perf perf;
+    double lat0, lon0;          /* origin of the CD records                                               */
+} bsg_traf_config;
+typedef struct bsg_traf_tensors {
+    double *pos;                /* [n][2] lat, lon [deg]                                                  */
+    float *kin;                 /* [n][4] alt, tas, hdg, vs                                               */
+    float *cmd;                 /* [n][4] selspd (CAS or Mach), selalt, selvs, ap.trk                     */
+    float *aux;                 /* [n][4] ax, actwp.curlegdir, actwp.next_qdr, actwp.turndist             */
+    double *actwp;              /* [n][2] active waypoint lat, lon                                        */
+    float *vnav1;               /* [n][4] actwp.nextaltco, actwp.xtoalt, actwp.vs, ap.dist2vs             */
+    float *vnav2;               /* [n][4] actwp.spd, actwp.nextspd, actwp.spdcon, ap.vnavvs               */
+    float *asas;                /* [n][4] cr.trk, cr.tas, cr.vs, cr.alt                                   */
+    uint32_t *flags;            /* [n] BSG_TF_*                                                           */
+    int32_t *partners;          /* [n][BSG_TRAF_PARTNERS] intruder indices of the aircraft's resopairs, -1 = free */
+    const double *rt_pos;       /* [n][W][2] route waypoints                                              */
+    const float *rt_con;        /* [n][W][4] wpalt, wpspd (< 0: none), wptoalt, wpxtoalt (Route.calcfp)   */
+    const float *rt_dir;        /* [n][W] direction of the leg from waypoint k to k + 1 [deg], -999 after the last */
+    uint32_t *counters;         /* [BSG_TRAF_CTR_COUNT]                                                   */
+} bsg_traf_tensors;
+/* Traffic state -> CD records of bsg_cd_detect (trk = hdg, gs = tas: no wind); d_rec holds bsg_cd_padded(n) records. */
+int bsg_traf_pack(const bsg_traf_config *cfg, const bsg_traf_tensors *t, float *d_rec, void *stream);
+/* Route.direct(first waypoint) + ComputeVNAV for every aircraft flagged BSG_TF_ACTIVATE (after the route tables changed). */
+int bsg_traf_activate(const bsg_traf_config *cfg, const bsg_traf_tensors *t, void *stream);
+/* One simulator substep.  d_rec: the records bsg_traf_pack made of the state BEFORE this substep (what the detection saw);
+ * d_keys: the detection's conflict pairs as own << 32 | intruder, sorted ascending, unused entries INT64_MAX, conf_cap of
+ * them; d_perm[k]: row of d_conf_attr (BSG_CD_ATTR_*) that belongs to d_keys[k]; d_npairs[0]: conflicts found.  All three
+ * may be NULL with reso == 0.  fms_ready: the FMS timer fires in this substep (sim step count % (10.5 // simdt) == 0). */
+int bsg_traf_substep(const bsg_traf_config *cfg, const bsg_traf_tensors *t, const float *d_rec, int32_t fms_ready,
+                     const int64_t *d_keys, const int32_t *d_perm, const float *d_conf_attr,
+                     const unsigned long long *d_npairs, int64_t conf_cap, void *stream);
 
 /* ---- roofline denominators measured on the spot (bench.py) ------------------------------------- */
 /* Dense FP32 FMA throughput [FLOP/s] of this device, timed with CUDA events. */
