@@ -437,6 +437,7 @@ def run_b200(args):
                         "bytes_per_env_step": BYTES_PER_ENV_STEP}}
         # CD at N = 100k on this GPU (BASELINE configs[4], single-GPU share)
         cd = bench_cd(torch, dev, StateBasedCD, fp32)
+        traffic_leg = bench_traffic(torch, dev, hbm_peak) if world == 1 else None
         cb = None if (args.skip_cpu or world > 1) else cpu_baseline(budget_s=10.0)
         # compact headline of the second BASELINE metric, early in the line (the full records follow at the end)
         cd_head = {"n_aircraft": cd["n_aircraft"], "ordered_pairs_per_s": cd["ordered_pairs_per_s"], "ms": cd["ms"],
@@ -454,6 +455,8 @@ def run_b200(args):
                 "cpu_baseline": cb, "clocks": clk.summary(), "cd_pairs": cd}
         if other is not None:
             line["other_envs"] = other
+        if traffic_leg is not None:
+            line["airspace_traffic"] = traffic_leg
         if cd_sharded is not None:
             line["cd_pairs_sharded"] = cd_sharded
     if world > 1:
@@ -580,6 +583,88 @@ def bench_cd(torch, dev, StateBasedCD, fp32_peak, n=CD_N, reps=5):
                      "n_los": int(outc["npairs"][1]),
                      "note": "bsg_cd_detect_culled on strip-sorted records: tile pairs out of reach (rpz + (v_a+v_b)*300 s) skipped"}
     return res
+
+
+def bench_traffic(torch, dev, hbm_peak, n=CD_N, reps=20):
+    """SURVEY 8f-4 leg: one airspace of n aircraft (the C5 box) flying four-waypoint routes with altitude constraints under
+    VNAV, state-based detection every substep (culled + symmetric K2 with pair lists) and MVP resolution: device time per
+    simulator substep and of bsg_traf_substep alone (HBM-bound: 328 algorithmic bytes per aircraft-substep)."""
+    import ctypes as C
+    from bluesky_gym_sasha_b200 import _lib
+    from bluesky_gym_sasha_b200.cd import StateBasedCD, _ptr
+    from bluesky_gym_sasha_b200.traffic import AirspaceTraffic
+    rng = np.random.default_rng(3)
+    lat, lon = 52 + 40 * (rng.random(n) - 0.5), 4 + 40 * (rng.random(n) - 0.5)
+    perm = StateBasedCD.spatial_order(torch.as_tensor(lat, device=dev), torch.as_tensor(lon, device=dev)).cpu().numpy()
+    lat, lon = lat[perm], lon[perm]                    # created in spatially coherent order: the culled detection needs it
+    alt = np.round(rng.uniform(3000, 12000, n) / 304.8) * 304.8
+    hdg, cas = rng.uniform(0, 360, n), rng.uniform(120, 150, n)
+    W = 4
+    wlat, wlon, walt = np.zeros((n, W)), np.zeros((n, W)), np.full((n, W), -999.0)
+    la, lo, brg = lat.copy(), lon.copy(), hdg.copy()
+    for k in range(W):
+        d = rng.uniform(60.0, 120.0, n) / 111.0
+        la = la + d * np.cos(np.radians(brg)); lo = lo + d * np.sin(np.radians(brg)) / np.cos(np.radians(np.clip(la, -80, 80)))
+        brg = brg + rng.uniform(-40, 40, n)
+        wlat[:, k], wlon[:, k] = la, lo
+        walt[:, k] = np.where(rng.random(n) < 0.5, np.clip(alt + rng.uniform(-2500, 1500, n), 1500, 12000), -999.0)
+    tr = AirspaceTraffic(n, device=dev.index, simdt=1.0, reso="MVP", reso_mode=1, max_wpts=W)
+    tr.create(lat, lon, hdg, alt, cas)
+    tr.set_routes(np.arange(n), wlat, wlon, walt, None)
+    tr.step(20)                                         # warm-up (first resolutions, VNAV profiles computed)
+    torch.cuda.synchronize(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps)]
+    for r in range(reps):
+        ev[2 * r].record(); tr.step(1); ev[2 * r + 1].record()
+    torch.cuda.synchronize(dev)
+    t_sub = sorted(ev[2 * r].elapsed_time(ev[2 * r + 1]) for r in range(reps))[reps // 2]
+    # the fused per-aircraft kernel alone, on the state and conflict list of the last substep
+    out = tr.last
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    cfg0 = _lib.TrafConfig.from_buffer_copy(tr.cfg)
+    cfg0.reso = 0                                       # the per-aircraft kernel alone would need the index of this list:
+    ts, ts_all = [], []                                 # timed (a) without ASAS and (b) as the whole call (index + kernel)
+    for r in range(2 * reps):
+        flush.fill_(float(r))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(tr.lib.bsg_traf_substep(C.byref(tr.cfg if r % 2 else cfg0), C.byref(tr.tt), _ptr(tr.rec), 0, _ptr(out["pairs"]),
+                                           _ptr(out["attr"]), _ptr(out["npairs"]), tr.cd.pair_capacity, _ptr(tr.work),
+                                           tr.work.numel(), st))
+        b.record()
+        torch.cuda.synchronize(dev)
+        (ts_all if r % 2 else ts).append(a.elapsed_time(b))
+    t_k, t_call = sorted(ts)[reps // 2], sorted(ts_all)[reps // 2]
+    nconf, nlos = (int(v) for v in out["npairs"].cpu())
+    bytes_per_ac = 328
+    # the same kernel where its bound shows: 2^20 aircraft (344 MB of state, larger than L2), detection off
+    big = 1 << 20
+    tb = AirspaceTraffic(big, device=dev.index, simdt=1.0, max_wpts=W, pair_capacity=4096)
+    reps_b = -(-big // n)
+    tile = lambda a: np.tile(a, (reps_b,) + (1,) * (a.ndim - 1))[:big]
+    tb.create(tile(lat), tile(lon), tile(hdg), tile(alt), tile(cas))
+    tb.set_routes(np.arange(big), tile(wlat), tile(wlon), tile(walt), None)
+    tb.step(3, detect=False)
+    tsb = []
+    for r in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); tb.step(1, detect=False); b.record()
+        torch.cuda.synchronize(dev)
+        tsb.append(a.elapsed_time(b))
+    t_big = sorted(tsb)[reps // 2]
+    del tb
+    return {"n_aircraft": n, "ms_per_substep": t_sub, "aircraft_substeps_per_s": n / (t_sub * 1e-3),
+            "realtime_factor": 1.0 / (t_sub * 1e-3), "n_conf": nconf, "n_los": nlos, "counters": tr.counters(),
+            "form": "bsg_traf_pack + culled symmetric K2 with pair lists + bsg_traf_substep (conflict index + fused per-aircraft kernel), MVP horizontal, VNAV routes",
+            "substep_call_us": t_call * 1e3,
+            "substep_kernel": {"us": t_k * 1e3, "l2": "flushed", "what": "traf_substep_kernel with reso off (autopilot / VNAV / limits / kinematics)", "roofline": {
+                "bound": "hbm", "achieved": bytes_per_ac * n / (t_k * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": bytes_per_ac * n / (t_k * 1e-3) / 1e9 / hbm_peak, "bytes_per_aircraft_substep": bytes_per_ac,
+                "kernel": "traf_substep_kernel"}},
+            "substep_kernel_2e20_aircraft": {"us": t_big * 1e3, "l2": "state (344 MB) exceeds L2", "roofline": {
+                "bound": "hbm", "achieved": bytes_per_ac * big / (t_big * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": bytes_per_ac * big / (t_big * 1e-3) / 1e9 / hbm_peak, "kernel": "traf_substep_kernel"}}}
 
 
 def bench_cd_sharded(torch, dist, dev, StateBasedCD, world, rank, max_over_ranks, barrier, n=CD_N, reps=5):

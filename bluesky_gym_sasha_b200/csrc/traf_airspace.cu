@@ -1,15 +1,16 @@
 // traf_airspace.cu -- one airspace of N aircraft with routes, VNAV and ASAS conflict resolution.
 //
-// Per simulator substep the caller runs  traf_pack_kernel -> K2 (cd_tiled.cu, with pair lists) -> a sort of the conflict
-// keys (own << 32 | intruder) -> traf_substep_kernel.  The substep kernel owns one aircraft per thread and fuses what
+// Per simulator substep the caller runs  traf_pack_kernel -> K2 (cd_tiled.cu, with pair lists) -> bsg_traf_substep, which
+// first indexes K2's unordered conflict list by own aircraft (count, allocate, scatter: three small kernels, no sort) and
+// then launches traf_substep_kernel.  The substep kernel owns one aircraft per thread and fuses what
 // upstream spreads over Autopilot.update, ConflictResolution.update, APorASAS.update, perfoap.update / limits and
 // Traffic.update_airspeed / groundspeed / pos (bluesky/traffic/{autopilot,route,aporasas,traffic}.py,
 // asas/{resolution,mvp}.py, performance/openap/perfoap.py as restated in oracle/traffic_ext.py, which it is checked
 // against).  An aircraft only ever WRITES its own records; everything it needs from other aircraft -- the intruders of
 // its conflicts and of its resopairs -- it reads from the CD records of this substep, an immutable snapshot of the state
 // the detection saw, so the update is in place and free of ordering effects.  An aircraft's conflicts sit in one
-// contiguous, intruder-ordered run of the sorted key list: the MVP velocity changes are summed in upstream's order
-// (confpairs is row-major), deterministically.
+// contiguous run of the index and are visited in ascending intruder order: the MVP velocity changes are summed in
+// upstream's order (confpairs is row-major), deterministically, whatever order K2 emitted them in.
 //
 // Bound: HBM.  Algorithmic bytes per aircraft-substep: the nine state records read and written (2 x 148 B) plus its
 // 32 B CD record = 328 B; the route table is only touched at a waypoint switch.
@@ -35,7 +36,8 @@ struct TrafParams {
     uint32_t* flags; int32_t* partners;
     const double2* rt_pos; const float4* rt_con; const float* rt_dir; uint32_t* counters;
     const float* rec;
-    const long long* keys; const int* perm; const float* attr; const unsigned long long* npairs; long long cap;
+    const int2* pairs; const float* attr; const unsigned long long* npairs; long long cap;      // K2's conflict list
+    int* count; int* offs; int* len; int* total; int* seg;     // index of that list by own aircraft: rows seg[offs[i] .. offs[i] + len[i])
 };
 
 // registers of one aircraft beyond the kinematic state (struct Ac)
@@ -201,13 +203,41 @@ __device__ __forceinline__ void mvp_pair(const TrafParams& P, const float qdr, c
     dv3 = vmove ? (iv / tsolv) * (-dvs / fabsf(dvs)) : iv / tsolv;
 }
 
-__device__ __forceinline__ long long lower_bound_key(const long long* keys, long long n, long long key) {
-    long long lo = 0, hi = n;
-    while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+// ---- index of K2's conflict list by own aircraft ---------------------------------------------------------------------
+__global__ void traf_conf_count_kernel(const TrafParams P) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long ntot = P.npairs[0];
+    const long long m = ntot < (unsigned long long)P.cap ? (long long)ntot : P.cap;
+    if (k == 0) *P.total = 0;                          // (the allocation kernel runs after this one)
+    if (k < m) atomicAdd(&P.count[P.pairs[k].x], 1);
+}
+// every aircraft with conflicts reserves a contiguous run of the index: warp-aggregated (one atomicAdd per warp on the
+// running total).  The runs come in no particular order -- nothing needs them ordered -- so no global scan is needed.
+__global__ void traf_conf_alloc_kernel(const TrafParams P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int c = i < P.n ? P.count[i] : 0;
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
     }
-    return lo;
+    const int wsum = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && wsum > 0) base = atomicAdd(P.total, wsum);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (i < P.n) { P.offs[i] = base + incl - c; P.len[i] = c; }
+}
+// rows of the list into their aircraft's run; the counters count back down to zero, ready for the next substep
+__global__ void traf_conf_scatter_kernel(const TrafParams P) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long ntot = P.npairs[0];
+    const long long m = ntot < (unsigned long long)P.cap ? (long long)ntot : P.cap;
+    if (k < m) {
+        const int i = P.pairs[k].x;
+        P.seg[P.offs[i] + atomicSub(&P.count[i], 1) - 1] = (int)k;
+    }
 }
 
 __global__ void __launch_bounds__(128) traf_substep_kernel(const TrafParams P) {
@@ -285,18 +315,22 @@ __global__ void __launch_bounds__(128) traf_substep_kernel(const TrafParams P) {
     if (P.reso) {
         const float own_u = rec_at(P.rec, i, RU), own_v = rec_at(P.rec, i, RV), own_alt = rec_at(P.rec, i, RALT), own_vs = rec_at(P.rec, i, RVS);
         const unsigned long long ntot = P.npairs[0];
-        const long long m = ntot < (unsigned long long)P.cap ? (long long)ntot : P.cap;
-        long long k0 = 0, k1 = 0;
-        if (m > 0) {
-            k0 = lower_bound_key(P.keys, m, i << 32);
-            k1 = k0;
-            while (k1 < m && (P.keys[k1] >> 32) == i) ++k1;
-        }
+        const int k0 = P.offs[i], k1 = k0 + P.len[i];
+        // the aircraft's conflicts in ascending intruder order (its run of the index is unordered; runs are short)
+        auto next_conflict = [&](int last, int& row) {
+            int best = 0x7fffffff;
+            for (int k = k0; k < k1; ++k) {
+                const int r = P.seg[k], j = P.pairs[r].y;
+                if (j > last && j < best) { best = j; row = r; }
+            }
+            return best;
+        };
         if (ntot > 0) {                                    // `if conf.confpairs:` -- resolve() rewrites every aircraft's commands
             float d1 = 0.0f, d2 = 0.0f, d3 = 0.0f, tsolv_min = 1e9f;
-            for (long long k = k0; k < k1; ++k) {
-                const long long j = P.keys[k] & 0xffffffffLL;
-                const float* q = P.attr + (long long)P.perm[k] * BSG_CD_ATTR_COUNT;
+            int row = 0;
+            for (int c = k0, j = -1; c < k1; ++c) {
+                j = next_conflict(j, row);
+                const float* q = P.attr + (long long)row * BSG_CD_ATTR_COUNT;
                 float e1, e2, e3, ts;
                 mvp_pair(P, q[BSG_CD_ATTR_QDR], q[BSG_CD_ATTR_DIST], q[BSG_CD_ATTR_TCPA], q[BSG_CD_ATTR_TINCONF],
                          rec_at(P.rec, j, RALT) - own_alt, rec_at(P.rec, j, RU) - own_u, rec_at(P.rec, j, RV) - own_v,
@@ -334,8 +368,8 @@ __global__ void __launch_bounds__(128) traf_substep_kernel(const TrafParams P) {
             part[4] = p1.x; part[5] = p1.y; part[6] = p1.z; part[7] = p1.w;
         }
         int overflow = 0;
-        for (long long k = k0; k < k1; ++k) {
-            const int j = (int)(P.keys[k] & 0xffffffffLL);
+        for (int k = k0; k < k1; ++k) {
+            const int j = P.pairs[P.seg[k]].y;
             bool have = false;
             int free_slot = -1;
 #pragma unroll
@@ -477,21 +511,36 @@ extern "C" int bsg_traf_activate(const bsg_traf_config* cfg, const bsg_traf_tens
     return bsg_cuda_check(cudaGetLastError(), "bsg_traf_activate launch");
 }
 
+extern "C" int64_t bsg_traf_workspace(int64_t n, int64_t conf_cap) {
+    if (n < 0 || conf_cap < 0) return 0;
+    return (int64_t)sizeof(int) * (3 * n + 1 + conf_cap) + 64;
+}
+
 extern "C" int bsg_traf_substep(const bsg_traf_config* cfg, const bsg_traf_tensors* t, const float* d_rec, int32_t fms_ready,
-                                const int64_t* d_keys, const int32_t* d_perm, const float* d_conf_attr,
-                                const unsigned long long* d_npairs, int64_t conf_cap, void* stream) {
+                                const int32_t* d_conf_pairs, const float* d_conf_attr, const unsigned long long* d_npairs,
+                                int64_t conf_cap, void* d_work, int64_t work_bytes, void* stream) {
     TrafParams P;
     int rc = traf_params(P, cfg, t, "bsg_traf_substep");
     if (rc != BSG_OK) return rc;
     if (P.n == 0) return BSG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
     if (P.reso) {
         if (P.reso != 1) return bsg_fail(BSG_EINVAL, "bsg_traf_substep: reso must be 0 (off) or 1 (MVP)");
-        if (!d_rec || !d_keys || !d_perm || !d_conf_attr || !d_npairs || conf_cap <= 0)
-            return bsg_fail(BSG_EINVAL, "bsg_traf_substep: reso needs the CD records and the sorted conflict list");
+        if (!d_rec || !d_conf_pairs || !d_conf_attr || !d_npairs || conf_cap <= 0)
+            return bsg_fail(BSG_EINVAL, "bsg_traf_substep: reso needs the CD records and the detection's conflict list");
+        if (conf_cap > 0x7fffff00LL) return bsg_fail(BSG_EINVAL, "bsg_traf_substep: conf_cap exceeds int32");
+        if (!d_work || work_bytes < bsg_traf_workspace(P.n, conf_cap)) return bsg_fail(BSG_EINVAL, "bsg_traf_substep: workspace too small");
+        P.rec = d_rec; P.pairs = (const int2*)d_conf_pairs; P.attr = d_conf_attr; P.npairs = d_npairs; P.cap = conf_cap;
+        // workspace: count[n] (zero on entry: the caller zeroes it once, the scatter leaves it zero) | offs[n] | len[n] | total | seg[cap]
+        P.count = (int*)d_work; P.offs = P.count + P.n; P.len = P.offs + P.n; P.total = P.len + P.n; P.seg = P.total + 1;
+        const unsigned blocks = (unsigned)((conf_cap + 255) / 256);
+        traf_conf_count_kernel<<<blocks, 256, 0, st>>>(P);
+        traf_conf_alloc_kernel<<<(unsigned)((P.n + 255) / 256), 256, 0, st>>>(P);
+        traf_conf_scatter_kernel<<<blocks, 256, 0, st>>>(P);
+        BSG_CUDA(cudaGetLastError());
     }
     P.fms_ready = fms_ready ? 1 : 0;
-    BSG_CUDA(cudaMemsetAsync(t->counters + BSG_TRAF_CTR_ACTIVE, 0, sizeof(uint32_t), (cudaStream_t)stream));   // (a per-substep figure)
-    P.rec = d_rec; P.keys = (const long long*)d_keys; P.perm = d_perm; P.attr = d_conf_attr; P.npairs = d_npairs; P.cap = conf_cap;
-    traf_substep_kernel<<<(unsigned)((P.n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P);
+    BSG_CUDA(cudaMemsetAsync(t->counters + BSG_TRAF_CTR_ACTIVE, 0, sizeof(uint32_t), st));   // (a per-substep figure)
+    traf_substep_kernel<<<(unsigned)((P.n + 127) / 128), 128, 0, st>>>(P);
     return bsg_cuda_check(cudaGetLastError(), "bsg_traf_substep launch");
 }

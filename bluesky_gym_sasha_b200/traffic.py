@@ -4,8 +4,7 @@ Interface mirrored: the handful of ``bs.traf`` / ``bs.stack`` calls a BlueSky sc
 ``cre`` (many at once), ``ADDWPT acid lat lon alt spd`` x n + ``LNAV / VNAV ON`` (``set_routes``), ``HDG / SPD / ALT``
 select commands, ``RESO MVP`` / ``RESO OFF`` (``reso=``; the reference's own line is ``reso off``, merge_env.py:157),
 ``RESOOFF acid``, ``bs.sim.step()`` (``step``) -- with the state arrays ``lat, lon, alt, tas, hdg, vs, ...`` as properties.
-Per substep: ``bsg_traf_pack`` -> ``bsg_cd_detect[_culled]`` with pair lists (K2) -> sort of the conflict keys (torch: plumbing)
--> ``bsg_traf_substep`` (include/bsg.h).  Restated for checking in oracle/traffic_ext.py.  No CPU fallback.
+Per substep: ``bsg_traf_pack`` -> ``bsg_cd_detect[_culled]`` with pair lists (K2) -> ``bsg_traf_substep`` (include/bsg.h).  Restated for checking in oracle/traffic_ext.py.  No CPU fallback.
 """
 import ctypes as C
 
@@ -16,7 +15,6 @@ from . import _lib
 from .cd import StateBasedCD, _ptr
 
 NM, FT, FPM, KTS = 1852.0, 0.3048, 0.3048 / 60.0, 0.514444
-_INT64_MAX = (1 << 63) - 1
 
 
 # ---- bluesky.tools.aero / geo on the host, float64 (creation-time conversions and Route.calcfp only) ---------------------
@@ -129,7 +127,7 @@ class AirspaceTraffic:
         self.tt = _lib.TrafTensors(**{k: _ptr(v) for k, v in self.t.items()})
         n_pad = int(self.lib.bsg_cd_padded(n))
         self.rec = torch.empty((max(n_pad // 256, 1), 8, 256), dtype=torch.float32, device=dev)
-        self.keys = torch.empty(cap, dtype=torch.int64, device=dev)
+        self.work = torch.zeros(int(self.lib.bsg_traf_workspace(n, cap)), dtype=torch.uint8, device=dev)      # (zeroed once)
         self.last = None                    # device outputs of the last substep's detection
         self.gpu_launches = 0
 
@@ -236,24 +234,19 @@ class AirspaceTraffic:
             for _ in range(n_sub):
                 self.nstep += 1
                 fms_ready = (self.nstep % self.fms_rel_freq) == 0
-                keys = perm = attr = npairs = None
+                pairs = attr = npairs = None
                 if detect:
                     _lib.check(self.lib.bsg_traf_pack(C.byref(self.cfg), C.byref(self.tt), _ptr(self.rec), st))
                     out = cd.detect_packed(self.rec, n, want_pairs=True, cull=self.cull, symmetric=self.symmetric)
                     self.last = out
                     self.gpu_launches += 1
                     if self.reso:
-                        # conflict keys own << 32 | intruder, unused entries last: an aircraft's conflicts become one
-                        # contiguous, intruder-ordered run (torch: plumbing)
-                        p = out["pairs"].to(torch.int64)
-                        k = (p[:, 0] << 32) | p[:, 1]
-                        valid = torch.arange(k.numel(), device=self.device) < out["npairs"][0]
-                        keys, perm64 = torch.sort(torch.where(valid, k, torch.full_like(k, _INT64_MAX)))
-                        perm, attr, npairs = perm64.to(torch.int32), out["attr"], out["npairs"]
-                        self._sorted = (keys, perm)
+                        pairs, attr, npairs = out["pairs"], out["attr"], out["npairs"]
+                        self.gpu_launches += 3
                 _lib.check(self.lib.bsg_traf_substep(C.byref(self.cfg), C.byref(self.tt), _ptr(self.rec), int(fms_ready),
-                                                     _ptr(keys), _ptr(perm), _ptr(attr), _ptr(npairs),
-                                                     cd.pair_capacity if keys is not None else 0, st))
+                                                     _ptr(pairs), _ptr(attr), _ptr(npairs),
+                                                     cd.pair_capacity if pairs is not None else 0,
+                                                     _ptr(self.work), self.work.numel(), st))
                 self.gpu_launches += 1
 
     # ------------------------------------------------------------------ state (device tensors, views)

@@ -328,8 +328,8 @@ int bsg_cd_detect_peers(const float *const *h_peer_rec, int32_t n_peers, int32_t
 
 /* ---- single-airspace traffic with routes, VNAV and ASAS resolution ---------------------------------
  * One airspace of n aircraft (the bs.traf of a BlueSky scenario at N = 1e5 instead of the handful a NumPy Traffic
- * can step): per simulator substep  bsg_traf_pack -> bsg_cd_detect[_culled] with pair lists -> (caller sorts the
- * conflict keys) -> bsg_traf_substep, which fuses per aircraft: Autopilot.update (LNAV, update_fms over multi-waypoint
+ * can step): per simulator substep  bsg_traf_pack -> bsg_cd_detect[_culled] with pair lists -> bsg_traf_substep, which
+ * indexes the conflict list by own aircraft and then fuses per aircraft: Autopilot.update (LNAV, update_fms over multi-waypoint
  * routes with altitude / speed constraints, ComputeVNAV, the continuous VNAV / speed guidance), ConflictResolution.update
  * (MVP.resolve over the aircraft's own conflicts in intruder order, resumenav with waypoint recovery), APorASAS.update,
  * perfoap.limits and Traffic.update_airspeed / update_groundspeed / update_pos.
@@ -375,12 +375,16 @@ int bsg_traf_pack(const bsg_traf_config *cfg, const bsg_traf_tensors *t, float *
 /* Route.direct(first waypoint) + ComputeVNAV for every aircraft flagged BSG_TF_ACTIVATE (after the route tables changed). */
 int bsg_traf_activate(const bsg_traf_config *cfg, const bsg_traf_tensors *t, void *stream);
 /* One simulator substep.  d_rec: the records bsg_traf_pack made of the state BEFORE this substep (what the detection saw);
- * d_keys: the detection's conflict pairs as own << 32 | intruder, sorted ascending, unused entries INT64_MAX, conf_cap of
- * them; d_perm[k]: row of d_conf_attr (BSG_CD_ATTR_*) that belongs to d_keys[k]; d_npairs[0]: conflicts found.  All three
- * may be NULL with reso == 0.  fms_ready: the FMS timer fires in this substep (sim step count % (10.5 // simdt) == 0). */
+ * d_conf_pairs [conf_cap][2], d_conf_attr [conf_cap][BSG_CD_ATTR_COUNT], d_npairs: the conflict list of that detection
+ * exactly as bsg_cd_detect[_culled] wrote it (bsg_cd_lists: any order); all may be NULL with reso == 0.
+ * d_work: device scratch of at least bsg_traf_workspace(n, conf_cap) bytes whose first n int32 are ZERO on entry (zero it
+ * once after allocation: every call leaves them zero again).  fms_ready: the FMS timer fires in this substep (sim step
+ * count % (10.5 // simdt) == 0).  Launches: 3 small index kernels (count / allocate / scatter of the conflict list by own
+ * aircraft; only with reso) + the fused per-aircraft kernel. */
+int64_t bsg_traf_workspace(int64_t n, int64_t conf_cap);
 int bsg_traf_substep(const bsg_traf_config *cfg, const bsg_traf_tensors *t, const float *d_rec, int32_t fms_ready,
-                     const int64_t *d_keys, const int32_t *d_perm, const float *d_conf_attr,
-                     const unsigned long long *d_npairs, int64_t conf_cap, void *stream);
+                     const int32_t *d_conf_pairs, const float *d_conf_attr, const unsigned long long *d_npairs,
+                     int64_t conf_cap, void *d_work, int64_t work_bytes, void *stream);
 
 /* ---- roofline denominators measured on the spot (bench.py) ------------------------------------- */
 /* Dense FP32 FMA throughput [FLOP/s] of this device, timed with CUDA events. */
