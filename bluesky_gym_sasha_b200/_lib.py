@@ -60,6 +60,7 @@ CD_ATTR = ("qdr", "dist", "dcpa", "tcpa", "tinconf")          # BSG_CD_ATTR_* co
 # single-airspace traffic (bsg_traf_*): BSG_TF_* flag bits, BSG_TRAF_* sizes
 (TF_ALIVE, TF_LNAV, TF_VNAV, TF_VNAVSPD, TF_LASTWP, TF_ASAS, TF_RESOOFF, TF_PH_GD, TF_PH_AP, TF_ACTIVATE) = (1 << b for b in range(10))
 TF_IWP_SHIFT, TF_NWP_SHIFT, TRAF_PARTNERS, TRAF_CTR_COUNT = 16, 24, 8, 4
+PRIM_LINE, PRIM_RING, PRIM_RECT, PRIM_EDGE, PRIM_EDGE_END, PRIM_FLOATS = 1, 2, 3, 4, 5, 8      # bsg_render records
 
 
 class TrafConfig(C.Structure):
@@ -91,7 +92,7 @@ class TensorTable(C.Structure):
 SYMBOLS = ("bsg_abi_version", "bsg_abi_struct_size", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
            "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_step_host_begin", "bsg_step_host_wait", "bsg_host_copy", "bsg_host_widen", "bsg_set_obs_noise", "bsg_get_noise_calls", "bsg_set_noise_calls", "bsg_load_state", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
            "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_cd_cull_workspace", "bsg_cd_detect_culled", "bsg_cd_detect_peers", "bsg_probe_fp32",
-           "bsg_traf_pack", "bsg_traf_activate", "bsg_traf_workspace", "bsg_traf_substep")
+           "bsg_traf_pack", "bsg_traf_activate", "bsg_traf_workspace", "bsg_traf_substep", "bsg_render")
 
 _lib = None
 
@@ -149,6 +150,9 @@ def load():
         lib.bsg_host_widen.restype = C.c_int
     lib.bsg_step_host_copy.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp]
     lib.bsg_traf_update.argtypes = [vp, i32, vp]
+    if hasattr(lib, "bsg_render"):              # (absent only in older A/B builds loaded through BSG_B200_LIB)
+        lib.bsg_render.argtypes = [vp, i32, i32, i32, u32, vp, vp]
+        lib.bsg_render.restype = C.c_int
     if hasattr(lib, "bsg_traf_substep"):        # (absent only in older A/B builds loaded through BSG_B200_LIB)
         lib.bsg_traf_pack.argtypes = [C.POINTER(TrafConfig), C.POINTER(TrafTensors), vp, vp]
         lib.bsg_traf_activate.argtypes = [C.POINTER(TrafConfig), C.POINTER(TrafTensors), vp]

@@ -18,9 +18,9 @@ class _ScalarEnv(Env):
 
     def __init__(self, render_mode=None, device=0, seed=0, cd_enabled=False, **kwargs):
         assert render_mode is None or render_mode in self.metadata["render_modes"]   # horizontal_cr_env.py:64
-        if render_mode is not None:
-            raise NotImplementedError("rendering is out of scope of the batched simulator (render_mode=None only)")
-        self.render_mode = None
+        if render_mode == "human":
+            raise NotImplementedError("render_mode='human' needs a pygame window; use render_mode='rgb_array' (frames from render())")
+        self.render_mode = render_mode
         self._seed = seed
         self._kw = dict(device=device, cd_enabled=cd_enabled, **kwargs)
         self._make(seed)
@@ -58,7 +58,8 @@ class _ScalarEnv(Env):
                 self._info(infos))
 
     def render(self):
-        return None
+        """``render_mode="rgb_array"``: the frame the reference's ``_render_frame`` draws, as a (height, width, 3) uint8 array."""
+        return self.vec.render(0) if self.render_mode == "rgb_array" else None
 
     def close(self):
         self.vec.close()

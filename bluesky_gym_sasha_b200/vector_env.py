@@ -13,6 +13,7 @@ Two ways to drive it:
   * ``reset_torch()`` / ``step_torch(a)`` -- CUDA float32 tensors in / out, no host sync.
 """
 import ctypes as C
+import sys
 from collections import OrderedDict
 
 import numpy as np
@@ -27,26 +28,51 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-_LEASE_TYPES = {}
+class _HostBlock:
+    """One pinned host block with the device output block's layout, a dense terminal-observation area behind it, and the
+    numpy views of both, made ONCE.  Every array handed to the caller is a view whose ``.base`` collapses to ``root`` (numpy
+    keeps the base of a view of a view pointing at the first array that is not itself an ndarray view), so
+    ``sys.getrefcount(root)`` above its value at construction means the caller still holds results of the step that
+    used this block: the caller owns a step's results for exactly as long as it keeps them and nothing is copied."""
+    __slots__ = ("tensor", "root", "ptr", "v", "final", "dirty", "refs", "wroot", "wide", "wfinal", "wdirty", "wrefs")
 
+    def __init__(self, env, pinned=True):
+        E, L = env.num_envs, env.layout
+        n_dense = E * L.obs_dim * 4 if env.autoreset_mode == "same_step" else 0
+        self.tensor = torch.zeros((env._out_bytes + n_dense,), dtype=torch.uint8)
+        if pinned:
+            self.tensor = self.tensor.pin_memory()
+        self.root = self.tensor.numpy()
+        self.ptr = self.tensor.data_ptr()
+        v = {k: self.root[off:off + n * np.dtype(dt).itemsize].view(dt) for k, (off, dt, n) in env._off.items()}
+        v["obs"] = v["obs"].reshape(E, L.obs_dim)
+        v["info"] = v["info"].reshape(L.info_dim, E)
+        v["final_obs"] = v["final_obs"].reshape(env._final_cap, L.obs_dim)
+        self.v = v
+        self.final = self.root[env._out_bytes:].view(np.float32).reshape(E, L.obs_dim) if n_dense else None
+        self.dirty = None               # rows of `final` written by the last step that used this block
+        self.wroot = self.wide = self.wfinal = self.wdirty = None
+        self.wrefs = 0
+        self.refs = sys.getrefcount(self.root)
 
-def _lease_type(nbytes):
-    """ctypes array type over a borrowed pinned block.  numpy arrays made from an instance (np.frombuffer) keep it alive
-    through their .base chain; when the last of them is garbage-collected the instance dies and puts the block back on its
-    pool's free list -- the caller owns a step's results for exactly as long as it holds on to them, and nothing is copied."""
-    t = _LEASE_TYPES.get(nbytes)
-    if t is None:
-        class Lease(C.c_uint8 * nbytes):
-            def __del__(self):
-                free = getattr(self, "free", None)
-                if free is not None:
-                    free.append(self.index)
-        t = _LEASE_TYPES[nbytes] = Lease
-    return t
+    def widen_area(self, env):
+        """float64 twin of the obs and dense terminal-obs areas (the dtype the reference's spaces declare): ordinary
+        memory, touched once here so that no step pays its page faults"""
+        if self.wroot is None:
+            E, L = env.num_envs, env.layout
+            self.wroot = np.zeros(2 * E * L.obs_dim, dtype=np.float64)
+            self.wroot.fill(0.0)
+            self.wide = self.wroot[:E * L.obs_dim].reshape(E, L.obs_dim)
+            self.wfinal = self.wroot[E * L.obs_dim:].reshape(E, L.obs_dim)
+            self.wrefs = sys.getrefcount(self.wroot)
+        return self.wide
+
+    def held(self):
+        return sys.getrefcount(self.root) != self.refs or (self.wroot is not None and sys.getrefcount(self.wroot) != self.wrefs)
 
 
 class BlueSkyVectorEnv(VectorEnv):
-    metadata = {"render_modes": [], "autoreset_mode": "next_step"}
+    metadata = {"render_modes": ["rgb_array"], "autoreset_mode": "next_step"}
 
     def __init__(self, env_id, num_envs, device=0, seed=0, cd_enabled=False, n_intruders=None,
                  autoreset_mode="next_step", env_id_offset=0, max_episode_steps=None, perf=None,
@@ -58,14 +84,14 @@ class BlueSkyVectorEnv(VectorEnv):
                                       "path yet (SURVEY.md section 8f)")
         if env_id not in SPECS:
             raise KeyError(f"unknown env id {env_id!r}")
-        assert render_mode is None, "the batched simulator has no renderer (render_mode=None only)"
+        assert render_mode in (None, "rgb_array"), "render_mode is None or 'rgb_array' (frames of one env index: render())"
         if not torch.cuda.is_available():
             raise _lib.BsgError("BlueSkyVectorEnv needs a CUDA device: there is no CPU fallback")
         self.spec_b200 = SPECS[env_id]
         self.env_id = env_id
         self.num_envs = int(num_envs)
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
-        self.render_mode = None
+        self.render_mode = render_mode
         # float32 arrays are valid members of the reference's float64 Box spaces (gymnasium checks
         # np.can_cast); the scalar Env classes ask for float64 to be byte-for-byte drop-in.
         self.obs_dtype = np.dtype(obs_dtype)
@@ -149,32 +175,21 @@ class BlueSkyVectorEnv(VectorEnv):
             info=d_info, actions_staging=z((E, L.act_dim), torch.float32),
             cd_pairs=z((E, self.cd_pair_cap), torch.int32) if self.cd_pair_cap else None,
             cd_attr=z((E, self.cd_pair_cap, _lib.PAIR_ATTR_COUNT), torch.float32) if self.cd_pair_cap else None)
-        # pinned host mirrors for the numpy API: two rotating blocks with the device block's layout; the numpy
-        # views are made once (torch -> numpy conversion per step costs more than the small copies themselves)
-        ph = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
-        self._hbuf = []
-        for _ in range(2):
-            blk = ph((self._out_bytes,), torch.uint8)
-            names = ("obs", "reward", "info", "final_count", "terminated", "truncated", "final_ids", "final_obs")
-            hb = {k: v.numpy() for k, v in zip(names, carve(blk, self._final_cap))}
-            hb["block"], hb["ptr"] = blk, _ptr(blk)
-            self._hbuf.append(hb)
-        self._hsel = 0
-        # copy=True (default): every step's results are views of a pinned block LEASED to the caller until the last view
-        # is dropped (see _lease_type): the device->host transfer lands directly in memory the caller may keep, no host
-        # copy.  The pool grows on demand (a rollout buffer that copies what it needs holds 1-2 blocks) up to
-        # `_LEASE_MAX` blocks; a caller that hoards more than that gets ordinary copies instead.
-        self._carve = carve
+        # host side of the numpy API: pinned blocks with the device block's layout (+ a dense terminal-observation area),
+        # their numpy views made once (_HostBlock).  copy=True (default): a step takes a block none of whose views the
+        # caller still holds, so the device->host transfer lands directly in memory the caller may keep -- no host copy;
+        # the pool grows on demand (a rollout buffer that copies what it needs holds 1-2 blocks) up to `_BLOCKS_MAX`, a
+        # caller that hoards more than that gets ordinary copies instead.  copy=False: the first two blocks take turns.
         self._off = dict(obs=(0, np.float32, E * L.obs_dim), reward=(n_obs, np.float32, E), info=(o_info, np.float32, E * L.info_dim),
                          final_count=(o_cnt, np.int32, 4), terminated=(o_term, np.uint8, E), truncated=(o_term + E, np.uint8, E),
                          final_ids=(o_fids, np.int32, E), final_obs=(o_fobs, np.float32, self._final_cap * L.obs_dim))
-        self._lease_blocks = [ph((self._out_bytes,), torch.uint8) for _ in range(2)] if self.copy else []
-        self._lease_free = list(range(len(self._lease_blocks)))
-        self._lease_cls = _lease_type(self._out_bytes)
-        self._pending = None        # mirrored block of a step_async() whose step_wait() has not run yet
+        self._blocks = [_HostBlock(self) for _ in range(3)]
+        self._bsel = 0
+        self._scratch = None        # (made on first use: the block behind copied-out results when the pool is exhausted)
+        self._pending = None        # (block, copy_out) of a step_async() whose step_wait() has not run yet
+        ph = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
         self.h = dict(actions=ph((E, L.act_dim), torch.float32))
         self._act_np, self._act_ptr = self.h["actions"].numpy(), _ptr(self.h["actions"])
-        self._final_np = np.zeros((E, L.obs_dim), dtype=np.float32)
         self._h_final = ph((E, L.obs_dim), torch.float32)          # overflow beyond `_final_cap` rows (rare)
         self._h_final_np = self._h_final.numpy()
 
@@ -309,46 +324,38 @@ class BlueSkyVectorEnv(VectorEnv):
         info = self.t["info"].cpu().numpy()
         return self._obs_dict_np(obs), self._infos_np(info)
 
-    _LEASE_MAX = 64
+    _BLOCKS_MAX = 64
 
     def _acquire(self):
-        """A host block for this step's results: a leased pinned block (copy=True, float32), else one of the two
-        rotating mirrors.  Returns the dict of numpy views (+ "ptr")."""
-        if not (self.copy and self.obs_dtype == np.float32):
-            self._hsel ^= 1
-            return self._hbuf[self._hsel]
-        if not self._lease_free:
-            if len(self._lease_blocks) >= self._LEASE_MAX:          # the caller keeps everything: hand out copies
-                self._hsel ^= 1
-                h = self._hbuf[self._hsel]
-                return dict(h, copy_out=True)
-            self._lease_blocks.append(torch.zeros((self._out_bytes,), dtype=torch.uint8).pin_memory())
-            self._lease_free.append(len(self._lease_blocks) - 1)
-        idx = self._lease_free.pop()
-        blk = self._lease_blocks[idx]
-        lease = self._lease_cls.from_address(blk.data_ptr())
-        lease.free, lease.index, lease.block = self._lease_free, idx, blk      # (the views keep the pinned block alive)
-        E, L = self.num_envs, self.layout
-        h = {k: np.frombuffer(lease, dtype=dt, count=n, offset=off) for k, (off, dt, n) in self._off.items()}
-        h["obs"] = h["obs"].reshape(E, L.obs_dim)
-        h["info"] = h["info"].reshape(L.info_dim, E)
-        h["final_obs"] = h["final_obs"].reshape(self._final_cap, L.obs_dim)
-        h["ptr"] = C.c_void_p(blk.data_ptr())
-        return h
+        """The host block for this step's results (see the constructor); second value: the results must be copied out
+        because the caller holds every block of a full pool."""
+        blocks = self._blocks
+        if not self.copy:
+            self._bsel ^= 1
+            return blocks[self._bsel], False
+        for b in blocks:
+            if not b.held():
+                return b, False
+        if len(blocks) < self._BLOCKS_MAX:
+            blocks.append(_HostBlock(self))
+            return blocks[-1], False
+        if self._scratch is None:
+            self._scratch = _HostBlock(self)
+        return self._scratch, True
 
     def step(self, actions):
         if self._pending is not None:
             raise _lib.BsgError("step(): a step_async() is in flight; call step_wait() first")
         E = self.num_envs
         self._act_np[...] = np.asarray(actions, dtype=np.float32).reshape(E, self.layout.act_dim)
-        h = self._acquire()
+        b, copy_out = self._acquire()
         # (the library sets the device itself; the stream is looked up per call because callers may switch streams)
-        rc = self._lib.bsg_step_host_block(self._h, self._act_ptr, h["ptr"], self._out_bytes,
+        rc = self._lib.bsg_step_host_block(self._h, self._act_ptr, b.ptr, self._out_bytes,
                                            torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             _lib.check(rc)
         self.gpu_launches += 1
-        return self._step_results(h)
+        return self._step_results(b, copy_out)
 
     def step_async(self, actions):
         """First half of ``step`` (the SB3 / older-gymnasium ``step_async`` / ``step_wait`` pair): copies the actions in,
@@ -358,62 +365,70 @@ class BlueSkyVectorEnv(VectorEnv):
             raise _lib.BsgError("step_async(): the previous step has not been waited for (one step in flight per env batch)")
         E = self.num_envs
         self._act_np[...] = np.asarray(actions, dtype=np.float32).reshape(E, self.layout.act_dim)
-        h = self._acquire()
-        rc = self._lib.bsg_step_host_begin(self._h, self._act_ptr, h["ptr"], self._out_bytes,
+        b, copy_out = self._acquire()
+        rc = self._lib.bsg_step_host_begin(self._h, self._act_ptr, b.ptr, self._out_bytes,
                                            torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             _lib.check(rc)
         self.gpu_launches += 1
-        self._pending = h
+        self._pending = (b, copy_out)
 
     def step_wait(self):
         """Second half: waits for the step enqueued by ``step_async`` and returns what ``step`` returns."""
-        h = getattr(self, "_pending", None)
-        if h is None:
+        pend = getattr(self, "_pending", None)
+        if pend is None:
             raise RuntimeError("step_wait() without step_async()")
         self._pending = None
-        rc = self._lib.bsg_step_host_wait(self._h, h["ptr"], None, 0)
+        rc = self._lib.bsg_step_host_wait(self._h, pend[0].ptr, None, 0)
         if rc:
             _lib.check(rc)
-        return self._step_results(h)
+        return self._step_results(*pend)
 
-    def _step_results(self, h):
-        """The (obs, reward, terminated, truncated, infos) tuple from host block ``h`` (views of a leased block, or of a
-        rotating mirror: then copied unless copy=False)."""
+    def _step_results(self, b, copy_out=False):
+        """The (obs, reward, terminated, truncated, infos) tuple from host block ``b``: views of the block (the caller's
+        for as long as it keeps them, see _HostBlock), float64 observations widened into the block's float64 twin."""
+        h = b.v
         flat = h["obs"]
-        if self.obs_dtype == np.float64:         # the reference's declared dtype: widened by the library's host threads
-            wide = np.empty(flat.shape, dtype=np.float64)
-            _lib.check(self._lib.bsg_host_widen(wide.ctypes.data, flat.ctypes.data, flat.size))
-            flat = wide
+        wide = self.obs_dtype == np.float64
+        if wide:                                 # the reference's declared dtype: widened by the library's host threads
+            dst = b.widen_area(self)
+            _lib.check(self._lib.bsg_host_widen(dst.ctypes.data, flat.ctypes.data, flat.size))
+            flat = dst
         elif flat.dtype != self.obs_dtype:
             flat = flat.astype(self.obs_dtype)
-        elif h.get("copy_out"):
+        if copy_out:
             flat = flat.copy()
         obs = OrderedDict((k, flat[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
         rew = h["reward"].astype(np.float64)
         term = h["terminated"].astype(bool)
         trunc = h["truncated"].astype(bool)
-        infos = self._infos_np(h["info"])
+        infos = self._infos_np(h["info"].copy() if copy_out else h["info"])
         if self.autoreset_mode == "same_step":
+            # terminal observations, dense [E, obs_dim] with zero rows for the envs that did not finish: the block's own
+            # area; only the rows written by the block's previous step are cleared, only the finished envs' rows written
+            fo = b.wfinal if wide else b.final
+            dirty = b.wdirty if wide else b.dirty
+            if dirty is not None:
+                fo[dirty] = 0.0
+                dirty = None
             fc = h["final_count"]
             n_fin = int(fc[fc[2]])              # two counters take turns; [2] names the live one (include/bsg.h)
             if n_fin:                   # compacted terminal observations of the envs that finished in this step
-                ids = h["final_ids"][:n_fin]
+                ids = h["final_ids"][:n_fin].copy()
                 cap = self._final_cap
-                # copy=True: a fresh array per step (callers such as SB3 read terminal observations later; np.zeros of
-                # this size is lazily mapped, so only the finished envs' rows are ever touched); copy=False: one
-                # persistent buffer, valid until the next step with a finished env
-                # (float64: only the finished rows are converted, on assignment)
-                dst = np.zeros((self.num_envs, self.layout.obs_dim), dtype=self.obs_dtype) if (self.copy or self.obs_dtype != np.float32) \
-                    else self._final_np
-                dst[ids[:cap]] = h["final_obs"][:min(n_fin, cap)]
+                fo[ids[:cap]] = h["final_obs"][:min(n_fin, cap)]
                 if n_fin > cap:         # more finished than the mirrored window holds: fetch the rest
                     self._h_final[cap:n_fin].copy_(self.t["final_obs"][cap:n_fin], non_blocking=True)
                     torch.cuda.current_stream(self.device).synchronize()
-                    dst[ids[cap:]] = self._h_final_np[cap:n_fin]
-                fo = dst
-                infos["final_obs"] = OrderedDict((k, fo[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
+                    fo[ids[cap:]] = self._h_final_np[cap:n_fin]
+                dirty = ids
+                out = fo.copy() if copy_out else (fo if fo.dtype == self.obs_dtype else fo.astype(self.obs_dtype))
+                infos["final_obs"] = OrderedDict((k, out[:, off:off + w]) for k, (off, w, _, _) in self.obs_layout.items())
                 infos["_final_obs"] = term | trunc
+            if wide:
+                b.wdirty = dirty
+            else:
+                b.dirty = dirty
         return obs, rew, term, trunc, infos
 
     def asas_pairs(self, e):
@@ -534,6 +549,12 @@ class BlueSkyVectorEnv(VectorEnv):
             keep.append(pl)
             st.poly = pl.ctypes.data
         _lib.check(self._lib.bsg_load_state(self._h, int(e), C.byref(st), self._stream()))
+
+    def render(self, env_index=0):
+        """rgb_array frame (height, width, 3) uint8 of ONE env, drawn like the reference's ``_render_frame`` of that env type
+        (render.py builds the draw calls from a snapshot of the env, ``bsg_render`` paints them on the device)."""
+        from . import render as _render
+        return _render.render_env(self, env_index)
 
     def close(self, **kwargs):
         if not self.closed and self._h:

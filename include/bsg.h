@@ -386,6 +386,18 @@ int bsg_traf_substep(const bsg_traf_config *cfg, const bsg_traf_tensors *t, cons
                      const int32_t *d_conf_pairs, const float *d_conf_attr, const unsigned long long *d_npairs,
                      int64_t conf_cap, void *d_work, int64_t work_bytes, void *stream);
 
+/* ---- rgb_array frames --------------------------------------------------------------------------------
+ * Paints a list of draw calls into an RGB frame on the device: d_prims [n_prims][BSG_PRIM_FLOATS] float32 records
+ * (type, x0, y0, x1, y1, width, colour as the bits of r | g << 8 | b << 16, unused), later records over earlier ones,
+ * d_rgb [height][width][3] uint8.  LINE: (x0, y0) - (x1, y1), pixels within max(width, 1) / 2 of the segment; RING: centre
+ * (x0, y0), radius x1, ring width `width` drawn inwards (0 = filled disc); RECT: filled [x0, x1) x [y0, y1); a polygon is
+ * a run of EDGE records closed by one EDGE_END record, filled by the even-odd rule.
+ * Replaces: the pygame draw calls of the reference's _render_frame (e.g. horizontal_cr_env.py:277-395), which only ever
+ * reach a window; bluesky_gym_sasha_b200/render.py builds the list per env type. */
+enum { BSG_PRIM_LINE = 1, BSG_PRIM_RING = 2, BSG_PRIM_RECT = 3, BSG_PRIM_EDGE = 4, BSG_PRIM_EDGE_END = 5, BSG_PRIM_FLOATS = 8 };
+int bsg_render(const float *d_prims, int32_t n_prims, int32_t width, int32_t height, uint32_t background_rgb,
+               uint8_t *d_rgb, void *stream);
+
 /* ---- roofline denominators measured on the spot (bench.py) ------------------------------------- */
 /* Dense FP32 FMA throughput [FLOP/s] of this device, timed with CUDA events. */
 int bsg_probe_fp32(int32_t device, double *flops_out);

@@ -13,6 +13,9 @@ from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
 E = 4096
 v = BlueSkyVectorEnv("HorizontalCREnv-v0", E, seed=0, cd_enabled=True, n_intruders=20, autoreset_mode="same_step")
 v.reset()
+at0 = torch.rand((E, 1), device="cuda") * 2 - 1
+for _ in range(400):                    # episodes of different lengths: the finished envs spread over the steps, as in bench.py
+    v.step_torch(at0)
 a = np.random.default_rng(0).uniform(-1, 1, (E, 1)).astype(np.float32)
 
 
@@ -28,8 +31,15 @@ def t(f, n=300):
 
 
 print("full step()                 %.1f us" % t(lambda: v.step(a)))
-h = v._hbuf[0]
-print("bsg_step_host_block only    %.1f us" % t(lambda: _lib.check(v._lib.bsg_step_host_block(v._h, v._act_ptr, h["ptr"], v._out_bytes, v._stream()))))
+blk = v._blocks[0]
+h = blk.v
+print("bsg_step_host_block only    %.1f us" % t(lambda: _lib.check(v._lib.bsg_step_host_block(v._h, v._act_ptr, blk.ptr, v._out_bytes, v._stream()))))
+print("_acquire                    %.1f us" % t(lambda: v._acquire()))
+print("_step_results               %.1f us" % t(lambda: v._step_results(blk)))
+v.obs_dtype = np.dtype(np.float64)
+print("full step() float64 obs     %.1f us" % t(lambda: v.step(a)))
+print("_step_results float64       %.1f us" % t(lambda: v._step_results(blk)))
+v.obs_dtype = np.dtype(np.float32)
 at = torch.from_numpy(a).cuda()
 print("step_torch (async)          %.1f us" % t(lambda: v.step_torch(at)))
 o32 = h["obs"]

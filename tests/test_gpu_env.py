@@ -733,3 +733,59 @@ def test_step_async_wait_equals_step(cuda):
             b.step_wait()
         a.close()
         b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("obs_dtype", [np.float32, np.float64])
+def test_step_results_belong_to_the_caller_while_held(cuda, obs_dtype):
+    """copy=True (default): the arrays of a step are views of a host block that no later step touches while the caller
+    holds any of them (vector_env._HostBlock) -- results kept over many steps equal the copies taken at once, for float32
+    and float64 observations, through same-step autoresets (dense terminal observations: zero rows for the envs that did not
+    finish), and past the block pool's capacity (then ordinary copies are handed out)."""
+    from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
+    E = 48
+    kw = dict(seed=5, n_intruders=20, cd_enabled=True, autoreset_mode="same_step", max_episode_steps=4, obs_dtype=obs_dtype)
+    v, w = BlueSkyVectorEnv("HorizontalCREnv-v0", E, **kw), BlueSkyVectorEnv("HorizontalCREnv-v0", E, copy=False, **kw)
+    v._BLOCKS_MAX = 5
+    v.reset()
+    w.reset()
+    rng = np.random.default_rng(2)
+    held, snap = [], []
+
+    def deep(r):
+        obs, rew, term, trunc, info = r
+        fo = {k: x.copy() for k, x in info["final_obs"].items()} if "final_obs" in info else None
+        return ({k: x.copy() for k, x in obs.items()}, rew.copy(), term.copy(), trunc.copy(),
+                {k: np.array(x, copy=True) for k, x in info.items() if k != "final_obs"}, fo)
+
+    n_final = 0
+    for step in range(14):
+        act = rng.uniform(-1, 1, (E, 1))
+        r = v.step(act)
+        rw = deep(w.step(act))                                # the rotating-mirror mode is the independent witness
+        held.append(r)
+        snap.append(rw)
+        assert r[0]["intruder_distance"].dtype == obs_dtype
+        if step >= 9:
+            held[step - 9] = None                             # blocks come back into circulation when their results are dropped
+    assert len(v._blocks) <= 5
+    for r, s in zip(held, snap):
+        if r is None:
+            continue
+        obs, rew, term, trunc, info = r
+        for k in obs:
+            assert np.array_equal(obs[k], s[0][k]), k
+        assert np.array_equal(rew, s[1]) and np.array_equal(term, s[2]) and np.array_equal(trunc, s[3])
+        for k in s[4]:
+            assert np.array_equal(info[k], s[4][k]), k
+        assert ("final_obs" in info) == (s[5] is not None)
+        if s[5] is not None:
+            m = info["_final_obs"]
+            n_final += int(m.sum())
+            for k in s[5]:
+                assert info["final_obs"][k].dtype == obs_dtype
+                assert np.array_equal(info["final_obs"][k][m], s[5][k][m])
+                assert not np.any(info["final_obs"][k][~m]) and not np.any(s[5][k][~m])
+    assert n_final >= E
+    v.close()
+    w.close()
