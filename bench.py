@@ -687,6 +687,7 @@ def bench_cd_sharded(torch, dist, dev, StateBasedCD, world, rank, max_over_ranks
     vs = np.where(rng.random(n_tot) < 0.8, 0.0, rng.choice([-1.0, 1.0], n_tot) * rng.uniform(5, 15, n_tot))
     sl = slice(rank * per, (rank + 1) * per)
     cd = StateBasedCD(device=dev.index)
+    align = torch.zeros(1, device=dev)
     rec, _ = cd.pack(lat[sl], lon[sl], trk[sl], gs[sl], alt[sl], vs[sl], 52.0, 4.0)
     for _ in range(2):
         out = cd.detect_sharded(rec, per, want_pairs=True)
@@ -695,6 +696,7 @@ def bench_cd_sharded(torch, dist, dev, StateBasedCD, world, rank, max_over_ranks
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        dist.all_reduce(align)         # (device-side: the ranks' streams reach e0 together, whatever the hosts' skew after the barrier)
         e0.record()
         out = cd.detect_sharded(rec, per, want_pairs=True)
         e1.record()
@@ -715,6 +717,7 @@ def bench_cd_sharded(torch, dist, dev, StateBasedCD, world, rank, max_over_ranks
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        dist.all_reduce(align)         # (device-side: the ranks' streams reach e0 together, whatever the hosts' skew after the barrier)
         e0.record()
         outc = cd.detect_sharded(rec_s, per, cull=True, want_pairs=True)
         e1.record()
@@ -733,6 +736,7 @@ def bench_cd_sharded(torch, dist, dev, StateBasedCD, world, rank, max_over_ranks
             for _ in range(reps):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 barrier()
+                dist.all_reduce(align)
                 e0.record()
                 outp = cd.detect_sharded_p2p(r, per, cull=cull, want_pairs=True)
                 e1.record()

@@ -2,6 +2,9 @@
 // termination, and the env-step megakernel that strings them around the substep loop of
 // env_kernels.cuh.  Every function cites the reference lines it restates; the float64 CPU
 // restatement these are parity-tested against is oracle/envs.py.
+#ifdef BSG_PHASE_TIMING
+#include <cstdio>
+#endif
 #include "env_kernels.cuh"
 
 namespace bsg {
@@ -224,8 +227,7 @@ constexpr int kSectorMaxV = 32, kSectorMaxAc = 32, kSectorMaxTries = 4096;
 // dependent float64 work and set the duration of the whole launch whenever any env of the batch reset).  Philox draws are
 // addressed by index, so every lane computes the draws it needs; the DRAW ORDER of the reference is unchanged:
 // draw k = polygon point k (k < nv), then the density draw(s), then num_ac perimeter positions, then two draws per
-// rejection-sampling try.  scratch per warp (float64): [0,32) cand x | [32,64) cand y | [64,96) cand angle, later reused
-// as [0,32) lat | [32,64) lon of the accepted aircraft; [96,128) sorted vx | [128,160) sorted vy | [160,192) edge length |
+// rejection-sampling try.  scratch per warp (float64): [0,32) lat | [32,64) lon of the accepted aircraft; [96,128) sorted vx | [128,160) sorted vy | [160,192) edge length |
 // [192,225) cumulative edge length | [225,257) sorted perimeter draws | [257,289) wx | [289,321) wy.
 constexpr int kSectorScratch = 324;
 
@@ -233,41 +235,88 @@ template <int G>
 __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long long e, int slot, double* scratch) {
     // (instantiated for every G by do_reset's dispatch, but only ever run with G == 32: one full warp per env)
     double* poly = P.poly + e * (2 * kSectorMaxV);
-    double* c_x = scratch, *c_y = scratch + 32, *c_a = scratch + 64;
     double* s_vx = scratch + 96, *s_vy = scratch + 128, *s_el = scratch + 160, *s_cum = scratch + 192;
     double* s_dl = scratch + 225, *s_wx = scratch + 257, *s_wy = scratch + 289;
     const Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);
     const double R = sqrt(3750.0 / 3.141592653589793);
     const double coslat0 = cos(kSectorLat0 * kDeg2RadD);
+#ifdef BSG_PHASE_TIMING
+    unsigned long long tq[6];
+#define BSG_RSTAMP(k) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq[k]) :: "memory")
+#else
+#define BSG_RSTAMP(k) do { } while (0)
+#endif
+    BSG_RSTAMP(0);
     // ---- A: candidate polygon point `slot` = random_point_on_circle with draw `slot` (functions.py:44-59) ----------
-    {
-        const double al = 6.283185307179586 * rng.u01((uint32_t)slot);
-        const double x = R * cos(al), y = R * sin(al);
-        c_x[slot] = x; c_y[slot] = y; c_a[slot] = atan2(y, x);
-    }
-    __syncwarp();
-    // ---- B (lane 0): insert points in draw order, keep them sorted by angle, until the area is large enough
-    //      (sector_cr_env.py:141-160); then density -> num_ac (:98-103), edge lengths and their running sum (:162-170)
+    const double al = 6.283185307179586 * rng.u01((uint32_t)slot);
+    const double cx = R * cos(al), cy = R * sin(al), ca = atan2(cy, cx);
+    BSG_RSTAMP(1);
+    // ---- B: the polygon = the first nv candidates sorted by angle (sort_points_clockwise = ascending atan2(y, x),
+    //      functions.py:61-75), nv the smallest count >= 3 whose area reaches 2400 (sector_cr_env.py:141-160: points are
+    //      inserted in draw order until the area is large enough).  All 32 prefixes at once instead of a serial loop of
+    //      insertions and shoelace sums on one lane (which took 7-30 us and set the duration of the launch): inserting
+    //      point n between its neighbours by angle among the points drawn before it replaces the edge pred -> succ by
+    //      pred -> p -> succ, so the signed shoelace sum of the first n + 1 points is a prefix sum of per-lane terms.
     int num_ac = 0, nv = 0, rflags = 0;
     uint32_t d = 0;
     double area = 0.0, perim = 0.0, minx = 0.0, maxx = 0.0, miny = 0.0, maxy = 0.0;
-    if (slot == 0) {
-        double vx[kSectorMaxV], vy[kSectorMaxV], va[kSectorMaxV];
-        auto shoelace = [&](int n) {
-            double acc = 0.0;
-            for (int i = 0; i < n; ++i) { int j = (i + 1 == n) ? 0 : i + 1; acc += vx[i] * vy[j] - vy[i] * vx[j]; }
-            return fabs(acc) / 2.0;
-        };
-        auto insert_point = [&]() {         // sort_points_clockwise = ascending atan2(y, x) (functions.py:61-75)
-            const double x = c_x[nv], y = c_y[nv], ang = c_a[nv];
-            int k = nv;
-            while (k > 0 && va[k - 1] > ang) { vx[k] = vx[k - 1]; vy[k] = vy[k - 1]; va[k] = va[k - 1]; --k; }
-            vx[k] = x; vy[k] = y; va[k] = ang; ++nv;
-        };
-        insert_point(); insert_point(); insert_point();
-        area = shoelace(nv);
-        while (area < 2400.0 && nv < kSectorMaxV) { insert_point(); area = shoelace(nv); }
-        if (area < 2400.0) rflags |= 1;
+    {
+        double pa = -1.0e300, px = 0.0, py = 0.0, sa = 1.0e300, sx = 0.0, sy = 0.0;        // nearest below / above by angle
+        double ma = -1.0e300, mx = 0.0, my = 0.0, na = 1.0e300, nx = 0.0, ny = 0.0;        // largest / smallest of all
+        for (int j = 0; j < 31; ++j) {                                                    // (no lane has lane 31 before it)
+            const double aj = __shfl_sync(0xffffffffu, ca, j), xj = __shfl_sync(0xffffffffu, cx, j), yj = __shfl_sync(0xffffffffu, cy, j);
+            if (j < slot) {
+                if (aj <= ca) { if (aj >= pa) { pa = aj; px = xj; py = yj; } }             // (equal angles: the earlier draw sorts first)
+                else if (aj < sa) { sa = aj; sx = xj; sy = yj; }
+                if (aj >= ma) { ma = aj; mx = xj; my = yj; }
+                if (aj < na) { na = aj; nx = xj; ny = yj; }
+            }
+        }
+        if (pa == -1.0e300) { px = mx; py = my; }                                          // the smallest angle follows the largest
+        if (sa == 1.0e300) { sx = nx; sy = ny; }
+        double S = slot > 0 ? (px * cy - py * cx) + (cx * sy - cy * sx) - (px * sy - py * sx) : 0.0;
+        for (int o = 1; o < 32; o <<= 1) {                                                 // inclusive prefix sum over the lanes
+            const double up = __shfl_up_sync(0xffffffffu, S, o);
+            if (slot >= o) S += up;
+        }
+        const unsigned big = __ballot_sync(0xffffffffu, slot >= 2 && fabs(S) * 0.5 >= 2400.0);
+        nv = big ? __ffs((int)big) : kSectorMaxV;                                          // lane n - 1 holds the polygon of n points
+        if (!big) rflags |= 1;
+        int rank = 0;                                                                      // my place among the first nv by angle (stable)
+        for (int j = 0; j < nv; ++j) {
+            const double aj = __shfl_sync(0xffffffffu, ca, j);
+            rank += (aj < ca || (aj == ca && j < slot)) ? 1 : 0;
+        }
+        if (slot < nv) { s_vx[rank] = cx; s_vy[rank] = cy; }
+        __syncwarp();
+        // area of the chosen polygon with the reference's own shoelace sum (fn.polygon_area), edge lengths, bounding box
+        const int jn = (slot + 1 == nv) ? 0 : slot + 1;
+        const bool vert = slot < nv;
+        const double vx = vert ? s_vx[slot] : 0.0, vy = vert ? s_vy[slot] : 0.0;
+        const double wx = vert ? s_vx[jn] : 0.0, wy = vert ? s_vy[jn] : 0.0;
+        const double term = vx * wy - vy * wx;
+        const double ex = wx - vx, ey = wy - vy;
+        const double el = sqrt(ex * ex + ey * ey);
+        double acc = 0.0;
+        for (int i = 0; i < nv; ++i) {                  // sums in the reference's order (i = 0 .. nv - 1), on every lane alike
+            acc += __shfl_sync(0xffffffffu, term, i);
+            const double eli = __shfl_sync(0xffffffffu, el, i);
+            if (i == slot) s_cum[i] = perim;            // cum[i] = el[0] + ... + el[i-1]
+            perim += eli;
+        }
+        area = fabs(acc) / 2.0;
+        if (vert) {
+            s_el[slot] = el;
+            poly[2 * slot] = kSectorLat0 + vx / 60.0;                                     // nm_to_latlong: x north, y east
+            poly[2 * slot + 1] = kSectorLon0 + vy / (60.0 * coslat0);
+        }
+        double lox = vert ? vx : 1.0e300, hix = vert ? vx : -1.0e300, loy = vert ? vy : 1.0e300, hiy = vert ? vy : -1.0e300;
+        for (int o = 16; o > 0; o >>= 1) {
+            lox = fmin(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmax(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+            loy = fmin(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmax(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+        }
+        minx = lox; maxx = hix; miny = loy; maxy = hiy;
+        // density -> number of aircraft (sector_cr_env.py:98-103); every lane evaluates the same draws
         d = (uint32_t)nv;
         double rho;
         if (P.sector_uniform) { rho = rng.uniform(d, 0.003, 0.007); d += 1; }
@@ -275,23 +324,9 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
         double nraw = fmax(ceil(rho * area), 5.0);
         if (nraw > (double)kSectorMaxAc) { nraw = (double)kSectorMaxAc; rflags |= 2; }
         num_ac = (int)nraw;
-        minx = maxx = vx[0]; miny = maxy = vy[0];
-        for (int i = 0; i < nv; ++i) {
-            const int j = (i + 1 == nv) ? 0 : i + 1;
-            const double ex = vx[j] - vx[i], ey = vy[j] - vy[i];
-            const double el = sqrt(ex * ex + ey * ey);
-            s_vx[i] = vx[i]; s_vy[i] = vy[i]; s_el[i] = el; s_cum[i] = perim;      // cum[i] = el[0] + ... + el[i-1]
-            perim += el;
-            minx = fmin(minx, vx[i]); maxx = fmax(maxx, vx[i]); miny = fmin(miny, vy[i]); maxy = fmax(maxy, vy[i]);
-            poly[2 * i] = kSectorLat0 + vx[i] / 60.0;                              // nm_to_latlong: x north, y east
-            poly[2 * i + 1] = kSectorLon0 + vy[i] / (60.0 * coslat0);
-        }
     }
     __syncwarp();
-    num_ac = group_bcast<G>(num_ac, 0); nv = group_bcast<G>(nv, 0); rflags = group_bcast<G>(rflags, 0);
-    d = (uint32_t)group_bcast<G>((int)d, 0);
-    area = group_bcast<G>(area, 0); perim = group_bcast<G>(perim, 0);
-    minx = group_bcast<G>(minx, 0); maxx = group_bcast<G>(maxx, 0); miny = group_bcast<G>(miny, 0); maxy = group_bcast<G>(maxy, 0);
+    BSG_RSTAMP(2);
     // ---- C: _generate_waypoints (:162-188): num_ac draws along the perimeter, sorted, mapped onto the edges ----------
     {
         const bool mine = slot < num_ac;
@@ -315,6 +350,7 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
         d += (uint32_t)num_ac;
     }
     __syncwarp();
+    BSG_RSTAMP(3);
     // ---- D: _generate_ac (:190-217): rejection sampling in the bounding box, 32 tries at a time; try t uses draws
     //         d + 2t and d + 2t + 1 and accepted points keep their try order, exactly as in the serial loop ----------
     double* a_lat = scratch, *a_lon = scratch + 32;    // (the candidate arrays are no longer needed)
@@ -331,6 +367,7 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
     }
     __syncwarp();
     if (got < num_ac) { rflags |= 4; num_ac = got > 0 ? got : 1; }
+    BSG_RSTAMP(4);
     // ---- E: one aircraft per lane: heading towards its waypoint (fn.get_hdg, functions.py:150-178) and Traffic.cre
     double w0lat = 0.0, w0lon = 0.0;
     if (slot < num_ac && got > 0) {
@@ -351,6 +388,12 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
     s.num_ac = num_ac; s.nvert = nv; s.rflags = rflags; s.poly_area = area;
     s.wpt_lat = w0lat; s.wpt_lon = w0lon;
     s.total_reward = 0.0f; s.intrusions = 0; s.drift_sum = 0.0f; s.drift_n = 0; s.wpt_reach = 0;
+#ifdef BSG_PHASE_TIMING
+    BSG_RSTAMP(5);
+    if (slot == 0 && P.mode == kModeStep && (e & 31) == 0)
+        printf("sector_reset e=%lld nv=%d num_ac=%d: A %llu B %llu C %llu D %llu E %llu ns\n", e, nv, num_ac, tq[1] - tq[0], tq[2] - tq[1],
+               tq[3] - tq[2], tq[4] - tq[3], tq[5] - tq[4]);
+#endif
 }
 template <int G>
 __device__ inline void sector_action(Ac& a, const EnvParams& P, const float* act, int slot) {

@@ -1,4 +1,9 @@
-"""One culled + one plain detection at N = 100k on strip-sorted records (for an ncu launch list)."""
+"""The detection forms at N = 100k on strip-sorted records, for ncu captures: default = three culled launches
+(`<0,1,0>`); with the argument `forms` one launch each of culled, culled + symmetric (`<0,1,1>`, the default of
+StateBasedCD.detect) and every ordered pair (`<0,0,0>`):
+
+    ncu --set full -k regex:cd_tiled_kernel -c 3 -o out python scripts/cd_culled_probe.py 100000 forms
+"""
 import os
 import sys
 
@@ -18,7 +23,12 @@ cd = StateBasedCD(device=0)
 d = [cd._as_dev(x) for x in (lat, lon, trk, gs, alt, vs)]
 perm = cd.spatial_order(d[0], d[1])
 rec, _ = cd.pack(*[x[perm] for x in d], 52.0, 4.0)
-for _ in range(3):
+if len(sys.argv) > 2 and sys.argv[2] == "forms":
     out = cd.detect_packed(rec, n, cull=True)
+    out = cd.detect_packed(rec, n, cull=True, symmetric=True)
+    out = cd.detect_packed(rec, n, cull=False)
+else:
+    for _ in range(3):
+        out = cd.detect_packed(rec, n, cull=True)
 torch.cuda.synchronize()
 print("conflicts", int(out["npairs"][0]))

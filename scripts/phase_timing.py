@@ -43,7 +43,11 @@ def main():
         st = raw.astype(np.float64)
         t0 = st[:, 0].min()
         st = (st - t0) * 1e-3                                    # us since the first warp started
-        rows.append((e0.elapsed_time(e1) * 1e3, st, int(v.t["final_count"][int(v.t["final_count"][2])]), smid))
+        i32 = v.t["env_i32"].cpu().numpy()
+        kin, cmd = v.t["kin"][:, 0].cpu().numpy(), v.t["cmd"][:, 0].cpu().numpy()
+        turning = np.abs((kin[:, 2] - cmd[:, 3] + 180.0) % 360.0 - 180.0) > 0.01        # ownship still turning after the step
+        rows.append((e0.elapsed_time(e1) * 1e3, st, int(v.t["final_count"][int(v.t["final_count"][2])]), smid,
+                     i32[:, 10].astype(np.float64), i32[:, 11].astype(np.float64), turning))
     ev = np.median([r[0] for r in rows])
     print(f"{env_id} E={E}: CUDA-event time per launch {ev:.1f} us (median of {len(rows)}), envs finishing per step "
           f"{np.mean([r[2] for r in rows]):.0f}")
@@ -76,6 +80,20 @@ def main():
               f"{(slow[0] & sel).sum() / max(slow[0].sum(), 1) * 100:.0f} %")
     sm_slow = np.bincount(sm[slow], minlength=160)
     print("slow warps per SM (top 8 SMs):", sorted(sm_slow.tolist(), reverse=True)[:8], "of", int(slow.sum()))
+    # what makes a warp slow?  conflicts / LoS found in the env's last substep (= exact pair evaluations), ownship turning
+    nconf, nlos, turning = (np.stack([r[k] for r in rows]) for k in (4, 5, 6))
+    print(f"correlation of warp lifetime with nconf {np.corrcoef(life.ravel(), nconf.ravel())[0, 1]:.2f}, nlos "
+          f"{np.corrcoef(life.ravel(), nlos.ravel())[0, 1]:.2f}, ownship turning {np.corrcoef(life.ravel(), turning.ravel().astype(float))[0, 1]:.2f}")
+    for lo, hi in ((0, 1), (1, 5), (5, 10), (10, 20), (20, 40), (40, 1000)):
+        sel = (nconf >= lo) & (nconf < hi)
+        if sel.any():
+            print(f"   nconf in [{lo}, {hi}): {sel.mean() * 100:5.1f} % of the envs, lifetime mean {life[sel].mean():.2f} p95 {np.percentile(life[sel], 95):.2f} us, "
+                  f"substeps 1..n-1 mean {d[:, :, 3][sel].mean():.2f} us")
+    print(f"   ownship turning: {turning.mean() * 100:.1f} % of the envs, lifetime mean {life[turning].mean():.2f} vs {life[~turning].mean():.2f} us")
+    sm_n = np.array([[nconf[l][sm[l] == k].sum() for k in range(160)] for l in range(sm.shape[0])])
+    sm_life = np.array([[life[l][sm[l] == k].max() if (sm[l] == k).any() else np.nan for k in range(160)] for l in range(sm.shape[0])])
+    ok = ~np.isnan(sm_life)
+    print(f"per SM: correlation of the SM's last warp end with the SM's total nconf {np.corrcoef(sm_life[ok], sm_n[ok])[0, 1]:.2f}")
     fin = d[:, :, 5] > 0.5
     print(f"envs that reset: {fin.mean() * 100:.1f} %; their lifetime median {np.median((end - start)[fin]) if fin.any() else 0:.2f} us")
 
