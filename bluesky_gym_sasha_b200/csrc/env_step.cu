@@ -249,7 +249,11 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
     BSG_RSTAMP(0);
     // ---- A: candidate polygon point `slot` = random_point_on_circle with draw `slot` (functions.py:44-59) ----------
     const double al = 6.283185307179586 * rng.u01((uint32_t)slot);
-    const double cx = R * cos(al), cy = R * sin(al), ca = atan2(cy, cx);
+    double sal, cal;
+    sincos(al, &sal, &cal);
+    const double cx = R * cal, cy = R * sal;
+    // sort key: atan2(cy, cx) is al itself folded into (-pi, pi] (to rounding: only the ORDER of the keys is used)
+    const double ca = al > 3.141592653589793 ? al - 6.283185307179586 : al;
     BSG_RSTAMP(1);
     // ---- B: the polygon = the first nv candidates sorted by angle (sort_points_clockwise = ascending atan2(y, x),
     //      functions.py:61-75), nv the smallest count >= 3 whose area reaches 2400 (sector_cr_env.py:141-160: points are
@@ -261,26 +265,31 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
     uint32_t d = 0;
     double area = 0.0, perim = 0.0, minx = 0.0, maxx = 0.0, miny = 0.0, maxy = 0.0;
     {
-        double pa = -1.0e300, px = 0.0, py = 0.0, sa = 1.0e300, sx = 0.0, sy = 0.0;        // nearest below / above by angle
-        double ma = -1.0e300, mx = 0.0, my = 0.0, na = 1.0e300, nx = 0.0, ny = 0.0;        // largest / smallest of all
-        for (int j = 0; j < 31; ++j) {                                                    // (no lane has lane 31 before it)
-            const double aj = __shfl_sync(0xffffffffu, ca, j), xj = __shfl_sync(0xffffffffu, cx, j), yj = __shfl_sync(0xffffffffu, cy, j);
-            if (j < slot) {
-                if (aj <= ca) { if (aj >= pa) { pa = aj; px = xj; py = yj; } }             // (equal angles: the earlier draw sorts first)
-                else if (aj < sa) { sa = aj; sx = xj; sy = yj; }
-                if (aj >= ma) { ma = aj; mx = xj; my = yj; }
-                if (aj < na) { na = aj; nx = xj; ny = yj; }
+        // (polygons rarely need more than a dozen points: the first 16 prefixes are tried first, all 32 only if none suffices)
+        unsigned big = 0u;
+        for (int pass = 0; pass < 2 && !big; ++pass) {
+            const int jmax = pass ? 31 : 15;                                                  // (no lane has lane 31 before it)
+            double pa = -1.0e300, px = 0.0, py = 0.0, sa = 1.0e300, sx = 0.0, sy = 0.0;        // nearest below / above by angle
+            double ma = -1.0e300, mx = 0.0, my = 0.0, na = 1.0e300, nx = 0.0, ny = 0.0;        // largest / smallest of all
+            for (int j = 0; j < jmax; ++j) {
+                const double aj = __shfl_sync(0xffffffffu, ca, j), xj = __shfl_sync(0xffffffffu, cx, j), yj = __shfl_sync(0xffffffffu, cy, j);
+                if (j < slot) {
+                    if (aj <= ca) { if (aj >= pa) { pa = aj; px = xj; py = yj; } }             // (equal angles: the earlier draw sorts first)
+                    else if (aj < sa) { sa = aj; sx = xj; sy = yj; }
+                    if (aj >= ma) { ma = aj; mx = xj; my = yj; }
+                    if (aj < na) { na = aj; nx = xj; ny = yj; }
+                }
             }
+            if (pa == -1.0e300) { px = mx; py = my; }                                          // the smallest angle follows the largest
+            if (sa == 1.0e300) { sx = nx; sy = ny; }
+            double S = slot > 0 ? (px * cy - py * cx) + (cx * sy - cy * sx) - (px * sy - py * sx) : 0.0;
+            for (int o = 1; o < 32; o <<= 1) {                                                 // inclusive prefix sum over the lanes
+                const double up = __shfl_up_sync(0xffffffffu, S, o);
+                if (slot >= o) S += up;
+            }
+            big = __ballot_sync(0xffffffffu, slot >= 2 && slot <= jmax && fabs(S) * 0.5 >= 2400.0);
         }
-        if (pa == -1.0e300) { px = mx; py = my; }                                          // the smallest angle follows the largest
-        if (sa == 1.0e300) { sx = nx; sy = ny; }
-        double S = slot > 0 ? (px * cy - py * cx) + (cx * sy - cy * sx) - (px * sy - py * sx) : 0.0;
-        for (int o = 1; o < 32; o <<= 1) {                                                 // inclusive prefix sum over the lanes
-            const double up = __shfl_up_sync(0xffffffffu, S, o);
-            if (slot >= o) S += up;
-        }
-        const unsigned big = __ballot_sync(0xffffffffu, slot >= 2 && fabs(S) * 0.5 >= 2400.0);
-        nv = big ? __ffs((int)big) : kSectorMaxV;                                          // lane n - 1 holds the polygon of n points
+        nv = big ? __ffs((int)big) : kSectorMaxV;                                              // lane n - 1 holds the polygon of n points
         if (!big) rflags |= 1;
         int rank = 0;                                                                      // my place among the first nv by angle (stable)
         for (int j = 0; j < nv; ++j) {
