@@ -2,9 +2,6 @@
 // termination, and the env-step megakernel that strings them around the substep loop of
 // env_kernels.cuh.  Every function cites the reference lines it restates; the float64 CPU
 // restatement these are parity-tested against is oracle/envs.py.
-#ifdef BSG_PHASE_TIMING
-#include <cstdio>
-#endif
 #include "env_kernels.cuh"
 
 namespace bsg {
@@ -240,13 +237,6 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
     const Philox rng = make_philox(P.seed, P.gid0 + e, (uint32_t)s.episode);
     const double R = sqrt(3750.0 / 3.141592653589793);
     const double coslat0 = cos(kSectorLat0 * kDeg2RadD);
-#ifdef BSG_PHASE_TIMING
-    unsigned long long tq[6];
-#define BSG_RSTAMP(k) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq[k]) :: "memory")
-#else
-#define BSG_RSTAMP(k) do { } while (0)
-#endif
-    BSG_RSTAMP(0);
     // ---- A: candidate polygon point `slot` = random_point_on_circle with draw `slot` (functions.py:44-59) ----------
     const double al = 6.283185307179586 * rng.u01((uint32_t)slot);
     double sal, cal;
@@ -254,7 +244,6 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
     const double cx = R * cal, cy = R * sal;
     // sort key: atan2(cy, cx) is al itself folded into (-pi, pi] (to rounding: only the ORDER of the keys is used)
     const double ca = al > 3.141592653589793 ? al - 6.283185307179586 : al;
-    BSG_RSTAMP(1);
     // ---- B: the polygon = the first nv candidates sorted by angle (sort_points_clockwise = ascending atan2(y, x),
     //      functions.py:61-75), nv the smallest count >= 3 whose area reaches 2400 (sector_cr_env.py:141-160: points are
     //      inserted in draw order until the area is large enough).  All 32 prefixes at once instead of a serial loop of
@@ -335,7 +324,6 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
         num_ac = (int)nraw;
     }
     __syncwarp();
-    BSG_RSTAMP(2);
     // ---- C: _generate_waypoints (:162-188): num_ac draws along the perimeter, sorted, mapped onto the edges ----------
     {
         const bool mine = slot < num_ac;
@@ -359,7 +347,6 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
         d += (uint32_t)num_ac;
     }
     __syncwarp();
-    BSG_RSTAMP(3);
     // ---- D: _generate_ac (:190-217): rejection sampling in the bounding box, 32 tries at a time; try t uses draws
     //         d + 2t and d + 2t + 1 and accepted points keep their try order, exactly as in the serial loop ----------
     double* a_lat = scratch, *a_lon = scratch + 32;    // (the candidate arrays are no longer needed)
@@ -376,7 +363,6 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
     }
     __syncwarp();
     if (got < num_ac) { rflags |= 4; num_ac = got > 0 ? got : 1; }
-    BSG_RSTAMP(4);
     // ---- E: one aircraft per lane: heading towards its waypoint (fn.get_hdg, functions.py:150-178) and Traffic.cre
     double w0lat = 0.0, w0lon = 0.0;
     if (slot < num_ac && got > 0) {
@@ -397,12 +383,6 @@ __device__ inline void sector_reset(Ac& a, EnvS& s, const EnvParams& P, long lon
     s.num_ac = num_ac; s.nvert = nv; s.rflags = rflags; s.poly_area = area;
     s.wpt_lat = w0lat; s.wpt_lon = w0lon;
     s.total_reward = 0.0f; s.intrusions = 0; s.drift_sum = 0.0f; s.drift_n = 0; s.wpt_reach = 0;
-#ifdef BSG_PHASE_TIMING
-    BSG_RSTAMP(5);
-    if (slot == 0 && P.mode == kModeStep && (e & 31) == 0)
-        printf("sector_reset e=%lld nv=%d num_ac=%d: A %llu B %llu C %llu D %llu E %llu ns\n", e, nv, num_ac, tq[1] - tq[0], tq[2] - tq[1],
-               tq[3] - tq[2], tq[4] - tq[3], tq[5] - tq[4]);
-#endif
 }
 template <int G>
 __device__ inline void sector_action(Ac& a, const EnvParams& P, const float* act, int slot) {
