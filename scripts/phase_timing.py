@@ -41,13 +41,21 @@ def main():
         raw = v.t["final_obs"].view(-1).view(torch.int64)[-8 * E:].view(E, 8).cpu().numpy()
         smid = (raw[:, 7] & 0xff).astype(np.int64)
         st = raw.astype(np.float64)
-        t0 = st[:, 0].min()
+        good = np.all(np.diff(raw[:, :7], axis=1) >= 0, axis=1) & (raw[:, 0] > 0) & (raw[:, 6] - raw[:, 0] < 10_000_000)
+        t0 = st[good, 0].min()
         st = (st - t0) * 1e-3                                    # us since the first warp started
+        st[~good] = st[good].mean(axis=0)                        # (envs whose stamps are incomplete take the average: not counted as outliers)
         i32 = v.t["env_i32"].cpu().numpy()
         kin, cmd = v.t["kin"][:, 0].cpu().numpy(), v.t["cmd"][:, 0].cpu().numpy()
         turning = np.abs((kin[:, 2] - cmd[:, 3] + 180.0) % 360.0 - 180.0) > 0.01        # ownship still turning after the step
+        fl = v.t["flags"].cpu().numpy()
+        kin_all, cmd_all = v.t["kin"].cpu().numpy(), v.t["cmd"].cpu().numpy()
+        alive = (fl & 1) != 0
+        nturn = (alive & (np.abs((kin_all[:, :, 2] - cmd_all[:, :, 3] + 180.0) % 360.0 - 180.0) > 0.01)).sum(axis=1)   # aircraft turning
+        nlnav = (alive & ((fl & 2) != 0)).sum(axis=1)
         rows.append((e0.elapsed_time(e1) * 1e3, st, int(v.t["final_count"][int(v.t["final_count"][2])]), smid,
-                     i32[:, 10].astype(np.float64), i32[:, 11].astype(np.float64), turning))
+                     i32[:, 10].astype(np.float64), i32[:, 11].astype(np.float64), turning, nturn.astype(np.float64),
+                     nlnav.astype(np.float64), alive.sum(axis=1).astype(np.float64), i32[:, 0].astype(np.float64)))
     ev = np.median([r[0] for r in rows])
     print(f"{env_id} E={E}: CUDA-event time per launch {ev:.1f} us (median of {len(rows)}), envs finishing per step "
           f"{np.mean([r[2] for r in rows]):.0f}")
@@ -90,6 +98,11 @@ def main():
             print(f"   nconf in [{lo}, {hi}): {sel.mean() * 100:5.1f} % of the envs, lifetime mean {life[sel].mean():.2f} p95 {np.percentile(life[sel], 95):.2f} us, "
                   f"substeps 1..n-1 mean {d[:, :, 3][sel].mean():.2f} us")
     print(f"   ownship turning: {turning.mean() * 100:.1f} % of the envs, lifetime mean {life[turning].mean():.2f} vs {life[~turning].mean():.2f} us")
+    for name, k in (("aircraft turning after the step", 7), ("aircraft under LNAV", 8), ("aircraft alive", 9), ("env step counter", 10)):
+        x = np.stack([r[k] for r in rows])
+        if x.std() > 0:
+            print(f"   correlation of warp lifetime with {name}: {np.corrcoef(life.ravel(), x.ravel())[0, 1]:.2f}; "
+                  + ", ".join(f"{int(q)}: {life[x == q].mean():.1f} us ({(x == q).mean() * 100:.0f} %)" for q in np.unique(x)[:12]))
     sm_n = np.array([[nconf[l][sm[l] == k].sum() for k in range(160)] for l in range(sm.shape[0])])
     sm_life = np.array([[life[l][sm[l] == k].max() if (sm[l] == k).any() else np.nan for k in range(160)] for l in range(sm.shape[0])])
     ok = ~np.isnan(sm_life)
