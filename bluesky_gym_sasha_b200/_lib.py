@@ -91,7 +91,7 @@ class TensorTable(C.Structure):
 
 SYMBOLS = ("bsg_abi_version", "bsg_abi_struct_size", "bsg_last_error", "bsg_device_count", "bsg_query_layout", "bsg_create",
            "bsg_destroy", "bsg_bind_state", "bsg_reset", "bsg_step", "bsg_step_host", "bsg_step_host_block", "bsg_step_host_copy", "bsg_step_host_begin", "bsg_step_host_wait", "bsg_host_copy", "bsg_host_widen", "bsg_set_obs_noise", "bsg_get_noise_calls", "bsg_set_noise_calls", "bsg_load_state", "bsg_set_seed", "bsg_set_wind", "bsg_traf_update",
-           "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_detect", "bsg_cd_cull_workspace", "bsg_cd_detect_culled", "bsg_cd_detect_peers", "bsg_probe_fp32",
+           "bsg_cd_padded", "bsg_cd_pack", "bsg_cd_order_workspace", "bsg_cd_pack_ordered", "bsg_cd_detect", "bsg_cd_cull_workspace", "bsg_cd_detect_culled", "bsg_cd_detect_peers", "bsg_probe_fp32",
            "bsg_traf_pack", "bsg_traf_activate", "bsg_traf_workspace", "bsg_traf_substep", "bsg_render")
 
 _lib = None
@@ -164,6 +164,10 @@ def load():
     lib.bsg_cd_padded.argtypes = [i64]
     lib.bsg_cd_padded.restype = i64
     lib.bsg_cd_pack.argtypes = [vp, vp, vp, vp, vp, vp, i64, f64, f64, vp, vp]
+    if hasattr(lib, "bsg_cd_pack_ordered"):     # (absent only in older A/B builds loaded through BSG_B200_LIB)
+        lib.bsg_cd_order_workspace.argtypes = [i64]
+        lib.bsg_cd_order_workspace.restype = i64
+        lib.bsg_cd_pack_ordered.argtypes = [vp, vp, vp, vp, vp, vp, i64, f64, f64, vp, vp, vp, i64, vp]
     lib.bsg_cd_detect.argtypes = [vp, i64, i64, i64, f32, f32, f32, u32, vp, vp, vp, vp, C.POINTER(CdLists), vp]
     if hasattr(lib, "bsg_cd_detect_culled"):
         lib.bsg_cd_cull_workspace.argtypes = [i64, i64]

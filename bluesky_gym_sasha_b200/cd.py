@@ -62,6 +62,23 @@ class StateBasedCD:
         self.gpu_launches += 1
         return rec, n
 
+    def pack_ordered(self, lat, lon, trk, gs, alt, vs, lat0, lon0, out=None):
+        """``pack`` with the aircraft laid out in a spatially coherent order chosen on the device (bsg_cd_pack_ordered:
+        grid binning, counting sort -- what makes the culled detection effective).  Returns (rec, n, perm): record k holds
+        aircraft ``perm[k]`` (int32 device tensor)."""
+        arrs = [self._as_dev(a) for a in (lat, lon, trk, gs, alt, vs)]
+        n = arrs[0].numel()
+        n_pad = int(self.lib.bsg_cd_padded(n))
+        rec = out if out is not None else torch.empty((max(n_pad // 256, 1), 8, 256), dtype=torch.float32, device=self.device)
+        perm = torch.empty((n,), dtype=torch.int32, device=self.device)
+        nbytes = int(self.lib.bsg_cd_order_workspace(n))
+        work = self._get("order_work", (nbytes,), torch.uint8)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bsg_cd_pack_ordered(*[_ptr(a) for a in arrs], n, float(lat0), float(lon0), _ptr(rec), _ptr(perm),
+                                                    _ptr(work), nbytes, self._stream()))
+        self.gpu_launches += 6
+        return rec, n, perm
+
     # ---------------------------------------------------------------- detection on packed records
     def _lists(self, want_pairs, want_attr=True):
         """Device pair lists of one detection (include/bsg.h::bsg_cd_lists) and the ctypes view handed to the library."""
@@ -149,10 +166,10 @@ class StateBasedCD:
         cull = cull and span < 90.0                       # (airspaces across the antimeridian: plain form)
         perm = None
         if cull:
-            perm = self.spatial_order(lat_d, lon_d)
-            lat_d, lon_d = lat_d[perm], lon_d[perm]
-            trk, gs, alt, vs = (self._as_dev(x)[perm] for x in (trk, gs, alt, vs))
-        rec, n = self.pack(lat_d, lon_d, trk, gs, alt, vs, lat0, lon0)
+            rec, n, perm = self.pack_ordered(lat_d, lon_d, trk, gs, alt, vs, lat0, lon0)
+            perm = perm.long()
+        else:
+            rec, n = self.pack(lat_d, lon_d, trk, gs, alt, vs, lat0, lon0)
         out = self.detect_packed(rec, n, lon_wrap=span >= 90.0, cull=cull, symmetric=symmetric and span < 90.0)
         torch.cuda.synchronize(self.device)
         n_conf, n_los = (int(v) for v in out["npairs"].cpu())
@@ -168,17 +185,18 @@ class StateBasedCD:
                 y[perm] = x
                 return y
             inconf, tcpamax, nconf_row, nlos_row = (unperm(x) for x in (inconf, tcpamax, nconf_row, nlos_row))
-        # upstream's order: row-major np.where (own index, then intruder index)
-        pairs, lospairs, attr = pairs.cpu().numpy(), lospairs.cpu().numpy(), attr.cpu().numpy().astype(np.float64)
-        o = np.lexsort((pairs[:, 1], pairs[:, 0]))
-        ol = np.lexsort((lospairs[:, 1], lospairs[:, 0]))
-        res = dict(confpairs=pairs[o], lospairs=lospairs[ol], inconf=inconf.cpu().numpy().astype(bool),
+        # upstream's order: row-major np.where (own index, then intruder index).  Keys are unique, so one sort of the
+        # combined 64-bit key on the device (plumbing of this convenience wrapper, after the detection) orders a list
+        o = torch.argsort(pairs[:, 0].long() * (1 << 32) + pairs[:, 1].long())
+        ol = torch.argsort(lospairs[:, 0].long() * (1 << 32) + lospairs[:, 1].long())
+        attr = attr[o].cpu().numpy().astype(np.float64)
+        res = dict(confpairs=pairs[o].cpu().numpy(), lospairs=lospairs[ol].cpu().numpy(), inconf=inconf.cpu().numpy().astype(bool),
                    tcpamax=tcpamax.cpu().numpy().astype(np.float64),
                    nconf_row=nconf_row.cpu().numpy().astype(np.int64),
                    nlos_row=nlos_row.cpu().numpy().astype(np.int64),
                    n_conf=n_conf, n_los=n_los, truncated=n_conf > self.pair_capacity or n_los > self.los_capacity)
         for c, name in enumerate(_lib.CD_ATTR):           # qdr, dist, dcpa, tcpa, tinconf of each conflict (detect()'s tail)
-            res[name] = attr[o, c]
+            res[name] = attr[:, c]
         return res
 
     # ---------------------------------------------------------------- multi-GPU: rows sharded over ranks

@@ -502,12 +502,14 @@ __global__ void cd_finalize_kernel(const uint32_t* __restrict__ nconf_row, uint8
 // float64 SoA -> tile-blocked float32 records (see cd_pair.cuh); padding entries are inert aircraft.
 __global__ void cd_pack_kernel(const double* __restrict__ lat, const double* __restrict__ lon,
                                const double* __restrict__ trk, const double* __restrict__ gs,
-                               const double* __restrict__ alt, const double* __restrict__ vs, long long n,
+                               const double* __restrict__ alt, const double* __restrict__ vs,
+                               const int32_t* __restrict__ perm, long long n,
                                long long n_pad, double lat0, double lon0, float* __restrict__ rec) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pad) return;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // record index
+    if (k >= n_pad) return;
     float f[8];
-    if (i < n) {
+    if (k < n) {
+        const long long i = perm ? (long long)perm[k] : k;                     // the aircraft it holds (bsg_cd_pack_ordered)
         double la = lat[i];
         double dl = fmod((lon[i] - lon0) + 180.0, 360.0);
         if (dl < 0.0) dl += 360.0;
@@ -522,9 +524,9 @@ __global__ void cd_pack_kernel(const double* __restrict__ lat, const double* __r
         f[FX] = 0.0f; f[FY] = 0.0f; f[FCH] = 1.0f; f[FSH] = 0.0f;
         f[FU] = 0.0f; f[FV] = 0.0f; f[FALT] = 3.0e9f; f[FVS] = 0.0f;   // |dalt| ~ 3e9: never a candidate
     }
-    float* t = rec + (size_t)(i / kTJ) * kTileFloats + (i % kTJ);
+    float* t = rec + (size_t)(k / kTJ) * kTileFloats + (k % kTJ);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t[k * kTJ] = f[k];
+    for (int q = 0; q < 8; ++q) t[q * kTJ] = f[q];
 }
 
 }  // namespace bsg
@@ -533,17 +535,22 @@ using namespace bsg;
 
 extern "C" int64_t bsg_cd_padded(int64_t n) { return ((n + kTJ - 1) / kTJ) * kTJ; }
 
+// (also the last stage of bsg_cd_pack_ordered, cd_order.cu: d_perm[k] = the aircraft record k holds)
+int bsg_cd_pack_launch(const double* d_lat, const double* d_lon, const double* d_trk, const double* d_gs, const double* d_alt,
+                       const double* d_vs, const int32_t* d_perm, int64_t n, double lat0, double lon0, float* d_rec, cudaStream_t st) {
+    int64_t n_pad = bsg_cd_padded(n);
+    if (n_pad == 0) return BSG_OK;
+    int blocks = (int)((n_pad + 255) / 256);
+    cd_pack_kernel<<<blocks, 256, 0, st>>>(d_lat, d_lon, d_trk, d_gs, d_alt, d_vs, d_perm, n, n_pad, lat0, lon0, d_rec);
+    return bsg_cuda_check(cudaGetLastError(), "bsg_cd_pack launch");
+}
+
 extern "C" int bsg_cd_pack(const double* d_lat, const double* d_lon, const double* d_trk, const double* d_gs,
                            const double* d_alt, const double* d_vs, int64_t n, double lat0, double lon0,
                            float* d_rec, void* stream) {
     if (n < 0 || (n > 0 && (!d_lat || !d_lon || !d_trk || !d_gs || !d_alt || !d_vs)) || !d_rec)
         return bsg_fail(BSG_EINVAL, "bsg_cd_pack: null pointer or negative n");
-    int64_t n_pad = bsg_cd_padded(n);
-    if (n_pad == 0) return BSG_OK;
-    int blocks = (int)((n_pad + 255) / 256);
-    cd_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_lat, d_lon, d_trk, d_gs, d_alt, d_vs, n, n_pad,
-                                                              lat0, lon0, d_rec);
-    return bsg_cuda_check(cudaGetLastError(), "bsg_cd_pack launch");
+    return bsg_cd_pack_launch(d_lat, d_lon, d_trk, d_gs, d_alt, d_vs, nullptr, n, lat0, lon0, d_rec, (cudaStream_t)stream);
 }
 
 // ---- launch plumbing shared by the three entry points ------------------------------------------------

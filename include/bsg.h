@@ -266,6 +266,18 @@ int bsg_cd_pack(const double *d_lat, const double *d_lon, const double *d_trk, c
                 const double *d_alt, const double *d_vs, int64_t n, double lat0, double lon0,
                 float *d_rec, void *stream);
 
+/* bsg_cd_pack with the aircraft laid out in a spatially coherent order chosen on the device (uniform grid over their
+ * bounding box, strip by strip, alternate strips reversed; counting sort, no library call): what makes
+ * bsg_cd_detect_culled effective.  d_perm [n] receives the order: record k holds aircraft d_perm[k] (indices in the
+ * detection's outputs are record indices: map them back through d_perm).  The order inside a grid cell is unspecified;
+ * the detection's outputs (sets, counts, maxima) do not depend on it.  d_work: 8-byte aligned device scratch of
+ * bsg_cd_order_workspace(n) bytes.  Replaces: the sort of StateBasedCD.detect(cull=True) (formerly two library radix
+ * sorts and six gathers). */
+int64_t bsg_cd_order_workspace(int64_t n);
+int bsg_cd_pack_ordered(const double *d_lat, const double *d_lon, const double *d_trk, const double *d_gs,
+                        const double *d_alt, const double *d_vs, int64_t n, double lat0, double lon0,
+                        float *d_rec, int32_t *d_perm, void *d_work, int64_t work_bytes, void *stream);
+
 enum { BSG_CD_LON_WRAP = 1,     /* pairs may straddle the +-180 deg meridian relative to lon0        */
        BSG_CD_SYMMETRIC = 2,    /* bsg_cd_detect_culled: evaluate each unordered tile pair once and emit both
                                  * ordered results (needs n_rows == n_all); same outputs, half the work  */
