@@ -16,7 +16,8 @@ import sys, os, json, hashlib, torch
 sys.path.insert(0, %r)
 from bluesky_gym_sasha_b200.vector_env import BlueSkyVectorEnv
 CASES = [("HorizontalCREnv-v0", 1024, dict(n_intruders=20), 10), ("HorizontalCREnv-v0", 1024, dict(n_intruders=12), 10),
-         ("SectorCREnv-v0", 1024, {}, 5), ("MergeEnv-v0", 1024, {}, 10), ("VerticalCREnv-v0", 1024, {}, 10)]
+         ("SectorCREnv-v0", 1024, {}, 5), ("MergeEnv-v0", 1024, {}, 10), ("VerticalCREnv-v0", 1024, {}, 10),
+         ("StaticObstacleEnv-v0", 1024, {}, 5)]
 out = {}
 for env_id, E, kw, nsub in CASES:
     v = BlueSkyVectorEnv(env_id, E, seed=3, cd_enabled=True, autoreset_mode="same_step", **kw)
