@@ -505,12 +505,22 @@ struct __align__(16) GroupSmem {
 // creep every substep) keeps a (B) list while every ring aircraft stays within kCdVelTol of the velocity the list was built
 // with; otherwise the list is rebuilt as soon as any ring aircraft moved at all (the intruders of HorizontalCR / SectorCR
 // never do).  Rebuilding more often never changes results: every list is a superset of what the exact phase accepts.
+#ifdef BSG_SUBSTEP_CLOCKS
+__device__ long long g_clk[16];
+#define BSG_CLK(k) do { if (clk_on) g_clk[k] = clock64(); } while (0)
+#else
+#define BSG_CLK(k) do { } while (0)
+#endif
 template <int G, bool TOL>
 __device__ __forceinline__ void group_cd(GroupSmem<G>& S, const int lane_g, Ac& a, bool alive, int nac, const EnvParams& P, float horizon,
                                          const uint16_t* s_pairs, int& nconf_env, int& nlos_env, const bool emit, const int e,
                                          const bool lane_moved, const double lat_ref, const double lon_ref) {
     const int lane = threadIdx.x & 31;
     const int wbase = lane - lane_g;                  // first lane of this group in the warp
+#ifdef BSG_SUBSTEP_CLOCKS
+    const bool clk_on = e == 0 && lane_g == 0 && horizon == 4.0f * P.simdt;
+#endif
+    BSG_CLK(0);
     // cos / sin of lat/2 from the cached cos(lat): half-angle identities (absolute error ~1e-7); sign of lat from its high word
     const float ch = sqrt_approx(fmaf(0.5f, a.coslat, 0.5f));
     const float sh = __int_as_float((__float_as_int(sqrt_approx(fmaxf(fmaf(-0.5f, a.coslat, 0.5f), 0.0f))) & 0x7fffffff) |
@@ -606,6 +616,7 @@ __device__ __forceinline__ void group_cd(GroupSmem<G>& S, const int lane_g, Ac& 
         LH = pk2(lh, lh);
     }
     __syncwarp(gm);
+    BSG_CLK(1);
     if (eval_b) {
         // ---- (B) hot phase ---------------------------------------------------------------------------
         unsigned cand = 0u;
@@ -671,6 +682,7 @@ __device__ __forceinline__ void group_cd(GroupSmem<G>& S, const int lane_g, Ac& 
         }
         if (lane_g == 0) S.nb = nb;
     }
+    BSG_CLK(2);
     // ---- (A) pairs with slot 0, every substep ----------------------------------------------------------------
     int ncand;
     {
@@ -689,12 +701,17 @@ __device__ __forceinline__ void group_cd(GroupSmem<G>& S, const int lane_g, Ac& 
         ncand = nb + __popc(bm);
         __syncwarp(gm);
     }
+    BSG_CLK(3);
     // ---- exact phase -------------------------------------------------------------------------------
     for (int p = lane_g; p < ncand; p += G) {
         const unsigned en = queue[p];
         exact_pair((int)(en >> 8), (int)(en & 0xffu));
     }
     found = ncand > 0;
+#ifdef BSG_SUBSTEP_CLOCKS
+    if (clk_on) g_clk[8] = ncand;
+#endif
+    BSG_CLK(4);
     }
     // one REDUX.OR over the group merges every lane's findings; each aircraft then reads its own bit
     if (found) {                                      // (group-uniform)
@@ -706,6 +723,7 @@ __device__ __forceinline__ void group_cd(GroupSmem<G>& S, const int lane_g, Ac& 
     nconf_env = counts & 0xffff;
     nlos_env = counts >> 16;
     __syncwarp(group_mask<G>());
+    BSG_CLK(5);
 }
 
 }  // namespace bsg

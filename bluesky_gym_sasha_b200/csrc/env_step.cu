@@ -2,6 +2,9 @@
 // termination, and the env-step megakernel that strings them around the substep loop of
 // env_kernels.cuh.  Every function cites the reference lines it restates; the float64 CPU
 // restatement these are parity-tested against is oracle/envs.py.
+#ifdef BSG_SUBSTEP_CLOCKS
+#include <cstdio>
+#endif
 #include "env_kernels.cuh"
 
 namespace bsg {
@@ -1041,6 +1044,9 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
                                                           nlos, emit, e, moved, lat_ref, lon_ref);
                 if (emit && slot == 0) P.ei32[(long long)e * BSG_I32_COUNT + BSG_I32_NPAIRS] = S.np;
             }
+#ifdef BSG_SUBSTEP_CLOCKS
+            if (e == 0 && slot == 0 && k == P.n_sub - 5) g_clk[6] = clock64();
+#endif
             if (BSG_FAST_STEADY && !WIND && ENV != BSG_ENV_MERGE && group_all<G>(fixed || !alive)) {
                 moved = false;
                 if (alive) {                                // update_pos alone (same expressions as ac_kinematics)
@@ -1054,6 +1060,14 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvBlocksPerSm) env_kernel(const
                 moved = a.gsn != o_gsn || a.gse != o_gse;
                 fixed = !moved && a.tas == o_tas && a.hdg == o_hdg && a.vs == o_vs && a.alt == o_alt && a.ax == o_ax;
             }
+#ifdef BSG_SUBSTEP_CLOCKS
+            if (e == 0 && slot == 0 && k == P.n_sub - 5) {
+                g_clk[7] = clock64();
+                printf("substep clocks [cycles]: record+sync %lld | (B) %lld | (A) filter %lld | exact (%lld cand) %lld | merge+readback %lld | to kin %lld | kinematics %lld | whole %lld\n",
+                       g_clk[1] - g_clk[0], g_clk[2] - g_clk[1], g_clk[3] - g_clk[2], g_clk[8], g_clk[4] - g_clk[3], g_clk[5] - g_clk[4],
+                       g_clk[6] - g_clk[5], g_clk[7] - g_clk[6], g_clk[7] - g_clk[0]);
+            }
+#endif
             if (ENV == BSG_ENV_STATIC_OBSTACLE && P.mode == kModeStep) {   // per-substep reward / termination
                 if (k == 0) env_load_post(s, P, e);
                 if (static_substep_check<G>(a, s, P, e, slot)) break;
