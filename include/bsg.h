@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BSG_ABI_VERSION 5
+#define BSG_ABI_VERSION 6
 
 enum { BSG_OK = 0, BSG_EINVAL = -1, BSG_ECUDA = -2, BSG_ESTATE = -3, BSG_ENOMEM = -4 };
 

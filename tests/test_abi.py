@@ -23,7 +23,7 @@ def test_header_symbols_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/bsg.h but not exported"
     assert set(_lib.SYMBOLS) == set(names)
-    assert lib.bsg_abi_version() == 5
+    assert lib.bsg_abi_version() == 6
     for which, st in enumerate((_lib.Config, _lib.Layout, _lib.TensorTable, _lib.Wind, _lib.Perf, _lib.AcState, _lib.CdLists, _lib.TrafConfig,
                                 _lib.TrafTensors)):
         assert lib.bsg_abi_struct_size(which) == C.sizeof(st), st.__name__          # the ctypes mirror of include/bsg.h
