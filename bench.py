@@ -30,6 +30,7 @@ ENVS_PER_GPU = 4096
 N_INTRUDERS = 20
 N_SUB = 10
 CD_N = 100_000
+PREROLL_STEPS = 150        # untimed env steps before the warm-up: episodes desynchronised (stationary regime)
 # algorithmic work (restated in DESIGN.md)
 F_PAIR = 67.0            # FP32 flop per ordered aircraft pair of state-based CD
 F_KIN = 250.0            # FP32 flop per aircraft-substep of Traffic.update
@@ -178,7 +179,7 @@ def workload_config(n_gpus):
     return {"workload": "HorizontalCREnv-v0 batched (BASELINE configs[1])", "envs_per_gpu": ENVS_PER_GPU,
             "envs_total": ENVS_PER_GPU * n_gpus, "n_intruders": N_INTRUDERS, "aircraft_per_env": A,
             "substeps_per_step": N_SUB, "simdt_s": 5.0, "cd": "StateBased every substep", "autoreset": "same_step",
-            "max_episode_steps": 300, "actions": "U(-1,1) float32, resident in HBM", "l2": "flushed between timed steps",
+            "max_episode_steps": 300, "preroll_steps": PREROLL_STEPS, "actions": "U(-1,1) float32, resident in HBM", "l2": "flushed between timed steps",
             "parallelism": f"env-sharded x{n_gpus}, no data-path collective"}
 
 
@@ -315,6 +316,12 @@ def run_b200(args):
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     bank = torch.rand((K + W, E, 1), generator=g, device=dev) * 2.0 - 1.0      # actions resident in HBM
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+    # set-up: the env population is advanced to its stationary regime (episodes of different lengths: ~3 % of the envs finish
+    # and re-generate their scenario in any step, ownships anywhere between the first turn and the waypoint) -- what a
+    # training run sees after its first seconds; straight after reset() every env would be in the first steps of its first
+    # episode at once.  Untimed, before the W warm-up steps; named in config.preroll_steps.
+    for i in range(PREROLL_STEPS):
+        venv.step_torch(bank[i % (K + W)])
     for i in range(W):
         venv.step_torch(bank[i])
     barrier()
@@ -478,8 +485,8 @@ def bench_env_leg(torch, dev, BlueSkyVectorEnv, env_id, E, kw, world, rank, max_
     v.reset_torch()
     g = torch.Generator(device=dev).manual_seed(77 + rank)
     a = torch.rand((steps + 5, E, v.layout.act_dim), device=dev, generator=g) * 2.0 - 1.0
-    for i in range(5):
-        v.step_torch(a[i])
+    for i in range(PREROLL_STEPS + 5):                     # (stationary regime first, as in the headline loop)
+        v.step_torch(a[i % (steps + 5)])
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     torch.cuda._sleep(int(steps * 60e-6 * 1.9e9))          # (head start for the host, as in the headline loop)
