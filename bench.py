@@ -215,7 +215,7 @@ class ClockSampler:
                     mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
                     r = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                     self.samples.append([mhz, self.max_mhz] + [bool(r & b) for b in self.bits])
-                    time.sleep(0.002)
+                    time.sleep(0.0005)
                     continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
