@@ -2,7 +2,7 @@
  *
  * The reference (svlaskin/bluesky-gym-sasha) is pure Python and has no FFI of its own; the boundary
  * its hot path sits behind is the gymnasium Env API (bluesky_gym/__init__.py:4-46 registration,
- * Env.reset / Env.step in bluesky_gym/envs/*.py).  Each entry point below therefore cites the
+ * Env.reset / Env.step in bluesky_gym/envs/<env>.py).  Each entry point below therefore cites the
  * reference *Python* interface it replaces; INTEGRATION.md shows the ctypes stub a maintainer adds.
  *
  * Conventions: extern "C", plain pointers and sizes, no torch / CUDA types in the signatures

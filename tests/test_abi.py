@@ -115,3 +115,42 @@ def test_host_thread_widen(lib):
         dst = np.full(n + 4, -7.0)
         assert lib.bsg_host_widen(C.c_void_p(dst.ctypes.data + 16), C.c_void_p(src.ctypes.data), n) == 0
         assert np.array_equal(dst[2:2 + n], src[:n].astype(np.float64)) and (dst[:2] == -7.0).all() and (dst[2 + n:] == -7.0).all()
+
+
+def _build_c_host(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None or not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("needs gcc and the CUDA runtime headers")
+    from bluesky_gym_sasha_b200 import build
+    build.build()
+    pkg = os.path.join(ROOT, "bluesky_gym_sasha_b200")
+    exe = str(tmp_path / "c_abi_detect")
+    cmd = ["gcc", os.path.join(ROOT, "examples", "c_abi_detect.c"), "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+           "-L" + pkg, "-lbsg_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-lm", "-Wl,-rpath," + pkg, "-Wall", "-Werror", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_host_links_against_the_abi(tmp_path):
+    """include/bsg.h is plain C and the library links into a C program with gcc alone (examples/c_abi_detect.c): no C++, no
+    torch, no Python in the boundary.  Without a device the program reports that and exits 1."""
+    import subprocess
+    exe = _build_c_host(tmp_path)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "100"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_host_runs_the_detection(cuda, tmp_path):
+    """The same program on a GPU: packs 20 000 aircraft in the device-chosen order, runs the culled + symmetric and the
+    all-pairs detection through the C ABI and finds the same conflicts with both."""
+    import subprocess
+    exe = _build_c_host(tmp_path)
+    r = subprocess.run([exe, "20000"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("ok") and "conflicts" in r.stdout
+    print(r.stdout.strip())
