@@ -409,6 +409,8 @@ def run_b200(args):
 
     # single airspace, rows sharded over the ranks after one NCCL all-gather (BASELINE configs[4])
     cd_sharded = bench_cd_sharded(torch, dist, dev, StateBasedCD, world, rank, max_over_ranks, barrier) if world > 1 else None
+    # one airspace with routes + MVP, its aircraft sharded over the ranks (SURVEY 8e + 8f-4)
+    traffic_sharded = bench_traffic_sharded(torch, dist, dev, world, rank, max_over_ranks, barrier) if world > 1 else None
 
     # the other BASELINE configs: every rank steps its shard (env-sharded like the headline; max over ranks)
     legs = {name: bench_env_leg(torch, dev, BlueSkyVectorEnv, env_id, E_, kw, world, rank, max_over_ranks, barrier)
@@ -470,6 +472,8 @@ def run_b200(args):
             line["airspace_traffic"] = traffic_leg
         if cd_sharded is not None:
             line["cd_pairs_sharded"] = cd_sharded
+        if traffic_sharded is not None:
+            line["airspace_traffic_sharded"] = traffic_sharded
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -643,7 +647,7 @@ def bench_traffic(torch, dev, hbm_peak, n=CD_N, reps=20):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         _lib.check(tr.lib.bsg_traf_substep(C.byref(tr.cfg if r % 2 else cfg0), C.byref(tr.tt), _ptr(tr.rec), 0, _ptr(out["pairs"]),
-                                           _ptr(out["attr"]), _ptr(out["npairs"]), tr.cd.pair_capacity, _ptr(tr.work),
+                                           _ptr(out["attr"]), _ptr(out["npairs"]), None, tr.cd.pair_capacity, _ptr(tr.work),
                                            tr.work.numel(), st))
         b.record()
         torch.cuda.synchronize(dev)
@@ -678,6 +682,54 @@ def bench_traffic(torch, dev, hbm_peak, n=CD_N, reps=20):
             "substep_kernel_2e20_aircraft": {"us": t_big * 1e3, "l2": "state (344 MB) exceeds L2", "roofline": {
                 "bound": "hbm", "achieved": bytes_per_ac * big / (t_big * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": bytes_per_ac * big / (t_big * 1e-3) / 1e9 / hbm_peak, "kernel": "traf_substep_kernel"}}}
+
+
+def bench_traffic_sharded(torch, dist, dev, world, rank, max_over_ranks, barrier, n=CD_N, reps=20):
+    """bench_traffic's airspace (N aircraft, four-waypoint VNAV routes, MVP) with the aircraft block-partitioned over the
+    ranks (AirspaceTraffic(group=True)): per substep every rank packs its block, the records are all-gathered over NVLink,
+    each rank detects its own rows against the whole airspace (culled form, pair lists) and advances its own aircraft.
+    Device time per substep, max over ranks."""
+    from bluesky_gym_sasha_b200.cd import StateBasedCD
+    from bluesky_gym_sasha_b200.traffic import AirspaceTraffic
+    rng = np.random.default_rng(3)
+    lat, lon = 52 + 40 * (rng.random(n) - 0.5), 4 + 40 * (rng.random(n) - 0.5)
+    perm = StateBasedCD.spatial_order(torch.as_tensor(lat, device=dev), torch.as_tensor(lon, device=dev)).cpu().numpy()
+    lat, lon = lat[perm], lon[perm]
+    alt = np.round(rng.uniform(3000, 12000, n) / 304.8) * 304.8
+    hdg, cas = rng.uniform(0, 360, n), rng.uniform(120, 150, n)
+    W = 4
+    wlat, wlon, walt = np.zeros((n, W)), np.zeros((n, W)), np.full((n, W), -999.0)
+    la, lo, brg = lat.copy(), lon.copy(), hdg.copy()
+    for k in range(W):
+        d = rng.uniform(60.0, 120.0, n) / 111.0
+        la = la + d * np.cos(np.radians(brg)); lo = lo + d * np.sin(np.radians(brg)) / np.cos(np.radians(np.clip(la, -80, 80)))
+        brg = brg + rng.uniform(-40, 40, n)
+        wlat[:, k], wlon[:, k] = la, lo
+        walt[:, k] = np.where(rng.random(n) < 0.5, np.clip(alt + rng.uniform(-2500, 1500, n), 1500, 12000), -999.0)
+    per = -(-(-(-n // world)) // 256) * 256
+    sl = slice(min(rank * per, n), min((rank + 1) * per, n))
+    tr = AirspaceTraffic(per, device=dev.index, simdt=1.0, reso="MVP", reso_mode=1, max_wpts=W, group=True)
+    if sl.stop > sl.start:
+        tr.create(lat[sl], lon[sl], hdg[sl], alt[sl], cas[sl])
+        tr.set_routes(np.arange(sl.stop - sl.start), wlat[sl], wlon[sl], walt[sl], None)
+    tr.step(20)
+    barrier()
+    best = 1e30
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        tr.step(reps)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        best = min(best, max_over_ranks(e0.elapsed_time(e1) / reps))
+    nconf = torch.tensor([int(tr.last["npairs"][0])], dtype=torch.int64, device=dev)
+    dist.all_reduce(nconf)
+    return {"n_aircraft": n, "aircraft_per_gpu": per, "ms_per_substep": best, "aircraft_substeps_per_s": n / (best * 1e-3),
+            "realtime_factor": 1.0 / (best * 1e-3), "n_conf": int(nconf.item()),
+            "form": "per substep: bsg_traf_pack of the own block, ncclAllGather of the 32 B records, culled K2 of the own rows "
+                    "against the whole airspace with pair lists, all-reduce of the conflict count, bsg_traf_substep of the own "
+                    "aircraft (MVP horizontal, VNAV routes); results identical to the unsharded airspace (scripts/traf_sharded_check.py)"}
 
 
 def bench_cd_sharded(torch, dist, dev, StateBasedCD, world, rank, max_over_ranks, barrier, n=CD_N, reps=5):

@@ -66,7 +66,7 @@ PRIM_LINE, PRIM_RING, PRIM_RECT, PRIM_EDGE, PRIM_EDGE_END, PRIM_FLOATS = 1, 2, 3
 class TrafConfig(C.Structure):
     _fields_ = [("n", C.c_int64), ("max_wpts", C.c_int32), ("reso", C.c_int32), ("reso_mode", C.c_int32), ("simdt", C.c_float),
                 ("rpz", C.c_float), ("hpz", C.c_float), ("dtlookahead", C.c_float), ("resofach", C.c_float),
-                ("resofacv", C.c_float), ("perf", Perf), ("lat0", C.c_double), ("lon0", C.c_double)]
+                ("resofacv", C.c_float), ("perf", Perf), ("lat0", C.c_double), ("lon0", C.c_double), ("row0", C.c_int64)]
 
 
 class TrafTensors(C.Structure):
@@ -156,7 +156,7 @@ def load():
     if hasattr(lib, "bsg_traf_substep"):        # (absent only in older A/B builds loaded through BSG_B200_LIB)
         lib.bsg_traf_pack.argtypes = [C.POINTER(TrafConfig), C.POINTER(TrafTensors), vp, vp]
         lib.bsg_traf_activate.argtypes = [C.POINTER(TrafConfig), C.POINTER(TrafTensors), vp]
-        lib.bsg_traf_substep.argtypes = [C.POINTER(TrafConfig), C.POINTER(TrafTensors), vp, i32, vp, vp, vp, i64, vp, i64, vp]
+        lib.bsg_traf_substep.argtypes = [C.POINTER(TrafConfig), C.POINTER(TrafTensors), vp, i32, vp, vp, vp, vp, i64, vp, i64, vp]
         lib.bsg_traf_workspace.argtypes = [i64, i64]
         lib.bsg_traf_workspace.restype = i64
         for f in (lib.bsg_traf_pack, lib.bsg_traf_activate, lib.bsg_traf_substep):

@@ -27,7 +27,7 @@ enum { RX = 0, RY = 1, RCH = 2, RSH = 3, RU = 4, RV = 5, RALT = 6, RVS = 7 };
 constexpr float kSteepness = 3000.0f * kFt / (10.0f * kNm);        // Autopilot.steepness
 
 struct TrafParams {
-    long long n;
+    long long n, row0;          // row0: global index (in the CD records and pair lists) of this block's aircraft 0
     int W, reso, reso_mode, fms_ready;
     float simdt, rpz, hpz, dtlook, resofach, resofacv;
     bsg_perf perf;
@@ -37,6 +37,7 @@ struct TrafParams {
     const double2* rt_pos; const float4* rt_con; const float* rt_dir; uint32_t* counters;
     const float* rec;
     const int2* pairs; const float* attr; const unsigned long long* npairs; long long cap;      // K2's conflict list
+    const unsigned long long* nconf_all;     // conflicts in the whole airspace (== npairs unless the airspace is sharded)
     int* count; int* offs; int* len; int* total; int* seg;     // index of that list by own aircraft: rows seg[offs[i] .. offs[i] + len[i])
 };
 
@@ -209,7 +210,7 @@ __global__ void traf_conf_count_kernel(const TrafParams P) {
     const unsigned long long ntot = P.npairs[0];
     const long long m = ntot < (unsigned long long)P.cap ? (long long)ntot : P.cap;
     if (k == 0) *P.total = 0;                          // (the allocation kernel runs after this one)
-    if (k < m) atomicAdd(&P.count[P.pairs[k].x], 1);
+    if (k < m) atomicAdd(&P.count[P.pairs[k].x - P.row0], 1);
 }
 // every aircraft with conflicts reserves a contiguous run of the index: warp-aggregated (one atomicAdd per warp on the
 // running total).  The runs come in no particular order -- nothing needs them ordered -- so no global scan is needed.
@@ -235,7 +236,7 @@ __global__ void traf_conf_scatter_kernel(const TrafParams P) {
     const unsigned long long ntot = P.npairs[0];
     const long long m = ntot < (unsigned long long)P.cap ? (long long)ntot : P.cap;
     if (k < m) {
-        const int i = P.pairs[k].x;
+        const long long i = P.pairs[k].x - P.row0;
         P.seg[P.offs[i] + atomicSub(&P.count[i], 1) - 1] = (int)k;
     }
 }
@@ -313,8 +314,9 @@ __global__ void __launch_bounds__(128) traf_substep_kernel(const TrafParams P) {
 
     // ---- ASAS: ConflictResolution.update = MVP.resolve (when the detection found any conflict) + resumenav -----------
     if (P.reso) {
-        const float own_u = rec_at(P.rec, i, RU), own_v = rec_at(P.rec, i, RV), own_alt = rec_at(P.rec, i, RALT), own_vs = rec_at(P.rec, i, RVS);
-        const unsigned long long ntot = P.npairs[0];
+        const long long ig = P.row0 + i;                   // this aircraft in the records of the whole airspace
+        const float own_u = rec_at(P.rec, ig, RU), own_v = rec_at(P.rec, ig, RV), own_alt = rec_at(P.rec, ig, RALT), own_vs = rec_at(P.rec, ig, RVS);
+        const unsigned long long ntot = P.nconf_all[0];
         const int k0 = P.offs[i], k1 = k0 + P.len[i];
         // the aircraft's conflicts in ascending intruder order (its run of the index is unordered; runs are short)
         auto next_conflict = [&](int last, int& row) {
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(128) traf_substep_kernel(const TrafParams P) {
             }
         }
         bool any_pair = false, active = false;
-        const float own_x = rec_at(P.rec, i, RX), own_y = rec_at(P.rec, i, RY), own_ch = rec_at(P.rec, i, RCH), own_sh = rec_at(P.rec, i, RSH);
+        const float own_x = rec_at(P.rec, ig, RX), own_y = rec_at(P.rec, ig, RY), own_ch = rec_at(P.rec, ig, RCH), own_sh = rec_at(P.rec, ig, RSH);
         const float own_trk = mod360(kRad2Deg * atan2f(own_u, own_v));
 #pragma unroll
         for (int s = 0; s < BSG_TRAF_PARTNERS; ++s) {
@@ -469,6 +471,7 @@ static int traf_params(TrafParams& P, const bsg_traf_config* cfg, const bsg_traf
     if (cfg->n < 0 || cfg->n > 0x7fffff00LL) return bsg_fail(BSG_EINVAL, "bsg_traf_*: n out of range");
     if (cfg->max_wpts < 0 || cfg->max_wpts > 255) return bsg_fail(BSG_EINVAL, "bsg_traf_*: max_wpts must be in [0, 255]");
     if (!(cfg->simdt > 0.0f)) return bsg_fail(BSG_EINVAL, "bsg_traf_*: simdt must be > 0");
+    if (cfg->row0 < 0 || cfg->row0 % 256 || cfg->row0 + cfg->n > 0x7fffff00LL) return bsg_fail(BSG_EINVAL, "bsg_traf_*: row0 must be a non-negative multiple of 256");
     if (cfg->n > 0 && (!t->pos || !t->kin || !t->cmd || !t->aux || !t->actwp || !t->vnav1 || !t->vnav2 || !t->asas || !t->flags ||
                        !t->partners || !t->counters))
         return bsg_fail(BSG_EINVAL, "bsg_traf_*: a required tensor pointer is null");
@@ -482,7 +485,7 @@ static int traf_params(TrafParams& P, const bsg_traf_config* cfg, const bsg_traf
     P.dtlook = cfg->dtlookahead > 0.0f ? cfg->dtlookahead : 300.0f;
     P.resofach = cfg->resofach > 0.0f ? cfg->resofach : 1.01f;
     P.resofacv = cfg->resofacv > 0.0f ? cfg->resofacv : 1.01f;
-    P.perf = cfg->perf; P.lat0 = cfg->lat0; P.lon0 = cfg->lon0;
+    P.perf = cfg->perf; P.lat0 = cfg->lat0; P.lon0 = cfg->lon0; P.row0 = cfg->row0;
     P.pos = (double2*)t->pos; P.kin = (float4*)t->kin; P.cmd = (float4*)t->cmd; P.aux = (float4*)t->aux;
     P.actwp = (double2*)t->actwp; P.vn1 = (float4*)t->vnav1; P.vn2 = (float4*)t->vnav2; P.asas = (float4*)t->asas;
     P.flags = t->flags; P.partners = t->partners;
@@ -518,7 +521,8 @@ extern "C" int64_t bsg_traf_workspace(int64_t n, int64_t conf_cap) {
 
 extern "C" int bsg_traf_substep(const bsg_traf_config* cfg, const bsg_traf_tensors* t, const float* d_rec, int32_t fms_ready,
                                 const int32_t* d_conf_pairs, const float* d_conf_attr, const unsigned long long* d_npairs,
-                                int64_t conf_cap, void* d_work, int64_t work_bytes, void* stream) {
+                                const unsigned long long* d_nconf_all, int64_t conf_cap, void* d_work, int64_t work_bytes,
+                                void* stream) {
     TrafParams P;
     int rc = traf_params(P, cfg, t, "bsg_traf_substep");
     if (rc != BSG_OK) return rc;
@@ -531,6 +535,7 @@ extern "C" int bsg_traf_substep(const bsg_traf_config* cfg, const bsg_traf_tenso
         if (conf_cap > 0x7fffff00LL) return bsg_fail(BSG_EINVAL, "bsg_traf_substep: conf_cap exceeds int32");
         if (!d_work || work_bytes < bsg_traf_workspace(P.n, conf_cap)) return bsg_fail(BSG_EINVAL, "bsg_traf_substep: workspace too small");
         P.rec = d_rec; P.pairs = (const int2*)d_conf_pairs; P.attr = d_conf_attr; P.npairs = d_npairs; P.cap = conf_cap;
+        P.nconf_all = d_nconf_all ? d_nconf_all : d_npairs;
         // workspace: count[n] (zero on entry: the caller zeroes it once, the scatter leaves it zero) | offs[n] | len[n] | total | seg[cap]
         P.count = (int*)d_work; P.offs = P.count + P.n; P.len = P.offs + P.n; P.total = P.len + P.n; P.seg = P.total + 1;
         const unsigned blocks = (unsigned)((conf_cap + 255) / 256);

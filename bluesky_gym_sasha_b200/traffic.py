@@ -95,7 +95,11 @@ class AirspaceTraffic:
 
     def __init__(self, n_max, device=0, simdt=1.0, rpz=5.0 * NM, hpz=1000.0 * FT, dtlookahead=300.0, reso=None, reso_mode=0,
                  resofach=1.01, resofacv=1.01, perf=None, max_wpts=8, lat0=52.0, lon0=4.0, cull=True, symmetric=True,
-                 pair_capacity=None, fms_dt=10.5):
+                 pair_capacity=None, fms_dt=10.5, group=None):
+        """``group``: a ``torch.distributed`` process group (``True`` = the default group) over which ONE airspace is sharded,
+        one rank per GPU: every rank owns the kinematics of up to ``n_max`` aircraft (its block); per substep the
+        ranks all-gather their CD records (32 B per aircraft over NVLink), each detects the conflicts of its own rows against
+        the whole airspace and advances its own aircraft.  Results equal the unsharded airspace's."""
         if not torch.cuda.is_available():
             raise _lib.BsgError("AirspaceTraffic needs a CUDA device: there is no CPU fallback")
         if reso not in (None, "OFF", "MVP"):
@@ -130,6 +134,20 @@ class AirspaceTraffic:
         self.work = torch.zeros(int(self.lib.bsg_traf_workspace(n, cap)), dtype=torch.uint8, device=dev)      # (zeroed once)
         self.last = None                    # device outputs of the last substep's detection
         self.gpu_launches = 0
+        # one airspace over several GPUs: block k of the records belongs to rank k, `per` records each (whole tiles)
+        self.group, self.world, self.rank, self.row0 = None, 1, 0, 0
+        if group is not None and group is not False:
+            import torch.distributed as dist
+            self.group = None if group is True else group
+            self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+            self.per = max(n_pad, 256)
+            self.row0 = self.rank * self.per
+            self.cfg.row0 = self.row0
+            self.rec.zero_()                # records this rank never packs (beyond its aircraft count) stay inert
+            self.rec[:, 2, :] = 1.0
+            self.rec[:, 6, :] = 3.0e9
+            self.allrec = torch.empty((self.per // 256 * self.world, 8, 256), dtype=torch.float32, device=dev)
+            self.nconf_all = torch.zeros(2, dtype=torch.int64, device=dev)
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -226,7 +244,7 @@ class AirspaceTraffic:
         if not detect and self.reso:
             raise ValueError("resolution needs the detection")
         n = self.n
-        if n == 0:
+        if n == 0 and self.world == 1:
             return
         cd = self.cd
         with torch.cuda.device(self.device):
@@ -234,17 +252,28 @@ class AirspaceTraffic:
             for _ in range(n_sub):
                 self.nstep += 1
                 fms_ready = (self.nstep % self.fms_rel_freq) == 0
-                pairs = attr = npairs = None
+                pairs = attr = npairs = nall = None
+                rec = self.rec
                 if detect:
                     _lib.check(self.lib.bsg_traf_pack(C.byref(self.cfg), C.byref(self.tt), _ptr(self.rec), st))
-                    out = cd.detect_packed(self.rec, n, want_pairs=True, cull=self.cull, symmetric=self.symmetric)
+                    if self.world > 1:
+                        import torch.distributed as dist
+                        dist.all_gather_into_tensor(self.allrec, self.rec[:self.per // 256], group=self.group)
+                        rec = self.allrec
+                        out = cd.detect_packed(rec, self.per * self.world, row0=self.row0, n_rows=n, want_pairs=True, cull=self.cull)
+                        if self.reso:       # upstream resolves whenever ANY conflict exists in the airspace
+                            self.nconf_all.copy_(out["npairs"])
+                            dist.all_reduce(self.nconf_all, group=self.group)
+                            nall = self.nconf_all
+                    else:
+                        out = cd.detect_packed(rec, n, want_pairs=True, cull=self.cull, symmetric=self.symmetric)
                     self.last = out
                     self.gpu_launches += 1
                     if self.reso:
                         pairs, attr, npairs = out["pairs"], out["attr"], out["npairs"]
                         self.gpu_launches += 3
-                _lib.check(self.lib.bsg_traf_substep(C.byref(self.cfg), C.byref(self.tt), _ptr(self.rec), int(fms_ready),
-                                                     _ptr(pairs), _ptr(attr), _ptr(npairs),
+                _lib.check(self.lib.bsg_traf_substep(C.byref(self.cfg), C.byref(self.tt), _ptr(rec), int(fms_ready),
+                                                     _ptr(pairs), _ptr(attr), _ptr(npairs), _ptr(nall),
                                                      cd.pair_capacity if pairs is not None else 0,
                                                      _ptr(self.work), self.work.numel(), st))
                 self.gpu_launches += 1

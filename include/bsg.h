@@ -365,6 +365,8 @@ typedef struct bsg_traf_config {
     float resofach, resofacv;   /* settings.asas_mar (1.01)                                               */
     bsg_perf perf;
     double lat0, lon0;          /* origin of the CD records                                               */
+    int64_t row0;               /* airspace sharded over GPUs: index of this block's aircraft 0 in the records of the
+                                 * whole airspace (a multiple of 256; 0 when the airspace is not sharded)  */
 } bsg_traf_config;
 typedef struct bsg_traf_tensors {
     double *pos;                /* [n][2] lat, lon [deg]                                                  */
@@ -391,12 +393,16 @@ int bsg_traf_activate(const bsg_traf_config *cfg, const bsg_traf_tensors *t, voi
  * exactly as bsg_cd_detect[_culled] wrote it (bsg_cd_lists: any order); all may be NULL with reso == 0.
  * d_work: device scratch of at least bsg_traf_workspace(n, conf_cap) bytes whose first n int32 are ZERO on entry (zero it
  * once after allocation: every call leaves them zero again).  fms_ready: the FMS timer fires in this substep (sim step
- * count % (10.5 // simdt) == 0).  Launches: 3 small index kernels (count / allocate / scatter of the conflict list by own
+ * count % (10.5 // simdt) == 0).  Airspace sharded over GPUs (cfg->row0 = this block's first global index; SURVEY 8e: a rank
+ * owns the kinematics of its block): d_rec holds the records of the WHOLE airspace (every rank's bsg_traf_pack output, all-gathered),
+ * the conflict list that of bsg_cd_detect*(row0, n_rows = this block) with global indices, and d_nconf_all the number of
+ * conflicts in the whole airspace (the all-reduced d_npairs[0]: upstream rewrites every aircraft's ASAS commands whenever ANY
+ * conflict exists); d_nconf_all == NULL means d_npairs.  Launches: 3 small index kernels (count / allocate / scatter of the conflict list by own
  * aircraft; only with reso) + the fused per-aircraft kernel. */
 int64_t bsg_traf_workspace(int64_t n, int64_t conf_cap);
 int bsg_traf_substep(const bsg_traf_config *cfg, const bsg_traf_tensors *t, const float *d_rec, int32_t fms_ready,
                      const int32_t *d_conf_pairs, const float *d_conf_attr, const unsigned long long *d_npairs,
-                     int64_t conf_cap, void *d_work, int64_t work_bytes, void *stream);
+                     const unsigned long long *d_nconf_all, int64_t conf_cap, void *d_work, int64_t work_bytes, void *stream);
 
 /* ---- rgb_array frames --------------------------------------------------------------------------------
  * Paints a list of draw calls into an RGB frame on the device: d_prims [n_prims][BSG_PRIM_FLOATS] float32 records

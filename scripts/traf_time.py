@@ -27,7 +27,7 @@ def step(self, n_sub=1, detect=True):
             out = timed("detect", lambda: cd.detect_packed(self.rec, self.n, want_pairs=True, cull=self.cull, symmetric=self.symmetric))
             self.last = out
             timed("substep", lambda: _lib.check(self.lib.bsg_traf_substep(C.byref(self.cfg), C.byref(self.tt), _ptr(self.rec), int(fms_ready),
-                  _ptr(out["pairs"]), _ptr(out["attr"]), _ptr(out["npairs"]), cd.pair_capacity, _ptr(self.work), self.work.numel(), st)))
+                  _ptr(out["pairs"]), _ptr(out["attr"]), _ptr(out["npairs"]), None, cd.pair_capacity, _ptr(self.work), self.work.numel(), st)))
 T.AirspaceTraffic.step = step
 r = bench.bench_traffic(torch, dev, 6543.4)
 torch.cuda.synchronize()

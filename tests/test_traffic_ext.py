@@ -349,3 +349,23 @@ def test_mvp_many_aircraft_culled_detection(cuda):
     off, on = los_after(None), los_after("MVP")
     print(f"LoS pair-samples over 240 s: {off} without resolution, {on} with MVP")
     assert on < 0.5 * off
+
+
+@pytest.mark.gpu
+def test_airspace_sharded_over_two_gpus_equals_one(cuda):
+    """SURVEY 8e for the traffic of 8f-4: ONE airspace with its aircraft block-partitioned over the ranks (a rank owns the
+    kinematics of its block; per substep an all-gather of the CD records, detection of the own rows against the whole
+    airspace, MVP on the own aircraft) gives the state of the unsharded airspace bit for bit (scripts/traf_sharded_check.py
+    under torchrun).  Needs two GPUs in the box: skipped on a single-GPU one."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(root, "scripts", "traf_sharded_check.py"), "5000", "40"],
+                       capture_output=True, text=True, timeout=300)
+    assert "SHARDED_TRAFFIC_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    print([l for l in r.stdout.splitlines() if l.startswith("world")][0])
