@@ -786,6 +786,24 @@ def bench_cd_sharded(torch, dist, dev, StateBasedCD, world, rank, max_over_ranks
     nconfc = torch.tensor([int(outc["npairs"][0])], dtype=torch.int64, device=dev)
     dist.all_reduce(nconfc)
     res["culled"] = {"ordered_pairs_per_s": n_tot * (n_tot - 1) / bestc, "ms": bestc * 1e3, "n_conf": int(nconfc.item())}
+    # symmetric forms with the row blocks dealt round-robin to the ranks (BSG_CD_DEAL): every unordered tile pair once in
+    # the whole job, per-aircraft outputs all-reduced (time incl. the gather and the three all-reduces)
+    for name, r, cull in (("symmetric_dealt", rec, False), ("culled_symmetric_dealt", rec_s, True)):
+        for _ in range(2):
+            outd = cd.detect_sharded_symmetric(r, per, cull=cull)
+        barrier()
+        bestd = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            dist.all_reduce(align)
+            e0.record()
+            outd = cd.detect_sharded_symmetric(r, per, cull=cull)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            bestd = min(bestd, max_over_ranks(e0.elapsed_time(e1) * 1e-3))
+        res[name] = {"ordered_pairs_per_s": n_tot * (n_tot - 1) / bestd, "ms": bestd * 1e3, "n_conf": int(outd["npairs"][0]),
+                     "collective": "ncclAllGather of the records, all-reduce of the per-aircraft counts / tcpamax / totals"}
     # no-gather forms: column tiles read from the owning GPU over NVLink inside the CD kernel (bsg_cd_detect_peers)
     try:
         for name, r, cull in (("p2p", rec, False), ("p2p_culled", rec_s, True)):

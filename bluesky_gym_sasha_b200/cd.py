@@ -91,7 +91,7 @@ class StateBasedCD:
         return lists, dict(pairs=pairs, attr=attr, lospairs=los, npairs=npairs)
 
     def detect_packed(self, rec, n_all, row0=0, n_rows=None, lon_wrap=False, want_pairs=True, cull=False, symmetric=False,
-                      want_attr=True):
+                      want_attr=True, deal=None):
         """Rows [row0, row0+n_rows) x all n_all columns.  Asynchronous; returns device tensors: per-row ``nconf_row``,
         ``nlos_row``, ``tcpamax``, ``inconf``; ``npairs`` = (conflicts, LoS pairs) found; with ``want_pairs`` the lists
         ``pairs`` [cap, 2] (+ ``attr`` [cap, 5] = qdr, dist, dcpa, tcpa, tinconf per conflict) and ``lospairs`` [cap, 2].
@@ -108,6 +108,8 @@ class StateBasedCD:
         flags = _lib.CD_LON_WRAP if lon_wrap else 0
         if symmetric:
             flags |= _lib.CD_SYMMETRIC | (0 if cull else _lib.CD_ALLTILES)
+        if deal is not None:                # (BSG_CD_DEAL(n, k): this GPU's share of the row blocks, see detect_sharded_symmetric)
+            flags |= ((int(deal[0]) & 0xff) << 8) | ((int(deal[1]) & 0xff) << 16)
         with torch.cuda.device(self.device):
             if cull or symmetric:
                 nbytes = int(self.lib.bsg_cd_cull_workspace(n_all, n_rows))
@@ -214,6 +216,28 @@ class StateBasedCD:
         return self.detect_packed(allrec, n_local * world, row0=rank * n_local, n_rows=n_local,
                                   lon_wrap=lon_wrap, want_pairs=want_pairs, cull=cull)
 
+
+    def detect_sharded_symmetric(self, rec_local, n_local, group=None, cull=False, want_pairs=False):
+        """Like ``detect_sharded``, but every unordered tile pair is evaluated once in the whole job (BSG_CD_SYMMETRIC) with
+        the row blocks dealt round-robin to the ranks (BSG_CD_DEAL): half the pair evaluations of the row-sharded form.  A
+        rank's kernel posts results to rows anywhere in the airspace, so the per-aircraft outputs are all-reduced (three small
+        collectives) and every rank ends up with the complete ``nconf_row / nlos_row / tcpamax / inconf`` of ALL aircraft;
+        ``npairs`` holds the global totals.  Pair lists (``want_pairs``) stay partitioned by tile-pair owner."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        assert n_local % 256 == 0, "shard size must be a multiple of the 256-aircraft tile"
+        allrec = self._get("allrec", (n_local // 256 * world, 8, 256), torch.float32)
+        dist.all_gather_into_tensor(allrec, rec_local[:n_local // 256].contiguous(), group=group)
+        out = self.detect_packed(allrec, n_local * world, want_pairs=want_pairs, cull=cull, symmetric=True, deal=(world, rank))
+        counts = self._get("sym_counts", (2, n_local * world), torch.int32)
+        counts[0].copy_(out["nconf_row"])
+        counts[1].copy_(out["nlos_row"])
+        dist.all_reduce(counts, group=group)
+        dist.all_reduce(out["tcpamax"], op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(out["npairs"], group=group)
+        out["nconf_row"], out["nlos_row"] = counts[0], counts[1]
+        out["inconf"] = counts[0] > 0
+        return out
 
     # ---------------------------------------------------------------- multi-GPU without a gather (peer memory)
     def detect_sharded_p2p(self, rec_local, n_local, group=None, want_pairs=False, cull=False):

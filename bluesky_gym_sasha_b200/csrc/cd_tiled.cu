@@ -96,6 +96,7 @@ struct CdArgs {
     int n_peers, tiles_per_peer;
     const float* rec_rows;        // the buffer holding this call's own rows; its first record has global index rows_base
     int rows_base;
+    int deal_n, deal_k;           // BSG_CD_DEAL: only the row blocks with (row tile % deal_n) == deal_k (0, 0: all)
 };
 
 __device__ __forceinline__ void load_record(const float* __restrict__ rec, int idx, float4& A, float4& B) {
@@ -455,10 +456,11 @@ __global__ void __launch_bounds__(kTJ) cd_tile_bounds_kernel(const CdArgs a, int
 // float rounding.  Kept tiles are appended to the row block's list in arbitrary order.
 __global__ void cd_cull_kernel(const float* __restrict__ bounds, int n_tiles, int row_tile0, int n_rowblocks, float R,
                                float hpz, float T, int32_t* __restrict__ list, int32_t* __restrict__ cnt, int stride,
-                               int sym, int alltiles) {
+                               int sym, int alltiles, int deal_n, int deal_k) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (long long)n_rowblocks * n_tiles) return;
     const int rb = (int)(p / n_tiles), ct = (int)(p % n_tiles);
+    if (deal_n > 1 && (row_tile0 + rb) % deal_n != deal_k) return;   // BSG_CD_DEAL: another GPU's row block (its list stays empty)
     if (sym && ct < row_tile0 + rb) return;                     // symmetric form: the mirror tile pair covers it
     if (alltiles) { list[(size_t)rb * stride + atomicAdd(&cnt[rb], 1)] = ct; return; }
     const float* A = bounds + (size_t)(row_tile0 + rb) * TB_COUNT;
@@ -608,7 +610,7 @@ static int cd_launch(CdArgs& a, bool wrap, bool cull, bool sym, bool alltiles, v
         const long long n_pairs = (long long)a.n_rowblocks * a.n_tiles;
         cd_cull_kernel<<<(int)((n_pairs + 255) / 256), 256, 0, st>>>(bounds, a.n_tiles, a.row0 / kRowsPerCta, a.n_rowblocks,
                                                                      sqrtf(a.R2), a.hpz, a.dtlook, list, cnt, a.list_stride,
-                                                                     sym ? 1 : 0, alltiles ? 1 : 0);
+                                                                     sym ? 1 : 0, alltiles ? 1 : 0, a.deal_n, a.deal_k);
         cd_chunk_scan_kernel<<<1, 1024, 0, st>>>(cnt, a.n_rowblocks, chunk_off);
         BSG_CUDA(cudaGetLastError());
         if (sym) BSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cd_tiled_kernel<false, true, true>, kNT, 0));
@@ -677,6 +679,8 @@ extern "C" int bsg_cd_detect_culled(const float* d_rec, int64_t n_all, int64_t r
     if (rc != BSG_OK) return rc;
     if (n_rows > 0 && !d_rec) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: null d_rec");
     a.rec = d_rec; a.rec_rows = d_rec; a.rows_base = 0;
+    a.deal_n = (int)((flags >> 8) & 0xffu); a.deal_k = (int)((flags >> 16) & 0xffu);
+    if (a.deal_n > 1 && a.deal_k >= a.deal_n) return bsg_fail(BSG_EINVAL, "bsg_cd_detect_culled: BSG_CD_DEAL(n, k) needs k < n");
     return cd_launch(a, (flags & BSG_CD_LON_WRAP) != 0, true, (flags & BSG_CD_SYMMETRIC) != 0, (flags & BSG_CD_ALLTILES) != 0, d_work, work_bytes,
                      d_inconf, (cudaStream_t)stream);
 }

@@ -284,6 +284,12 @@ enum { BSG_CD_LON_WRAP = 1,     /* pairs may straddle the +-180 deg meridian rel
        BSG_CD_CULL = 4,         /* bsg_cd_detect_peers: use the culled form (needs the workspace)    */
        BSG_CD_ALLTILES = 8 };   /* bsg_cd_detect_culled: keep every tile pair (no culling; with
                                  * BSG_CD_SYMMETRIC = brute force over unordered pairs)              */
+/* bsg_cd_detect_culled over several GPUs that all hold every record (after an all-gather): GPU k of n evaluates the row
+ * blocks (256 rows) whose index % n == k, the others' lists stay empty.  With BSG_CD_SYMMETRIC (row0 = 0, n_rows = n_all on
+ * every GPU) the unordered tile pairs are thereby dealt round-robin -- the lists shrink with the row index, so this balances
+ * -- and the per-row outputs of the GPUs add up: sum d_nconf_row / d_nlos_row / d_npairs and take the maximum of d_tcpamax
+ * over the GPUs (one all-reduce each); d_inconf is nconf > 0 after the sum.  n, k <= 255. */
+#define BSG_CD_DEAL(n, k) ((((uint32_t)(n)) & 0xffu) << 8 | (((uint32_t)(k)) & 0xffu) << 16)
 
 /* Pair lists of a detection = what upstream's StateBased.detect returns besides the per-aircraft flags:
  * confpairs, lospairs and, per conflict, qdr / dist / dcpa / tcpa / tinconf.  All DEVICE memory owned by the caller;

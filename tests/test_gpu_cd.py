@@ -339,3 +339,35 @@ def test_pack_ordered_is_a_spatial_permutation(cuda):
             frac = cnt.sum() / float(n_tiles * n_tiles)
             print(f"device order: {100 * frac:.2f} % of the tile pairs evaluated")
             assert frac < 0.06
+
+
+@pytest.mark.parametrize("cull", [False, True])
+def test_symmetric_form_dealt_over_ranks_adds_up(cuda, cull):
+    """BSG_CD_DEAL: the row blocks of the symmetric form dealt round-robin to n GPUs (emulated here one after the other on
+    one GPU): the per-aircraft counts and the pair totals of the shares add up to the undealt result, tcpamax is the maximum
+    over the shares, and the shares are balanced (the lists shrink with the row index)."""
+    import torch
+    from bluesky_gym_sasha_b200.cd import StateBasedCD
+    n = 20_000
+    s = synth_airspace(n, box_deg=12.0, seed=5, alt_jitter=0.0)
+    cd = StateBasedCD(device=0)
+    rec, _, _ = cd.pack_ordered(*s, 52.0, 4.0)
+    full = cd.detect_packed(rec, n, cull=cull, symmetric=True)
+    ref = {k: full[k].clone() for k in ("nconf_row", "nlos_row", "tcpamax", "npairs")}
+    assert int(ref["npairs"][0]) > 1000
+    for world in (2, 3, 8):
+        nconf = torch.zeros_like(ref["nconf_row"])
+        nlos = torch.zeros_like(ref["nlos_row"])
+        tmax = torch.zeros_like(ref["tcpamax"])
+        npairs = torch.zeros_like(ref["npairs"])
+        share = []
+        for rank in range(world):
+            o = cd.detect_packed(rec, n, cull=cull, symmetric=True, deal=(world, rank))
+            nconf += o["nconf_row"]
+            nlos += o["nlos_row"]
+            tmax = torch.maximum(tmax, o["tcpamax"])
+            npairs += o["npairs"]
+            share.append(int(o["npairs"][0]))
+        assert torch.equal(nconf, ref["nconf_row"]) and torch.equal(nlos, ref["nlos_row"]), (cull, world)
+        assert torch.equal(tmax, ref["tcpamax"]) and torch.equal(npairs, ref["npairs"]), (cull, world)
+        assert max(share) < 2.5 * (sum(share) / world) + 50, share
