@@ -460,6 +460,11 @@ def run_b200(args):
             cd_head.update({"sharded_ordered_pairs_per_s": cd_sharded["ordered_pairs_per_s"], "sharded_ms": cd_sharded["ms"],
                             "sharded_frac_of_fp32_peak_per_gpu": cd_sharded["roofline_frac_per_gpu"],
                             "sharded_form": f"rows over {world} GPUs after one NCCL all-gather, every ordered pair"})
+            if "symmetric_dealt" in cd_sharded:
+                cd_head.update({"sharded_symmetric_ordered_pairs_per_s": cd_sharded["symmetric_dealt"]["ordered_pairs_per_s"],
+                                "sharded_symmetric_ms": cd_sharded["symmetric_dealt"]["ms"],
+                                "sharded_symmetric_form": "every unordered tile pair once in the whole job, row blocks dealt round-robin "
+                                                          "(BSG_CD_DEAL), per-aircraft outputs all-reduced; identical conflicts"})
         line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (lat/lon f64)", "data": "synthetic", "config": workload_config(world),
